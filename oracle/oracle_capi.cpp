@@ -1,0 +1,107 @@
+// oracle/oracle_capi.cpp — TEST INFRASTRUCTURE ONLY: a flat C API over oracle.hpp so that tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg can drive the CPU oracle via
+// ctypes.  The product library (rustfst_b200/csrc) never links or calls this.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "oracle.hpp"
+
+using namespace oracle;
+static thread_local std::string g_err;
+
+#define GUARD(expr)                         \
+  try { expr; return 0; }                   \
+  catch (const std::exception& e) { g_err = e.what(); return 1; }
+
+extern "C" {
+const char* oracle_last_error() { return g_err.c_str(); }
+void* oracle_fst_new() { return new Fst(); }
+void oracle_fst_free(void* f) { delete (Fst*)f; }
+int oracle_fst_add_state(void* f, uint32_t* out) { GUARD(*out = ((Fst*)f)->add_state()); }
+int oracle_fst_set_start(void* f, uint32_t s) { GUARD(((Fst*)f)->set_start(s)); }
+int oracle_fst_set_final(void* f, uint32_t s, float w) { GUARD(((Fst*)f)->set_final(s, w)); }
+int oracle_fst_add_tr(void* f, uint32_t s, uint32_t il, uint32_t ol, float w, uint32_t ns) {
+  GUARD(((Fst*)f)->add_tr(s, Tr{il, ol, w, ns}));
+}
+int oracle_fst_tr_sort(void* f, int ilabel) { GUARD(tr_sort(*(Fst*)f, ilabel != 0)); }
+int oracle_fst_connect(void* f) { GUARD(connect(*(Fst*)f)); }
+int oracle_fst_compute_props(void* f) { GUARD(((Fst*)f)->props = compute_fst_properties_all(*(Fst*)f)); }
+uint64_t oracle_fst_props(void* f) { return ((Fst*)f)->props; }
+void oracle_fst_set_props(void* f, uint64_t p) { ((Fst*)f)->props = p; }
+uint64_t oracle_fst_num_states(void* f) { return ((Fst*)f)->num_states(); }
+uint64_t oracle_fst_num_trs(void* f) { return ((Fst*)f)->num_trs_total(); }
+int64_t oracle_fst_start(void* f) { return ((Fst*)f)->has_start ? (int64_t)((Fst*)f)->start : -1; }
+int oracle_fst_equal(void* a, void* b) { return fst_equal(*(Fst*)a, *(Fst*)b) ? 1 : 0; }
+
+int oracle_fst_from_bytes(const uint8_t* data, uint64_t len, void** out) {
+  GUARD(*out = new Fst(fst_from_bytes(data, (size_t)len, true)));
+}
+// Two-call protocol: returns the size; copies when buf != NULL and cap >= size.
+int oracle_fst_to_bytes(void* f, uint8_t* buf, uint64_t cap, uint64_t* size) {
+  GUARD({
+    auto b = fst_to_bytes(*(Fst*)f);
+    *size = b.size();
+    if (buf && cap >= b.size()) std::memcpy(buf, b.data(), b.size());
+  });
+}
+// CSR export for bulk comparisons: offsets[N+1], arcs[A] (16-byte Tr), finals[N] (+inf = non final)
+int oracle_fst_to_csr(void* fp, uint64_t* offsets, Tr* arcs, float* finals) {
+  GUARD({
+    Fst& f = *(Fst*)fp;
+    uint64_t o = 0;
+    for (size_t s = 0; s < f.states.size(); s++) {
+      offsets[s] = o;
+      finals[s] = f.states[s].has_final ? f.states[s].final_weight : W_ZERO;
+      for (auto& t : f.states[s].trs) arcs[o++] = t;
+    }
+    offsets[f.states.size()] = o;
+  });
+}
+// Bulk build from CSR (props taken verbatim, like a header read).
+int oracle_fst_from_csr(uint64_t nstates, const uint64_t* offsets, const Tr* arcs, const float* finals,
+                        int64_t start, uint64_t props, void** out) {
+  GUARD({
+    auto* f = new Fst();
+    f->states.resize(nstates);
+    for (uint64_t s = 0; s < nstates; s++) {
+      State& st = f->states[s];
+      if (!w_eq(finals[s], W_ZERO)) { st.has_final = true; st.final_weight = finals[s]; }
+      st.trs.assign(arcs + offsets[s], arcs + offsets[s + 1]);
+      for (auto& t : st.trs) { if (t.ilabel == 0) st.niepsilons++; if (t.olabel == 0) st.noepsilons++; }
+    }
+    f->has_start = start >= 0; f->start = (StateId)start; f->props = props & P::TRINARY;
+    *out = f;
+  });
+}
+
+// stats: [states_expanded, arcs_iterated, arcs_emitted]; seconds: wall time of the algorithm only
+int oracle_compose(void* a, void* b, int filter, int do_connect, void** out, uint64_t* stats, double* seconds) {
+  GUARD({
+    ComposeConfig cfg; cfg.filter = filter; cfg.connect = do_connect != 0;
+    ComposeStats st;
+    auto t0 = std::chrono::steady_clock::now();
+    Fst r = compose(*(Fst*)a, *(Fst*)b, cfg, &st);
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (stats) { stats[0] = st.states_expanded; stats[1] = st.arcs_iterated; stats[2] = st.arcs_emitted; }
+    *out = new Fst(std::move(r));
+  });
+}
+// stats: [arcs_relaxed, states_dequeued]; distance (optional, N floats)
+int oracle_shortest_path(void* a, uint64_t nshortest, int unique, float delta, void** out, uint64_t* stats,
+                         double* seconds, float* distance) {
+  GUARD({
+    ShortestPathConfig cfg; cfg.nshortest = (size_t)nshortest; cfg.unique = unique != 0; cfg.delta = delta;
+    SsspStats st;
+    std::vector<float> dist;
+    auto t0 = std::chrono::steady_clock::now();
+    Fst r = shortest_path(*(Fst*)a, cfg, &st, distance ? &dist : nullptr);
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (stats) { stats[0] = st.arcs_relaxed; stats[1] = st.states_dequeued; }
+    if (distance) std::memcpy(distance, dist.data(), dist.size() * sizeof(float));
+    *out = new Fst(std::move(r));
+  });
+}
+}

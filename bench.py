@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — the driver-facing benchmark of the B200 compose + shortest-path engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C3|C2] [--scale S]
+
+One "step" = one pass of the hot path over one synthetic workload:
+  * compose  : BASELINE.json configs[2] "C3" — 1M-state/10M-arc acceptor o 1M-state/10M-arc transducer
+               (TropicalWeight, AutoFilter, connect=true) — the configuration north_star's target is quoted on;
+  * sssp     : BASELINE.json configs[3] "C4" — shortest_path(n=1) on a 5M-state/50M-arc acyclic lattice.
+The JSON line's `metric`/`value` is the composed-arcs/s of the compose leg (whole job, inputs resident in HBM);
+the SSSP leg is reported in the `sssp` object of the same line.  N > 1 runs one replica per GPU with different
+seeds (weak scaling, no data-path collective: a single compose does not shard — DESIGN.md §5); NCCL is only used
+for the barrier / max-over-ranks reduction of the timings.
+
+`--impl reference` times the CPU oracle (oracle/liboracle.so, the restated reference algorithm; the Rust
+reference itself cannot be built here) on the box's host cores — it is single-threaded like rustfst.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(float(parts[0]))
+                    self.max_mhz = float(parts[1])
+                    for n, v in zip(names, parts[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def gen_compose_workload(name, scale, rank):
+    from rustfst_b200 import synth
+    if name == "C2":
+        n, a, lv, v, ov = int(100_000 * scale), int(1_000_000 * scale), 25, 32, 2000
+    else:
+        n, a, lv, v, ov = int(1_000_000 * scale), int(10_000_000 * scale), 50, 32, 20000
+    a1 = synth.layered_acceptor(n, a, v, 3 + 100 * rank, lv)
+    a2 = synth.bigram_transducer(n, a, v, 4 + 100 * rank, lv, out_vocab=ov)
+    return a1, a2
+
+
+def gen_sssp_workload(scale, rank):
+    from rustfst_b200 import synth
+    return synth.layered_acceptor(int(5_000_000 * scale), int(50_000_000 * scale), 1000, 6 + 100 * rank, 50)
+
+
+def csr_bytes(d):
+    return int(d["offsets"].nbytes + d["arcs"].nbytes + d["finals"].nbytes)
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of rustfst's compose on the host cores (1 thread: the reference is single-threaded)."""
+    if rank != 0:
+        return
+    from tests import oracle_lib as O
+    sample_scale = 0.25 * args.scale
+    a1, a2 = gen_compose_workload(args.workload, sample_scale, 0)
+    oa = O.OFst.from_csr(a1["offsets"].astype(np.uint64), a1["arcs"], a1["finals"], a1["start"], a1["props"])
+    ob = O.OFst.from_csr(a2["offsets"].astype(np.uint64), a2["arcs"], a2["finals"], a2["start"], a2["props"])
+    arcs = 0
+    for _ in range(args.warmup):
+        O.compose(oa, ob)
+    t = 0.0
+    for _ in range(args.steps):
+        _, st = O.compose(oa, ob, want_stats=True)
+        t += st["seconds"]
+        arcs += st["arcs_emitted"]
+    value = arcs / t
+    sample = (f"{args.workload} generator at scale {sample_scale} ({a1['num_states']} x {a2['num_states']} states, "
+              f"{len(a1['arcs'])} + {len(a2['arcs'])} arcs), full compose+connect per step")
+    line = {
+        "impl": "reference", "metric": "composed_arcs_per_sec", "value": value, "unit": "arcs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} compose (bounded CPU sample)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "arcs/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": "arcs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=["C3", "C2"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; full size = 1.0)")
+    ap.add_argument("--no-sssp", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import rustfst_b200 as R
+    from rustfst_b200.ffi import check_ffi_error, lib
+    from rustfst_b200 import synth
+
+    if not torch.cuda.is_available() or R.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    check_ffi_error(lib.b200_set_device(local_rank), "b200_set_device")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        check_ffi_error(lib.b200_device_synchronize(), "sync")
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    peak_gbs, peak_src = measured_peak_gbs()
+
+    # ------------------------------------------------------------------ compose leg
+    a1, a2 = gen_compose_workload(args.workload, args.scale, rank)
+    h1, h2 = synth.to_vector_fst(a1), synth.to_vector_fst(a2)
+    d1, d2 = R.DeviceFst.upload(h1), R.DeviceFst.upload(h2)  # inputs resident in HBM before the timed region
+    for _ in range(args.warmup):
+        out, st = R.device_compose(d1, d2)
+        del out
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    tot = {"arcs_emitted": 0, "arcs_iterated": 0, "states_expanded": 0, "kernel_launches": 0, "emit_launches": 0,
+           "ms_emit_kernel": 0.0, "ms_expand": 0.0, "ms_connect": 0.0, "waves": 0}
+    for _ in range(args.steps):
+        out, st = R.device_compose(d1, d2)  # blocks until the result is complete in HBM
+        for k in tot:
+            tot[k] += st[k]
+        del out
+    ev1.record()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    ms_region = max_over_ranks(dev_ms)
+    arcs_all = sum_over_ranks(float(tot["arcs_emitted"]))
+    value = arcs_all / (ms_region * 1e-3)
+    steps = args.steps
+    bytes_compose = 16.0 * tot["arcs_iterated"] + 48.0 * tot["arcs_emitted"] + 32.0 * tot["states_expanded"]
+    emit_bytes = 48.0 * tot["arcs_emitted"]
+    emit_gbs = emit_bytes / (tot["ms_emit_kernel"] * 1e-3) / 1e9 if tot["ms_emit_kernel"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "emit_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "kernel": "k_emit (arc scan: gather matched arc, write output arc, state-table probe)",
+        "achieved": emit_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": emit_gbs / peak_gbs, "peak_source": peak_src,
+        "traffic": traffic,
+        "algorithmic_bytes_per_launch": emit_bytes / max(1, tot["emit_launches"]),
+        "avg_launch_ms": tot["ms_emit_kernel"] / max(1, tot["emit_launches"]),
+        "launches": tot["emit_launches"],
+        "whole_compose": {"bytes_model": "16*A_it + 48*A_out + 32*S", "bytes_per_step": bytes_compose / steps,
+                          "device_ms_per_step": (tot["ms_expand"] + tot["ms_connect"]) / steps,
+                          "achieved_GBps": bytes_compose / ((tot["ms_expand"] + tot["ms_connect"]) * 1e-3) / 1e9,
+                          "frac": bytes_compose / ((tot["ms_expand"] + tot["ms_connect"]) * 1e-3) / 1e9 / peak_gbs},
+    }
+
+    # ------------------------------------------------------------------ end-to-end through the C-ABI (host buffers)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_arcs, d2h = 0, 0
+    for _ in range(max(1, min(steps, 3))):
+        res, st = R.compose_with_stats(h1, h2)  # fst_compose path: H2D of both operands, kernels, D2H of the result
+        e2e_arcs += st["arcs_emitted"]
+        d2h = 4 * (res.num_states() + 1) + 16 * res.num_trs_total() + 4 * res.num_states()
+        del res
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"value": sum_over_ranks(float(e2e_arcs)) / (e2e_ms * 1e-3), "unit": "arcs/s",
+           "h2d_bytes_per_step": csr_bytes(a1) + csr_bytes(a2), "d2h_bytes_per_step": int(d2h),
+           "api": "fst_compose (b200_compose_with_stats) on host VectorFst handles"}
+    del d1, d2
+
+    # ------------------------------------------------------------------ SSSP leg (C4)
+    sssp = None
+    if not args.no_sssp:
+        g = gen_sssp_workload(args.scale, rank)
+        hg = synth.to_vector_fst(g)
+        dg = R.DeviceFst.upload(hg)
+        for _ in range(args.warmup):
+            R.device_shortest_path(dg)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        stot = {"arcs_relaxed": 0, "states_settled": 0, "ms_relax_kernel": 0.0, "ms_device": 0.0, "relax_launches": 0,
+                "kernel_launches": 0}
+        path_kind = None
+        for _ in range(steps):
+            sp, sst = R.device_shortest_path(dg)
+            for k in stot:
+                stot[k] += sst[k]
+            path_kind = sst["path"]
+        s1.record()
+        barrier()
+        sssp_ms = max_over_ranks(s0.elapsed_time(s1))
+        edges = sum_over_ranks(float(stot["arcs_relaxed"]))
+        n_states = g["num_states"]
+        sssp_bytes = 16.0 * stot["arcs_relaxed"] + 20.0 * n_states * steps
+        relax_gbs = (16.0 * stot["arcs_relaxed"] + 12.0 * stot["states_settled"]) / (stot["ms_relax_kernel"] * 1e-3) / 1e9
+        sssp = {
+            "metric": "sssp_edges_per_sec", "value": edges / (sssp_ms * 1e-3), "unit": "edges/s",
+            "ms_per_step": sssp_ms / steps, "workload": f"C4: shortest_path(n=1), {n_states}-state/{len(g['arcs'])}-arc "
+            "layered acyclic lattice, TOP_SORTED known (StateOrderQueue), dyadic weights",
+            "device_path": "parallel relaxation + certificate" if path_kind == 0 else "serial replay",
+            "roofline": {"bound": "hbm", "kernel": "k_relax", "achieved": relax_gbs, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": relax_gbs / peak_gbs, "traffic": None,
+                         "whole_call": {"bytes_model": "16*E + 20*N", "achieved_GBps": sssp_bytes / (stot["ms_device"] * 1e-3) / 1e9,
+                                        "frac": sssp_bytes / (stot["ms_device"] * 1e-3) / 1e9 / peak_gbs}},
+            "gpu_launches": stot["kernel_launches"],
+        }
+        # end to end through fst_shortest_path on the host handle (H2D of the lattice inside)
+        barrier()
+        t0 = time.perf_counter()
+        _, sst = R.shortestpath_with_stats(hg)
+        barrier()
+        sssp["e2e"] = {"value": sst["arcs_relaxed"] / (time.perf_counter() - t0), "unit": "edges/s",
+                       "h2d_bytes_per_step": csr_bytes(g), "d2h_bytes_per_step": 16 * 64}
+        del dg
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from tests import oracle_lib as O
+        oa = O.OFst.from_csr(a1["offsets"].astype(np.uint64), a1["arcs"], a1["finals"], a1["start"], a1["props"])
+        ob = O.OFst.from_csr(a2["offsets"].astype(np.uint64), a2["arcs"], a2["finals"], a2["start"], a2["props"])
+        _, ost = O.compose(oa, ob, want_stats=True)
+        cpu = {"value": ost["arcs_emitted"] / ost["seconds"], "unit": "arcs/s", "cores": 1, "kind": "port",
+               "host_cores": os.cpu_count(),
+               "sample": f"one full {args.workload} compose+connect of the same inputs "
+                         f"({ost['arcs_emitted']} arcs in {ost['seconds']:.2f} s), oracle port of rustfst, 1 thread"}
+        if sssp is not None:
+            og = O.OFst.from_csr(g["offsets"].astype(np.uint64), g["arcs"], g["finals"], g["start"], g["props"])
+            _, sst = O.shortest_path(og, want_stats=True)
+            cpu["sssp"] = {"value": sst["arcs_relaxed"] / sst["seconds"], "unit": "edges/s",
+                           "sample": f"one full C4 shortest_path ({sst['arcs_relaxed']} edges in {sst['seconds']:.2f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": "composed_arcs_per_sec", "value": value, "unit": "arcs/s", "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms_region / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: layered acyclic acceptor ({a1['num_states']} states, "
+                                   f"{len(a1['arcs'])} arcs, olabel-sorted) o bigram-structured transducer "
+                                   f"({a2['num_states']} states, {len(a2['arcs'])} arcs, ilabel-sorted), "
+                                   "TropicalWeight, AutoFilter, connect=true",
+                       "scale": args.scale, "replicas": world, "parallelism": f"replicas x{world} (no data-path collective)",
+                       "l2": "operands + table + output (>= 0.8 GB) exceed the 126 MB L2; no flush needed",
+                       "states_expanded_per_step": tot["states_expanded"] // steps,
+                       "arcs_emitted_per_step": tot["arcs_emitted"] // steps, "waves_per_step": tot["waves"] // steps},
+            "wall_ms_per_step": wall_ms / steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sssp": sssp,
+            "gpu_launches": int(tot["kernel_launches"]), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,179 @@
+"""compose / shortest path — mirror of rustfst-python/rustfst/algorithms/{compose,shortest_path}.py."""
+from __future__ import annotations
+
+import ctypes as C
+from enum import Enum
+from typing import List, Optional, Union
+
+from .ffi import CIntArray, ComposeStats, SsspStats, check_ffi_error, lib
+from .fst import VectorFst
+
+KSHORTESTDELTA = 1e-6
+
+
+class MatcherRewriteMode(Enum):  # compose.py:17-20
+    AUTO = 0
+    ALWAYS = 1
+    NEVER = 2
+
+
+class MatcherConfig:  # compose.py:27-55
+    def __init__(self, sigma_label: int, rewrite_mode: MatcherRewriteMode = MatcherRewriteMode.AUTO,
+                 sigma_allowed_matches: Optional[List[int]] = None):
+        array = sigma_allowed_matches or []
+        arr = CIntArray()
+        arr.size = len(array)
+        self._keep = (C.c_uint32 * len(array))(*array)
+        arr.data = C.cast(self._keep, C.POINTER(C.c_uint32))
+        self.ptr = C.c_void_p()
+        check_ffi_error(lib.fst_matcher_config_new(sigma_label, rewrite_mode.value, arr, C.byref(self.ptr)),
+                        "Error creating MatcherConfig")
+
+    def __del__(self):
+        try:
+            lib.fst_matcher_config_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+class ComposeFilter(Enum):  # compose.py:58-65
+    AUTOFILTER = 0
+    NULLFILTER = 1
+    TRIVIALFILTER = 2
+    SEQUENCEFILTER = 3
+    ALTSEQUENCEFILTER = 4
+    MATCHFILTER = 5
+    NOMATCHFILTER = 6
+
+
+class ComposeConfig:  # compose.py:68-107
+    def __init__(self, compose_filter: ComposeFilter = ComposeFilter.AUTOFILTER, connect: bool = True,
+                 matcher1_config: Optional[MatcherConfig] = None, matcher2_config: Optional[MatcherConfig] = None):
+        self.ptr = C.c_void_p()
+        value = compose_filter.value if isinstance(compose_filter, ComposeFilter) else int(compose_filter)
+        check_ffi_error(lib.fst_compose_config_new(value, bool(connect),
+                                                   matcher1_config.ptr if matcher1_config else None,
+                                                   matcher2_config.ptr if matcher2_config else None,
+                                                   C.byref(self.ptr)), "Error creating ComposeConfig")
+
+    def __del__(self):
+        try:
+            lib.fst_compose_config_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+def compose(fst: VectorFst, other_fst: VectorFst) -> VectorFst:  # compose.py:110-125
+    out = C.c_void_p()
+    check_ffi_error(lib.fst_compose(fst.ptr, other_fst.ptr, C.byref(out)), "Error Composing FSTs")
+    return VectorFst(ptr=out)
+
+
+def compose_with_config(fst: VectorFst, other_fst: VectorFst, config: ComposeConfig) -> VectorFst:  # :128-148
+    out = C.c_void_p()
+    check_ffi_error(lib.fst_compose_with_config(fst.ptr, other_fst.ptr, config.ptr, C.byref(out)),
+                    "Error Composing FSTs")
+    return VectorFst(ptr=out)
+
+
+def compose_with_stats(fst: VectorFst, other_fst: VectorFst, config: Optional[ComposeConfig] = None):
+    """b200 addition: same call through host buffers, plus device counters/timings."""
+    out = C.c_void_p()
+    st = ComposeStats()
+    check_ffi_error(lib.b200_compose_with_stats(fst.ptr, other_fst.ptr, config.ptr if config else None,
+                                                C.byref(out), C.byref(st)), "Error Composing FSTs")
+    return VectorFst(ptr=out), st.as_dict()
+
+
+class ShortestPathConfig:  # shortest_path.py:15-41
+    def __init__(self, nshortest: int = 1, unique: bool = False, delta: Union[float, None] = None):
+        if delta is None:
+            delta = KSHORTESTDELTA
+        self.ptr = C.c_void_p()
+        check_ffi_error(lib.fst_shortest_path_config_new(delta, nshortest, bool(unique), C.byref(self.ptr)),
+                        "Error creating ShortestPathConfig")
+
+    def __del__(self):
+        try:
+            lib.b200_shortest_path_config_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+def shortestpath(fst: VectorFst) -> VectorFst:  # shortest_path.py:44-57
+    out = C.c_void_p()
+    check_ffi_error(lib.fst_shortest_path(fst.ptr, C.byref(out)), "Error computing shortest path")
+    return VectorFst(ptr=out)
+
+
+def shortestpath_with_config(fst: VectorFst, config: ShortestPathConfig) -> VectorFst:  # shortest_path.py:60-76
+    out = C.c_void_p()
+    check_ffi_error(lib.fst_shortest_path_with_config(fst.ptr, config.ptr, C.byref(out)),
+                    "Error computing shortest path")
+    return VectorFst(ptr=out)
+
+
+def shortestpath_with_stats(fst: VectorFst, config: Optional[ShortestPathConfig] = None, force_serial=False):
+    out = C.c_void_p()
+    st = SsspStats()
+    check_ffi_error(lib.b200_shortest_path_with_stats(fst.ptr, config.ptr if config else None, C.byref(out),
+                                                      C.byref(st), bool(force_serial)),
+                    "Error computing shortest path")
+    return VectorFst(ptr=out), st.as_dict()
+
+
+class DeviceFst:
+    """An FST resident in HBM (b200 addition): inputs uploaded once, results left on the device."""
+
+    def __init__(self, ptr, host: Optional[VectorFst] = None):
+        self.ptr = ptr
+        self.host = host
+
+    @classmethod
+    def upload(cls, fst: VectorFst) -> "DeviceFst":
+        p = C.c_void_p()
+        check_ffi_error(lib.b200_device_fst_upload(fst.ptr, C.byref(p)), "Error uploading FST")
+        return cls(p, fst)
+
+    def download(self) -> VectorFst:
+        p = C.c_void_p()
+        check_ffi_error(lib.b200_device_fst_download(self.ptr, C.byref(p)), "Error downloading FST")
+        return VectorFst(p)
+
+    def info(self):
+        n, a, pr = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check_ffi_error(lib.b200_device_fst_info(self.ptr, C.byref(n), C.byref(a), C.byref(pr)), "info failed")
+        return n.value, a.value, pr.value
+
+    def __del__(self):
+        try:
+            lib.b200_device_fst_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+def device_compose(a: DeviceFst, b: DeviceFst, config: Optional[ComposeConfig] = None):
+    out = C.c_void_p()
+    st = ComposeStats()
+    check_ffi_error(lib.b200_device_compose(a.ptr, b.ptr, config.ptr if config else None, C.byref(out), C.byref(st)),
+                    "Error Composing FSTs")
+    return DeviceFst(out), st.as_dict()
+
+
+def device_shortest_path(d: DeviceFst, plan_from: Optional[VectorFst] = None, force_serial=False):
+    host = plan_from or d.host
+    out = C.c_void_p()
+    st = SsspStats()
+    check_ffi_error(lib.b200_device_shortest_path(d.ptr, host.ptr, C.byref(out), C.byref(st), bool(force_serial)),
+                    "Error computing shortest path")
+    return VectorFst(out), st.as_dict()
+
+
+def compose_batch(acceptors: List[VectorFst], transducer: VectorFst, config: Optional[ComposeConfig] = None):
+    n = len(acceptors)
+    ins = (C.c_void_p * n)(*[a.ptr.value if isinstance(a.ptr, C.c_void_p) else a.ptr for a in acceptors])
+    outs = (C.c_void_p * n)()
+    st = ComposeStats()
+    check_ffi_error(lib.b200_compose_batch(ins, n, transducer.ptr, config.ptr if config else None, outs, C.byref(st)),
+                    "Error in batched compose")
+    return [VectorFst(C.c_void_p(outs[i])) for i in range(n)], st.as_dict()

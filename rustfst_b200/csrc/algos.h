@@ -1,0 +1,71 @@
+// algos.h — device algorithms behind fst_compose* / fst_connect / fst_shortest_path* (see include/rustfst_b200.h).
+#pragma once
+#include "device_common.cuh"
+
+namespace b200 {
+
+// rustfst-ffi/src/algorithms/compose.rs:20-33 (values of the size_t passed to fst_compose_config_new)
+enum ComposeFilter : int {
+  kAutoFilter = 0, kNullFilter = 1, kTrivialFilter = 2, kSequenceFilter = 3, kAltSequenceFilter = 4,
+  kMatchFilter = 5, kNoMatchFilter = 6
+};
+
+struct ComposeOptions {  // rustfst/src/algorithms/compose/compose_static.rs:80-97
+  int filter = kAutoFilter;
+  bool connect = true;
+};
+
+struct ComposeStats {
+  uint64_t states_expanded = 0;  // S   product states expanded
+  uint64_t arcs_iterated = 0;    // A_it arcs scanned on the iterated side (excludes the implicit eps loops)
+  uint64_t arcs_emitted = 0;     // A_out arcs emitted before trimming
+  uint64_t waves = 0;            // BFS levels
+  uint64_t states_out = 0, arcs_out = 0;  // after connect (== S, A_out when connect is off)
+  float ms_expand = 0, ms_connect = 0;    // device time (CUDA events on the call's stream)
+  float ms_emit_kernel = 0;               // summed duration of the emit kernel (roofline numerator's time)
+  uint64_t emit_launches = 0;
+  uint64_t kernel_launches = 0;           // kernels of this library launched by the call
+};
+
+// a must be olabel-sorted and/or b ilabel-sorted as recorded in their property words (A.1 of SURVEY.md);
+// throws FstError with the reference's message otherwise.
+DevFst compose_device(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
+                      cudaStream_t s);
+
+// Trim: keep states that are accessible and coaccessible, order-preserving renumbering
+// (rustfst/src/algorithms/connect.rs:51-66, rustfst/src/fst_impls/vector_fst/mutable_fst.rs:132-189).
+// assume_accessible skips the forward pass (true for a freshly composed FST: every state was reached by the BFS).
+DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launches, cudaStream_t s);
+
+// ---- shortest path (n = 1)
+enum QueueKind : int { kStateOrderQueue = 0, kTopOrderQueue = 1, kLifoQueue = 2, kSccQueue = 3 };
+
+// Host-built mirror of AutoQueue::new (rustfst/src/algorithms/queues/auto_queue.rs:23-99): which discipline the
+// reference would pick from the stored property bits, plus the DFS-derived orders it needs.
+struct QueuePlan {
+  QueueKind kind = kStateOrderQueue;
+  std::vector<uint32_t> order;      // kTopOrderQueue: order[state] (reverse DFS finish order or reversed SCC number)
+  std::vector<uint32_t> scc;        // kSccQueue: scc[state]
+  std::vector<uint8_t> scc_is_fifo; // kSccQueue: per component, 1 = FifoQueue, 0 = TrivialQueue
+  double host_ms = 0;               // time spent on the host DFS
+};
+QueuePlan build_queue_plan(const CsrFst& fst);
+
+struct SsspStats {
+  uint64_t arcs_relaxed = 0;   // E
+  uint64_t states_settled = 0; // N touched
+  uint64_t waves = 0;
+  int path = 0;                // 0 = parallel relaxation path, 1 = order-faithful serial kernel
+  float ms_device = 0;         // device time of the whole call
+  float ms_relax_kernel = 0;   // summed duration of the relaxation kernel
+  uint64_t relax_launches = 0;
+  uint64_t kernel_launches = 0;
+  double plan_host_ms = 0;
+};
+
+// Returns the single-shortest-path FST exactly as rustfst's single_shortest_path + backtrace would
+// (rustfst/src/algorithms/shortest_path.rs:173-282): state 0 = final-most state, start = last state.
+CsrFst shortest_path_device(const DevFst& fst, const QueuePlan& plan, SsspStats* stats, cudaStream_t s,
+                            bool force_serial = false);
+
+}  // namespace b200

@@ -1,0 +1,532 @@
+// capi.cu — the extern "C" surface declared in include/rustfst_b200.h.
+// Error convention and handle ownership follow rustfst-ffi/src/lib.rs:29-85 and rustfst-ffi/src/fst/mod.rs.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/rustfst_b200.h"
+#include "algos.h"
+
+using namespace b200;
+
+// ---- opaque handle types
+struct CFst { HostFst fst; };
+struct CTrs { std::shared_ptr<std::vector<Tr>> v; };
+struct CTrsIterator { std::vector<Tr> trs; size_t index = 0; };
+struct CMutTrsIterator { CFst* fst; StateId state; size_t index = 0; };
+struct CStateIterator { size_t n; size_t index = 0; };
+struct CMatcherConfig { uint32_t sigma_label; size_t rewrite_mode; std::vector<uint32_t> allowed; };
+struct CComposeConfig { size_t filter; bool connect; bool has_m1, has_m2; CMatcherConfig m1, m2; };
+struct CShortestPathConfig { float delta; size_t nshortest; bool unique; };
+struct B200DeviceFst {
+  Stream stream;
+  DevFst d;
+  B200DeviceFst() : d(stream.s) {}
+};
+
+static_assert(sizeof(CTr) == sizeof(Tr), "CTr and the device arc record must coincide");
+
+namespace {
+thread_local std::string g_last_error;
+thread_local bool g_has_error = false;
+
+template <class F>
+RUSTFST_FFI_RESULT wrap(F&& f) {  // rustfst-ffi/src/lib.rs:43-55
+  try {
+    f();
+    return RUSTFST_FFI_RESULT_OK;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    g_has_error = true;
+    if (std::getenv("AMSTRAM_FFI_ERROR_STDERR")) std::fprintf(stderr, "%s\n", e.what());
+    return RUSTFST_FFI_RESULT_KO;
+  }
+}
+char* dup_cstr(const std::string& s) {
+  char* p = (char*)std::malloc(s.size() + 1);
+  std::memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+const Tr& as_tr(const CTr* t) { return *reinterpret_cast<const Tr*>(t); }
+CTr* new_ctr(const Tr& t) {
+  CTr* c = new CTr;
+  std::memcpy(c, &t, sizeof(Tr));
+  return c;
+}
+template <class T>
+T* nn(T* p, const char* what) {  // ffi_convert raw_borrow on a null pointer is an error, not UB
+  if (!p) throw FstError(std::string("unexpected null pointer: ") + what);
+  return p;
+}
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+ComposeOptions to_options(const CComposeConfig* c) {
+  ComposeOptions o;
+  if (!c) return o;
+  if (c->filter > 6) throw FstError("EnumConversionError");
+  o.filter = (int)c->filter;
+  o.connect = c->connect;
+  if (c->has_m1 || c->has_m2) {
+    if (o.filter == kAutoFilter)  // compose_static.rs:219-223
+      throw FstError("Custom MatcherConfig not supported with AutoFilter");
+    throw FstError("SigmaMatcher configurations are not supported by this build of librustfst_b200");
+  }
+  return o;
+}
+void fill(B200ComposeStats* out, const ComposeStats& st, float h2d, float d2h) {
+  if (!out) return;
+  out->states_expanded = st.states_expanded; out->arcs_iterated = st.arcs_iterated;
+  out->arcs_emitted = st.arcs_emitted; out->waves = st.waves; out->states_out = st.states_out;
+  out->arcs_out = st.arcs_out; out->kernel_launches = st.kernel_launches; out->emit_launches = st.emit_launches;
+  out->ms_expand = st.ms_expand; out->ms_connect = st.ms_connect; out->ms_emit_kernel = st.ms_emit_kernel;
+  out->ms_h2d = h2d; out->ms_d2h = d2h;
+}
+void fill(B200SsspStats* out, const SsspStats& st, int kind, float h2d) {
+  if (!out) return;
+  out->arcs_relaxed = st.arcs_relaxed; out->states_settled = st.states_settled; out->waves = st.waves;
+  out->kernel_launches = st.kernel_launches; out->relax_launches = st.relax_launches; out->path = st.path;
+  out->queue_kind = kind; out->ms_device = st.ms_device; out->ms_relax_kernel = st.ms_relax_kernel;
+  out->ms_h2d = h2d; out->ms_queue_plan_host = st.plan_host_ms;
+}
+
+CFst* compose_host(const CFst* a, const CFst* b, const CComposeConfig* cfg, B200ComposeStats* stats) {
+  ComposeOptions opt = to_options(cfg);
+  const CsrFst& ha = nn(a, "fst_1")->fst.freeze();
+  const CsrFst& hb = nn(b, "fst_2")->fst.freeze();
+  Stream st;
+  double t0 = now_ms();
+  DevFst da = upload(ha, st.s);
+  DevFst db = upload(hb, st.s);
+  double t1 = now_ms();
+  ComposeStats cs;
+  DevFst dr = compose_device(da, db, opt, &cs, st.s);
+  double t2 = now_ms();
+  CsrFst hr = download(dr, st.s);
+  double t3 = now_ms();
+  fill(stats, cs, (float)(t1 - t0), (float)(t3 - t2));
+  return new CFst{HostFst(std::move(hr))};
+}
+
+CFst* shortest_path_host(const CFst* in, const CShortestPathConfig* cfg, B200SsspStats* stats, bool force_serial) {
+  size_t nshortest = cfg ? cfg->nshortest : 1;  // shortest_path.rs:30-38 defaults
+  if (nshortest == 0) {                          // shortest_path.rs:120-122
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    return new CFst{};
+  }
+  if (nshortest != 1)
+    throw FstError("shortest_path with nshortest > 1 is not supported by this build of librustfst_b200");
+  const CsrFst& h = nn(in, "fst")->fst.freeze();
+  QueuePlan plan = build_queue_plan(h);
+  Stream st;
+  double t0 = now_ms();
+  DevFst d = upload(h, st.s);
+  double t1 = now_ms();
+  SsspStats ss;
+  CsrFst r = shortest_path_device(d, plan, &ss, st.s, force_serial);
+  fill(stats, ss, (int)plan.kind, (float)(t1 - t0));
+  return new CFst{HostFst(std::move(r))};
+}
+}  // namespace
+
+extern "C" {
+
+const char* b200_version(void) { return "rustfst_b200 0.1.0 (sm_100a)"; }
+
+RUSTFST_FFI_RESULT rustfst_ffi_get_last_error(char** error) {
+  return wrap([&] {
+    std::string msg = g_has_error ? g_last_error : std::string("No error message");
+    g_has_error = false;
+    g_last_error.clear();
+    *error = dup_cstr(msg);
+  });
+}
+RUSTFST_FFI_RESULT rustfst_destroy_string(char* string) {
+  return wrap([&] { std::free(string); });
+}
+
+// ---------------------------------------------------------------- hot path
+RUSTFST_FFI_RESULT fst_compose(const CFst* a, const CFst* b, const CFst** out) {
+  return wrap([&] { *out = compose_host(a, b, nullptr, nullptr); });
+}
+RUSTFST_FFI_RESULT fst_compose_with_config(const CFst* a, const CFst* b, const CComposeConfig* cfg, const CFst** out) {
+  return wrap([&] { *out = compose_host(a, b, nn(cfg, "config"), nullptr); });
+}
+RUSTFST_FFI_RESULT b200_compose_with_stats(const CFst* a, const CFst* b, const CComposeConfig* cfg, const CFst** out,
+                                           B200ComposeStats* stats) {
+  return wrap([&] { *out = compose_host(a, b, cfg, stats); });
+}
+RUSTFST_FFI_RESULT fst_compose_config_new(size_t filter, bool connect, const CMatcherConfig* m1,
+                                          const CMatcherConfig* m2, const CComposeConfig** config) {
+  return wrap([&] {
+    auto* c = new CComposeConfig{filter, connect, m1 != nullptr, m2 != nullptr, {}, {}};
+    if (m1) c->m1 = *m1;
+    if (m2) c->m2 = *m2;
+    *config = c;
+  });
+}
+RUSTFST_FFI_RESULT fst_compose_config_destroy(CComposeConfig* p) { return wrap([&] { delete p; }); }
+RUSTFST_FFI_RESULT fst_matcher_config_new(size_t sigma_label, size_t rewrite_mode, CIntArray allowed,
+                                          const CMatcherConfig** config) {
+  return wrap([&] {
+    auto* c = new CMatcherConfig{(uint32_t)sigma_label, rewrite_mode, {}};
+    if (allowed.data && allowed.size) c->allowed.assign(allowed.data, allowed.data + allowed.size);
+    *config = c;
+  });
+}
+RUSTFST_FFI_RESULT fst_matcher_config_destroy(CMatcherConfig* p) { return wrap([&] { delete p; }); }
+
+RUSTFST_FFI_RESULT fst_shortest_path(const CFst* in, const CFst** out) {
+  return wrap([&] { *out = shortest_path_host(in, nullptr, nullptr, false); });
+}
+RUSTFST_FFI_RESULT fst_shortest_path_with_config(const CFst* in, const CShortestPathConfig* cfg, const CFst** out) {
+  return wrap([&] { *out = shortest_path_host(in, nn(cfg, "config"), nullptr, false); });
+}
+RUSTFST_FFI_RESULT b200_shortest_path_with_stats(const CFst* in, const CShortestPathConfig* cfg, const CFst** out,
+                                                 B200SsspStats* stats, bool force_serial) {
+  return wrap([&] { *out = shortest_path_host(in, cfg, stats, force_serial); });
+}
+RUSTFST_FFI_RESULT fst_shortest_path_config_new(float delta, size_t nshortest, bool unique,
+                                                const CShortestPathConfig** ptr) {
+  return wrap([&] { *ptr = new CShortestPathConfig{delta, nshortest, unique}; });
+}
+RUSTFST_FFI_RESULT b200_shortest_path_config_destroy(CShortestPathConfig* p) { return wrap([&] { delete p; }); }
+
+RUSTFST_FFI_RESULT fst_connect(CFst* ptr) {
+  return wrap([&] {
+    const CsrFst& h = nn(ptr, "fst")->fst.freeze();
+    Stream st;
+    DevFst d = upload(h, st.s);
+    DevFst r = connect_device(d, false, nullptr, st.s);
+    ptr->fst.replace(download(r, st.s));
+  });
+}
+RUSTFST_FFI_RESULT fst_tr_sort(CFst* ptr, bool ilabel_comp) {
+  return wrap([&] { nn(ptr, "fst")->fst.tr_sort(ilabel_comp); });
+}
+
+// ---------------------------------------------------------------- Fst accessors
+RUSTFST_FFI_RESULT fst_start(const CFst* fst, CStateId* state) {
+  return wrap([&] { StateId s; if (nn(fst, "fst")->fst.start(&s)) *state = s; });
+}
+RUSTFST_FFI_RESULT fst_final_weight(const CFst* fst, CStateId s, float* w) {
+  return wrap([&] { float v; if (nn(fst, "fst")->fst.final_weight(s, &v)) *w = v; });
+}
+RUSTFST_FFI_RESULT fst_num_trs(const CFst* fst, CStateId s, size_t* n) {
+  return wrap([&] { *n = nn(fst, "fst")->fst.num_trs(s); });
+}
+RUSTFST_FFI_RESULT fst_get_trs(const CFst* fst, CStateId s, const CTrs** trs) {
+  return wrap([&] { *trs = new CTrs{std::make_shared<std::vector<Tr>>(nn(fst, "fst")->fst.get_trs(s))}; });
+}
+RUSTFST_FFI_RESULT fst_is_final(const CFst* fst, CStateId s, size_t* is_final) {
+  return wrap([&] { float v; *is_final = nn(fst, "fst")->fst.final_weight(s, &v) ? 1 : 0; });
+}
+RUSTFST_FFI_RESULT fst_is_start(const CFst* fst, CStateId s, size_t* is_start) {
+  return wrap([&] { StateId st; *is_start = (nn(fst, "fst")->fst.start(&st) && st == s) ? 1 : 0; });
+}
+// Symbol tables are outside the hot path: handles never carry one, so the optional out slot is left untouched.
+RUSTFST_FFI_RESULT fst_input_symbols(const CFst* fst, const CSymbolTable**) { return wrap([&] { nn(fst, "fst"); }); }
+RUSTFST_FFI_RESULT fst_output_symbols(const CFst* fst, const CSymbolTable**) { return wrap([&] { nn(fst, "fst"); }); }
+RUSTFST_FFI_RESULT fst_weight_one(float* w) { return wrap([&] { *w = 0.0f; }); }
+RUSTFST_FFI_RESULT fst_weight_zero(float* w) { return wrap([&] { *w = w_zero(); }); }
+RUSTFST_FFI_RESULT fst_destroy(CFst* p) { return wrap([&] { delete p; }); }
+
+// ---------------------------------------------------------------- VectorFst
+RUSTFST_FFI_RESULT vec_fst_new(const CFst** ptr) { return wrap([&] { *ptr = new CFst{}; }); }
+RUSTFST_FFI_RESULT vec_fst_set_start(CFst* f, CStateId s) { return wrap([&] { nn(f, "fst")->fst.set_start(s); }); }
+RUSTFST_FFI_RESULT vec_fst_set_final(CFst* f, CStateId s, float w) {
+  return wrap([&] { nn(f, "fst")->fst.set_final(s, w); });
+}
+RUSTFST_FFI_RESULT vec_fst_add_state(CFst* f, CStateId* s) { return wrap([&] { *s = nn(f, "fst")->fst.add_state(); }); }
+RUSTFST_FFI_RESULT vec_fst_delete_states(CFst* f) { return wrap([&] { nn(f, "fst")->fst.del_all_states(); }); }
+RUSTFST_FFI_RESULT vec_fst_add_tr(CFst* f, CStateId s, const CTr* tr) {
+  return wrap([&] { nn(f, "fst")->fst.add_tr(s, as_tr(nn(tr, "tr"))); });
+}
+RUSTFST_FFI_RESULT vec_fst_del_final_weight(CFst* f, CStateId s) {
+  return wrap([&] { nn(f, "fst")->fst.delete_final_weight(s); });
+}
+RUSTFST_FFI_RESULT vec_fst_from_path(const CFst** ptr, const char* path) {
+  return wrap([&] {
+    auto bytes = io::read_file(nn(path, "path"));
+    *ptr = new CFst{HostFst(io::parse_vector_fst(bytes.data(), bytes.size()))};
+  });
+}
+RUSTFST_FFI_RESULT vec_fst_write_file(const CFst* f, const char* path) {
+  return wrap([&] { io::write_file(nn(path, "path"), io::store_vector_fst(nn(f, "fst")->fst.freeze())); });
+}
+RUSTFST_FFI_RESULT vec_fst_num_states(const CFst* f, size_t* n) {
+  return wrap([&] { *n = nn(f, "fst")->fst.num_states(); });
+}
+RUSTFST_FFI_RESULT vec_fst_equals(const CFst* a, const CFst* b, size_t* eq) {
+  return wrap([&] { *eq = nn(a, "fst")->fst.equals(nn(b, "other_fst")->fst) ? 1 : 0; });
+}
+RUSTFST_FFI_RESULT vec_fst_copy(const CFst* f, const CFst** clone) {
+  return wrap([&] { *clone = new CFst{HostFst(nn(f, "fst")->fst)}; });
+}
+RUSTFST_FFI_RESULT vec_fst_display(const CFst* f, const char** s) {
+  return wrap([&] { *s = dup_cstr(nn(f, "fst")->fst.display()); });
+}
+RUSTFST_FFI_RESULT vec_fst_to_bytes(const CFst* f, const CArrayU8** out) {
+  return wrap([&] {
+    auto bytes = io::store_vector_fst(nn(f, "fst")->fst.freeze());
+    uint8_t* p = (uint8_t*)std::malloc(bytes.size() ? bytes.size() : 1);
+    std::memcpy(p, bytes.data(), bytes.size());
+    *out = new CArrayU8{p, bytes.size()};
+  });
+}
+RUSTFST_FFI_RESULT b200_bytes_destroy(CArrayU8* b) {
+  return wrap([&] { if (b) { std::free((void*)b->data_ptr); delete b; } });
+}
+RUSTFST_FFI_RESULT vec_fst_from_bytes(const CArrayU8* bytes, const CFst** ptr) {
+  return wrap([&] {
+    nn(bytes, "bytes");
+    *ptr = new CFst{HostFst(io::parse_vector_fst(bytes->data_ptr, bytes->size))};
+  });
+}
+
+// ---------------------------------------------------------------- Tr
+RUSTFST_FFI_RESULT tr_new(CLabel il, CLabel ol, float w, CStateId ns, const CTr** out) {
+  return wrap([&] { *out = new CTr{il, ol, w, ns}; });
+}
+RUSTFST_FFI_RESULT tr_ilabel(const CTr* t, CLabel* v) { return wrap([&] { *v = nn(t, "tr")->ilabel; }); }
+RUSTFST_FFI_RESULT tr_set_ilabel(CTr* t, size_t v) { return wrap([&] { nn(t, "tr")->ilabel = (CLabel)v; }); }
+RUSTFST_FFI_RESULT tr_olabel(const CTr* t, CLabel* v) { return wrap([&] { *v = nn(t, "tr")->olabel; }); }
+RUSTFST_FFI_RESULT tr_set_olabel(CTr* t, size_t v) { return wrap([&] { nn(t, "tr")->olabel = (CLabel)v; }); }
+RUSTFST_FFI_RESULT tr_weight(const CTr* t, float* v) { return wrap([&] { *v = nn(t, "tr")->weight; }); }
+RUSTFST_FFI_RESULT tr_set_weight(CTr* t, float v) { return wrap([&] { nn(t, "tr")->weight = v; }); }
+RUSTFST_FFI_RESULT tr_next_state(const CTr* t, CStateId* v) { return wrap([&] { *v = nn(t, "tr")->nextstate; }); }
+RUSTFST_FFI_RESULT tr_set_next_state(CTr* t, size_t v) { return wrap([&] { nn(t, "tr")->nextstate = (CStateId)v; }); }
+RUSTFST_FFI_RESULT tr_delete(CTr* t) { return wrap([&] { delete t; }); }
+
+// ---------------------------------------------------------------- Trs
+RUSTFST_FFI_RESULT trs_vec_new(const CTrs** out) {
+  return wrap([&] { *out = new CTrs{std::make_shared<std::vector<Tr>>()}; });
+}
+RUSTFST_FFI_RESULT trs_vec_remove(CTrs* trs, size_t index, const CTr** removed) {
+  return wrap([&] {
+    auto& v = *nn(trs, "trs")->v;
+    if (index >= v.size()) throw FstError("removal index (is " + std::to_string(index) + ") should be < len (is " +
+                                          std::to_string(v.size()) + ")");
+    // TrsVec::remove goes through Arc::make_mut: copy-on-write when shared (rustfst/src/trs.rs)
+    if (trs->v.use_count() > 1) trs->v = std::make_shared<std::vector<Tr>>(*trs->v);
+    Tr t = (*trs->v)[index];
+    trs->v->erase(trs->v->begin() + (long)index);
+    *removed = new_ctr(t);
+  });
+}
+RUSTFST_FFI_RESULT trs_vec_push(CTrs* trs, const CTr* tr) {
+  return wrap([&] {
+    nn(trs, "trs");
+    if (trs->v.use_count() > 1) trs->v = std::make_shared<std::vector<Tr>>(*trs->v);
+    trs->v->push_back(as_tr(nn(tr, "tr")));
+  });
+}
+RUSTFST_FFI_RESULT trs_vec_shallow_clone(const CTrs* trs, const CTrs** out) {
+  return wrap([&] { *out = new CTrs{nn(trs, "trs")->v}; });
+}
+RUSTFST_FFI_RESULT trs_vec_len(const CTrs* trs, size_t* n) { return wrap([&] { *n = nn(trs, "trs")->v->size(); }); }
+RUSTFST_FFI_RESULT trs_vec_display(const CTrs* trs, const char** out) {
+  return wrap([&] {
+    std::string s = "TrsVec([";
+    bool first = true;
+    for (const Tr& t : *nn(trs, "trs")->v) {
+      if (!first) s += ", ";
+      first = false;
+      s += "Tr { ilabel: " + std::to_string(t.ilabel) + ", olabel: " + std::to_string(t.olabel) +
+           ", weight: TropicalWeight { value: " + std::to_string(t.weight) + " }, nextstate: " +
+           std::to_string(t.nextstate) + " }";
+    }
+    s += "])";
+    *out = dup_cstr(s);
+  });
+}
+RUSTFST_FFI_RESULT trs_vec_delete(CTrs* p) { return wrap([&] { delete p; }); }
+
+// ---------------------------------------------------------------- iterators
+RUSTFST_FFI_RESULT trs_iterator_new(CFst* fst, CStateId s, const CTrsIterator** out) {
+  return wrap([&] {
+    nn(fst, "fst");
+    // an unknown state leaves the caller's slot untouched and still returns OK (iterators.rs:49-62)
+    if (s < fst->fst.num_states()) *out = new CTrsIterator{fst->fst.get_trs(s), 0};
+  });
+}
+RUSTFST_FFI_RESULT trs_iterator_next(CTrsIterator* it, const CTr** out) {
+  return wrap([&] {
+    nn(it, "iter");
+    if (it->index < it->trs.size()) *out = new_ctr(it->trs[it->index]);
+    it->index++;
+  });
+}
+RUSTFST_FFI_RESULT trs_iterator_done(const CTrsIterator* it, size_t* done) {
+  return wrap([&] { *done = nn(it, "iter")->trs.size() == it->index ? 1 : 0; });
+}
+RUSTFST_FFI_RESULT trs_iterator_reset(CTrsIterator* it) { return wrap([&] { nn(it, "iter")->index = 0; }); }
+RUSTFST_FFI_RESULT trs_iterator_destroy(CTrsIterator* it) { return wrap([&] { delete it; }); }
+
+RUSTFST_FFI_RESULT mut_trs_iterator_new(CFst* fst, CStateId s, const CMutTrsIterator** out) {
+  return wrap([&] {
+    nn(fst, "fst")->fst.num_trs(s);  // validates the state
+    *out = new CMutTrsIterator{fst, s, 0};
+  });
+}
+RUSTFST_FFI_RESULT mut_trs_iterator_next(CMutTrsIterator* it) { return wrap([&] { nn(it, "iter")->index++; }); }
+RUSTFST_FFI_RESULT mut_trs_iterator_value(CMutTrsIterator* it, const CTr** out) {
+  return wrap([&] {
+    nn(it, "iter");
+    auto trs = it->fst->fst.get_trs(it->state);
+    if (it->index < trs.size()) *out = new_ctr(trs[it->index]);
+  });
+}
+RUSTFST_FFI_RESULT mut_trs_iterator_set_value(CMutTrsIterator* it, const CTr* tr) {
+  return wrap([&] { nn(it, "iter")->fst->fst.set_tr(it->state, it->index, as_tr(nn(tr, "tr"))); });
+}
+RUSTFST_FFI_RESULT mut_trs_iterator_done(const CMutTrsIterator* it, size_t* done) {
+  return wrap([&] { *done = nn(it, "iter")->index >= it->fst->fst.num_trs(it->state) ? 1 : 0; });
+}
+RUSTFST_FFI_RESULT mut_trs_iterator_reset(CMutTrsIterator* it) { return wrap([&] { nn(it, "iter")->index = 0; }); }
+RUSTFST_FFI_RESULT mut_trs_iterator_destroy(CMutTrsIterator* it) { return wrap([&] { delete it; }); }
+
+RUSTFST_FFI_RESULT state_iterator_new(CFst* fst, const CStateIterator** out) {
+  return wrap([&] { *out = new CStateIterator{nn(fst, "fst")->fst.num_states(), 0}; });
+}
+RUSTFST_FFI_RESULT state_iterator_next(CStateIterator* it, CStateId* state) {
+  return wrap([&] {
+    nn(it, "iter");
+    if (it->index < it->n) *state = (CStateId)it->index;
+    it->index++;
+  });
+}
+RUSTFST_FFI_RESULT state_iterator_done(CStateIterator* it, size_t* done) {
+  return wrap([&] { *done = nn(it, "iter")->index >= it->n ? 1 : 0; });
+}
+RUSTFST_FFI_RESULT state_iterator_destroy(CStateIterator* it) { return wrap([&] { delete it; }); }
+
+// ---------------------------------------------------------------- b200_ additions
+RUSTFST_FFI_RESULT b200_fst_properties(const CFst* f, uint64_t* p) {
+  return wrap([&] { *p = nn(f, "fst")->fst.properties(); });
+}
+RUSTFST_FFI_RESULT b200_fst_set_properties(CFst* f, uint64_t p) {
+  return wrap([&] { nn(f, "fst")->fst.set_properties(p); });
+}
+RUSTFST_FFI_RESULT b200_fst_from_csr(uint64_t n, const uint32_t* offsets, const CTr* arcs, const float* finals,
+                                     int64_t start, uint64_t props_word, const CFst** out) {
+  return wrap([&] {
+    if (n >= 0x7FFFFFFFull) throw FstError("too many states");
+    CsrFst c;
+    c.offsets.assign(offsets, offsets + n + 1);
+    size_t a = c.offsets[n];
+    c.arcs.resize(a);
+    if (a) std::memcpy(c.arcs.data(), arcs, a * sizeof(Tr));
+    c.finals.assign(finals, finals + n);
+    c.has_start = start >= 0;
+    c.start = (StateId)start;
+    if (c.has_start && (uint64_t)start >= n) throw FstError("The state " + std::to_string(start) + " doesn't exist");
+    c.props = props_word & props::kTrinary;
+    *out = new CFst{HostFst(std::move(c))};
+  });
+}
+RUSTFST_FFI_RESULT b200_fst_num_trs_total(const CFst* f, uint64_t* n) {
+  return wrap([&] { *n = nn(f, "fst")->fst.freeze().arcs.size(); });
+}
+RUSTFST_FFI_RESULT b200_fst_to_csr(const CFst* f, uint32_t* offsets, CTr* arcs, float* finals, int64_t* start) {
+  return wrap([&] {
+    const CsrFst& c = nn(f, "fst")->fst.freeze();
+    if (offsets) std::memcpy(offsets, c.offsets.data(), c.offsets.size() * 4);
+    if (arcs && !c.arcs.empty()) std::memcpy(arcs, c.arcs.data(), c.arcs.size() * sizeof(Tr));
+    if (finals && !c.finals.empty()) std::memcpy(finals, c.finals.data(), c.finals.size() * 4);
+    if (start) *start = c.has_start ? (int64_t)c.start : -1;
+  });
+}
+
+RUSTFST_FFI_RESULT b200_device_fst_upload(const CFst* f, const B200DeviceFst** out) {
+  return wrap([&] {
+    const CsrFst& h = nn(f, "fst")->fst.freeze();
+    auto d = std::make_unique<B200DeviceFst>();
+    d->d = upload(h, d->stream.s);
+    *out = d.release();
+  });
+}
+RUSTFST_FFI_RESULT b200_device_fst_download(const B200DeviceFst* d, const CFst** out) {
+  return wrap([&] { *out = new CFst{HostFst(download(nn(d, "dfst")->d, d->stream.s))}; });
+}
+RUSTFST_FFI_RESULT b200_device_fst_info(const B200DeviceFst* d, uint64_t* n, uint64_t* a, uint64_t* p) {
+  return wrap([&] {
+    nn(d, "dfst");
+    if (n) *n = d->d.num_states;
+    if (a) *a = d->d.num_arcs;
+    if (p) *p = d->d.props;
+  });
+}
+RUSTFST_FFI_RESULT b200_device_fst_destroy(B200DeviceFst* d) {
+  return wrap([&] {
+    if (!d) return;
+    cudaStreamSynchronize(d->stream.s);
+    delete d;
+  });
+}
+RUSTFST_FFI_RESULT b200_device_compose(const B200DeviceFst* a, const B200DeviceFst* b, const CComposeConfig* cfg,
+                                       const B200DeviceFst** out, B200ComposeStats* stats) {
+  return wrap([&] {
+    ComposeOptions opt = to_options(cfg);
+    auto r = std::make_unique<B200DeviceFst>();
+    ComposeStats cs;
+    r->d = compose_device(nn(a, "fst_1")->d, nn(b, "fst_2")->d, opt, &cs, r->stream.s);
+    fill(stats, cs, 0.0f, 0.0f);
+    *out = r.release();
+  });
+}
+RUSTFST_FFI_RESULT b200_device_shortest_path(const B200DeviceFst* d, const CFst* plan_from, const CFst** out,
+                                             B200SsspStats* stats, bool force_serial) {
+  return wrap([&] {
+    QueuePlan plan = build_queue_plan(nn(plan_from, "plan_from")->fst.freeze());
+    SsspStats ss;
+    CsrFst r = shortest_path_device(nn(d, "dfst")->d, plan, &ss, d->stream.s, force_serial);
+    fill(stats, ss, (int)plan.kind, 0.0f);
+    *out = new CFst{HostFst(std::move(r))};
+  });
+}
+RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, const CFst* transducer,
+                                      const CComposeConfig* cfg, const CFst** results, B200ComposeStats* total) {
+  return wrap([&] {
+    ComposeOptions opt = to_options(cfg);
+    Stream st;
+    DevFst dt = upload(nn(transducer, "transducer")->fst.freeze(), st.s);
+    B200ComposeStats acc;
+    std::memset(&acc, 0, sizeof(acc));
+    for (size_t i = 0; i < n; i++) results[i] = nullptr;
+    for (size_t i = 0; i < n; i++) {
+      DevFst da = upload(nn(acceptors[i], "acceptor")->fst.freeze(), st.s);
+      ComposeStats cs;
+      DevFst dr = compose_device(da, dt, opt, &cs, st.s);
+      results[i] = new CFst{HostFst(download(dr, st.s))};
+      acc.states_expanded += cs.states_expanded; acc.arcs_iterated += cs.arcs_iterated;
+      acc.arcs_emitted += cs.arcs_emitted; acc.waves += cs.waves; acc.states_out += cs.states_out;
+      acc.arcs_out += cs.arcs_out; acc.kernel_launches += cs.kernel_launches; acc.emit_launches += cs.emit_launches;
+      acc.ms_expand += cs.ms_expand; acc.ms_connect += cs.ms_connect; acc.ms_emit_kernel += cs.ms_emit_kernel;
+    }
+    if (total) *total = acc;
+  });
+}
+RUSTFST_FFI_RESULT b200_set_device(int device) {
+  return wrap([&] {
+    require_device();
+    B200_CUDA(cudaSetDevice(device));
+    configure_device_pool(device);
+  });
+}
+RUSTFST_FFI_RESULT b200_device_count(int* count) {
+  return wrap([&] {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+  });
+}
+RUSTFST_FFI_RESULT b200_device_synchronize(void) {
+  return wrap([&] { require_device(); B200_CUDA(cudaDeviceSynchronize()); });
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// connect.cu — trim (accessible AND coaccessible) with order-preserving renumbering, on device.
+//
+// Replaces (paths relative to /root/reference):
+//   rustfst/src/algorithms/connect.rs:51-189        connect + ConnectVisitor (Tarjan DFS -> access/coaccess flags)
+//   rustfst/src/algorithms/dfs_visit.rs:97-187      the sequential DFS driver
+//   rustfst/src/fst_impls/vector_fst/mutable_fst.rs:132-189  del_states (stable compaction of states and arcs)
+//
+// The DFS only serves to compute two set-valued facts that do not depend on the visiting order — which states
+// are reachable from the start and which can reach a final state — so they are recomputed as two frontier BFS
+// sweeps (forward over the CSR, backward over a reverse CSR built with one histogram + one scatter), and
+// del_states becomes two prefix sums (state keep-flags, surviving out-degrees) plus one gather.
+#include "algos.h"
+
+namespace b200 {
+namespace {
+
+__global__ void k_rev_degree(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n,
+                             uint32_t* __restrict__ rdeg) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  for (uint32_t i = off[s]; i < off[s + 1]; i++) atomicAdd(&rdeg[__ldg(&arcs[i].nextstate)], 1u);
+}
+__global__ void k_rev_fill(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n,
+                           const uint32_t* __restrict__ roff, uint32_t* __restrict__ cursor,
+                           uint32_t* __restrict__ rsrc) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  for (uint32_t i = off[s]; i < off[s + 1]; i++) {
+    uint32_t t = __ldg(&arcs[i].nextstate);
+    rsrc[roff[t] + atomicAdd(&cursor[t], 1u)] = s;
+  }
+}
+__global__ void k_seed_finals(const float* __restrict__ fin, uint32_t n, uint32_t* __restrict__ mark,
+                              uint32_t* __restrict__ frontier, uint32_t* __restrict__ count) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  bool f = s < n && fin[s] != w_zero();
+  if (s < n) mark[s] = f ? 1u : 0u;
+  // warp-aggregated append
+  uint32_t m = __ballot_sync(0xFFFFFFFFu, f);
+  if (!m) return;
+  uint32_t lane = threadIdx.x & 31, leader = __ffs(m) - 1, basep = 0;
+  if (lane == leader) basep = atomicAdd(count, __popc(m));
+  basep = __shfl_sync(0xFFFFFFFFu, basep, leader);
+  if (f) frontier[basep + __popc(m & ((1u << lane) - 1u))] = s;
+}
+// One BFS level.  kForward: neighbours are arcs[i].nextstate; otherwise adj[i] (reverse CSR sources).
+template <bool kForward>
+__global__ void k_bfs_level(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs,
+                            const uint32_t* __restrict__ adj, const uint32_t* __restrict__ fin_in, uint32_t n_in,
+                            uint32_t* __restrict__ mark, uint32_t* __restrict__ fout, uint32_t* __restrict__ count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_in) return;
+  uint32_t v = fin_in[i];
+  for (uint32_t k = off[v]; k < off[v + 1]; k++) {
+    uint32_t u = kForward ? __ldg(&arcs[k].nextstate) : __ldg(&adj[k]);
+    if (mark[u] == 0 && atomicExch(&mark[u], 1u) == 0) fout[atomicAdd(count, 1u)] = u;
+  }
+}
+__global__ void k_keep_flags(const uint32_t* __restrict__ access, const uint32_t* __restrict__ coaccess, uint32_t n,
+                             uint32_t* __restrict__ keep) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > n) return;
+  keep[s] = (s < n && (access ? access[s] != 0 : true) && coaccess[s] != 0) ? 1u : 0u;
+}
+__global__ void k_new_degree(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n,
+                             const uint32_t* __restrict__ keep, const uint32_t* __restrict__ new_id, uint32_t n_keep,
+                             uint32_t* __restrict__ ndeg) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == n) { ndeg[n_keep] = 0; return; }
+  if (s > n || !keep[s]) return;
+  uint32_t c = 0;
+  for (uint32_t i = off[s]; i < off[s + 1]; i++) c += keep[__ldg(&arcs[i].nextstate)];
+  ndeg[new_id[s]] = c;
+}
+__global__ void k_compact(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs,
+                          const float* __restrict__ fin, uint32_t n, const uint32_t* __restrict__ keep,
+                          const uint32_t* __restrict__ new_id, const uint32_t* __restrict__ noff,
+                          Tr* __restrict__ narcs, float* __restrict__ nfin) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n || !keep[s]) return;
+  uint32_t ns = new_id[s];
+  nfin[ns] = fin[s];
+  uint32_t o = noff[ns];
+  for (uint32_t i = off[s]; i < off[s + 1]; i++) {
+    int4 v = __ldg(reinterpret_cast<const int4*>(&arcs[i]));
+    uint32_t t = (uint32_t)v.w;
+    if (keep[t]) {
+      v.w = (int)new_id[t];
+      *reinterpret_cast<int4*>(&narcs[o++]) = v;
+    }
+  }
+}
+
+}  // namespace
+
+DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launches, cudaStream_t s) {
+  uint64_t nl = 0;
+  DevFst out(s);
+  out.props = props::after_connect(in.props);
+  const uint32_t n = in.num_states;
+  // dfs_visit returns at once without a start state (dfs_visit.rs:103-109): nothing is accessible
+  if (n == 0 || !in.has_start) {
+    out.offsets.reserve_discard(1);
+    B200_CUDA(cudaMemsetAsync(out.offsets.p, 0, 4, s));
+    if (launches) *launches = 0;
+    return out;
+  }
+  DevBuf<uint8_t> scan_tmp(s);
+  DevBuf<uint32_t> fa(s, n), fb(s, n), count(s, 1);
+  uint32_t* fin_p = fa.p;
+  uint32_t* fout_p = fb.p;
+
+  // ---- forward reachability from the start state
+  DevBuf<uint32_t> access(s);
+  if (!assume_accessible) {
+    access.reserve_discard(n);
+    B200_CUDA(cudaMemsetAsync(access.p, 0, (size_t)n * 4, s));
+    uint32_t one = 1, st0 = in.start;
+    B200_CUDA(cudaMemcpyAsync(access.p + in.start, &one, 4, cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaMemcpyAsync(fin_p, &st0, 4, cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    uint32_t nf = 1;
+    while (nf) {
+      B200_CUDA(cudaMemsetAsync(count.p, 0, 4, s));
+      k_bfs_level<true><<<blocks_for(nf), kThreads, 0, s>>>(in.offsets.p, in.arcs.p, nullptr, fin_p, nf, access.p,
+                                                            fout_p, count.p);
+      nl++;
+      nf = read_u32(count.p, s);
+      std::swap(fin_p, fout_p);
+    }
+  }
+
+  // ---- reverse CSR (histogram -> scan -> scatter) and backward reachability from the final states
+  DevBuf<uint32_t> roff(s, (size_t)n + 1), cursor(s, n), rsrc(s, in.num_arcs ? in.num_arcs : 1), coaccess(s, n);
+  B200_CUDA(cudaMemsetAsync(roff.p, 0, ((size_t)n + 1) * 4, s));
+  B200_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)n * 4, s));
+  k_rev_degree<<<blocks_for(n), kThreads, 0, s>>>(in.offsets.p, in.arcs.p, n, roff.p);
+  exclusive_sum_u32(roff.p, roff.p, (size_t)n + 1, scan_tmp, s);
+  k_rev_fill<<<blocks_for(n), kThreads, 0, s>>>(in.offsets.p, in.arcs.p, n, roff.p, cursor.p, rsrc.p);
+  B200_CUDA(cudaMemsetAsync(count.p, 0, 4, s));
+  k_seed_finals<<<blocks_for(n), kThreads, 0, s>>>(in.finals.p, n, coaccess.p, fin_p, count.p);
+  nl += 4;
+  uint32_t nf = read_u32(count.p, s);
+  while (nf) {
+    B200_CUDA(cudaMemsetAsync(count.p, 0, 4, s));
+    k_bfs_level<false><<<blocks_for(nf), kThreads, 0, s>>>(roff.p, nullptr, rsrc.p, fin_p, nf, coaccess.p, fout_p,
+                                                           count.p);
+    nl++;
+    nf = read_u32(count.p, s);
+    std::swap(fin_p, fout_p);
+  }
+
+  // ---- del_states: stable compaction of states, then of the arcs that stay inside the kept set
+  DevBuf<uint32_t> keep(s, (size_t)n + 1), new_id(s, (size_t)n + 1);
+  k_keep_flags<<<blocks_for((size_t)n + 1), kThreads, 0, s>>>(assume_accessible ? nullptr : access.p, coaccess.p, n,
+                                                              keep.p);
+  exclusive_sum_u32(keep.p, new_id.p, (size_t)n + 1, scan_tmp, s);
+  nl += 2;
+  uint32_t n_keep = read_u32(new_id.p + n, s);
+  out.offsets.reserve_discard((size_t)n_keep + 1);
+  out.finals.reserve_discard(n_keep);
+  k_new_degree<<<blocks_for((size_t)n + 1), kThreads, 0, s>>>(in.offsets.p, in.arcs.p, n, keep.p, new_id.p, n_keep,
+                                                              out.offsets.p);
+  exclusive_sum_u32(out.offsets.p, out.offsets.p, (size_t)n_keep + 1, scan_tmp, s);
+  nl += 2;
+  uint32_t a_keep = read_u32(out.offsets.p + n_keep, s);
+  out.arcs.reserve_discard(a_keep);
+  k_compact<<<blocks_for(n), kThreads, 0, s>>>(in.offsets.p, in.arcs.p, in.finals.p, n, keep.p, new_id.p,
+                                               out.offsets.p, out.arcs.p, out.finals.p);
+  nl++;
+  out.num_states = n_keep;
+  out.num_arcs = a_keep;
+  // start remap (mutable_fst.rs:176-183)
+  uint32_t kv[2];
+  B200_CUDA(cudaMemcpyAsync(&kv[0], keep.p + in.start, 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(&kv[1], new_id.p + in.start, 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  out.has_start = kv[0] != 0;
+  out.start = kv[0] ? kv[1] : 0;
+  if (launches) *launches = nl;
+  return out;
+}
+
+}  // namespace b200

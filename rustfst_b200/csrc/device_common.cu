@@ -1,0 +1,88 @@
+// device_common.cu — device discovery and host<->HBM marshalling of CSR FSTs.
+#include <cub/device/device_scan.cuh>
+
+#include <mutex>
+
+#include "device_common.cuh"
+
+namespace b200 {
+void configure_device_pool(int dev);
+namespace {
+std::once_flag g_once;
+int g_sms = 0;
+std::string g_init_error;
+
+void init_device() {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_init_error = std::string("librustfst_b200: no CUDA device available (") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                   "); this library has no CPU fallback";
+    cudaGetLastError();
+    return;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+  configure_device_pool(dev);
+}
+}  // namespace
+
+// Keep freed blocks in the stream-ordered pool: the per-wave scratch buffers are re-allocated constantly.
+void configure_device_pool(int dev) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  } else {
+    cudaGetLastError();
+  }
+}
+
+void require_device() {
+  std::call_once(g_once, init_device);
+  if (!g_init_error.empty()) throw CudaError(g_init_error);
+}
+int sm_count() { require_device(); return g_sms; }
+
+DevFst upload(const CsrFst& h, cudaStream_t s) {
+  if (!h.inf_finals.empty())
+    throw FstError("final weights equal to +inf (TropicalWeight::zero) are not supported on the device path");
+  DevFst d(s);
+  size_t n = h.num_states(), a = h.arcs.size();
+  d.offsets.reserve_discard(n + 1);
+  d.arcs.reserve_discard(a);
+  d.finals.reserve_discard(n);
+  B200_CUDA(cudaMemcpyAsync(d.offsets.p, h.offsets.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (a) B200_CUDA(cudaMemcpyAsync(d.arcs.p, h.arcs.data(), a * sizeof(Tr), cudaMemcpyHostToDevice, s));
+  if (n) B200_CUDA(cudaMemcpyAsync(d.finals.p, h.finals.data(), n * 4, cudaMemcpyHostToDevice, s));
+  d.num_states = (uint32_t)n; d.num_arcs = (uint32_t)a;
+  d.has_start = h.has_start; d.start = h.start; d.props = h.props;
+  B200_CUDA(cudaStreamSynchronize(s));
+  return d;
+}
+
+CsrFst download(const DevFst& d, cudaStream_t s) {
+  CsrFst h;
+  size_t n = d.num_states, a = d.num_arcs;
+  h.offsets.resize(n + 1);
+  h.arcs.resize(a);
+  h.finals.resize(n);
+  B200_CUDA(cudaMemcpyAsync(h.offsets.data(), d.offsets.p, (n + 1) * 4, cudaMemcpyDeviceToHost, s));
+  if (a) B200_CUDA(cudaMemcpyAsync(h.arcs.data(), d.arcs.p, a * sizeof(Tr), cudaMemcpyDeviceToHost, s));
+  if (n) B200_CUDA(cudaMemcpyAsync(h.finals.data(), d.finals.p, n * 4, cudaMemcpyDeviceToHost, s));
+  h.has_start = d.has_start; h.start = d.start; h.props = d.props & props::kTrinary;
+  B200_CUDA(cudaStreamSynchronize(s));
+  return h;
+}
+
+void exclusive_sum_u32(const uint32_t* in, uint32_t* out, size_t n, DevBuf<uint8_t>& temp, cudaStream_t s) {
+  if (n == 0) return;
+  size_t bytes = 0;
+  B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n, s));
+  temp.reserve_discard(bytes);
+  B200_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, bytes, in, out, (int64_t)n, s));
+}
+
+}  // namespace b200

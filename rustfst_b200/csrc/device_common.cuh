@@ -1,0 +1,119 @@
+// device_common.cuh — CUDA plumbing shared by the compose / connect / shortest-path kernels:
+// error checking, a per-call stream context with stream-ordered (cudaMallocAsync) buffers, device-resident CSR
+// FSTs and thin wrappers over the CUB prefix sums used between the hand-written kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <utility>
+
+#include "fst_types.h"
+#include "host_fst.h"
+
+namespace b200 {
+
+struct CudaError : FstError {
+  using FstError::FstError;
+};
+
+#define B200_CUDA(expr)                                                                                      \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess)                                                                                   \
+      throw ::b200::CudaError(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                              std::to_string(__LINE__) + " (" #expr ")");                                    \
+  } while (0)
+
+constexpr int kThreads = 256;
+inline unsigned blocks_for(size_t n, int threads = kThreads) { return (unsigned)((n + threads - 1) / threads); }
+
+// Fails loudly when there is no usable GPU: there is no CPU fallback anywhere in this library.
+void require_device();
+int sm_count();
+void configure_device_pool(int dev);
+
+// One stream per C-ABI call: concurrent calls from different host threads do not serialise on the legacy stream.
+struct Stream {
+  cudaStream_t s = nullptr;
+  Stream() {
+    require_device();
+    B200_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  }
+  ~Stream() { if (s) cudaStreamDestroy(s); }
+  Stream(const Stream&) = delete;
+  Stream& operator=(const Stream&) = delete;
+  void sync() const { B200_CUDA(cudaStreamSynchronize(s)); }
+};
+
+// Stream-ordered device buffer (cudaMallocAsync pool; growth preserves contents).
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  explicit DevBuf(cudaStream_t st) : s(st) {}
+  DevBuf(cudaStream_t st, size_t n) : s(st) { reserve_discard(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap), s(o.s) { o.p = nullptr; o.cap = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; cap = o.cap; s = o.s; o.p = nullptr; o.cap = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr; cap = 0;
+  }
+  // Grow to >= n elements, discarding contents.
+  void reserve_discard(size_t n) {
+    if (n <= cap) return;
+    release();
+    size_t c = n < 16 ? 16 : n;
+    B200_CUDA(cudaMallocAsync((void**)&p, c * sizeof(T), s));
+    cap = c;
+  }
+  // Grow to >= n elements keeping the first `keep` elements (geometric growth).
+  void reserve_keep(size_t n, size_t keep) {
+    if (n <= cap) return;
+    size_t c = cap * 2 > n ? cap * 2 : n;
+    if (c < 16) c = 16;
+    T* q = nullptr;
+    B200_CUDA(cudaMallocAsync((void**)&q, c * sizeof(T), s));
+    if (p && keep) B200_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (p) cudaFreeAsync(p, s);
+    p = q; cap = c;
+  }
+};
+
+// Device-resident CSR FST (what the kernels read and produce).
+struct DevFst {
+  DevBuf<uint32_t> offsets;  // num_states + 1
+  DevBuf<Tr> arcs;
+  DevBuf<float> finals;
+  uint32_t num_states = 0;
+  uint32_t num_arcs = 0;
+  bool has_start = false;
+  StateId start = 0;
+  uint64_t props = props::kNull;
+  DevFst() = default;
+  explicit DevFst(cudaStream_t s) : offsets(s), arcs(s), finals(s) {}
+  size_t bytes() const { return (size_t)(num_states + 1) * 4 + (size_t)num_arcs * 16 + (size_t)num_states * 4; }
+};
+
+DevFst upload(const CsrFst& h, cudaStream_t s);
+CsrFst download(const DevFst& d, cudaStream_t s);
+
+// Exclusive prefix sum of n uint32 values (CUB DeviceScan; compiled once in device_common.cu); out may alias in.
+void exclusive_sum_u32(const uint32_t* in, uint32_t* out, size_t n, DevBuf<uint8_t>& temp, cudaStream_t s);
+
+inline uint32_t read_u32(const uint32_t* dptr, cudaStream_t s) {
+  uint32_t v = 0;
+  B200_CUDA(cudaMemcpyAsync(&v, dptr, 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  return v;
+}
+
+}  // namespace b200

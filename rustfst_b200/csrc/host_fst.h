@@ -1,0 +1,402 @@
+// host_fst.h — host-side VectorFst<TropicalWeight> container behind the opaque CFst handle of the C-ABI.
+//
+// Mirrors the reference container's observable behaviour (paths relative to /root/reference):
+//   rustfst/src/fst_impls/vector_fst/{data_structure,fst,mutable_fst}.rs  (state = final weight + arc vector,
+//   property word maintained on every mutation), rustfst/src/fst_impls/vector_fst/serializable_fst.rs (OpenFst
+//   binary "vector" format), rustfst/src/fst_traits/macros.rs (text display).
+//
+// Layout is B200-first rather than a Vec<Arc<Vec<Tr>>>: the canonical representation is one CSR block
+// (u32 state->arc offsets, 16-byte arcs, f32 final weights) that is copied to/from HBM with three plain
+// memcpys.  Incremental mutation through the FFI (vec_fst_add_tr & co) uses a per-state "builder"
+// representation that is frozen to CSR on first algorithmic use.
+#pragma once
+#include <algorithm>
+#include <charconv>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fst_types.h"
+
+namespace b200 {
+
+struct FstError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+// Plain CSR block: what travels to and from the device.
+struct CsrFst {
+  std::vector<uint32_t> offsets{0};  // num_states + 1
+  std::vector<Tr> arcs;
+  std::vector<float> finals;         // +inf == not final
+  std::vector<StateId> inf_finals;   // states that are final with weight +inf (Some(inf)); sorted, almost always empty
+  bool has_start = false;
+  StateId start = 0;
+  uint64_t props = props::kNull;
+  size_t num_states() const { return finals.size(); }
+};
+
+class HostFst {
+ public:
+  HostFst() = default;
+  explicit HostFst(CsrFst&& csr) : csr_(std::move(csr)), is_builder_(false) {
+    has_start_ = csr_.has_start; start_ = csr_.start; props_ = csr_.props;
+  }
+  HostFst(const HostFst& o) {
+    std::lock_guard<std::mutex> g(o.mu_);
+    b_ = o.b_; csr_ = o.csr_; is_builder_ = o.is_builder_;
+    has_start_ = o.has_start_; start_ = o.start_; props_ = o.props_;
+  }
+
+  // ---- inspection (fst_impls/vector_fst/fst.rs:40-106)
+  size_t num_states() const { std::lock_guard<std::mutex> g(mu_); return n_states(); }
+  bool start(StateId* out) const { std::lock_guard<std::mutex> g(mu_); if (has_start_) *out = start_; return has_start_; }
+  uint64_t properties() const { std::lock_guard<std::mutex> g(mu_); return props_; }
+  void set_properties(uint64_t p) { std::lock_guard<std::mutex> g(mu_); props_ = p & props::kTrinary; }
+  bool final_weight(StateId s, float* out) const {
+    std::lock_guard<std::mutex> g(mu_);
+    check_state(s);
+    if (is_builder_) { if (b_[s].has_final) *out = b_[s].final_w; return b_[s].has_final; }
+    if (csr_.finals[s] != w_zero()) { *out = csr_.finals[s]; return true; }
+    if (is_inf_final(s)) { *out = w_zero(); return true; }
+    return false;
+  }
+  size_t num_trs(StateId s) const {
+    std::lock_guard<std::mutex> g(mu_);
+    check_state(s);
+    return is_builder_ ? b_[s].trs.size() : (size_t)(csr_.offsets[s + 1] - csr_.offsets[s]);
+  }
+  std::vector<Tr> get_trs(StateId s) const {
+    std::lock_guard<std::mutex> g(mu_);
+    check_state(s);
+    if (is_builder_) return b_[s].trs;
+    return std::vector<Tr>(csr_.arcs.begin() + csr_.offsets[s], csr_.arcs.begin() + csr_.offsets[s + 1]);
+  }
+
+  // ---- mutation (fst_impls/vector_fst/mutable_fst.rs)
+  StateId add_state() {  // :79-84
+    std::lock_guard<std::mutex> g(mu_);
+    StateId id = (StateId)n_states();
+    if (is_builder_) b_.emplace_back();
+    else { csr_.offsets.push_back(csr_.offsets.back()); csr_.finals.push_back(w_zero()); }
+    props_ = props::on_add_state(props_);
+    return id;
+  }
+  void set_start(StateId s) {  // :35-44
+    std::lock_guard<std::mutex> g(mu_);
+    if (s >= n_states()) throw FstError("The state " + std::to_string(s) + " doesn't exist");
+    has_start_ = true; start_ = s;
+    props_ = props::on_set_start(props_);
+  }
+  void set_final(StateId s, float w) {  // :51-64
+    std::lock_guard<std::mutex> g(mu_);
+    if (s >= n_states()) throw FstError("Stateid " + std::to_string(s) + " doesn't exist");
+    float old_w; bool had = final_unlocked(s, &old_w);
+    props_ = props::on_set_final(props_, had ? &old_w : nullptr, &w);
+    set_final_unlocked(s, true, w);
+  }
+  void delete_final_weight(StateId s) {  // :283-291
+    std::lock_guard<std::mutex> g(mu_);
+    if (s >= n_states()) throw FstError("State " + std::to_string(s) + " doesn't exist");
+    float old_w; bool had = final_unlocked(s, &old_w);
+    props_ = props::on_set_final(props_, had ? &old_w : nullptr, nullptr);
+    set_final_unlocked(s, false, w_zero());
+  }
+  void add_tr(StateId s, const Tr& tr) {  // :236-245 + data_structure.rs:80-91
+    std::lock_guard<std::mutex> g(mu_);
+    if (s >= n_states()) throw FstError("State " + std::to_string(s) + " doesn't exist");
+    const Tr* prev = nullptr;
+    Tr prev_copy;
+    if (!is_builder_ && (size_t)s + 1 == n_states()) {  // append to the tail state keeps the CSR valid
+      if (csr_.offsets[s + 1] > csr_.offsets[s]) { prev_copy = csr_.arcs.back(); prev = &prev_copy; }
+      csr_.arcs.push_back(tr);
+      csr_.offsets[s + 1]++;
+    } else {
+      to_builder_unlocked();
+      if (!b_[s].trs.empty()) { prev_copy = b_[s].trs.back(); prev = &prev_copy; }
+      b_[s].trs.push_back(tr);
+    }
+    props_ = props::on_add_tr(props_, s, tr, prev);
+  }
+  void set_tr(StateId s, size_t idx, const Tr& tr) {  // trs_iter_mut: properties of a set arc are unknown
+    std::lock_guard<std::mutex> g(mu_);
+    check_state(s);
+    to_builder_unlocked();
+    if (idx >= b_[s].trs.size()) throw FstError("transition index out of range");
+    b_[s].trs[idx] = tr;
+    props_ &= props::kBinary;  // properties.rs set_arc_properties() == empty
+  }
+  void del_all_states() {  // :191-199
+    std::lock_guard<std::mutex> g(mu_);
+    b_.clear(); csr_ = CsrFst(); is_builder_ = true;
+    has_start_ = false; props_ = props::kNull;
+  }
+  void tr_sort(bool ilabel) {  // algorithms/tr_sort.rs:51-62 (stable)
+    std::lock_guard<std::mutex> g(mu_);
+    auto by_i = [](const Tr& a, const Tr& b) { return a.ilabel < b.ilabel; };
+    auto by_o = [](const Tr& a, const Tr& b) { return a.olabel < b.olabel; };
+    size_t n = n_states();
+    for (size_t s = 0; s < n; s++) {
+      Tr *b, *e;
+      if (is_builder_) { b = b_[s].trs.data(); e = b + b_[s].trs.size(); }
+      else { b = csr_.arcs.data() + csr_.offsets[s]; e = csr_.arcs.data() + csr_.offsets[s + 1]; }
+      if (ilabel) std::stable_sort(b, e, by_i); else std::stable_sort(b, e, by_o);
+    }
+    props_ = props::after_tr_sort(props_, ilabel) & props::kTrinary;
+  }
+
+  // ---- CSR access for the device path. freeze() makes CSR the live representation.
+  const CsrFst& freeze() const {
+    std::lock_guard<std::mutex> g(mu_);
+    to_csr_unlocked();
+    csr_.has_start = has_start_; csr_.start = start_; csr_.props = props_;
+    return csr_;
+  }
+  void replace(CsrFst&& csr) {  // in-place algorithms (fst_connect) install their result
+    std::lock_guard<std::mutex> g(mu_);
+    csr_ = std::move(csr); b_.clear(); is_builder_ = false;
+    has_start_ = csr_.has_start; start_ = csr_.start; props_ = csr_.props;
+  }
+
+  // ---- equality: data_structure.rs:36-41 (ignores properties/symbol tables, weights approx-equal)
+  bool equals(const HostFst& o) const {
+    const CsrFst& a = freeze();
+    const CsrFst& b = o.freeze();
+    if (a.has_start != b.has_start || (a.has_start && a.start != b.start)) return false;
+    if (a.num_states() != b.num_states()) return false;
+    if (a.inf_finals != b.inf_finals) return false;
+    for (size_t s = 0; s < a.num_states(); s++) {
+      bool fa = a.finals[s] != w_zero(), fb = b.finals[s] != w_zero();
+      if (fa != fb) return false;
+      if (fa && !w_approx_eq(a.finals[s], b.finals[s])) return false;
+      uint32_t na = a.offsets[s + 1] - a.offsets[s], nb = b.offsets[s + 1] - b.offsets[s];
+      if (na != nb) return false;
+      const Tr* x = a.arcs.data() + a.offsets[s];
+      const Tr* y = b.arcs.data() + b.offsets[s];
+      for (uint32_t i = 0; i < na; i++)
+        if (x[i].ilabel != y[i].ilabel || x[i].olabel != y[i].olabel || x[i].nextstate != y[i].nextstate ||
+            !w_approx_eq(x[i].weight, y[i].weight))
+          return false;
+    }
+    return true;
+  }
+
+  // ---- text form: fst_traits/macros.rs:1-70 (write_fst!(self, f, show_weight_one=true, use_symt=true))
+  std::string display() const {
+    const CsrFst& c = freeze();
+    std::string out;
+    if (!c.has_start) return out;
+    auto fmt_w = [](float w) {
+      if (w == w_zero()) return std::string("inf");
+      char buf[64];
+      auto r = std::to_chars(buf, buf + sizeof(buf), w, std::chars_format::fixed);
+      return std::string(buf, r.ptr);
+    };
+    auto one_state = [&](StateId s) {
+      for (uint32_t i = c.offsets[s]; i < c.offsets[s + 1]; i++) {
+        const Tr& t = c.arcs[i];
+        out += std::to_string(s) + "\t" + std::to_string(t.nextstate) + "\t" + std::to_string(t.ilabel) + "\t" +
+               std::to_string(t.olabel) + "\t" + fmt_w(t.weight) + "\n";
+      }
+    };
+    one_state(c.start);
+    for (size_t s = 0; s < c.num_states(); s++) if (s != c.start) one_state((StateId)s);
+    for (size_t s = 0; s < c.num_states(); s++) {
+      bool inf_final = std::binary_search(c.inf_finals.begin(), c.inf_finals.end(), (StateId)s);
+      if (c.finals[s] != w_zero() || inf_final) out += std::to_string(s) + "\t" + fmt_w(c.finals[s]) + "\n";
+    }
+    return out;
+  }
+
+ private:
+  struct BState {
+    bool has_final = false;
+    float final_w = 0.0f;
+    std::vector<Tr> trs;
+  };
+  size_t n_states() const { return is_builder_ ? b_.size() : csr_.finals.size(); }
+  void check_state(StateId s) const {
+    if (s >= n_states()) throw FstError("State " + std::to_string(s) + " doesn't exist");
+  }
+  bool is_inf_final(StateId s) const {
+    return !csr_.inf_finals.empty() && std::binary_search(csr_.inf_finals.begin(), csr_.inf_finals.end(), s);
+  }
+  bool final_unlocked(StateId s, float* w) const {
+    if (is_builder_) { *w = b_[s].final_w; return b_[s].has_final; }
+    if (csr_.finals[s] != w_zero()) { *w = csr_.finals[s]; return true; }
+    if (is_inf_final(s)) { *w = w_zero(); return true; }
+    return false;
+  }
+  void set_final_unlocked(StateId s, bool has, float w) {
+    if (is_builder_) { b_[s].has_final = has; b_[s].final_w = w; return; }
+    auto it = std::lower_bound(csr_.inf_finals.begin(), csr_.inf_finals.end(), s);
+    bool present = it != csr_.inf_finals.end() && *it == s;
+    bool want_inf = has && w == w_zero();
+    if (want_inf && !present) csr_.inf_finals.insert(it, s);
+    if (!want_inf && present) csr_.inf_finals.erase(it);
+    csr_.finals[s] = has ? w : w_zero();
+  }
+  void to_builder_unlocked() const {
+    if (is_builder_) return;
+    size_t n = csr_.finals.size();
+    b_.assign(n, BState());
+    for (size_t s = 0; s < n; s++) {
+      b_[s].trs.assign(csr_.arcs.begin() + csr_.offsets[s], csr_.arcs.begin() + csr_.offsets[s + 1]);
+      if (csr_.finals[s] != w_zero()) { b_[s].has_final = true; b_[s].final_w = csr_.finals[s]; }
+    }
+    for (StateId s : csr_.inf_finals) { b_[s].has_final = true; b_[s].final_w = w_zero(); }
+    csr_ = CsrFst();
+    is_builder_ = true;
+  }
+  void to_csr_unlocked() const {
+    if (!is_builder_) return;
+    size_t n = b_.size(), total = 0;
+    for (auto& st : b_) total += st.trs.size();
+    if (total > 0xFFFFFFF0ull) throw FstError("FST has more than 2^32 transitions");
+    CsrFst c;
+    c.offsets.resize(n + 1);
+    c.arcs.resize(total);
+    c.finals.resize(n);
+    size_t o = 0;
+    for (size_t s = 0; s < n; s++) {
+      c.offsets[s] = (uint32_t)o;
+      if (!b_[s].trs.empty()) std::memcpy(c.arcs.data() + o, b_[s].trs.data(), b_[s].trs.size() * sizeof(Tr));
+      o += b_[s].trs.size();
+      c.finals[s] = b_[s].has_final ? b_[s].final_w : w_zero();
+      if (b_[s].has_final && b_[s].final_w == w_zero()) c.inf_finals.push_back((StateId)s);
+    }
+    c.offsets[n] = (uint32_t)o;
+    csr_ = std::move(c);
+    b_.clear(); b_.shrink_to_fit();
+    is_builder_ = false;
+  }
+
+  mutable std::mutex mu_;
+  mutable std::vector<BState> b_;
+  mutable CsrFst csr_;
+  mutable bool is_builder_ = true;
+  bool has_start_ = false;
+  StateId start_ = 0;
+  uint64_t props_ = props::kNull;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// OpenFst binary "vector" format — rustfst/src/parsers/bin_fst/fst_header.rs:71-137,
+// rustfst/src/fst_impls/vector_fst/serializable_fst.rs:46-88 (store), :129-168 (load)
+// ---------------------------------------------------------------------------------------------------------------
+namespace io {
+constexpr int32_t kMagic = 2125659606;
+constexpr int32_t kSymtMagic = 2125658996;
+
+struct Reader {
+  const uint8_t* p; size_t n; size_t off = 0;
+  template <class T> T get() {
+    if (off + sizeof(T) > n) throw FstError("Error while parsing binary VectorFst. Error kind Eof");
+    T v; std::memcpy(&v, p + off, sizeof(T)); off += sizeof(T); return v;
+  }
+  std::string str() {
+    int32_t len = get<int32_t>();
+    if (len < 0 || off + (size_t)len > n) throw FstError("Error while parsing binary VectorFst. Error kind Eof");
+    std::string s((const char*)p + off, (size_t)len); off += (size_t)len; return s;
+  }
+};
+// Symbol tables are presentation metadata outside the hot path: parsed to find the body, then dropped.
+inline void skip_symbol_table(Reader& r) {  // parsers/bin_symt/nom_parser.rs
+  if (r.get<int32_t>() != kSymtMagic) throw FstError("Error while parsing symbolTable from binary VectorFst");
+  r.str();
+  r.get<int64_t>();
+  int64_t n = r.get<int64_t>();
+  for (int64_t i = 0; i < n; i++) { r.str(); r.get<int64_t>(); }
+}
+
+inline CsrFst parse_vector_fst(const uint8_t* data, size_t len) {
+  Reader r{data, len};
+  if (r.get<int32_t>() != kMagic) throw FstError("Error while parsing binary VectorFst. Error kind Verify");
+  if (r.str() != "vector") throw FstError("Error while parsing binary VectorFst. Error kind Verify");
+  if (r.str() != "standard") throw FstError("Error while parsing binary VectorFst. Error kind Verify");
+  if (r.get<int32_t>() < 2) throw FstError("Error while parsing binary VectorFst. Error kind Verify");
+  uint32_t flags = r.get<uint32_t>();
+  if (flags & ~7u) throw FstError("Error while parsing binary VectorFst. Error kind MapRes");
+  uint64_t props_word = r.get<uint64_t>();
+  int64_t start = r.get<int64_t>();
+  int64_t num_states = r.get<int64_t>();
+  r.get<int64_t>();  // header num_arcs is unreliable for vector files (OpenFst writes 0); per-state counts rule
+  if (flags & 1) skip_symbol_table(r);
+  if (flags & 2) skip_symbol_table(r);
+  if (num_states < 0) throw FstError("Error while parsing binary VectorFst. Error kind Count");
+  CsrFst c;
+  c.props = props_word & props::kTrinary;  // FstProperties::from_bits_truncate
+  c.has_start = start != -1;
+  c.start = (StateId)start;
+  c.offsets.resize((size_t)num_states + 1);
+  c.finals.resize((size_t)num_states);
+  // One pass to size, one pass to copy: the arc records are already in the 16-byte device layout.
+  size_t total = 0;
+  {
+    Reader q = r;
+    for (int64_t s = 0; s < num_states; s++) {
+      q.get<float>();
+      int64_t na = q.get<int64_t>();
+      if (na < 0 || q.off + (size_t)na * 16 > q.n) throw FstError("Error while parsing binary VectorFst. Error kind Eof");
+      q.off += (size_t)na * 16;
+      total += (size_t)na;
+    }
+  }
+  if (total > 0xFFFFFFF0ull) throw FstError("FST has more than 2^32 transitions");
+  c.arcs.resize(total);
+  size_t o = 0;
+  for (int64_t s = 0; s < num_states; s++) {
+    float fw = r.get<float>();
+    // parsers/bin_fst/utils_parsing.rs:17-26: None iff approx-equal to zero() (i.e. +inf)
+    c.finals[s] = w_approx_eq(fw, w_zero()) ? w_zero() : fw;
+    int64_t na = r.get<int64_t>();
+    c.offsets[s] = (uint32_t)o;
+    if (na) std::memcpy(c.arcs.data() + o, r.p + r.off, (size_t)na * 16);
+    r.off += (size_t)na * 16;
+    o += (size_t)na;
+  }
+  c.offsets[num_states] = (uint32_t)o;
+  return c;
+}
+
+inline std::vector<uint8_t> store_vector_fst(const CsrFst& c) {
+  size_t n = c.num_states();
+  std::vector<uint8_t> buf;
+  buf.reserve(64 + n * 12 + c.arcs.size() * 16);
+  auto put = [&](const void* p, size_t k) { const uint8_t* b = (const uint8_t*)p; buf.insert(buf.end(), b, b + k); };
+  auto put_i32 = [&](int32_t v) { put(&v, 4); };
+  auto put_i64 = [&](int64_t v) { put(&v, 8); };
+  auto put_str = [&](const char* s) { int32_t l = (int32_t)std::strlen(s); put_i32(l); put(s, (size_t)l); };
+  put_i32(kMagic);
+  put_str("vector");
+  put_str("standard");
+  put_i32(2);
+  uint32_t flags = 0; put(&flags, 4);
+  uint64_t p = c.props | props::kExpanded | props::kMutable; put(&p, 8);
+  put_i64(c.has_start ? (int64_t)c.start : -1);
+  put_i64((int64_t)n);
+  put_i64((int64_t)c.arcs.size());
+  for (size_t s = 0; s < n; s++) {
+    put(&c.finals[s], 4);
+    uint32_t na = c.offsets[s + 1] - c.offsets[s];
+    put_i64((int64_t)na);
+    if (na) put(c.arcs.data() + c.offsets[s], (size_t)na * 16);
+  }
+  return buf;
+}
+
+inline std::vector<uint8_t> read_file(const std::string& path) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) throw FstError("Error while opening file \"" + path + "\"");
+  return std::vector<uint8_t>((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+}
+inline void write_file(const std::string& path, const std::vector<uint8_t>& b) {
+  std::ofstream out(path, std::ios::binary);
+  if (!out) throw FstError("Error while creating file \"" + path + "\"");
+  out.write((const char*)b.data(), (std::streamsize)b.size());
+}
+}  // namespace io
+}  // namespace b200

@@ -1,0 +1,501 @@
+// sssp.cu — single shortest path over the tropical semiring on B200.
+//
+// Replaces (paths relative to /root/reference):
+//   rustfst/src/algorithms/shortest_path.rs:173-239  single_shortest_path (queue-ordered label-correcting relaxation)
+//   rustfst/src/algorithms/shortest_path.rs:241-282  single_shortest_path_backtrace
+//   rustfst/src/algorithms/queues/{state_order,top_order,lifo,fifo,trivial,scc}_queue.rs  (serial kernel only)
+//
+// Two device paths, selected per call:
+//
+//  (1) PARALLEL path — taken when the reference would process states in a topological order (StateOrderQueue on a
+//      TOP_SORTED input, or TopOrderQueue).  Distances are exact minima computed by frontier relaxation waves with
+//      atomicMin on order-preserving integer images of the f32 distances and warp-aggregated frontier
+//      compaction.  One more edge scan then (a) selects for every state the parent the reference would end up
+//      with: the first candidate, in its processing order (order[src], arc position), that attains the minimum,
+//      and (b) CERTIFIES that the reference's approximate relaxation test (`d != min(d, c)` with KDELTA = 1/1024
+//      tolerance, shortest_path.rs:225) cannot have kept a non-minimal candidate: no candidate value c of any
+//      state lies in (m, fl(m + KDELTA)] where m is that state's minimum.  When the certificate holds the
+//      reference's sequential fold provably ends with the same (distance, parent) at every state.
+//
+//  (2) ORDER-FAITHFUL SERIAL kernel — one device thread replays the reference's loop verbatim (queue discipline
+//      included) for everything else: cyclic inputs (SccQueue / LIFO) and inputs whose certificate fails.
+//
+// The backtrace runs on the device as well; only the shortest path itself (a few hundred bytes) returns to the host.
+#include <vector>
+
+#include "algos.h"
+
+namespace b200 {
+namespace {
+
+constexpr uint32_t kEncInf = 0xFF800000u;  // enc(+inf)
+constexpr unsigned long long kNoParent = ~0ull;
+
+__host__ __device__ __forceinline__ uint32_t enc_f32(float f) {  // monotone float -> uint32
+#if defined(__CUDA_ARCH__)
+  uint32_t b = __float_as_uint(f);
+#else
+  uint32_t b; memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f32(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// warp-aggregated append of `v` for lanes with pred set
+__device__ __forceinline__ void warp_push(bool pred, uint32_t v, uint32_t* __restrict__ list,
+                                          uint32_t* __restrict__ count) {
+  uint32_t active = __activemask();
+  uint32_t m = __ballot_sync(active, pred);
+  if (!m) return;
+  uint32_t lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+  if (lane == leader) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(active, base, leader);
+  if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = v;
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_fill_u64(unsigned long long* p, unsigned long long v, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// One relaxation wave: every frontier state pushes d[s] (x) w over its arcs with atomicMin.
+// counters[0] = next frontier size, counters[1] (64-bit at +2) = arcs relaxed.
+__global__ void __launch_bounds__(kThreads)
+k_relax(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, const uint32_t* __restrict__ frontier,
+        uint32_t nf, uint32_t* __restrict__ dist, uint32_t* __restrict__ stamp, uint32_t wave,
+        uint32_t* __restrict__ next, uint32_t* __restrict__ counters) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t relaxed = 0;
+  if (i < nf) {
+    uint32_t s = frontier[i];
+    float ds = dec_f32(dist[s]);
+    uint32_t b = off[s], e = off[s + 1];
+    relaxed = e - b;
+    for (uint32_t k = b; k < e; k++) {
+      int4 v = __ldg(reinterpret_cast<const int4*>(&arcs[k]));
+      float c = w_times(ds, __int_as_float(v.z));
+      uint32_t t = (uint32_t)v.w;
+      bool push = false;
+      if (c != w_zero()) {
+        uint32_t ec = enc_f32(c);
+        if (ec < dist[t]) {  // cheap pre-test; the atomic decides
+          uint32_t old = atomicMin(&dist[t], ec);
+          if (ec < old) push = atomicExch(&stamp[t], wave) != wave;
+        }
+      }
+      warp_push(push, t, next, &counters[0]);
+    }
+  }
+  // arcs-relaxed statistic: one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) relaxed += __shfl_down_sync(0xFFFFFFFFu, relaxed, o);
+  if ((threadIdx.x & 31) == 0 && relaxed) atomicAdd(reinterpret_cast<unsigned long long*>(&counters[2]), relaxed);
+}
+
+// Parent selection + certificate over all arcs of reached states.  flags[0] = certificate violations.
+__global__ void __launch_bounds__(kThreads)
+k_parents(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n,
+          const uint32_t* __restrict__ dist, const uint32_t* __restrict__ order,
+          unsigned long long* __restrict__ pkey, uint32_t* __restrict__ flags) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  uint32_t es = dist[s];
+  if (es == kEncInf) return;
+  float ds = dec_f32(es);
+  unsigned long long hi = (unsigned long long)(order ? order[s] : s) << 32;
+  uint32_t b = off[s], e = off[s + 1];
+  bool bad = false;
+  for (uint32_t k = b; k < e; k++) {
+    int4 v = __ldg(reinterpret_cast<const int4*>(&arcs[k]));
+    float c = w_times(ds, __int_as_float(v.z));
+    if (c == w_zero()) continue;
+    uint32_t t = (uint32_t)v.w;
+    float m = dec_f32(dist[t]);
+    if (c == m) atomicMin(&pkey[t], hi | (k - b));
+    else if (!(c > m + kDelta)) bad = true;
+  }
+  if (bad) atomicAdd(&flags[0], 1u);
+}
+
+// Best final state: key = (enc(d[s] (x) rho(s)) << 32) | order[s]   (shortest_path.rs:214-220)
+__global__ void k_final_min(const float* __restrict__ fin, uint32_t n, const uint32_t* __restrict__ dist,
+                            const uint32_t* __restrict__ order, unsigned long long* __restrict__ fkey) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  float rho = fin[s];
+  if (rho == w_zero() || dist[s] == kEncInf) return;
+  float v = w_times(dec_f32(dist[s]), rho);
+  atomicMin(fkey, ((unsigned long long)enc_f32(v) << 32) | (order ? order[s] : s));
+}
+__global__ void k_final_check(const float* __restrict__ fin, uint32_t n, const uint32_t* __restrict__ dist,
+                              const unsigned long long* __restrict__ fkey, uint32_t* __restrict__ flags) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  float rho = fin[s];
+  if (rho == w_zero() || dist[s] == kEncInf || *fkey == kNoParent) return;
+  float v = w_times(dec_f32(dist[s]), rho);
+  float m = dec_f32((uint32_t)(*fkey >> 32));
+  if (v != m && !(v > m + kDelta)) atomicAdd(&flags[0], 1u);
+}
+__global__ void k_invert_order(const uint32_t* __restrict__ order, uint32_t n, uint32_t* __restrict__ inv) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) inv[order[s]] = s;
+}
+
+// Walk the parent chain from the best final state (shortest_path.rs:241-282).  out_arcs[k-1] is the single arc of
+// output state k (k >= 1), already pointing at output state k-1; meta = {found, length L (arcs), f_parent, overflow}.
+__global__ void k_backtrace_keys(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n,
+                                 const unsigned long long* __restrict__ pkey,
+                                 const unsigned long long* __restrict__ fkey, const uint32_t* __restrict__ inv_order,
+                                 Tr* __restrict__ out_arcs, uint32_t cap, uint32_t* __restrict__ meta) {
+  if (blockIdx.x || threadIdx.x) return;
+  meta[0] = meta[1] = meta[2] = meta[3] = 0;
+  if (*fkey == kNoParent) return;
+  uint32_t ford = (uint32_t)(*fkey & 0xFFFFFFFFull);
+  uint32_t state = inv_order ? inv_order[ford] : ford;
+  meta[0] = 1; meta[2] = state;
+  uint32_t L = 0;
+  while (true) {
+    unsigned long long key = pkey[state];
+    if (key == kNoParent) break;
+    uint32_t pord = (uint32_t)(key >> 32), pos = (uint32_t)(key & 0xFFFFFFFFull);
+    uint32_t src = inv_order ? inv_order[pord] : pord;
+    if (L >= cap || L >= n) { meta[3] = 1; break; }
+    Tr tr = arcs[off[src] + pos];
+    tr.nextstate = L;  // previous output state
+    out_arcs[L] = tr;
+    L++;
+    state = src;
+  }
+  meta[1] = L;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Order-faithful serial kernel: the reference loop, one thread.
+// ---------------------------------------------------------------------------------------------------------------
+struct SerialArgs {
+  const uint32_t* off; const Tr* arcs; const float* fin; uint32_t n; uint32_t start;
+  int kind;
+  const uint32_t* order;      // kTopOrderQueue
+  const uint32_t* scc;        // kSccQueue
+  const uint8_t* scc_fifo;    // kSccQueue
+  const uint32_t* scc_base;   // kSccQueue: ring buffer base per component (size nscc + 1)
+  // scratch
+  float* dist; uint32_t* pstate; uint32_t* ppos; uint8_t* enq;
+  int32_t* slot;      // StateOrder: presence flag per state; TopOrder: state stored at order position (-1 none)
+  uint32_t* stack;    // Lifo storage / Scc ring storage
+  uint32_t* qhead; uint32_t* qlen;  // per component ring head / length (Trivial uses length 0/1)
+  // out
+  Tr* out_arcs; uint32_t cap; uint32_t* meta; unsigned long long* counters;
+};
+
+struct SerialQueue {
+  const SerialArgs& a;
+  // StateOrder / TopOrder
+  uint32_t front = 0, back = 0; bool has_back = false;
+  // Lifo
+  uint32_t sp = 0;
+  // Scc
+  long long sfront = 0, sback = -1;
+  __device__ explicit SerialQueue(const SerialArgs& args) : a(args) {}
+
+  __device__ bool scc_q_empty(uint32_t c) const { return a.qlen[c] == 0; }
+  __device__ void enqueue(uint32_t s) {
+    switch (a.kind) {
+      case kStateOrderQueue:
+      case kTopOrderQueue: {  // state_order_queue.rs:16-31, top_order_queue.rs:45-56
+        uint32_t o = a.kind == kTopOrderQueue ? a.order[s] : s;
+        if (!has_back || front > back) { front = o; back = o; has_back = true; }
+        else if (o > back) back = o;
+        else if (o < front) front = o;
+        a.slot[o] = a.kind == kTopOrderQueue ? (int32_t)s : 1;
+        break;
+      }
+      case kLifoQueue: a.stack[sp++] = s; break;  // lifo_queue.rs
+      default: {  // scc_queue.rs:34-45
+        long long c = a.scc[s];
+        if (sfront > sback) { sfront = c; sback = c; }
+        else if (c > sback) sback = c;
+        else if (c < sfront) sfront = c;
+        uint32_t size = a.scc_base[c + 1] - a.scc_base[c];
+        if (a.scc_fifo[c]) {  // FifoQueue (ring sized to the component: a state is enqueued at most once at a time)
+          a.stack[a.scc_base[c] + (a.qhead[c] + a.qlen[c]) % size] = s;
+          a.qlen[c]++;
+        } else {              // TrivialQueue: enqueue overwrites (trivial_queue.rs)
+          a.stack[a.scc_base[c]] = s;
+          a.qlen[c] = 1;
+        }
+      }
+    }
+  }
+  __device__ bool dequeue(uint32_t* out) {
+    switch (a.kind) {
+      case kStateOrderQueue: {  // state_order_queue.rs:32-45
+        if (!has_back || front > back) return false;
+        *out = front;
+        a.slot[front] = 0;
+        while (front <= back && !a.slot[front]) front++;
+        return true;
+      }
+      case kTopOrderQueue: {  // top_order_queue.rs:57-68
+        if (!has_back || front > back) return false;
+        int32_t head = a.slot[front];
+        a.slot[front] = -1;
+        while (front <= back && a.slot[front] < 0) front++;
+        if (head < 0) return false;
+        *out = (uint32_t)head;
+        return true;
+      }
+      case kLifoQueue:
+        if (sp == 0) return false;
+        *out = a.stack[--sp];
+        return true;
+      default: {  // scc_queue.rs:46-62
+        bool empty = sfront < sback ? false : (sfront > sback ? true : scc_q_empty((uint32_t)sfront));
+        if (empty) return false;
+        while (sfront <= sback && scc_q_empty((uint32_t)sfront)) sfront++;
+        uint32_t c = (uint32_t)sfront;
+        if (a.qlen[c] == 0) return false;
+        uint32_t size = a.scc_base[c + 1] - a.scc_base[c];
+        *out = a.stack[a.scc_base[c] + a.qhead[c]];
+        if (a.scc_fifo[c]) a.qhead[c] = (a.qhead[c] + 1) % size;
+        a.qlen[c]--;
+        return true;
+      }
+    }
+  }
+};
+
+__global__ void k_serial_sssp(SerialArgs a) {
+  if (blockIdx.x || threadIdx.x) return;
+  const float inf = w_zero();
+  for (uint32_t s = 0; s < a.n; s++) { a.dist[s] = inf; a.pstate[s] = kNoState; a.ppos[s] = 0; a.enq[s] = 0; }
+  if (a.kind == kStateOrderQueue) for (uint32_t s = 0; s < a.n; s++) a.slot[s] = 0;
+  if (a.kind == kTopOrderQueue) for (uint32_t s = 0; s < a.n; s++) a.slot[s] = -1;
+  SerialQueue q(a);
+  float f_distance = inf;
+  bool has_f_parent = false;
+  uint32_t f_parent = 0;
+  unsigned long long relaxed = 0, dequeued = 0;
+  a.dist[a.start] = 0.0f;
+  a.enq[a.start] = 1;
+  q.enqueue(a.start);
+  uint32_t s;
+  while (q.dequeue(&s)) {
+    a.enq[s] = 0;
+    float sd = a.dist[s];
+    dequeued++;
+    float rho = a.fin[s];
+    if (rho != inf) {  // shortest_path.rs:214-220
+      float plus = w_plus(f_distance, w_times(sd, rho));
+      if (!w_approx_eq(f_distance, plus)) { f_distance = plus; f_parent = s; has_f_parent = true; }
+    }
+    uint32_t b = a.off[s], e = a.off[s + 1];
+    relaxed += e - b;
+    for (uint32_t k = b; k < e; k++) {  // shortest_path.rs:222-236
+      Tr tr = a.arcs[k];
+      float nd = a.dist[tr.nextstate];
+      float p = w_plus(nd, w_times(sd, tr.weight));
+      if (!w_approx_eq(nd, p)) {
+        a.dist[tr.nextstate] = p;
+        a.pstate[tr.nextstate] = s;
+        a.ppos[tr.nextstate] = k - b;
+        if (!a.enq[tr.nextstate]) { q.enqueue(tr.nextstate); a.enq[tr.nextstate] = 1; }
+      }
+    }
+  }
+  a.counters[0] = relaxed; a.counters[1] = dequeued;
+  // backtrace (shortest_path.rs:241-282)
+  a.meta[0] = has_f_parent ? 1u : 0u; a.meta[1] = 0; a.meta[2] = f_parent; a.meta[3] = 0;
+  if (!has_f_parent) return;
+  uint32_t state = f_parent, L = 0;
+  while (a.pstate[state] != kNoState) {
+    uint32_t src = a.pstate[state];
+    if (L >= a.cap) { a.meta[3] = 1; break; }
+    Tr tr = a.arcs[a.off[src] + a.ppos[state]];
+    tr.nextstate = L;
+    a.out_arcs[L++] = tr;
+    state = src;
+  }
+  a.meta[1] = L;
+}
+
+// Rebuild the output FST on the host from the path arcs, replaying the reference's mutation sequence so the
+// property word comes out identical (add_state; add_tr | set_final; ...; set_start; shortest_path_properties).
+CsrFst build_path_fst(bool found, const std::vector<Tr>& path, float final_w) {
+  CsrFst o;
+  uint64_t p = props::kNull;
+  if (found) {
+    size_t L = path.size();
+    o.offsets.assign(L + 2, 0);
+    o.finals.assign(L + 1, w_zero());
+    o.arcs = path;
+    for (size_t k = 0; k <= L; k++) {
+      p = props::on_add_state(p);
+      if (k == 0) {
+        p = props::on_set_final(p, nullptr, &final_w);
+        o.finals[0] = final_w;
+        if (final_w == w_zero()) o.inf_finals.push_back(0);
+      } else {
+        p = props::on_add_tr(p, (StateId)k, path[k - 1], nullptr);
+      }
+      o.offsets[k + 1] = (uint32_t)k;
+    }
+    o.offsets[0] = 0;
+    o.has_start = true; o.start = (StateId)L;
+    p = props::on_set_start(p);
+  }
+  o.props = props::of_shortest_path(p, true) & props::kTrinary;
+  return o;
+}
+
+}  // namespace
+
+CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* stats, cudaStream_t s,
+                            bool force_serial) {
+  SsspStats local;
+  SsspStats& st = stats ? *stats : local;
+  st = SsspStats();
+  st.plan_host_ms = plan.host_ms;
+  const uint32_t n = f.num_states;
+  if (!f.has_start || n == 0) return build_path_fst(false, {}, 0.0f);  // shortest_path.rs:186-189
+
+  cudaEvent_t ev0, ev1;
+  B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1));
+  B200_CUDA(cudaEventRecord(ev0, s));
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> relax_events;
+
+  const uint32_t cap = n;  // a shortest path visits each state at most once
+  DevBuf<Tr> out_arcs(s, cap);
+  DevBuf<uint32_t> meta(s, 4);
+  DevBuf<uint32_t> d_order(s);
+  const uint32_t* order_p = nullptr;
+  if (plan.kind == kTopOrderQueue) {
+    d_order.reserve_discard(n);
+    B200_CUDA(cudaMemcpyAsync(d_order.p, plan.order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    order_p = d_order.p;
+  }
+
+  bool parallel_ok = !force_serial && (plan.kind == kStateOrderQueue || plan.kind == kTopOrderQueue);
+  bool done = false;
+  uint32_t hmeta[4] = {0, 0, 0, 0};
+
+  if (parallel_ok) {
+    DevBuf<uint32_t> dist(s, n), stamp(s, n), fr_a(s, n), fr_b(s, n), counters(s, 4), flags(s, 1), inv(s);
+    DevBuf<unsigned long long> pkey(s, n), fkey(s, 1);
+    k_fill_u32<<<blocks_for(n), kThreads, 0, s>>>(dist.p, kEncInf, n);
+    B200_CUDA(cudaMemsetAsync(stamp.p, 0xFF, (size_t)n * 4, s));
+    k_fill_u64<<<blocks_for(n), kThreads, 0, s>>>(pkey.p, kNoParent, n);
+    B200_CUDA(cudaMemsetAsync(fkey.p, 0xFF, 8, s));
+    B200_CUDA(cudaMemsetAsync(flags.p, 0, 4, s));
+    B200_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
+    uint32_t zero_enc = enc_f32(0.0f), src = f.start;
+    B200_CUDA(cudaMemcpyAsync(dist.p + src, &zero_enc, 4, cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaMemcpyAsync(fr_a.p, &src, 4, cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    st.kernel_launches += 2;
+    uint32_t* fin_p = fr_a.p; uint32_t* fout_p = fr_b.p;
+    uint32_t nf = 1, wave = 0;
+    while (nf) {
+      if (wave > n) throw FstError("shortest_path: relaxation did not converge (negative cycle?)");
+      B200_CUDA(cudaMemsetAsync(counters.p, 0, 4, s));
+      cudaEvent_t ea, eb;
+      B200_CUDA(cudaEventCreate(&ea)); B200_CUDA(cudaEventCreate(&eb));
+      B200_CUDA(cudaEventRecord(ea, s));
+      k_relax<<<blocks_for(nf), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, fin_p, nf, dist.p, stamp.p, wave, fout_p,
+                                                  counters.p);
+      B200_CUDA(cudaEventRecord(eb, s));
+      relax_events.emplace_back(ea, eb);
+      st.relax_launches++; st.kernel_launches++;
+      st.states_settled += nf;
+      nf = read_u32(counters.p, s);
+      std::swap(fin_p, fout_p);
+      wave++;
+    }
+    st.waves = wave;
+    k_parents<<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, dist.p, order_p, pkey.p, flags.p);
+    k_final_min<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, dist.p, order_p, fkey.p);
+    k_final_check<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, dist.p, fkey.p, flags.p);
+    st.kernel_launches += 3;
+    uint32_t violations = read_u32(flags.p, s);
+    if (violations == 0) {
+      const uint32_t* inv_p = nullptr;
+      if (order_p) {
+        inv.reserve_discard(n);
+        k_invert_order<<<blocks_for(n), kThreads, 0, s>>>(order_p, n, inv.p);
+        inv_p = inv.p; st.kernel_launches++;
+      }
+      k_backtrace_keys<<<1, 32, 0, s>>>(f.offsets.p, f.arcs.p, n, pkey.p, fkey.p, inv_p, out_arcs.p, cap, meta.p);
+      st.kernel_launches++;
+      B200_CUDA(cudaMemcpyAsync(hmeta, meta.p, 16, cudaMemcpyDeviceToHost, s));
+      unsigned long long relaxed = 0;
+      B200_CUDA(cudaMemcpyAsync(&relaxed, counters.p + 2, 8, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      st.arcs_relaxed = relaxed;
+      st.path = 0;
+      done = true;
+    }
+  }
+
+  if (!done) {  // order-faithful serial replay
+    st.path = 1;
+    DevBuf<float> dist(s, n);
+    DevBuf<uint32_t> pstate(s, n), ppos(s, n), stack(s, (size_t)n + 1), d_scc(s), d_base(s), qhead(s), qlen(s);
+    DevBuf<uint8_t> enq(s, n), d_fifo(s);
+    DevBuf<int32_t> slot(s, n);
+    DevBuf<unsigned long long> counters(s, 2);
+    SerialArgs a{};
+    a.off = f.offsets.p; a.arcs = f.arcs.p; a.fin = f.finals.p; a.n = n; a.start = f.start;
+    a.kind = plan.kind; a.order = order_p;
+    if (plan.kind == kSccQueue) {
+      size_t nscc = plan.scc_is_fifo.size();
+      std::vector<uint32_t> base(nscc + 1, 0);
+      for (uint32_t c : plan.scc) base[c + 1]++;
+      for (size_t c = 0; c < nscc; c++) base[c + 1] += base[c];
+      d_scc.reserve_discard(n); d_base.reserve_discard(nscc + 1); d_fifo.reserve_discard(nscc);
+      qhead.reserve_discard(nscc); qlen.reserve_discard(nscc);
+      B200_CUDA(cudaMemcpyAsync(d_scc.p, plan.scc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+      B200_CUDA(cudaMemcpyAsync(d_base.p, base.data(), (nscc + 1) * 4, cudaMemcpyHostToDevice, s));
+      B200_CUDA(cudaMemcpyAsync(d_fifo.p, plan.scc_is_fifo.data(), nscc, cudaMemcpyHostToDevice, s));
+      B200_CUDA(cudaMemsetAsync(qhead.p, 0, nscc * 4, s));
+      B200_CUDA(cudaMemsetAsync(qlen.p, 0, nscc * 4, s));
+      B200_CUDA(cudaStreamSynchronize(s));  // base is a host temporary
+      a.scc = d_scc.p; a.scc_base = d_base.p; a.scc_fifo = d_fifo.p; a.qhead = qhead.p; a.qlen = qlen.p;
+    }
+    a.dist = dist.p; a.pstate = pstate.p; a.ppos = ppos.p; a.enq = enq.p; a.slot = slot.p; a.stack = stack.p;
+    a.out_arcs = out_arcs.p; a.cap = cap; a.meta = meta.p; a.counters = counters.p;
+    k_serial_sssp<<<1, 32, 0, s>>>(a);
+    st.kernel_launches++;
+    unsigned long long hc[2] = {0, 0};
+    B200_CUDA(cudaMemcpyAsync(hmeta, meta.p, 16, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    st.arcs_relaxed = hc[0]; st.states_settled = hc[1]; st.waves = 0;
+  }
+
+  if (hmeta[3]) throw FstError("shortest_path: parent chain does not terminate (zero/negative cycle)");
+  std::vector<Tr> path(hmeta[1]);
+  float final_w = 0.0f;
+  if (hmeta[0]) {
+    if (hmeta[1]) B200_CUDA(cudaMemcpyAsync(path.data(), out_arcs.p, (size_t)hmeta[1] * 16, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaMemcpyAsync(&final_w, f.finals.p + hmeta[2], 4, cudaMemcpyDeviceToHost, s));
+  }
+  B200_CUDA(cudaEventRecord(ev1, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  B200_CUDA(cudaEventElapsedTime(&st.ms_device, ev0, ev1));
+  for (auto& pr : relax_events) {
+    float ms = 0;
+    B200_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    st.ms_relax_kernel += ms;
+    cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+  }
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  return build_path_fst(hmeta[0] != 0, path, final_w);
+}
+
+}  // namespace b200

@@ -1,0 +1,215 @@
+"""GPU parity tests proper: every result of the CUDA path (called through the C-ABI) is compared bit-for-bit
+with the CPU oracle on the same inputs: state ids, arc order, labels, next states, weight bit patterns,
+final weights and property words."""
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+from tests.parity_utils import FIXTURES, assert_same, both_from_dict, both_from_path, golden_path, random_fst
+
+pytestmark = pytest.mark.gpu
+
+FILTERS = [0, 1, 2, 3, 4, 5, 6]
+
+
+def _compose_both(pa, oa, pb, ob, filt, connect):
+    import rustfst_b200 as R
+    try:
+        o = O.compose(oa, ob, filter=filt, connect=connect)
+    except O.OracleError as e:
+        with pytest.raises(ValueError):
+            R.compose_with_config(pa, pb, R.ComposeConfig(R.ComposeFilter(filt), connect))
+        return None, str(e)
+    p = R.compose_with_config(pa, pb, R.ComposeConfig(R.ComposeFilter(filt), connect))
+    return (p, o), None
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+@pytest.mark.parametrize("connect", [False, True])
+def test_fixture_compose_all_filters(name, connect):
+    """fst_NNN.get_fst() o fst_NNN.get_fst_compose() (rustfst-tests-data/main.cpp:1191-1194) under the seven
+    filter settings of tests_openfst/algorithms/compose.rs:256-302, with and without connect."""
+    pa, oa = both_from_path(golden_path(name, "raw"))
+    pb, ob = both_from_path(golden_path(name, "compose"))
+    for filt in FILTERS:
+        res, err = _compose_both(pa, oa, pb, ob, filt, connect)
+        if res:
+            assert_same(res[0], res[1], f"{name} filter={filt} connect={connect}")
+
+
+def test_fixture_default_compose_and_cross_pair():
+    import rustfst_b200 as R
+    for name in FIXTURES:
+        pa, oa = both_from_path(golden_path(name, "raw"))
+        pb, ob = both_from_path(golden_path(name, "compose"))
+        try:
+            o = O.compose(oa, ob)
+        except O.OracleError:
+            with pytest.raises(ValueError):
+                pa.compose(pb)
+            continue
+        assert_same(pa.compose(pb), o, f"{name} default")
+    # the literal fst_003 o fst_004 pairing of BASELINE.json configs[0]: no common labels -> empty after connect
+    pa, oa = both_from_path(golden_path("fst_003", "raw"))
+    pb, ob = both_from_path(golden_path("fst_004", "raw"))
+    r = pa.compose(pb)
+    assert r.num_states() == 0 and r.start() is None
+    assert_same(r, O.compose(oa, ob), "fst_003 o fst_004")
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_fixture_shortest_path(name):
+    """shortest_path(n=1) on every fixture input (cyclic, epsilon-rich: SccQueue / LIFO / TopOrder branches)."""
+    import rustfst_b200 as R
+    for which in ("raw", "compose"):
+        p, o = both_from_path(golden_path(name, which))
+        expected = O.shortest_path(o)
+        got, st = R.shortestpath_with_stats(p)
+        assert_same(got, expected, f"{name}/{which} shortest_path (path={st['path']} queue={st['queue_kind']})")
+        # the order-faithful serial kernel must agree as well
+        got2, _ = R.shortestpath_with_stats(p, force_serial=True)
+        assert_same(got2, expected, f"{name}/{which} shortest_path serial")
+
+
+def test_fixture_compose_then_shortest_path():
+    """BASELINE.json configs[0] plumbing: compose + shortest_path chained on the device results."""
+    import rustfst_b200 as R
+    for name in FIXTURES:
+        pa, oa = both_from_path(golden_path(name, "raw"))
+        pb, ob = both_from_path(golden_path(name, "compose"))
+        try:
+            oc = O.compose(oa, ob)
+        except O.OracleError:
+            continue
+        pc = pa.compose(pb)
+        assert_same(pc.shortest_path(), O.shortest_path(oc), f"{name} compose+shortest_path")
+
+
+def test_python_kats_through_cabi():
+    """The reference's own FFI-level known answers (rustfst-python/tests/algorithms/test_compose.py:13-154,
+    test_shortest_path.py:5-51), written with the mirrored API."""
+    from rustfst_b200 import ComposeConfig, ComposeFilter, ShortestPathConfig, Tr, VectorFst
+
+    def mk():
+        fst1 = VectorFst()
+        s1, s2, s3 = fst1.add_state(), fst1.add_state(), fst1.add_state()
+        fst1.set_start(s1); fst1.set_final(s2); fst1.set_final(s3)
+        fst1.add_tr(s1, Tr(1, 2, 1.0, s2)); fst1.add_tr(s1, Tr(1, 4, 2.0, s3)); fst1.add_tr(s2, Tr(3, 5, 2.0, s2))
+        fst2 = VectorFst()
+        s1, s2, s3 = fst2.add_state(), fst2.add_state(), fst2.add_state()
+        fst2.set_start(s1); fst2.set_final(s3)
+        fst2.add_tr(s1, Tr(2, 6, 1.0, s2)); fst2.add_tr(s2, Tr(5, 7, 2.5, s3)); fst2.add_tr(s3, Tr(5, 8, 1.5, s3))
+        fst2.add_tr(s1, Tr(4, 9, 3.0, s3))
+        e = VectorFst()
+        s1, s2, s3, s4 = e.add_state(), e.add_state(), e.add_state(), e.add_state()
+        e.set_start(s1); e.set_final(s3); e.set_final(s4)
+        e.add_tr(s1, Tr(1, 6, 2.0, s2)); e.add_tr(s1, Tr(1, 9, 5.0, s3)); e.add_tr(s2, Tr(3, 7, 4.5, s4))
+        e.add_tr(s4, Tr(3, 8, 3.5, s4))
+        return fst1, fst2, e
+
+    fst1, fst2, expected = mk()
+    assert fst1.compose(fst2) == expected
+    assert fst1.compose(fst2, ComposeConfig(ComposeFilter.TRIVIALFILTER, True)) == expected
+
+    f = VectorFst()
+    s1, s2, s3, s4 = f.add_state(), f.add_state(), f.add_state(), f.add_state()
+    f.set_start(s1); f.set_final(s4, 2.0)
+    f.add_tr(s1, Tr(1, 1, 3.0, s2)); f.add_tr(s2, Tr(2, 2, 2.0, s2)); f.add_tr(s2, Tr(3, 3, 4.0, s4))
+    f.add_tr(s1, Tr(4, 4, 5.0, s3)); f.add_tr(s3, Tr(5, 5, 4.0, s4))
+    e = VectorFst()
+    s1, s2, s3 = e.add_state(), e.add_state(), e.add_state()
+    e.set_start(s3); e.set_final(s1, 2.0)
+    e.add_tr(s3, Tr(1, 1, 3.0, s2)); e.add_tr(s2, Tr(3, 3, 4.0, s1))
+    assert f.shortest_path(ShortestPathConfig(1, True)) == e
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_compose_fuzz(seed):
+    """Random small FSTs with epsilons and cycles; one or both sides sorted; all filters."""
+    rng = np.random.default_rng(1000 + seed)
+    sort_a = [None, "olabel", "olabel"][seed % 3]
+    sort_b = ["ilabel", None, "ilabel"][seed % 3]
+    da = random_fst(rng, int(rng.integers(1, 30)), 6, 6, eps_prob=0.25, sort=sort_a)
+    db = random_fst(rng, int(rng.integers(1, 30)), 6, 6, eps_prob=0.25, sort=sort_b)
+    pa, oa = both_from_dict(da)
+    pb, ob = both_from_dict(db)
+    for filt in FILTERS:
+        for connect in (False, True):
+            res, err = _compose_both(pa, oa, pb, ob, filt, connect)
+            if res:
+                assert_same(res[0], res[1], f"fuzz seed={seed} filter={filt} connect={connect}")
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_shortest_path_fuzz(seed):
+    import rustfst_b200 as R
+    rng = np.random.default_rng(2000 + seed)
+    cyclic = seed % 2 == 0
+    d = random_fst(rng, int(rng.integers(2, 60)), 5, 8, eps_prob=0.1, cyclic=cyclic, weight_grid=(seed % 4 < 2))
+    p, o = both_from_dict(d)
+    expected = O.shortest_path(o)
+    got, st = R.shortestpath_with_stats(p)
+    assert_same(got, expected, f"sssp fuzz seed={seed} path={st['path']}")
+    got2, _ = R.shortestpath_with_stats(p, force_serial=True)
+    assert_same(got2, expected, f"sssp fuzz serial seed={seed}")
+
+
+@pytest.mark.parametrize("scale", [0.02, 0.25])
+def test_synthetic_compose_and_sssp(scale):
+    """BASELINE.json configs[1] (C2) shrunk so the oracle finishes in seconds; same generator as bench.py."""
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    a, b = synth.workload("C2", scale=scale)
+    pa, oa = both_from_dict(a)
+    pb, ob = both_from_dict(b)
+    for connect in (False, True):
+        o, ost = O.compose(oa, ob, connect=connect, want_stats=True)
+        p, st = R.compose_with_stats(pa, pb, R.ComposeConfig(R.ComposeFilter.AUTOFILTER, connect))
+        assert st["states_expanded"] == ost["states_expanded"] and st["arcs_emitted"] == ost["arcs_emitted"]
+        assert_same(p, o, f"C2 x{scale} connect={connect}")
+    # shortest path on the composed lattice (ACYCLIC known, TOP_SORTED unknown -> TopOrderQueue via DFS order)
+    expected = O.shortest_path(o)
+    got, st = R.shortestpath_with_stats(p)
+    assert st["path"] == 0, "dyadic weights must pass the certificate"
+    assert_same(got, expected, "C2 lattice shortest path")
+    # and directly on the TOP_SORTED acceptor (StateOrderQueue)
+    got, st = R.shortestpath_with_stats(pa)
+    assert st["queue_kind"] == 0 and st["path"] == 0
+    assert_same(got, O.shortest_path(oa), "acceptor shortest path")
+
+
+def test_device_resident_api_matches_host_api():
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    a, b = synth.workload("C2", scale=0.05)
+    pa, _ = both_from_dict(a)
+    pb, _ = both_from_dict(b)
+    da, db = R.DeviceFst.upload(pa), R.DeviceFst.upload(pb)
+    dr, st = R.device_compose(da, db)
+    host = pa.compose(pb)
+    r = dr.download()
+    assert r == host and r.properties == host.properties
+    sp, _ = R.device_shortest_path(dr, plan_from=r)
+    assert sp == host.shortest_path()
+
+
+def test_tr_sort_then_compose_chain():
+    """Compose output has unknown sortedness (mutate_properties.rs:151-184): composing it on the LEFT of an unsorted
+    machine must fail until fst_tr_sort restores the bit."""
+    import rustfst_b200 as R
+    rng = np.random.default_rng(7)
+    da = random_fst(rng, 12, 4, 5, sort="olabel", cyclic=False)
+    db = random_fst(rng, 12, 4, 5, sort="ilabel", cyclic=False)
+    dc = random_fst(rng, 12, 4, 5, sort=None, cyclic=False)
+    pa, oa = both_from_dict(da); pb, ob = both_from_dict(db); pc, oc = both_from_dict(dc)
+    pab, oab = pa.compose(pb), O.compose(oa, ob)
+    assert_same(pab, oab, "a o b")
+    unsorted_c = not (oc.props & R.props.I_LABEL_SORTED)
+    if unsorted_c:
+        with pytest.raises(ValueError):
+            pab.compose(pc)
+        with pytest.raises(O.OracleError):
+            O.compose(oab, oc)
+    pab.tr_sort(ilabel_cmp=False); oab.tr_sort(ilabel=False)
+    assert_same(pab, oab, "tr_sort(olabel)")
+    assert_same(pab.compose(pc), O.compose(oab, oc), "(a o b) o c")

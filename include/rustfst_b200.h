@@ -198,6 +198,7 @@ typedef struct B200ComposeStats {
   uint64_t kernel_launches, emit_launches;
   float ms_expand, ms_connect, ms_emit_kernel;
   float ms_h2d, ms_d2h; /* host<->device marshalling inside the host-buffer entry points (wall clock) */
+  float ms_phase_match, ms_phase_emit, ms_phase_rank, ms_phase_resolve; /* persistent kernel, %globaltimer */
 } B200ComposeStats;
 typedef struct B200SsspStats {
   uint64_t arcs_relaxed, states_settled, waves, kernel_launches, relax_launches;

@@ -25,12 +25,21 @@ struct ComposeStats {
   float ms_emit_kernel = 0;               // summed duration of the emit kernel (roofline numerator's time)
   uint64_t emit_launches = 0;
   uint64_t kernel_launches = 0;           // kernels of this library launched by the call
+  float ms_phase[4] = {0, 0, 0, 0};       // persistent back end: device time inside phases A (match), B (emit),
+                                          // C (rank), D (resolve), from %globaltimer
 };
 
 // a must be olabel-sorted and/or b ilabel-sorted as recorded in their property words (A.1 of SURVEY.md);
 // throws FstError with the reference's message otherwise.
 DevFst compose_device(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
                       cudaStream_t s);
+// Back end 1: one kernel per phase and wave, launch sizes read back by the host (grows every buffer on demand).
+DevFst compose_device_waves(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
+                            cudaStream_t s);
+// Back end 2: one persistent cooperative kernel runs the whole BFS (no host round trips); returns false when a
+// pre-sized buffer overflowed, in which case the caller falls back to back end 1.
+bool compose_device_coop(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
+                         cudaStream_t s, DevFst* out);
 
 // Trim: keep states that are accessible and coaccessible, order-preserving renumbering
 // (rustfst/src/algorithms/connect.rs:51-66, rustfst/src/fst_impls/vector_fst/mutable_fst.rs:132-189).

@@ -85,6 +85,8 @@ void fill(B200ComposeStats* out, const ComposeStats& st, float h2d, float d2h) {
   out->arcs_out = st.arcs_out; out->kernel_launches = st.kernel_launches; out->emit_launches = st.emit_launches;
   out->ms_expand = st.ms_expand; out->ms_connect = st.ms_connect; out->ms_emit_kernel = st.ms_emit_kernel;
   out->ms_h2d = h2d; out->ms_d2h = d2h;
+  out->ms_phase_match = st.ms_phase[0]; out->ms_phase_emit = st.ms_phase[1];
+  out->ms_phase_rank = st.ms_phase[2]; out->ms_phase_resolve = st.ms_phase[3];
 }
 void fill(B200SsspStats* out, const SsspStats& st, int kind, float h2d) {
   if (!out) return;
@@ -507,6 +509,8 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
       acc.arcs_emitted += cs.arcs_emitted; acc.waves += cs.waves; acc.states_out += cs.states_out;
       acc.arcs_out += cs.arcs_out; acc.kernel_launches += cs.kernel_launches; acc.emit_launches += cs.emit_launches;
       acc.ms_expand += cs.ms_expand; acc.ms_connect += cs.ms_connect; acc.ms_emit_kernel += cs.ms_emit_kernel;
+      acc.ms_phase_match += cs.ms_phase[0]; acc.ms_phase_emit += cs.ms_phase[1];
+      acc.ms_phase_rank += cs.ms_phase[2]; acc.ms_phase_resolve += cs.ms_phase[3];
     }
     if (total) *total = acc;
   });

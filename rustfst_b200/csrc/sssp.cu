@@ -21,9 +21,13 @@
 //      included) for everything else: cyclic inputs (SccQueue / LIFO) and inputs whose certificate fails.
 //
 // The backtrace runs on the device as well; only the shortest path itself (a few hundred bytes) returns to the host.
+#include <cooperative_groups.h>
+
 #include <vector>
 
 #include "algos.h"
+
+namespace cg = cooperative_groups;
 
 namespace b200 {
 namespace {
@@ -95,6 +99,65 @@ k_relax(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, const uin
   // arcs-relaxed statistic: one atomic per warp
   for (int o = 16; o > 0; o >>= 1) relaxed += __shfl_down_sync(0xFFFFFFFFu, relaxed, o);
   if ((threadIdx.x & 31) == 0 && relaxed) atomicAdd(reinterpret_cast<unsigned long long*>(&counters[2]), relaxed);
+}
+
+// Persistent variant: the whole relaxation (all waves) in one cooperative launch.  kG lanes share a frontier state
+// and stride over its arcs (coalesced 128-bit loads); three frontier counters rotate so that no reset races with a
+// read: wave w consumes cnt[w % 3] (filled during wave w-1), fills cnt[(w+1) % 3] and clears cnt[(w+2) % 3].
+// out[0] = waves, out[1] = overflow/non-convergence flag, out64[0] = arcs relaxed, out64[1] = states settled.
+template <int kG>
+__global__ void __launch_bounds__(kThreads)
+k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t* __restrict__ dist,
+             uint32_t* __restrict__ stamp, uint32_t* __restrict__ fr_a, uint32_t* __restrict__ fr_b,
+             uint32_t* __restrict__ cnt /*3*/, uint32_t* __restrict__ out, unsigned long long* __restrict__ out64) {
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t lane = threadIdx.x % kG;
+  const uint32_t groups = gridDim.x * (kThreads / kG);
+  const uint32_t gid = blockIdx.x * (kThreads / kG) + threadIdx.x / kG;
+  uint32_t* cur = fr_a;
+  uint32_t* nxt = fr_b;
+  unsigned long long relaxed = 0, settled = 0;
+  uint32_t wave = 0;
+  while (true) {
+    const uint32_t nf = __ldcg(&cnt[wave % 3]);
+    if (nf == 0 || wave > n) break;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[(wave + 2) % 3] = 0;
+    uint32_t* next_count = &cnt[(wave + 1) % 3];
+    for (uint32_t i = gid; i < nf; i += groups) {
+      const uint32_t s = __ldcg(&cur[i]);
+      const float ds = dec_f32(__ldcg(&dist[s]));
+      const uint32_t b = off[s], e = off[s + 1];
+      if (lane == 0) { relaxed += e - b; settled++; }
+      for (uint32_t k0 = b; k0 < e; k0 += kG) {
+        const uint32_t k = k0 + lane;
+        bool push = false;
+        uint32_t t = 0;
+        if (k < e) {
+          int4 v = __ldg(reinterpret_cast<const int4*>(&arcs[k]));
+          float c = w_times(ds, __int_as_float(v.z));
+          t = (uint32_t)v.w;
+          if (c != w_zero()) {
+            uint32_t ec = enc_f32(c);
+            if (ec < __ldcg(&dist[t])) {
+              uint32_t old = atomicMin(&dist[t], ec);
+              if (ec < old) push = atomicExch(&stamp[t], wave) != wave;
+            }
+          }
+        }
+        warp_push(push, t, nxt, next_count);
+      }
+    }
+    wave++;
+    uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+    grid.sync();
+  }
+  // statistics: one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    relaxed += __shfl_down_sync(0xFFFFFFFFu, relaxed, o);
+    settled += __shfl_down_sync(0xFFFFFFFFu, settled, o);
+  }
+  if ((threadIdx.x & 31) == 0) { if (relaxed) atomicAdd(&out64[0], relaxed); if (settled) atomicAdd(&out64[1], settled); }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = wave; out[1] = (wave > n) ? 1u : 0u; }
 }
 
 // Parent selection + certificate over all arcs of reached states.  flags[0] = certificate violations.
@@ -399,25 +462,38 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
     B200_CUDA(cudaMemcpyAsync(fr_a.p, &src, 4, cudaMemcpyHostToDevice, s));
     B200_CUDA(cudaStreamSynchronize(s));
     st.kernel_launches += 2;
-    uint32_t* fin_p = fr_a.p; uint32_t* fout_p = fr_b.p;
-    uint32_t nf = 1, wave = 0;
-    while (nf) {
-      if (wave > n) throw FstError("shortest_path: relaxation did not converge (negative cycle?)");
-      B200_CUDA(cudaMemsetAsync(counters.p, 0, 4, s));
+    {
+      // one cooperative launch runs every relaxation wave
+      DevBuf<uint32_t> cnt(s, 3), outw(s, 2);
+      DevBuf<unsigned long long> out64(s, 2);
+      uint32_t init_cnt[3] = {1, 0, 0};
+      B200_CUDA(cudaMemcpyAsync(cnt.p, init_cnt, 12, cudaMemcpyHostToDevice, s));
+      B200_CUDA(cudaMemsetAsync(outw.p, 0, 8, s));
+      B200_CUDA(cudaMemsetAsync(out64.p, 0, 16, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      int per_sm = 0;
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_relax_coop<8>, kThreads, 0));
+      if (per_sm < 1) throw FstError("cooperative relaxation kernel does not fit on the device");
+      int grid = sm_count() * per_sm;
+      const uint32_t* a_off = f.offsets.p; const Tr* a_arcs = f.arcs.p;
+      uint32_t nn = n;
+      uint32_t* a_dist = dist.p; uint32_t* a_stamp = stamp.p; uint32_t* a_fa = fr_a.p; uint32_t* a_fb = fr_b.p;
+      uint32_t* a_cnt = cnt.p; uint32_t* a_out = outw.p; unsigned long long* a_out64 = out64.p;
+      void* args[] = {&a_off, &a_arcs, &nn, &a_dist, &a_stamp, &a_fa, &a_fb, &a_cnt, &a_out, &a_out64};
       cudaEvent_t ea, eb;
       B200_CUDA(cudaEventCreate(&ea)); B200_CUDA(cudaEventCreate(&eb));
       B200_CUDA(cudaEventRecord(ea, s));
-      k_relax<<<blocks_for(nf), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, fin_p, nf, dist.p, stamp.p, wave, fout_p,
-                                                  counters.p);
+      B200_CUDA(cudaLaunchCooperativeKernel((void*)k_relax_coop<8>, dim3(grid), dim3(kThreads), args, 0, s));
       B200_CUDA(cudaEventRecord(eb, s));
       relax_events.emplace_back(ea, eb);
       st.relax_launches++; st.kernel_launches++;
-      st.states_settled += nf;
-      nf = read_u32(counters.p, s);
-      std::swap(fin_p, fout_p);
-      wave++;
+      uint32_t hw[2]; unsigned long long h64[2];
+      B200_CUDA(cudaMemcpyAsync(hw, outw.p, 8, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaMemcpyAsync(h64, out64.p, 16, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      if (hw[1]) throw FstError("shortest_path: relaxation did not converge (negative cycle?)");
+      st.waves = hw[0]; st.arcs_relaxed = h64[0]; st.states_settled = h64[1];
     }
-    st.waves = wave;
     k_parents<<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, dist.p, order_p, pkey.p, flags.p);
     k_final_min<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, dist.p, order_p, fkey.p);
     k_final_check<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, dist.p, fkey.p, flags.p);
@@ -433,10 +509,7 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
       k_backtrace_keys<<<1, 32, 0, s>>>(f.offsets.p, f.arcs.p, n, pkey.p, fkey.p, inv_p, out_arcs.p, cap, meta.p);
       st.kernel_launches++;
       B200_CUDA(cudaMemcpyAsync(hmeta, meta.p, 16, cudaMemcpyDeviceToHost, s));
-      unsigned long long relaxed = 0;
-      B200_CUDA(cudaMemcpyAsync(&relaxed, counters.p + 2, 8, cudaMemcpyDeviceToHost, s));
       B200_CUDA(cudaStreamSynchronize(s));
-      st.arcs_relaxed = relaxed;
       st.path = 0;
       done = true;
     }

@@ -33,7 +33,9 @@ class ComposeStats(C.Structure):
                 ("waves", C.c_uint64), ("states_out", C.c_uint64), ("arcs_out", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("emit_launches", C.c_uint64),
                 ("ms_expand", C.c_float), ("ms_connect", C.c_float), ("ms_emit_kernel", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float)]
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+                ("ms_phase_match", C.c_float), ("ms_phase_emit", C.c_float), ("ms_phase_rank", C.c_float),
+                ("ms_phase_resolve", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

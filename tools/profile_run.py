@@ -1,0 +1,34 @@
+"""Minimal driver for ncu captures: one device-resident C3 compose (+ optionally one C4 shortest path).
+
+    ncu ... python tools/profile_run.py [--scale S] [--sssp] [--reps R]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import rustfst_b200 as R  # noqa: E402
+from rustfst_b200 import synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--levels", type=int, default=50)
+ap.add_argument("--sssp", action="store_true")
+ap.add_argument("--reps", type=int, default=1)
+args = ap.parse_args()
+
+n, a = int(1_000_000 * args.scale), int(10_000_000 * args.scale)
+a1 = synth.layered_acceptor(n, a, 32, 3, args.levels)
+a2 = synth.bigram_transducer(n, a, 32, 4, args.levels, out_vocab=20000)
+d1, d2 = R.DeviceFst.upload(synth.to_vector_fst(a1)), R.DeviceFst.upload(synth.to_vector_fst(a2))
+for _ in range(args.reps):
+    out, st = R.device_compose(d1, d2)
+    print({k: st[k] for k in ("states_expanded", "arcs_emitted", "waves", "kernel_launches", "ms_expand", "ms_connect",
+                              "ms_emit_kernel")})
+if args.sssp:
+    g = synth.layered_acceptor(int(5_000_000 * args.scale), int(50_000_000 * args.scale), 1000, 6, 50)
+    dg = R.DeviceFst.upload(synth.to_vector_fst(g))
+    for _ in range(args.reps):
+        sp, sst = R.device_shortest_path(dg)
+        print({k: sst[k] for k in ("arcs_relaxed", "waves", "kernel_launches", "ms_device", "ms_relax_kernel", "path")})

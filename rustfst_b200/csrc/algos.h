@@ -45,6 +45,11 @@ bool compose_device_coop(const DevFst& a, const DevFst& b, const ComposeOptions&
 // (rustfst/src/algorithms/connect.rs:51-66, rustfst/src/fst_impls/vector_fst/mutable_fst.rs:132-189).
 // assume_accessible skips the forward pass (true for a freshly composed FST: every state was reached by the BFS).
 DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launches, cudaStream_t s);
+// Same result for a freshly composed FST whose BFS wave boundaries are known (wave k = ids [wave_lo[k], wave_lo[k+1]),
+// device array of n_waves + 1 entries, start state = 0): one persistent kernel, coaccessibility pulled in reverse
+// wave order.
+DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_t n_waves, uint64_t* launches,
+                            cudaStream_t s);
 
 // ---- shortest path (n = 1)
 enum QueueKind : int { kStateOrderQueue = 0, kTopOrderQueue = 1, kLifoQueue = 2, kSccQueue = 3 };

@@ -26,18 +26,19 @@
 #include <string>
 
 #include "compose_common.cuh"
+#include "coop_utils.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace b200 {
 namespace {
 using namespace composeimpl;
+using namespace coop;
 
-constexpr int kCoopThreads = 256;
 constexpr uint32_t kTempFlag = 0x80000000u;   // slot.id holds (cta << 20 | local rank) between phases C and D
 constexpr uint32_t kLocalRankBits = 20;
 
-enum Overflow : uint32_t { kOvArcs = 1, kOvStates = 2, kOvTable = 4, kOvScratch = 8, kOvChunk = 16 };
+enum Overflow : uint32_t { kOvArcs = 1, kOvStates = 2, kOvTable = 4, kOvScratch = 8, kOvChunk = 16, kOvWaves = 32 };
 
 struct CoopParams {
   FstView a, b;
@@ -46,59 +47,48 @@ struct CoopParams {
   uint32_t* out_offsets; float* out_finals;
   Tr* out_arcs; uint32_t arcs_cap;
   Slot* slots; uint32_t mask; uint32_t table_cap;
-  uint2* scratch; uint32_t scratch_cap;   // per-item records of the current wave
-  uint32_t* st_cnt; uint32_t st_cnt_cap;  // arcs emitted per frontier state of the current wave
-  uint32_t* part_arcs;    // gridDim entries: arcs emitted by each CTA's state chunk
-  uint32_t* part_items;   // gridDim entries: items of each CTA's state chunk (statistics)
-  uint32_t* part_new;     // gridDim entries: first emissions found in each CTA's arc chunk
-  uint32_t* ctl;          // [0] scratch cursor, [1] overflow flags, [2..]: results
+  // per-wave scratch, indexed by frontier-local state
+  uint32_t* item_loc;     // slice-local exclusive item offset | side bit
+  uint32_t* st_arc_loc;   // slice-local emission index of the state's first arc
+  uint8_t* st_flags;      // alleps1 | noeps1<<1 | alleps2<<2 | noeps2<<3
+  // per-wave scratch, indexed by item (active items compacted in place inside each CTA's slice)
+  uint4* recs;            // x = first match, y = count|flags, z = frontier-local state, w = iterated arc (abs) or ~0
+  uint32_t* arc_loc;      // slice-local emission index of the record's first arc
+  uint32_t items_cap;
+  uint32_t* part_items;   // gridDim entries: items of each CTA's state slice
+  uint32_t* part_arcs;    // gridDim entries: arcs emitted by each CTA's item slice
+  uint32_t* part_new;     // gridDim entries: first emissions found in each CTA's arc slice
+  uint32_t* ctl;          // [1] overflow flags, [2] #states, [3] #arcs
+  uint32_t* wave_lo; uint32_t wave_cap;  // first product id of every BFS wave (+ one-past-the-end sentinel)
   unsigned long long* stats;  // states_expanded, arcs_iterated, arcs_emitted, waves, ns phase A, B, C, D
 };
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
-// Sum of v[0..n) and of v[0..upto) computed by the whole CTA (n <= a few thousand).
-__device__ __forceinline__ void cta_sum_prefix(const uint32_t* __restrict__ v, uint32_t n, uint32_t upto,
-                                               uint32_t* smem2, uint32_t& total, uint32_t& prefix) {
-  uint32_t t = 0, p = 0;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    uint32_t x = __ldcg(&v[i]);
-    t += x;
-    if (i < upto) p += x;
-  }
-  for (int o = 16; o > 0; o >>= 1) { t += __shfl_down_sync(0xFFFFFFFFu, t, o); p += __shfl_down_sync(0xFFFFFFFFu, p, o); }
-  __syncthreads();
-  if (threadIdx.x == 0) { smem2[0] = 0; smem2[1] = 0; }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&smem2[0], t); atomicAdd(&smem2[1], p); }
-  __syncthreads();
-  total = smem2[0]; prefix = smem2[1];
-  __syncthreads();
-}
+constexpr uint32_t kSideBit = 0x80000000u;
+constexpr uint32_t kTile = kCoopThreads;
 
-template <int G>
-__global__ void __launch_bounds__(kCoopThreads)
+// One persistent kernel = the whole BFS.  Per wave:
+//   A0 states   : CTA c owns a contiguous slice of the frontier; per state: #items (1 + degree of the iterated side),
+//                 which side is iterated, filter flags, final weight; CTA-local exclusive offsets + CTA total
+//   A1 items    : CTA c owns a contiguous slice of the ITEMS (load-balanced: states located through a 257-entry
+//                 shared-memory window per 256-item tile); per item: binary search of the sorted side + filter;
+//                 active items are compacted in place with CTA-local arc offsets; CTA total
+//   B  arcs     : CTA c emits the arcs of its own items, one thread per ARC (records located through a shared-
+//                 memory window again); 128-bit gathers, CAS insert, atomicMin(first emission), 128-bit store
+//   C  rank     : contiguous arc slices; ballot/popc ranks of first emissions published through slot.id
+//   D  resolve  : CTA prefix -> ids; nextstate patch; tuple publication
+// Five grid barriers per wave; every size is recomputed identically by every CTA from per-CTA partial arrays.
+__global__ void __launch_bounds__(kCoopThreads, 4)
 k_compose_coop(CoopParams P) {
   cg::grid_group grid = cg::this_grid();
-  constexpr int kGroupsPerCta = kCoopThreads / G;
-  __shared__ uint32_t s_group_arcs[kGroupsPerCta];
-  __shared__ uint32_t s_group_off[kGroupsPerCta];
-  __shared__ uint32_t s_tmp[2];
   __shared__ uint32_t s_warp[kCoopThreads / 32];
-  __shared__ uint32_t s_tile_base;
-  extern __shared__ uint32_t s_prefix[];  // gridDim entries (phase D)
+  __shared__ uint32_t s_seg[kTile + 2];
+  __shared__ uint32_t s_misc[4];
+  extern __shared__ uint32_t s_dyn[];          // two prefix arrays of gridDim + 1 entries
+  uint32_t* s_pref_a = s_dyn;                  // items (A1/B) then new-state counts (D)
+  uint32_t* s_pref_b = s_dyn + gridDim.x + 1;  // arcs (B)
 
-  const uint32_t lane = threadIdx.x % G;
-  const uint32_t group_in_cta = threadIdx.x / G;
-  const uint32_t n_groups = gridDim.x * kGroupsPerCta;
-  const uint32_t gid = blockIdx.x * kGroupsPerCta + group_in_cta;
-  // lanes of my group inside the warp
-  const uint32_t group_mask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-
+  const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
   uint32_t lo = 0, hi = 1, base = 0;  // uniform across the grid by construction
   unsigned long long n_states_exp = 0, n_items = 0, n_arcs = 0, n_waves = 0;
   unsigned long long t_a = 0, t_b = 0, t_c = 0, t_d = 0;
@@ -107,42 +97,88 @@ k_compose_coop(CoopParams P) {
   while (lo < hi) {
     const uint32_t F = hi - lo;
     unsigned long long tp0 = globaltimer_ns();
-    const uint32_t chunk = (F + n_groups - 1) / n_groups;
-    const uint32_t c_begin = min(F, gid * chunk), c_end = min(F, c_begin + chunk);
-
-    // ------------------------------------------------------------------ phase A: match
-    // scratch region for my chunk: one atomic per group
-    uint32_t my_items = 0;
-    for (uint32_t i = c_begin + lane; i < c_end; i += G) {
-      uint32_t fs, s1, s2;
-      unpack_key(P.tuples[lo + i], fs, s1, s2);
-      uint32_t d1 = P.a.off[s1 + 1] - P.a.off[s1], d2 = P.b.off[s2 + 1] - P.b.off[s2];
-      bool mi = P.side == kMatchInput || (P.side == kMatchBoth && d1 <= d2);
-      my_items += 1u + (mi ? d1 : d2);
+    if (n_waves + 1 >= P.wave_cap) { overflow |= kOvWaves; break; }  // uniform
+    if (c == 0 && tid == 0) P.wave_lo[n_waves] = lo;
+    // ------------------------------------------------------------------ A0: per-state setup
+    const uint32_t sc = (F + G - 1) / G;  // states per CTA slice
+    {
+      const uint32_t s_begin = min(F, c * sc), s_end = min(F, s_begin + sc);
+      uint32_t run = 0;
+      for (uint32_t i0 = s_begin; i0 < s_end; i0 += kTile) {
+        const uint32_t i = i0 + tid;
+        uint32_t nitems = 0, side = 0;
+        if (i < s_end) {
+          uint32_t fs, s1, s2;
+          unpack_key(__ldcg(&P.tuples[lo + i]), fs, s1, s2);
+          const uint32_t d1 = P.a.off[s1 + 1] - P.a.off[s1], d2 = P.b.off[s2 + 1] - P.b.off[s2];
+          const bool mi = P.side == kMatchInput || (P.side == kMatchBoth && d1 <= d2);
+          nitems = 1u + (mi ? d1 : d2);
+          side = mi ? kSideBit : 0u;
+          const float f1 = P.a.fin[s1], f2 = P.b.fin[s2];
+          const uint32_t ne1 = P.a.neps ? P.a.neps[s1] : 0u, ne2 = P.b.neps ? P.b.neps[s2] : 0u;
+          const uint8_t fl = (uint8_t)(((d1 == ne1 && f1 == w_zero()) ? 1 : 0) | ((ne1 == 0) ? 2 : 0) |
+                                       ((d2 == ne2 && f2 == w_zero()) ? 4 : 0) | ((ne2 == 0) ? 8 : 0));
+          P.st_flags[i] = fl;
+          const float fw = w_times(f1, f2);  // compose_fst_op.rs:420-449
+          P.out_finals[lo + i] = w_is_zero(fw) ? w_zero() : fw;
+        }
+        uint32_t tile_total;
+        const uint32_t ex = cta_exclusive_scan(nitems, s_warp, tile_total);
+        if (i < s_end) P.item_loc[i] = (run + ex) | side;
+        run += tile_total;
+      }
+      if (tid == 0) P.part_items[c] = run;
     }
-    for (int o = G / 2; o > 0; o >>= 1) my_items += __shfl_xor_sync(group_mask, my_items, o, G);
-    uint32_t region = 0;
-    if (lane == 0 && my_items) region = atomicAdd(&P.ctl[0], my_items);
-    region = __shfl_sync(group_mask, region, 0, G);
-    const bool scratch_ok = (unsigned long long)region + my_items <= P.scratch_cap;
-    if (!scratch_ok && lane == 0) atomicOr(&P.ctl[1], (uint32_t)kOvScratch);
+    grid.sync();
 
-    uint32_t group_arcs = 0, cursor = region;
-    for (uint32_t i = c_begin; i < c_end; i++) {
-      uint32_t fs, s1, s2;
-      unpack_key(P.tuples[lo + i], fs, s1, s2);
-      const uint32_t alo = P.a.off[s1], ahi = P.a.off[s1 + 1], blo = P.b.off[s2], bhi = P.b.off[s2 + 1];
-      const bool match_input = P.side == kMatchInput || (P.side == kMatchBoth && (ahi - alo) <= (bhi - blo));
-      const uint32_t nitems = 1u + (match_input ? (ahi - alo) : (bhi - blo));
-      const FsFlags ff = state_flags(P.a, P.b, s1, s2);
-      uint32_t state_arcs = 0;
-      for (uint32_t j0 = 0; j0 < nitems; j0 += G) {
-        const uint32_t j = j0 + lane;
+    // ------------------------------------------------------------------ A1: per-item matching
+    cta_prefix_to_smem(P.part_items, G, s_pref_a, s_warp);
+    const uint32_t T = s_pref_a[G];
+    overflow = __ldcg(&P.ctl[1]);
+    if (T > P.items_cap) overflow |= kOvScratch;
+    if (overflow) break;  // uniform
+    const uint32_t ic = (((T + G - 1) / G) + kTile - 1) / kTile * kTile;  // items per CTA slice (multiple of a tile)
+    const uint32_t it_begin = min(T, c * ic), it_end = min(T, it_begin + ic);
+    uint32_t my_active = 0, my_arcs = 0;
+    if (it_begin < it_end) {
+      // state containing my first item: producing CTA slice from the shared prefix, then bisect its local offsets
+      if (tid == 0) {
+        const uint32_t p = smem_segment(s_pref_a, G, it_begin);
+        const uint32_t want = it_begin - s_pref_a[p];
+        uint32_t l = min(F, p * sc), h = min(F, l + sc);
+        while (h - l > 1) {
+          const uint32_t mid = (l + h) >> 1;
+          if ((__ldcg(&P.item_loc[mid]) & ~kSideBit) <= want) l = mid; else h = mid;
+        }
+        s_misc[0] = l;
+      }
+      __syncthreads();
+      uint32_t i_cur = s_misc[0];
+      for (uint32_t t0 = it_begin; t0 < it_end; t0 += kTile) {
+        // window of item start offsets for states i_cur .. i_cur + 256
+        for (uint32_t k = tid; k < kTile + 1; k += kCoopThreads) {
+          const uint32_t i = i_cur + k;
+          s_seg[k] = i < F ? s_pref_a[i / sc] + (__ldcg(&P.item_loc[i]) & ~kSideBit) : T;
+        }
+        __syncthreads();
+        const uint32_t t = t0 + tid;
         uint32_t cnt_out = 0;
-        if (j < nitems) {
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        if (t < it_end) {
+          const uint32_t k = smem_segment(s_seg, kTile + 1, t);
+          const uint32_t i = i_cur + k, j = t - s_seg[k];
+          uint32_t fs, s1, s2;
+          unpack_key(__ldcg(&P.tuples[lo + i]), fs, s1, s2);
+          const bool match_input = (__ldcg(&P.item_loc[i]) & kSideBit) != 0;
+          const uint8_t fl = __ldcg(&P.st_flags[i]);
+          FsFlags ff;
+          ff.alleps1 = fl & 1; ff.noeps1 = fl & 2; ff.alleps2 = fl & 4; ff.noeps2 = fl & 8;
+          const uint32_t alo = P.a.off[s1], ahi = P.a.off[s1 + 1], blo = P.b.off[s2], bhi = P.b.off[s2 + 1];
           Label label;
+          uint32_t it_idx = 0xFFFFFFFFu;  // absolute index of the iterated arc; all ones = implicit epsilon loop
           if (j == 0) label = kNoLabel;
-          else label = match_input ? __ldg(&P.a.arcs[alo + j - 1].olabel) : __ldg(&P.b.arcs[blo + j - 1].ilabel);
+          else if (match_input) { it_idx = alo + j - 1; label = __ldg(&P.a.arcs[it_idx].olabel); }
+          else { it_idx = blo + j - 1; label = __ldg(&P.b.arcs[it_idx].ilabel); }
           const bool has_loop = (label == kEps);
           const Label key = (label == kNoLabel) ? kEps : label;
           uint32_t pos, end, fs_loop, fs_real;
@@ -161,202 +197,158 @@ k_compose_coop(CoopParams P) {
           const bool loop_ok = has_loop && fs_loop != kNoFs;
           const bool real_ok = fs_real != kNoFs && cnt > 0;
           cnt_out = (loop_ok ? 1u : 0u) + (real_ok ? cnt : 0u);
-          // record: x = pos, y = count of REAL matches that are emitted (27 bits) | loop_ok | fs_loop | fs_real
-          if (scratch_ok)
-            P.scratch[cursor + j] = make_uint2(pos, (real_ok ? cnt : 0u) | (loop_ok ? 1u << 27 : 0u) |
-                                                        ((fs_loop & 3u) << 28) | ((fs_real & 3u) << 30));
+          // y: emitted real matches (26 bits) | loop_ok | fs_loop(2) | fs_real(2) | match_input
+          rec = make_uint4(pos, (real_ok ? cnt : 0u) | (loop_ok ? 1u << 26 : 0u) | ((fs_loop & 3u) << 27) |
+                                    ((fs_real & 3u) << 29) | (match_input ? 1u << 31 : 0u), i, it_idx);
         }
-        uint32_t s = cnt_out;
-        for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(group_mask, s, o, G);
-        state_arcs += s;
-      }
-      cursor += nitems;
-      if (lane == 0) {
-        P.st_cnt[i] = state_arcs;
-        float fw = w_times(P.a.fin[s1], P.b.fin[s2]);  // compose_fst_op.rs:420-449
-        P.out_finals[lo + i] = w_is_zero(fw) ? w_zero() : fw;
-      }
-      group_arcs += state_arcs;
-    }
-    if (lane == 0) s_group_arcs[group_in_cta] = group_arcs;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t ta = 0;
-      for (int g = 0; g < kGroupsPerCta; g++) { s_group_off[g] = ta; ta += s_group_arcs[g]; }
-      P.part_arcs[blockIdx.x] = ta;
-    }
-    {
-      // items of the CTA (statistics only)
-      uint32_t it = (lane == 0) ? my_items : 0;
-      for (int o = 16; o > 0; o >>= 1) it += __shfl_down_sync(0xFFFFFFFFu, it, o);
-      if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x / 32] = it;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kCoopThreads / 32; w++) t += s_warp[w];
-        P.part_items[blockIdx.x] = t;
+        uint32_t tile_active, tile_arcs;
+        const uint32_t act = cnt_out ? 1u : 0u;
+        const uint32_t ex_act = cta_exclusive_scan(act, s_warp, tile_active);
+        const uint32_t ex_arcs = cta_exclusive_scan(cnt_out, s_warp, tile_arcs);
+        if (t < it_end) {
+          if (rec.w == 0xFFFFFFFFu) P.st_arc_loc[rec.z] = my_arcs + ex_arcs;  // first arc of state rec.z (slice-local)
+          if (act) {
+            const uint32_t r = it_begin + my_active + ex_act;  // in-place compaction inside my own item slice
+            P.recs[r] = rec;
+            P.arc_loc[r] = my_arcs + ex_arcs;
+          }
+        }
+        my_active += tile_active; my_arcs += tile_arcs;
+        // advance the state window to the state that contains the first item of the next tile
+        const uint32_t nxt = t0 + kTile;
+        __syncthreads();
+        if (tid == 0) s_misc[0] = i_cur + smem_segment(s_seg, kTile + 1, min(nxt, T - 1));
+        __syncthreads();
+        i_cur = s_misc[0];
       }
     }
+    if (tid == 0) P.part_arcs[c] = my_arcs;
     grid.sync();
     unsigned long long tp1 = globaltimer_ns();
 
-    // ------------------------------------------------------------------ phase B: emit
-    uint32_t E, cta_off, T_items, dummy;
-    cta_sum_prefix(P.part_arcs, gridDim.x, blockIdx.x, s_tmp, E, cta_off);
-    cta_sum_prefix(P.part_items, gridDim.x, 0, s_tmp, T_items, dummy);
-    overflow = __ldcg(&P.ctl[1]);
+    // ------------------------------------------------------------------ B: emit
+    cta_prefix_to_smem(P.part_arcs, G, s_pref_b, s_warp);
+    const uint32_t E = s_pref_b[G];
     if ((unsigned long long)base + E > P.arcs_cap) overflow |= kOvArcs;
     if (((unsigned long long)hi + E) * 2ull > P.table_cap) overflow |= kOvTable;
-    const uint32_t arc_chunk = ((E + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
+    const uint32_t arc_chunk = ((E + G - 1) / G + 31u) & ~31u;
     if (arc_chunk > (1u << kLocalRankBits)) overflow |= kOvChunk;
-    if (overflow) break;  // uniform: every CTA derives the same flags from the same global data
-
+    if (overflow) break;  // uniform
     {
-      uint32_t state_base = cta_off + s_group_off[group_in_cta];  // wave-local emission index of my next state
-      uint32_t cur = region;
+      const uint32_t cta_off = s_pref_b[c];
       Tr* __restrict__ wave_arcs = P.out_arcs + base;
-      for (uint32_t i = c_begin; i < c_end; i++) {
-        uint32_t fs, s1, s2;
-        unpack_key(P.tuples[lo + i], fs, s1, s2);
-        const uint32_t alo = P.a.off[s1], ahi = P.a.off[s1 + 1], blo = P.b.off[s2], bhi = P.b.off[s2 + 1];
-        const bool match_input = P.side == kMatchInput || (P.side == kMatchBoth && (ahi - alo) <= (bhi - blo));
-        const uint32_t nitems = 1u + (match_input ? (ahi - alo) : (bhi - blo));
-        if (lane == 0) P.out_offsets[lo + i] = base + state_base;
-        uint32_t run = state_base;
-        for (uint32_t j0 = 0; j0 < nitems; j0 += G) {
-          const uint32_t j = j0 + lane;
-          uint2 rec = make_uint2(0, 0);
-          if (j < nitems) rec = P.scratch[cur + j];
-          const bool loop_ok = (rec.y >> 27) & 1u;
-          const uint32_t n_real = rec.y & 0x07FFFFFFu;
-          const uint32_t mine = n_real + (loop_ok ? 1u : 0u);
-          // exclusive scan of `mine` across the group's lanes
-          uint32_t incl = mine;
-          for (int o = 1; o < G; o <<= 1) {
-            uint32_t v = __shfl_up_sync(group_mask, incl, o, G);
-            if ((int)lane >= o) incl += v;
+      uint32_t cursor = 0;  // first record (slice-local) that can contain the next tile's first arc
+      for (uint32_t e0 = 0; e0 < my_arcs; e0 += kTile) {
+        for (uint32_t k = tid; k < kTile + 1; k += kCoopThreads)
+          s_seg[k] = (cursor + k) < my_active ? P.arc_loc[it_begin + cursor + k] : my_arcs;
+        __syncthreads();
+        const uint32_t el = e0 + tid;
+        if (el < my_arcs) {
+          const uint32_t k = smem_segment(s_seg, kTile + 1, el);
+          const uint4 rec = P.recs[it_begin + cursor + k];
+          const uint32_t kk = el - s_seg[k];
+          const bool loop_ok = (rec.y >> 26) & 1u;
+          const bool match_input = rec.y >> 31;
+          uint32_t s1 = 0, s2 = 0;
+          const bool need_tuple = (rec.w == 0xFFFFFFFFu) || (loop_ok && kk == 0);
+          if (need_tuple) { uint32_t fs; unpack_key(__ldcg(&P.tuples[lo + rec.z]), fs, s1, s2); }
+          Tr it;
+          if (rec.w == 0xFFFFFFFFu) it = match_input ? Tr{kEps, kNoLabel, 0.0f, s1} : Tr{kNoLabel, kEps, 0.0f, s2};
+          else it = match_input ? load_tr(&P.a.arcs[rec.w]) : load_tr(&P.b.arcs[rec.w]);
+          Tr cand;
+          uint32_t fsn;
+          if (loop_ok && kk == 0) {
+            cand = match_input ? Tr{kNoLabel, kEps, 0.0f, s2} : Tr{kEps, kNoLabel, 0.0f, s1};
+            fsn = (rec.y >> 27) & 3u;
+          } else {
+            const uint32_t idx = rec.x + kk - (loop_ok ? 1u : 0u);
+            cand = match_input ? load_tr(&P.b.arcs[idx]) : load_tr(&P.a.arcs[idx]);
+            fsn = (rec.y >> 29) & 3u;
           }
-          const uint32_t total = __shfl_sync(group_mask, incl, G - 1, G);
-          uint32_t e = run + incl - mine;
-          if (mine) {
-            Tr it;
-            if (j == 0) it = match_input ? Tr{kEps, kNoLabel, 0.0f, s1} : Tr{kNoLabel, kEps, 0.0f, s2};
-            else it = match_input ? load_tr(&P.a.arcs[alo + j - 1]) : load_tr(&P.b.arcs[blo + j - 1]);
-            for (uint32_t k = 0; k < mine; k++, e++) {
-              Tr cand;
-              uint32_t fsn;
-              if (loop_ok && k == 0) {
-                cand = match_input ? Tr{kNoLabel, kEps, 0.0f, s2} : Tr{kEps, kNoLabel, 0.0f, s1};
-                fsn = (rec.y >> 28) & 3u;
-              } else {
-                const uint32_t idx = rec.x + k - (loop_ok ? 1u : 0u);
-                cand = match_input ? load_tr(&P.b.arcs[idx]) : load_tr(&P.a.arcs[idx]);
-                fsn = (rec.y >> 30) & 3u;
-              }
-              const Tr& arc1 = match_input ? it : cand;
-              const Tr& arc2 = match_input ? cand : it;
-              Tr out;
-              out.ilabel = arc1.ilabel;
-              out.olabel = arc2.olabel;
-              out.weight = w_times(arc1.weight, arc2.weight);
-              const unsigned long long key = pack_key(fsn, arc1.nextstate, arc2.nextstate);
-              uint32_t h = hash_key(key) & P.mask;
-              while (true) {
-                unsigned long long curk = *reinterpret_cast<volatile unsigned long long*>(&P.slots[h].key);
-                if (curk == key) break;
-                if (curk == kEmptyKey) {
-                  unsigned long long prev = atomicCAS(&P.slots[h].key, kEmptyKey, key);
-                  if (prev == kEmptyKey || prev == key) break;
-                }
-                h = (h + 1) & P.mask;
-              }
-              const uint32_t id = *reinterpret_cast<volatile uint32_t*>(&P.slots[h].id);
-              if (id != kUnassigned) out.nextstate = id;
-              else { atomicMin(&P.slots[h].emin, e); out.nextstate = kPendingBit | h; }
-              store_tr(&wave_arcs[e], out);
+          const Tr& arc1 = match_input ? it : cand;
+          const Tr& arc2 = match_input ? cand : it;
+          Tr out;
+          out.ilabel = arc1.ilabel;
+          out.olabel = arc2.olabel;
+          out.weight = w_times(arc1.weight, arc2.weight);
+          const unsigned long long key = pack_key(fsn, arc1.nextstate, arc2.nextstate);
+          const uint32_t e = cta_off + el;  // canonical wave-local emission index
+          uint32_t h = hash_key(key) & P.mask;
+          while (true) {
+            unsigned long long curk = *reinterpret_cast<volatile unsigned long long*>(&P.slots[h].key);
+            if (curk == key) break;
+            if (curk == kEmptyKey) {
+              unsigned long long prev = atomicCAS(&P.slots[h].key, kEmptyKey, key);
+              if (prev == kEmptyKey || prev == key) break;
             }
+            h = (h + 1) & P.mask;
           }
-          run += total;
+          const uint32_t id = *reinterpret_cast<volatile uint32_t*>(&P.slots[h].id);
+          if (id != kUnassigned) out.nextstate = id;
+          else { atomicMin(&P.slots[h].emin, e); out.nextstate = kPendingBit | h; }
+          store_tr(&wave_arcs[e], out);
         }
-        cur += nitems;
-        state_base = run;
+        __syncthreads();
+        if (tid == 0) s_misc[1] = cursor + smem_segment(s_seg, kTile + 1, min(e0 + kTile, my_arcs - 1));
+        __syncthreads();
+        cursor = s_misc[1];
+      }
+      // state -> first arc (CSR offsets of the result): slice of the arc owner = slice that processed item 0 of the state
+      for (uint32_t i = c * sc + tid; i < min(F, (c + 1) * sc); i += kCoopThreads) {
+        const uint32_t t_first = s_pref_a[i / sc] + (__ldcg(&P.item_loc[i]) & ~kSideBit);
+        P.out_offsets[lo + i] = base + s_pref_b[t_first / ic] + __ldcg(&P.st_arc_loc[i]);
       }
     }
     grid.sync();
     unsigned long long tp2 = globaltimer_ns();
 
-    // ------------------------------------------------------------------ phase C: rank first emissions
-    const uint32_t e_begin = min(E, blockIdx.x * arc_chunk), e_end = min(E, e_begin + arc_chunk);
+    // ------------------------------------------------------------------ C: rank first emissions
+    const uint32_t e_begin = min(E, c * arc_chunk), e_end = min(E, e_begin + arc_chunk);
     {
       const Tr* __restrict__ wave_arcs = P.out_arcs + base;
-      uint32_t cta_new = 0;  // running count (uniform inside the CTA)
+      uint32_t cta_new = 0;
       for (uint32_t t0 = e_begin; t0 < e_end; t0 += kCoopThreads) {
-        const uint32_t e = t0 + threadIdx.x;
+        const uint32_t e = t0 + tid;
         bool owner = false;
         uint32_t h = 0;
         if (e < e_end) {
-          uint32_t ns = __ldcg(&wave_arcs[e].nextstate);
+          const uint32_t ns = __ldcg(&wave_arcs[e].nextstate);
           if (ns & kPendingBit) { h = ns & ~kPendingBit; owner = (__ldcg(&P.slots[h].emin) == e); }
         }
-        const uint32_t word = __ballot_sync(0xFFFFFFFFu, owner);
-        const uint32_t wl = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        if (wl == 0) s_warp[wid] = __popc(word);
-        __syncthreads();
-        uint32_t before = 0, tile_total = 0;
-        for (int w = 0; w < kCoopThreads / 32; w++) { uint32_t c = s_warp[w]; if (w < (int)wid) before += c; tile_total += c; }
-        if (owner) {
-          uint32_t local = cta_new + before + __popc(word & ((1u << wl) - 1u));
-          P.slots[h].id = kTempFlag | (blockIdx.x << kLocalRankBits) | local;
-        }
+        uint32_t tile_total;
+        const uint32_t ex = cta_exclusive_scan(owner ? 1u : 0u, s_warp, tile_total);
+        if (owner) P.slots[h].id = kTempFlag | (c << kLocalRankBits) | (cta_new + ex);
         cta_new += tile_total;
-        __syncthreads();
       }
-      if (threadIdx.x == 0) P.part_new[blockIdx.x] = cta_new;
+      if (tid == 0) P.part_new[c] = cta_new;
     }
     grid.sync();
     unsigned long long tp3 = globaltimer_ns();
 
-    // ------------------------------------------------------------------ phase D: resolve
-    // exclusive prefix of part_new over all CTAs, kept in shared memory
-    {
-      for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) s_prefix[i] = __ldcg(&P.part_new[i]);
-      __syncthreads();
-      if (threadIdx.x < 32) {
-        uint32_t carry = 0;
-        for (uint32_t i0 = 0; i0 < gridDim.x; i0 += 32) {
-          uint32_t i = i0 + threadIdx.x;
-          uint32_t v = i < gridDim.x ? s_prefix[i] : 0u, incl = v;
-          for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)threadIdx.x >= o) incl += u; }
-          if (i < gridDim.x) s_prefix[i] = carry + incl - v;
-          carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
-        }
-        if (threadIdx.x == 0) s_tile_base = carry;
-      }
-      __syncthreads();
-    }
-    const uint32_t n_new = s_tile_base;
+    // ------------------------------------------------------------------ D: resolve
+    cta_prefix_to_smem(P.part_new, G, s_pref_a, s_warp);
+    const uint32_t n_new = s_pref_a[G];
     if ((unsigned long long)hi + n_new > P.states_cap || (unsigned long long)hi + n_new >= 0x7FFFFFFFull) {
       overflow |= kOvStates;
       break;  // uniform
     }
     {
       Tr* __restrict__ wave_arcs = P.out_arcs + base;
-      for (uint32_t e = e_begin + threadIdx.x; e < e_end; e += kCoopThreads) {
-        uint32_t ns = wave_arcs[e].nextstate;
+      for (uint32_t e = e_begin + tid; e < e_end; e += kCoopThreads) {
+        const uint32_t ns = __ldcg(&wave_arcs[e].nextstate);
         if (!(ns & kPendingBit)) continue;
         const uint32_t h = ns & ~kPendingBit;
         const uint32_t v = *reinterpret_cast<volatile uint32_t*>(&P.slots[h].id);
         uint32_t id = v;
-        if (v & kTempFlag) id = hi + s_prefix[(v & ~kTempFlag) >> kLocalRankBits] + (v & ((1u << kLocalRankBits) - 1u));
+        if (v & kTempFlag) id = hi + s_pref_a[(v & ~kTempFlag) >> kLocalRankBits] + (v & ((1u << kLocalRankBits) - 1u));
         wave_arcs[e].nextstate = id;
         if (__ldcg(&P.slots[h].emin) == e) {  // first emitter: publish
           P.slots[h].id = id;
-          P.tuples[id] = P.slots[h].key;
+          P.tuples[id] = __ldcg(&P.slots[h].key);
         }
       }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.ctl[0] = 0;  // scratch cursor for the next wave
-    n_states_exp += F; n_items += T_items; n_arcs += E; n_waves++;
+    n_states_exp += F; n_items += T; n_arcs += E; n_waves++;
     base += E;
     lo = hi;
     hi += n_new;
@@ -365,11 +357,12 @@ k_compose_coop(CoopParams P) {
     t_a += tp1 - tp0; t_b += tp2 - tp1; t_c += tp3 - tp2; t_d += tp4 - tp3;
   }
 
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (c == 0 && tid == 0) {
     P.ctl[1] = overflow;
     P.ctl[2] = hi;    // number of product states
     P.ctl[3] = base;  // number of arcs
     P.out_offsets[hi] = base;
+    P.wave_lo[n_waves] = hi;
     P.stats[0] = n_states_exp; P.stats[1] = n_items - n_states_exp; P.stats[2] = n_arcs; P.stats[3] = n_waves;
     P.stats[4] = t_a; P.stats[5] = t_b; P.stats[6] = t_c; P.stats[7] = t_d;
   }
@@ -383,28 +376,26 @@ __global__ void k_coop_init(Slot* slots, uint32_t mask, unsigned long long* tupl
   ctl[0] = ctl[1] = ctl[2] = ctl[3] = 0;
 }
 
-template <int G>
-bool run_coop(const CoopParams& P0, int sms, cudaStream_t s, float* ms_kernel) {
+float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   CoopParams P = P0;
   int per_sm = 0;
-  // dynamic smem = gridDim entries; grid <= 148 * 8 -> < 8 KB; query occupancy with a safe upper bound
-  size_t dyn = (size_t)sms * 16 * sizeof(uint32_t);
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compose_coop<G>, kCoopThreads, dyn));
+  size_t dyn = 2 * 2049 * sizeof(uint32_t);
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compose_coop, kCoopThreads, dyn));
   if (per_sm < 1) throw FstError("cooperative compose kernel does not fit on the device");
-  if (per_sm > 8) per_sm = 8;
   int grid = sms * per_sm;
-  if (grid >= 2048) grid = 2047;  // CTA index must fit 11 bits next to the 20-bit local rank
-  dyn = (size_t)grid * sizeof(uint32_t);
+  if (grid > 2047) grid = 2047;  // CTA index must fit 11 bits next to the 20-bit local rank; prefix arrays hold 2048
+  dyn = 2 * ((size_t)grid + 1) * sizeof(uint32_t);
   void* args[] = {(void*)&P};
   cudaEvent_t e0, e1;
+  float ms = 0;
   B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
   B200_CUDA(cudaEventRecord(e0, s));
-  B200_CUDA(cudaLaunchCooperativeKernel((void*)k_compose_coop<G>, dim3(grid), dim3(kCoopThreads), args, dyn, s));
+  B200_CUDA(cudaLaunchCooperativeKernel((void*)k_compose_coop, dim3(grid), dim3(kCoopThreads), args, dyn, s));
   B200_CUDA(cudaEventRecord(e1, s));
   B200_CUDA(cudaStreamSynchronize(s));
-  B200_CUDA(cudaEventElapsedTime(ms_kernel, e0, e1));
+  B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return true;
+  return ms;
 }
 
 }  // namespace
@@ -450,7 +441,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   arcs_cap = std::min<size_t>(arcs_cap, 0xFFFFFFF0ull);
   size_t table_cap = 1 << 17;
   while (table_cap < 2 * states_cap && table_cap < (1ull << 30)) table_cap <<= 1;
-  size_t scratch_cap = std::max<size_t>(1 << 18, arcs_cap / 2);
+  size_t items_cap = std::max<size_t>(1 << 18, arcs_cap / 2);
 
   DevFst out(s);
   out.offsets.reserve_discard(states_cap + 1);
@@ -458,29 +449,26 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   out.arcs.reserve_discard(arcs_cap);
   DevBuf<unsigned long long> tuples(s, states_cap), dstats(s, 8);
   DevBuf<Slot> slots(s, table_cap);
-  DevBuf<uint2> scratch(s, scratch_cap);
-  DevBuf<uint32_t> st_cnt(s, states_cap), parts(s, 3 * 2048), ctl(s, 8);
+  DevBuf<uint4> recs(s, items_cap);
+  DevBuf<uint32_t> arc_loc(s, items_cap), item_loc(s, states_cap), st_arc_loc(s, states_cap), parts(s, 3 * 2048), ctl(s, 8);
+  DevBuf<uint8_t> st_flags(s, states_cap);
+  const uint32_t wave_cap = 1u << 20;
+  DevBuf<uint32_t> wave_lo(s, wave_cap);
   B200_CUDA(cudaMemsetAsync(slots.p, 0xFF, table_cap * sizeof(Slot), s));
   B200_CUDA(cudaMemsetAsync(dstats.p, 0, 8 * sizeof(unsigned long long), s));
   P.tuples = tuples.p; P.states_cap = (uint32_t)states_cap;
   P.out_offsets = out.offsets.p; P.out_finals = out.finals.p; P.out_arcs = out.arcs.p; P.arcs_cap = (uint32_t)arcs_cap;
   P.slots = slots.p; P.mask = (uint32_t)table_cap - 1; P.table_cap = (uint32_t)table_cap;
-  P.scratch = scratch.p; P.scratch_cap = (uint32_t)scratch_cap;
-  P.st_cnt = st_cnt.p; P.st_cnt_cap = (uint32_t)states_cap;
+  P.item_loc = item_loc.p; P.st_arc_loc = st_arc_loc.p; P.st_flags = st_flags.p;
+  P.recs = recs.p; P.arc_loc = arc_loc.p; P.items_cap = (uint32_t)std::min<size_t>(items_cap, 0xFFFFFFF0ull);
   P.part_arcs = parts.p; P.part_items = parts.p + 2048; P.part_new = parts.p + 4096;
   P.ctl = ctl.p; P.stats = dstats.p;
+  P.wave_lo = wave_lo.p; P.wave_cap = wave_cap;
   uint32_t start_fs = (kind == kNullFilter || kind == kTrivialFilter || kind == kNoMatchFilter) ? 1u : 0u;
   k_coop_init<<<1, 1, 0, s>>>(slots.p, P.mask, tuples.p, pack_key(start_fs, fa.start, fb.start), ctl.p);
   st.kernel_launches++;
 
-  // lanes per frontier state: enough to cover the average (1 + degree) of the smaller-degree side
-  double d1 = fa.num_states ? (double)fa.num_arcs / fa.num_states : 0, d2 = fb.num_states ? (double)fb.num_arcs / fb.num_states : 0;
-  double items = 1.0 + (side == kMatchInput ? d1 : side == kMatchOutput ? d2 : std::min(d1, d2));
-  float ms_kernel = 0;
-  int sms = sm_count();
-  if (items > 16.0) run_coop<32>(P, sms, s, &ms_kernel);
-  else if (items > 8.0) run_coop<16>(P, sms, s, &ms_kernel);
-  else run_coop<8>(P, sms, s, &ms_kernel);
+  float ms_kernel = run_coop(P, sm_count(), s);
   st.kernel_launches++; st.emit_launches = 1;
 
   uint32_t hctl[4];
@@ -502,7 +490,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   B200_CUDA(cudaEventRecord(ev1, s));
   if (opt.connect) {
     uint64_t launches = 0;
-    DevFst trimmed = connect_device(out, true, &launches, s);
+    DevFst trimmed = connect_waves_device(out, wave_lo.p, (uint32_t)st.waves, &launches, s);
     st.kernel_launches += launches;
     out = std::move(trimmed);
   }

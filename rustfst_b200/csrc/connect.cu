@@ -10,9 +10,13 @@
 // sweeps (forward over the CSR, backward over a reverse CSR built with one histogram + one scatter), and
 // del_states becomes two prefix sums (state keep-flags, surviving out-degrees) plus one gather.
 #include "algos.h"
+#include "coop_utils.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b200 {
 namespace {
+using namespace coop;
 
 __global__ void k_rev_degree(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n,
                              uint32_t* __restrict__ rdeg) {
@@ -89,6 +93,124 @@ __global__ void k_compact(const uint32_t* __restrict__ off, const Tr* __restrict
       *reinterpret_cast<int4*>(&narcs[o++]) = v;
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent trim for a freshly composed FST.  The BFS that built it numbered the states wave by wave
+// (wave k = ids [wave_lo[k], wave_lo[k+1])) and every state is accessible, so coaccessibility can be PULLED in one
+// reverse sweep over the waves: a state is coaccessible iff it is final or one of its arcs reaches a coaccessible
+// state; arcs into later waves see final values, arcs into the same or an earlier wave (cycles) may see stale ones,
+// in which case the sweep is repeated until nothing changes (monotone fixpoint).  No reverse CSR, no atomics.
+// Then del_states: slice-local scans of the keep flags and of the surviving out-degrees (global offsets are
+// slice prefix + local), and one gather.  n_waves + 3 grid barriers per sweep, one launch.
+struct TrimParams {
+  const uint32_t* off; const Tr* arcs; const float* fin; uint32_t n;
+  const uint32_t* wave_lo; uint32_t n_waves;
+  uint8_t* coacc;
+  uint32_t* id_loc;      // slice-local new id of every state
+  uint32_t* deg_loc;     // slice-local new arc offset of every KEPT state (indexed by old id)
+  uint32_t* part_keep; uint32_t* part_deg;
+  uint32_t* noff; Tr* narcs; float* nfin;
+  uint32_t* ctl;         // [0] changed flag per sweep, [1] back-arc seen, [2] n_keep, [3] a_keep, [4] sweeps
+};
+
+__global__ void __launch_bounds__(kCoopThreads)
+k_trim_coop(TrimParams P) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t s_warp[kCoopThreads / 32];
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t* s_pref_id = s_dyn;
+  uint32_t* s_pref_deg = s_dyn + gridDim.x + 1;
+  const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
+  const uint32_t gsize = G * kCoopThreads, gtid = c * kCoopThreads + tid;
+
+  // ---- coaccessibility: reverse sweeps over the BFS waves
+  uint32_t sweeps = 0;
+  while (true) {
+    for (uint32_t k = P.n_waves; k-- > 0;) {
+      const uint32_t wlo = P.wave_lo[k], whi = P.wave_lo[k + 1];
+      for (uint32_t s = wlo + gtid; s < whi; s += gsize) {
+        uint8_t co = __ldcg(&P.coacc[s]);
+        if (!co) {
+          bool back = false;
+          co = (sweeps == 0 && P.fin[s] != w_zero()) ? 1 : 0;
+          for (uint32_t i = P.off[s]; i < P.off[s + 1] && !co; i++) {
+            const uint32_t t = __ldg(&P.arcs[i].nextstate);
+            if (t < whi) back = true;  // same or earlier wave: value may still change in this sweep
+            co = __ldcg(&P.coacc[t]);
+          }
+          if (co) { P.coacc[s] = 1; if (sweeps > 0) P.ctl[0] = 1; }
+          else if (back) P.ctl[1] = 1;
+        }
+      }
+      grid.sync();
+    }
+    sweeps++;
+    // another sweep is needed only if some undecided state has an arc that was looked at too early
+    const uint32_t back_seen = __ldcg(&P.ctl[1]), changed = __ldcg(&P.ctl[0]);
+    grid.sync();
+    if (!back_seen || (sweeps > 1 && !changed)) break;
+    if (c == 0 && tid == 0) { P.ctl[0] = 0; P.ctl[1] = 0; }
+    grid.sync();
+  }
+
+  // ---- new state ids: slice-local exclusive scan of the keep flags
+  const uint32_t sc = ((P.n + G - 1) / G + kCoopThreads - 1) / kCoopThreads * kCoopThreads;
+  const uint32_t s_begin = min(P.n, c * sc), s_end = min(P.n, s_begin + sc);
+  {
+    uint32_t run = 0;
+    for (uint32_t s0 = s_begin; s0 < s_end; s0 += kCoopThreads) {
+      const uint32_t s = s0 + tid;
+      const uint32_t keep = (s < s_end) ? (uint32_t)__ldcg(&P.coacc[s]) : 0u;
+      uint32_t tot;
+      const uint32_t ex = cta_exclusive_scan(keep, s_warp, tot);
+      if (s < s_end) P.id_loc[s] = run + ex;
+      run += tot;
+    }
+    if (tid == 0) P.part_keep[c] = run;
+  }
+  grid.sync();
+  cta_prefix_to_smem(P.part_keep, G, s_pref_id, s_warp);
+  const uint32_t n_keep = s_pref_id[G];
+
+  // ---- surviving out-degrees: slice-local scan, indexed by old state id
+  {
+    uint32_t run = 0;
+    for (uint32_t s0 = s_begin; s0 < s_end; s0 += kCoopThreads) {
+      const uint32_t s = s0 + tid;
+      uint32_t d = 0;
+      if (s < s_end && __ldcg(&P.coacc[s])) {
+        for (uint32_t i = P.off[s]; i < P.off[s + 1]; i++) d += __ldcg(&P.coacc[__ldg(&P.arcs[i].nextstate)]);
+      }
+      uint32_t tot;
+      const uint32_t ex = cta_exclusive_scan(d, s_warp, tot);
+      if (s < s_end) P.deg_loc[s] = run + ex;
+      run += tot;
+    }
+    if (tid == 0) P.part_deg[c] = run;
+  }
+  grid.sync();
+  cta_prefix_to_smem(P.part_deg, G, s_pref_deg, s_warp);
+  const uint32_t a_keep = s_pref_deg[G];
+
+  // ---- gather (mutable_fst.rs:132-189: survivors keep their relative order, arcs into deleted states are dropped)
+  for (uint32_t s = s_begin + tid; s < s_end; s += kCoopThreads) {
+    if (!__ldcg(&P.coacc[s])) continue;
+    const uint32_t ns = s_pref_id[c] + P.id_loc[s];
+    uint32_t o = s_pref_deg[c] + P.deg_loc[s];
+    P.nfin[ns] = P.fin[s];
+    P.noff[ns] = o;
+    for (uint32_t i = P.off[s]; i < P.off[s + 1]; i++) {
+      int4 v = __ldg(reinterpret_cast<const int4*>(&P.arcs[i]));
+      const uint32_t t = (uint32_t)v.w;
+      if (__ldcg(&P.coacc[t])) {
+        v.w = (int)(s_pref_id[t / sc] + __ldcg(&P.id_loc[t]));
+        *reinterpret_cast<int4*>(&P.narcs[o++]) = v;
+      }
+    }
+  }
+  if (c == 0 && tid == 0) { P.noff[n_keep] = a_keep; P.ctl[2] = n_keep; P.ctl[3] = a_keep; P.ctl[4] = sweeps; }
 }
 
 }  // namespace
@@ -178,6 +300,53 @@ DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launch
   out.has_start = kv[0] != 0;
   out.start = kv[0] ? kv[1] : 0;
   if (launches) *launches = nl;
+  return out;
+}
+
+DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_t n_waves, uint64_t* launches,
+                            cudaStream_t s) {
+  DevFst out(s);
+  out.props = props::after_connect(in.props);
+  const uint32_t n = in.num_states;
+  if (launches) *launches = 0;
+  if (in.has_start && in.start != 0) throw FstError("connect_waves_device expects the start state to be state 0");
+  if (n == 0 || !in.has_start || n_waves == 0) {
+    out.offsets.reserve_discard(1);
+    B200_CUDA(cudaMemsetAsync(out.offsets.p, 0, 4, s));
+    return out;
+  }
+  DevBuf<uint8_t> coacc(s, n);
+  DevBuf<uint32_t> id_loc(s, n), deg_loc(s, n), parts(s, 2 * 2049), ctl(s, 8);
+  B200_CUDA(cudaMemsetAsync(coacc.p, 0, n, s));
+  B200_CUDA(cudaMemsetAsync(ctl.p, 0, 32, s));
+  out.offsets.reserve_discard((size_t)n + 1);
+  out.finals.reserve_discard(n);
+  out.arcs.reserve_discard(in.num_arcs ? in.num_arcs : 1);
+  TrimParams P{};
+  P.off = in.offsets.p; P.arcs = in.arcs.p; P.fin = in.finals.p; P.n = n;
+  P.wave_lo = d_wave_lo; P.n_waves = n_waves;
+  P.coacc = coacc.p; P.id_loc = id_loc.p; P.deg_loc = deg_loc.p;
+  P.part_keep = parts.p; P.part_deg = parts.p + 2049;
+  P.noff = out.offsets.p; P.narcs = out.arcs.p; P.nfin = out.finals.p; P.ctl = ctl.p;
+  int per_sm = 0;
+  size_t dyn = 2 * 2049 * sizeof(uint32_t);
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trim_coop, kCoopThreads, dyn));
+  if (per_sm < 1) throw FstError("cooperative trim kernel does not fit on the device");
+  int grid = std::min(sm_count() * per_sm, 2047);
+  dyn = 2 * ((size_t)grid + 1) * sizeof(uint32_t);
+  void* args[] = {(void*)&P};
+  B200_CUDA(cudaLaunchCooperativeKernel((void*)k_trim_coop, dim3(grid), dim3(kCoopThreads), args, dyn, s));
+  if (launches) *launches = 1;
+  uint32_t h[5];
+  B200_CUDA(cudaMemcpyAsync(h, ctl.p, 20, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  out.num_states = h[2]; out.num_arcs = h[3];
+  // start remap (mutable_fst.rs:176-183): the start state is id 0 of the composed FST
+  uint8_t keep0 = 0;
+  B200_CUDA(cudaMemcpyAsync(&keep0, coacc.p + in.start, 1, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  out.has_start = keep0 != 0;  // state 0 keeps id 0 when it survives
+  out.start = 0;
   return out;
 }
 

@@ -1,7 +1,10 @@
 // device_common.cu — device discovery and host<->HBM marshalling of CSR FSTs.
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
+#include <map>
 #include <mutex>
+#include <vector>
 
 #include "device_common.cuh"
 
@@ -75,6 +78,63 @@ CsrFst download(const DevFst& d, cudaStream_t s) {
   h.has_start = d.has_start; h.start = d.start; h.props = d.props & props::kTrinary;
   B200_CUDA(cudaStreamSynchronize(s));
   return h;
+}
+
+// ---- page-locked host pool ------------------------------------------------------------------------------------
+namespace {
+constexpr size_t kPinThreshold = 256 * 1024;          // smaller blocks: plain malloc
+constexpr size_t kPoolKeepBytes = 24ull << 30;        // cached free blocks above this are returned to the driver
+std::mutex g_pool_mu;
+std::map<size_t, std::vector<void*>> g_pool_free;     // size class -> cached blocks
+size_t g_pool_cached = 0;
+int g_pin_state = 0;                                  // 0 unknown, 1 pinned allocations work, -1 no device
+size_t size_class(size_t b) { size_t c = kPinThreshold; while (c < b) c <<= 1; return c; }
+}  // namespace
+
+void* host_pool_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  void* p = nullptr;
+  if (bytes < kPinThreshold) {
+    p = std::malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+  }
+  size_t cls = size_class(bytes);
+  {
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    auto it = g_pool_free.find(cls);
+    if (it != g_pool_free.end() && !it->second.empty()) {
+      p = it->second.back(); it->second.pop_back(); g_pool_cached -= cls;
+      return p;
+    }
+    if (g_pin_state == 0) {
+      int n = 0;
+      g_pin_state = (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : -1;
+      cudaGetLastError();
+    }
+  }
+  if (g_pin_state == 1 && cudaHostAlloc(&p, cls, cudaHostAllocPortable) == cudaSuccess) return p;
+  cudaGetLastError();
+  // no device (CPU-only box) or pinning refused: ordinary memory, tagged by a side table so free() knows
+  p = std::malloc(cls);
+  if (!p) throw std::bad_alloc();
+  std::lock_guard<std::mutex> g(g_pool_mu);
+  g_pool_free[0].push_back(p);  // class 0 = registry of malloc'ed large blocks
+  return p;
+}
+
+void host_pool_free(void* p, size_t bytes) noexcept {
+  if (!p) return;
+  if (bytes == 0) bytes = 1;
+  if (bytes < kPinThreshold) { std::free(p); return; }
+  size_t cls = size_class(bytes);
+  std::lock_guard<std::mutex> g(g_pool_mu);
+  auto& reg = g_pool_free[0];
+  for (size_t i = 0; i < reg.size(); i++)
+    if (reg[i] == p) { reg[i] = reg.back(); reg.pop_back(); std::free(p); return; }
+  if (g_pool_cached + cls > kPoolKeepBytes) { cudaFreeHost(p); return; }
+  g_pool_free[cls].push_back(p);
+  g_pool_cached += cls;
 }
 
 void exclusive_sum_u32(const uint32_t* in, uint32_t* out, size_t n, DevBuf<uint8_t>& temp, cudaStream_t s) {

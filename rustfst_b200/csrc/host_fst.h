@@ -15,6 +15,9 @@
 #include <cstring>
 #include <fstream>
 #include <mutex>
+#include <new>
+#include <type_traits>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -27,11 +30,35 @@ struct FstError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
 
+// Large host arrays live in page-locked memory taken from a process-wide pool (device_common.cu) so that the three
+// CSR arrays move to and from HBM at PCIe/C2C line rate with plain cudaMemcpyAsync; on a box without a CUDA device the
+// pool degrades to malloc.  The allocator default-initialises (no zero fill of buffers that are overwritten anyway).
+void* host_pool_alloc(size_t bytes);
+void host_pool_free(void* p, size_t bytes) noexcept;
+
+template <class T>
+struct PoolAllocator {
+  using value_type = T;
+  PoolAllocator() noexcept = default;
+  template <class U> PoolAllocator(const PoolAllocator<U>&) noexcept {}
+  T* allocate(size_t n) { return static_cast<T*>(host_pool_alloc(n * sizeof(T))); }
+  void deallocate(T* p, size_t n) noexcept { host_pool_free(p, n * sizeof(T)); }
+  template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+    ::new (static_cast<void*>(p)) U;  // default-init: trivially constructible types stay uninitialised
+  }
+  template <class U, class... Args> void construct(U* p, Args&&... args) {
+    ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+  }
+  template <class U> bool operator==(const PoolAllocator<U>&) const noexcept { return true; }
+  template <class U> bool operator!=(const PoolAllocator<U>&) const noexcept { return false; }
+};
+template <class T> using PoolVec = std::vector<T, PoolAllocator<T>>;
+
 // Plain CSR block: what travels to and from the device.
 struct CsrFst {
-  std::vector<uint32_t> offsets{0};  // num_states + 1
-  std::vector<Tr> arcs;
-  std::vector<float> finals;         // +inf == not final
+  PoolVec<uint32_t> offsets{0};  // num_states + 1
+  PoolVec<Tr> arcs;
+  PoolVec<float> finals;         // +inf == not final
   std::vector<StateId> inf_finals;   // states that are final with weight +inf (Some(inf)); sorted, almost always empty
   bool has_start = false;
   StateId start = 0;

@@ -397,7 +397,7 @@ CsrFst build_path_fst(bool found, const std::vector<Tr>& path, float final_w) {
     size_t L = path.size();
     o.offsets.assign(L + 2, 0);
     o.finals.assign(L + 1, w_zero());
-    o.arcs = path;
+    o.arcs.assign(path.begin(), path.end());
     for (size_t k = 0; k <= L; k++) {
       p = props::on_add_state(p);
       if (k == 0) {

@@ -25,7 +25,7 @@ d1, d2 = R.DeviceFst.upload(synth.to_vector_fst(a1)), R.DeviceFst.upload(synth.t
 for _ in range(args.reps):
     out, st = R.device_compose(d1, d2)
     print({k: st[k] for k in ("states_expanded", "arcs_emitted", "waves", "kernel_launches", "ms_expand", "ms_connect",
-                              "ms_emit_kernel")})
+                              "ms_emit_kernel", "ms_phase_match", "ms_phase_emit", "ms_phase_rank", "ms_phase_resolve")})
 if args.sssp:
     g = synth.layered_acceptor(int(5_000_000 * args.scale), int(50_000_000 * args.scale), 1000, 6, 50)
     dg = R.DeviceFst.upload(synth.to_vector_fst(g))

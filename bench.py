@@ -254,11 +254,14 @@ def main():
     }
 
     # ------------------------------------------------------------------ end-to-end through the C-ABI (host buffers)
+    for _ in range(args.warmup):  # first calls populate the page-locked host pool that result handles come from
+        res, st = R.compose_with_stats(h1, h2)
+        del res
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_arcs, d2h = 0, 0
-    for _ in range(max(1, min(steps, 3))):
+    for _ in range(steps):
         res, st = R.compose_with_stats(h1, h2)  # fst_compose path: H2D of both operands, kernels, D2H of the result
         e2e_arcs += st["arcs_emitted"]
         d2h = 4 * (res.num_states() + 1) + 16 * res.num_trs_total() + 4 * res.num_states()
@@ -311,9 +314,12 @@ def main():
         # end to end through fst_shortest_path on the host handle (H2D of the lattice inside)
         barrier()
         t0 = time.perf_counter()
-        _, sst = R.shortestpath_with_stats(hg)
+        e2e_edges = 0
+        for _ in range(steps):
+            _, sst = R.shortestpath_with_stats(hg)
+            e2e_edges += sst["arcs_relaxed"]
         barrier()
-        sssp["e2e"] = {"value": sst["arcs_relaxed"] / (time.perf_counter() - t0), "unit": "edges/s",
+        sssp["e2e"] = {"value": e2e_edges / (time.perf_counter() - t0), "unit": "edges/s",
                        "h2d_bytes_per_step": csr_bytes(g), "d2h_bytes_per_step": 16 * 64}
         del dg
 

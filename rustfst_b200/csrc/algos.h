@@ -38,8 +38,17 @@ DevFst compose_device_waves(const DevFst& a, const DevFst& b, const ComposeOptio
                             cudaStream_t s);
 // Back end 2: one persistent cooperative kernel runs the whole BFS (no host round trips); returns false when a
 // pre-sized buffer overflowed, in which case the caller falls back to back end 1.
+// Batched mode: `a` is the disjoint union of many acceptors; the BFS starts from the n tuples (starts1[i], start(b))
+// (product ids 0..n-1) and the result is the union of the individual compositions.  out_s1[id] = fst1 state of every
+// result state (identifies its acceptor), out_start_map[i] = result id of start tuple i or 0xFFFFFFFF if trimmed.
+struct BatchStarts {
+  const uint32_t* d_starts1 = nullptr;
+  uint32_t n = 0;
+  DevBuf<uint32_t>* out_s1 = nullptr;
+  DevBuf<uint32_t>* out_start_map = nullptr;
+};
 bool compose_device_coop(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
-                         cudaStream_t s, DevFst* out);
+                         cudaStream_t s, DevFst* out, const BatchStarts* batch = nullptr);
 
 // Trim: keep states that are accessible and coaccessible, order-preserving renumbering
 // (rustfst/src/algorithms/connect.rs:51-66, rustfst/src/fst_impls/vector_fst/mutable_fst.rs:132-189).
@@ -48,8 +57,14 @@ DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launch
 // Same result for a freshly composed FST whose BFS wave boundaries are known (wave k = ids [wave_lo[k], wave_lo[k+1]),
 // device array of n_waves + 1 entries, start state = 0): one persistent kernel, coaccessibility pulled in reverse
 // wave order.
+struct TrimExtras {  // optional per-state payload carried through the compaction (batched mode)
+  const unsigned long long* tuples = nullptr;  // packed (s1, s2, fs) of every input state
+  uint32_t n_starts = 1;
+  DevBuf<uint32_t>* out_tag = nullptr;         // s1 of every KEPT state, in new-id order
+  DevBuf<uint32_t>* out_start_map = nullptr;   // new id of input states 0..n_starts-1 (0xFFFFFFFF = deleted)
+};
 DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_t n_waves, uint64_t* launches,
-                            cudaStream_t s);
+                            cudaStream_t s, const TrimExtras* extras = nullptr);
 
 // ---- shortest path (n = 1)
 enum QueueKind : int { kStateOrderQueue = 0, kTopOrderQueue = 1, kLifoQueue = 2, kSccQueue = 3 };

@@ -495,22 +495,125 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
                                       const CComposeConfig* cfg, const CFst** results, B200ComposeStats* total) {
   return wrap([&] {
     ComposeOptions opt = to_options(cfg);
-    Stream st;
-    DevFst dt = upload(nn(transducer, "transducer")->fst.freeze(), st.s);
+    const CsrFst& ht = nn(transducer, "transducer")->fst.freeze();
+    for (size_t i = 0; i < n; i++) results[i] = nullptr;
     B200ComposeStats acc;
     std::memset(&acc, 0, sizeof(acc));
-    for (size_t i = 0; i < n; i++) results[i] = nullptr;
+    Stream st;
+    double t0 = now_ms();
+    DevFst dt = upload(ht, st.s);
+    acc.ms_h2d += (float)(now_ms() - t0);
+
+    // ---- one BFS for the whole batch: the acceptors become one FST with disjoint state ranges and n start tuples.
+    // Every acceptor must lead to the same match side (same sortedness bits); otherwise fall back to a loop.
+    std::vector<const CsrFst*> hs(n);
+    bool uniform = n > 0 && ht.has_start;
+    uint64_t and_props = ~0ull, or_props = 0;
+    size_t sum_states = 0, sum_arcs = 0;
     for (size_t i = 0; i < n; i++) {
-      DevFst da = upload(nn(acceptors[i], "acceptor")->fst.freeze(), st.s);
+      hs[i] = &nn(acceptors[i], "acceptor")->fst.freeze();
+      if (!hs[i]->inf_finals.empty()) uniform = false;
+      if (!hs[i]->has_start) uniform = false;
+      and_props &= hs[i]->props; or_props |= hs[i]->props;
+      sum_states += hs[i]->num_states(); sum_arcs += hs[i]->arcs.size();
+    }
+    const uint64_t steer = props::kOLabelSorted | props::kNotOLabelSorted | props::kAcceptor | props::kNotAcceptor |
+                           props::kNoEpsilons | props::kNoIEpsilons | props::kNoOEpsilons | props::kAcyclic |
+                           props::kInitialAcyclic | props::kIDeterministic | props::kODeterministic;
+    if ((and_props & steer) != (or_props & steer)) uniform = false;  // property bits that steer compose must agree
+    if (sum_states >= 0x7FFFFFF0ull || sum_arcs >= 0xFFFFFFF0ull) uniform = false;
+
+    bool done = false;
+    if (uniform) {
+      CsrFst u;
+      u.offsets.resize(sum_states + 1);
+      u.arcs.resize(sum_arcs);
+      u.finals.resize(sum_states);
+      std::vector<uint32_t> starts(n), base_state(n + 1), acc_of(sum_states);
+      size_t so = 0, ao = 0;
+      for (size_t i = 0; i < n; i++) {
+        const CsrFst& h = *hs[i];
+        base_state[i] = (uint32_t)so;
+        starts[i] = (uint32_t)(so + h.start);
+        const size_t ns = h.num_states(), na = h.arcs.size();
+        for (size_t s = 0; s < ns; s++) { u.offsets[so + s] = (uint32_t)(ao + h.offsets[s]); acc_of[so + s] = (uint32_t)i; }
+        std::memcpy(u.finals.data() + so, h.finals.data(), ns * 4);
+        for (size_t k = 0; k < na; k++) { Tr t = h.arcs[k]; t.nextstate += (uint32_t)so; u.arcs[ao + k] = t; }
+        so += ns; ao += na;
+      }
+      base_state[n] = (uint32_t)so;
+      u.offsets[sum_states] = (uint32_t)ao;
+      u.has_start = true; u.start = starts[0];
+      u.props = and_props & props::kTrinary;
+      t0 = now_ms();
+      DevFst du = upload(u, st.s);
+      DevBuf<uint32_t> d_starts(st.s, n), d_s1(st.s), d_map(st.s);
+      B200_CUDA(cudaMemcpyAsync(d_starts.p, starts.data(), n * 4, cudaMemcpyHostToDevice, st.s));
+      B200_CUDA(cudaStreamSynchronize(st.s));
+      acc.ms_h2d += (float)(now_ms() - t0);
+      BatchStarts bs;
+      bs.d_starts1 = d_starts.p; bs.n = (uint32_t)n; bs.out_s1 = &d_s1; bs.out_start_map = &d_map;
       ComposeStats cs;
-      DevFst dr = compose_device(da, dt, opt, &cs, st.s);
-      results[i] = new CFst{HostFst(download(dr, st.s))};
-      acc.states_expanded += cs.states_expanded; acc.arcs_iterated += cs.arcs_iterated;
-      acc.arcs_emitted += cs.arcs_emitted; acc.waves += cs.waves; acc.states_out += cs.states_out;
-      acc.arcs_out += cs.arcs_out; acc.kernel_launches += cs.kernel_launches; acc.emit_launches += cs.emit_launches;
-      acc.ms_expand += cs.ms_expand; acc.ms_connect += cs.ms_connect; acc.ms_emit_kernel += cs.ms_emit_kernel;
-      acc.ms_phase_match += cs.ms_phase[0]; acc.ms_phase_emit += cs.ms_phase[1];
-      acc.ms_phase_rank += cs.ms_phase[2]; acc.ms_phase_resolve += cs.ms_phase[3];
+      DevFst dr(st.s);
+      if (compose_device_coop(du, dt, opt, &cs, st.s, &dr, &bs)) {
+        t0 = now_ms();
+        CsrFst r = download(dr, st.s);
+        const size_t rn = r.num_states();
+        std::vector<uint32_t> tag(rn ? rn : 1), smap(n);
+        if (rn) B200_CUDA(cudaMemcpyAsync(tag.data(), d_s1.p, rn * 4, cudaMemcpyDeviceToHost, st.s));
+        B200_CUDA(cudaMemcpyAsync(smap.data(), d_map.p, n * 4, cudaMemcpyDeviceToHost, st.s));
+        B200_CUDA(cudaStreamSynchronize(st.s));
+        acc.ms_d2h += (float)(now_ms() - t0);
+        // ---- split the union result per acceptor; ids inside a component keep their relative order, which is
+        // exactly the numbering of the stand-alone composition (same BFS restricted to that component)
+        std::vector<uint32_t> comp(rn), local(rn), n_st(n, 0), n_ar(n, 0);
+        for (size_t s = 0; s < rn; s++) {
+          uint32_t c = acc_of[tag[s]];
+          comp[s] = c; local[s] = n_st[c]++;
+          n_ar[c] += r.offsets[s + 1] - r.offsets[s];
+        }
+        std::vector<CsrFst> parts(n);
+        std::vector<uint32_t> arc_fill(n, 0);
+        for (size_t i = 0; i < n; i++) {
+          parts[i].offsets.resize((size_t)n_st[i] + 1);
+          parts[i].arcs.resize(n_ar[i]);
+          parts[i].finals.resize(n_st[i]);
+          parts[i].offsets[n_st[i]] = n_ar[i];
+          uint64_t p = props::of_compose(hs[i]->props, ht.props);
+          if (opt.connect) p = props::after_connect(p);
+          parts[i].props = p & props::kTrinary;
+          parts[i].has_start = smap[i] != 0xFFFFFFFFu;
+          parts[i].start = parts[i].has_start ? local[smap[i]] : 0;
+        }
+        for (size_t s = 0; s < rn; s++) {
+          CsrFst& p = parts[comp[s]];
+          const uint32_t ls = local[s];
+          p.finals[ls] = r.finals[s];
+          uint32_t o = arc_fill[comp[s]];
+          p.offsets[ls] = o;
+          for (uint32_t k = r.offsets[s]; k < r.offsets[s + 1]; k++) {
+            Tr t = r.arcs[k];
+            t.nextstate = local[t.nextstate];
+            p.arcs[o++] = t;
+          }
+          arc_fill[comp[s]] = o;
+        }
+        for (size_t i = 0; i < n; i++) results[i] = new CFst{HostFst(std::move(parts[i]))};
+        fill(&acc, cs, acc.ms_h2d, acc.ms_d2h);
+        done = true;
+      }
+    }
+    if (!done) {  // heterogeneous batch or pre-sized buffers too small: one composition at a time
+      for (size_t i = 0; i < n; i++) {
+        DevFst da = upload(nn(acceptors[i], "acceptor")->fst.freeze(), st.s);
+        ComposeStats cs;
+        DevFst dr = compose_device(da, dt, opt, &cs, st.s);
+        results[i] = new CFst{HostFst(download(dr, st.s))};
+        acc.states_expanded += cs.states_expanded; acc.arcs_iterated += cs.arcs_iterated;
+        acc.arcs_emitted += cs.arcs_emitted; acc.waves += cs.waves; acc.states_out += cs.states_out;
+        acc.arcs_out += cs.arcs_out; acc.kernel_launches += cs.kernel_launches; acc.emit_launches += cs.emit_launches;
+        acc.ms_expand += cs.ms_expand; acc.ms_connect += cs.ms_connect; acc.ms_emit_kernel += cs.ms_emit_kernel;
+      }
     }
     if (total) *total = acc;
   });

@@ -60,6 +60,7 @@ struct CoopParams {
   uint32_t* part_new;     // gridDim entries: first emissions found in each CTA's arc slice
   uint32_t* ctl;          // [1] overflow flags, [2] #states, [3] #arcs
   uint32_t* wave_lo; uint32_t wave_cap;  // first product id of every BFS wave (+ one-past-the-end sentinel)
+  uint32_t n_starts;      // initial frontier = product ids [0, n_starts) (1 for a plain compose, batch size otherwise)
   unsigned long long* stats;  // states_expanded, arcs_iterated, arcs_emitted, waves, ns phase A, B, C, D
 };
 
@@ -89,7 +90,7 @@ k_compose_coop(CoopParams P) {
   uint32_t* s_pref_b = s_dyn + gridDim.x + 1;  // arcs (B)
 
   const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
-  uint32_t lo = 0, hi = 1, base = 0;  // uniform across the grid by construction
+  uint32_t lo = 0, hi = P.n_starts, base = 0;  // uniform across the grid by construction
   unsigned long long n_states_exp = 0, n_items = 0, n_arcs = 0, n_waves = 0;
   unsigned long long t_a = 0, t_b = 0, t_c = 0, t_d = 0;
   uint32_t overflow = 0;
@@ -368,12 +369,31 @@ k_compose_coop(CoopParams P) {
   }
 }
 
-__global__ void k_coop_init(Slot* slots, uint32_t mask, unsigned long long* tuples, unsigned long long key0,
-                            uint32_t* ctl) {
-  uint32_t h = hash_key(key0) & mask;
-  slots[h].key = key0; slots[h].id = 0; slots[h].emin = 0;
-  tuples[0] = key0;
-  ctl[0] = ctl[1] = ctl[2] = ctl[3] = 0;
+// Seeds the state table with the start tuples: id i <- (start_fs, starts1[i], start2).  The s1 components are
+// pairwise distinct (different acceptors of a batch live in disjoint state ranges), so are the keys.
+__global__ void k_coop_init(Slot* slots, uint32_t mask, unsigned long long* tuples, uint32_t start_fs,
+                            const uint32_t* __restrict__ starts1, uint32_t single_start1, uint32_t start2,
+                            uint32_t n_starts, uint32_t* ctl) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { ctl[0] = ctl[1] = ctl[2] = ctl[3] = 0; }
+  if (i >= n_starts) return;
+  const unsigned long long key = pack_key(start_fs, starts1 ? starts1[i] : single_start1, start2);
+  uint32_t h = hash_key(key) & mask;
+  while (atomicCAS(&slots[h].key, kEmptyKey, key) != kEmptyKey) h = (h + 1) & mask;
+  slots[h].id = i; slots[h].emin = 0;
+  tuples[i] = key;
+}
+
+__global__ void k_unpack_s1(const unsigned long long* __restrict__ tuples, uint32_t n, uint32_t* __restrict__ s1_out,
+                            uint32_t n_starts, uint32_t* __restrict__ start_map) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { uint32_t fs, s1, s2; unpack_key(tuples[i], fs, s1, s2); s1_out[i] = s1; }
+  if (i < n_starts) start_map[i] = i;
+}
+void launch_unpack_s1(const unsigned long long* tuples, uint32_t n, uint32_t* s1_out, uint32_t n_starts,
+                      uint32_t* start_map, cudaStream_t s) {
+  uint32_t m = n > n_starts ? n : n_starts;
+  if (m) k_unpack_s1<<<blocks_for(m), kThreads, 0, s>>>(tuples, n, s1_out, n_starts, start_map);
 }
 
 float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
@@ -401,13 +421,15 @@ float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
 }  // namespace
 
 bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOptions& opt, ComposeStats* stats,
-                         cudaStream_t s, DevFst* result) {
+                         cudaStream_t s, DevFst* result, const BatchStarts* batch) {
   int kind = opt.filter == kAutoFilter ? kSequenceFilter : opt.filter;
   if (kind < kNullFilter || kind > kNoMatchFilter) throw FstError("EnumConversionError");
   int side = resolve_match_side(fa.props, fb.props);
   if (fa.num_states >= 0x7FFFFFFFu || fb.num_states >= 0x7FFFFFFFu)
     throw FstError("compose: operands with >= 2^31 states are not supported");
-  if (!fa.has_start || !fb.has_start) return false;  // trivial case handled by the multi-kernel back end
+  if (!batch && (!fa.has_start || !fb.has_start)) return false;  // trivial case: multi-kernel back end
+  if (batch && (!fb.has_start || batch->n == 0)) throw FstError("batched compose needs a start state on both sides");
+  const uint32_t n_starts = batch ? batch->n : 1u;
 
   ComposeStats local;
   ComposeStats& st = stats ? *stats : local;
@@ -435,7 +457,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
 
   // ---- pre-sized buffers (HBM is plentiful: 180 GB); an overflow falls back to the growing back end
   const size_t sum_states = (size_t)fa.num_states + fb.num_states, sum_arcs = (size_t)fa.num_arcs + fb.num_arcs;
-  size_t states_cap = std::max<size_t>(1 << 16, 8 * sum_states);
+  size_t states_cap = std::max<size_t>(1 << 16, 8 * sum_states + 2 * (size_t)n_starts);
   size_t arcs_cap = std::max<size_t>(1 << 18, 4 * sum_arcs);
   states_cap = std::min<size_t>(states_cap, 0x7FFFFFF0ull);
   arcs_cap = std::min<size_t>(arcs_cap, 0xFFFFFFF0ull);
@@ -465,7 +487,9 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   P.ctl = ctl.p; P.stats = dstats.p;
   P.wave_lo = wave_lo.p; P.wave_cap = wave_cap;
   uint32_t start_fs = (kind == kNullFilter || kind == kTrivialFilter || kind == kNoMatchFilter) ? 1u : 0u;
-  k_coop_init<<<1, 1, 0, s>>>(slots.p, P.mask, tuples.p, pack_key(start_fs, fa.start, fb.start), ctl.p);
+  P.n_starts = n_starts;
+  k_coop_init<<<blocks_for(n_starts), kThreads, 0, s>>>(slots.p, P.mask, tuples.p, start_fs,
+                                                        batch ? batch->d_starts1 : nullptr, fa.start, fb.start, n_starts, ctl.p);
   st.kernel_launches++;
 
   float ms_kernel = run_coop(P, sm_count(), s);
@@ -490,9 +514,21 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   B200_CUDA(cudaEventRecord(ev1, s));
   if (opt.connect) {
     uint64_t launches = 0;
-    DevFst trimmed = connect_waves_device(out, wave_lo.p, (uint32_t)st.waves, &launches, s);
+    TrimExtras extras;
+    extras.tuples = batch ? tuples.p : nullptr;
+    extras.n_starts = n_starts;
+    extras.out_tag = batch ? batch->out_s1 : nullptr;
+    extras.out_start_map = batch ? batch->out_start_map : nullptr;
+    DevFst trimmed = connect_waves_device(out, wave_lo.p, (uint32_t)st.waves, &launches, s, &extras);
     st.kernel_launches += launches;
     out = std::move(trimmed);
+  }
+  else if (batch) {
+    // untrimmed batch result: s1 of every product state + identity start map
+    batch->out_s1->reserve_discard(out.num_states ? out.num_states : 1);
+    batch->out_start_map->reserve_discard(n_starts);
+    launch_unpack_s1(tuples.p, out.num_states, batch->out_s1->p, n_starts, batch->out_start_map->p, s);
+    st.kernel_launches++;
   }
   st.states_out = out.num_states; st.arcs_out = out.num_arcs;
   B200_CUDA(cudaEventRecord(ev2, s));
@@ -510,7 +546,7 @@ DevFst compose_device(const DevFst& a, const DevFst& b, const ComposeOptions& op
   bool want_waves = impl && std::string(impl) == "waves";
   if (!want_waves) {
     DevFst out(s);
-    if (compose_device_coop(a, b, opt, stats, s, &out)) return out;
+    if (compose_device_coop(a, b, opt, stats, s, &out, nullptr)) return out;
   }
   return compose_device_waves(a, b, opt, stats, s);
 }

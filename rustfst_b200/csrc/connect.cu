@@ -113,6 +113,8 @@ struct TrimParams {
   uint32_t* part_keep; uint32_t* part_deg;
   uint32_t* noff; Tr* narcs; float* nfin;
   uint32_t* ctl;         // [0] changed flag per sweep, [1] back-arc seen, [2] n_keep, [3] a_keep, [4] sweeps
+  const unsigned long long* tuples; uint32_t* ntag;   // optional: s1 component of the packed tuple, gathered
+  uint32_t n_starts; uint32_t* start_map;             // optional: new ids of input states 0..n_starts-1
 };
 
 __global__ void __launch_bounds__(kCoopThreads)
@@ -201,6 +203,7 @@ k_trim_coop(TrimParams P) {
     uint32_t o = s_pref_deg[c] + P.deg_loc[s];
     P.nfin[ns] = P.fin[s];
     P.noff[ns] = o;
+    if (P.ntag) P.ntag[ns] = (uint32_t)(P.tuples[s] & 0x7FFFFFFFull);
     for (uint32_t i = P.off[s]; i < P.off[s + 1]; i++) {
       int4 v = __ldg(reinterpret_cast<const int4*>(&P.arcs[i]));
       const uint32_t t = (uint32_t)v.w;
@@ -210,6 +213,9 @@ k_trim_coop(TrimParams P) {
       }
     }
   }
+  if (P.start_map)
+    for (uint32_t i = gtid; i < P.n_starts; i += gsize)
+      P.start_map[i] = __ldcg(&P.coacc[i]) ? s_pref_id[i / sc] + __ldcg(&P.id_loc[i]) : 0xFFFFFFFFu;
   if (c == 0 && tid == 0) { P.noff[n_keep] = a_keep; P.ctl[2] = n_keep; P.ctl[3] = a_keep; P.ctl[4] = sweeps; }
 }
 
@@ -304,13 +310,18 @@ DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launch
 }
 
 DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_t n_waves, uint64_t* launches,
-                            cudaStream_t s) {
+                            cudaStream_t s, const TrimExtras* extras) {
   DevFst out(s);
   out.props = props::after_connect(in.props);
   const uint32_t n = in.num_states;
   if (launches) *launches = 0;
   if (in.has_start && in.start != 0) throw FstError("connect_waves_device expects the start state to be state 0");
   if (n == 0 || !in.has_start || n_waves == 0) {
+    if (extras && extras->out_tag) {
+      extras->out_tag->reserve_discard(1);
+      extras->out_start_map->reserve_discard(extras->n_starts ? extras->n_starts : 1);
+      B200_CUDA(cudaMemsetAsync(extras->out_start_map->p, 0xFF, (size_t)(extras->n_starts ? extras->n_starts : 1) * 4, s));
+    }
     out.offsets.reserve_discard(1);
     B200_CUDA(cudaMemsetAsync(out.offsets.p, 0, 4, s));
     return out;
@@ -328,6 +339,12 @@ DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_
   P.coacc = coacc.p; P.id_loc = id_loc.p; P.deg_loc = deg_loc.p;
   P.part_keep = parts.p; P.part_deg = parts.p + 2049;
   P.noff = out.offsets.p; P.narcs = out.arcs.p; P.nfin = out.finals.p; P.ctl = ctl.p;
+  if (extras && extras->out_tag) {
+    extras->out_tag->reserve_discard(n);
+    extras->out_start_map->reserve_discard(extras->n_starts);
+    P.tuples = extras->tuples; P.ntag = extras->out_tag->p;
+    P.n_starts = extras->n_starts; P.start_map = extras->out_start_map->p;
+  }
   int per_sm = 0;
   size_t dyn = 2 * 2049 * sizeof(uint32_t);
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trim_coop, kCoopThreads, dyn));

@@ -213,3 +213,44 @@ def test_tr_sort_then_compose_chain():
     pab.tr_sort(ilabel_cmp=False); oab.tr_sort(ilabel=False)
     assert_same(pab, oab, "tr_sort(olabel)")
     assert_same(pab.compose(pc), O.compose(oab, oc), "(a o b) o c")
+
+
+@pytest.mark.parametrize("connect", [True, False])
+def test_batched_compose_equals_individual_composes(connect):
+    """BASELINE.json configs[4] shape: many acceptors against one shared transducer in ONE device BFS
+    (b200_compose_batch); every result must equal the stand-alone composition bit-for-bit."""
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    t = synth.random_graph_transducer(3000, 30000, 40, seed=5)
+    rng = np.random.default_rng(9)
+    t["finals"] = np.where(rng.random(3000) < 0.6, rng.integers(0, 640, size=3000) / 64.0, np.inf).astype(np.float32)
+    pt, ot = both_from_dict(t)
+    accs = []
+    for i in range(64):
+        if i % 4 == 3:   # a label string that T does not necessarily accept
+            labels = np.random.default_rng(100 + i).integers(1, 41, size=12)
+        else:            # sampled from T: accepted at least up to a dead end
+            labels = synth.sample_path_labels(t, 12 + (i % 5), seed=100 + i)
+        accs.append(synth.linear_acceptor(labels, seed=300 + i))
+    pairs = [both_from_dict(a) for a in accs]
+    cfg = R.ComposeConfig(R.ComposeFilter.AUTOFILTER, connect)
+    results, st = R.compose_batch([p for p, _ in pairs], pt, cfg)
+    assert st["waves"] <= 20, "the batch must run as one BFS, not 64"
+    nonempty = 0
+    for i, ((p, o), r) in enumerate(zip(pairs, results)):
+        expected = O.compose(o, ot, connect=connect)
+        assert_same(r, expected, f"batch item {i} connect={connect}")
+        nonempty += expected.num_states > 0
+    assert nonempty > 10
+
+
+def test_batched_compose_heterogeneous_falls_back():
+    import rustfst_b200 as R
+    rng = np.random.default_rng(11)
+    db = random_fst(rng, 10, 4, 4, sort="ilabel")
+    pb, ob = both_from_dict(db)
+    das = [random_fst(rng, 8, 3, 4, eps_prob=0.2, sort=("olabel" if i % 2 else None)) for i in range(6)]
+    pairs = [both_from_dict(d) for d in das]
+    results, _ = R.compose_batch([p for p, _ in pairs], pb)
+    for (p, o), r in zip(pairs, results):
+        assert_same(r, O.compose(o, ob), "heterogeneous batch")

@@ -108,12 +108,17 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from tests import oracle_lib as O
-    sample_scale = 0.25 * args.scale
-    a1, a2 = gen_compose_workload(args.workload, sample_scale, 0)
+    # One full C3 compose costs ~9 s on one core.  Time the FULL workload whenever steps + warm-up fit in a few
+    # minutes (CPU throughput drops with size, so a smaller sample would flatter the CPU); otherwise a 1/4-scale
+    # instance of the same generator.  The CPU needs no clock/cache warm-up beyond one pass.
+    warm = min(args.warmup, 1)
+    sample_scale = args.scale if (args.steps + warm) <= 12 else 0.25 * args.scale
+    workload = "C3" if args.workload == "C5" else args.workload
+    a1, a2 = gen_compose_workload(workload, sample_scale, 0)
     oa = O.OFst.from_csr(a1["offsets"].astype(np.uint64), a1["arcs"], a1["finals"], a1["start"], a1["props"])
     ob = O.OFst.from_csr(a2["offsets"].astype(np.uint64), a2["arcs"], a2["finals"], a2["start"], a2["props"])
     arcs = 0
-    for _ in range(args.warmup):
+    for _ in range(warm):
         O.compose(oa, ob)
     t = 0.0
     for _ in range(args.steps):
@@ -121,18 +126,76 @@ def run_reference(args, rank, world):
         t += st["seconds"]
         arcs += st["arcs_emitted"]
     value = arcs / t
-    sample = (f"{args.workload} generator at scale {sample_scale} ({a1['num_states']} x {a2['num_states']} states, "
-              f"{len(a1['arcs'])} + {len(a2['arcs'])} arcs), full compose+connect per step")
+    sample = (f"{workload} generator at scale {sample_scale} ({a1['num_states']} x {a2['num_states']} states, "
+              f"{len(a1['arcs'])} + {len(a2['arcs'])} arcs), full compose+connect per step, {warm} warm-up pass(es), "
+              "oracle port of rustfst's algorithm (C++ -O3), 1 thread: the reference is single-threaded")
     line = {
         "impl": "reference", "metric": "composed_arcs_per_sec", "value": value, "unit": "arcs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload} compose (bounded CPU sample)", "sample": sample},
+        "config": {"workload": f"{workload} compose on the host CPU", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "arcs/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "arcs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks):
+    """BASELINE.json configs[4]: `--batch` linear acceptors (200 arcs each, label strings sampled as walks of T)
+    against one shared 500K-state/5M-arc transducer.  Acceptors are block-sharded over the ranks, T is replicated,
+    every rank runs ONE device BFS for its whole shard (b200_compose_batch), and the result FSTs are gathered on
+    rank 0 over NCCL (strong scaling: the batch is fixed)."""
+    import torch
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    from rustfst_b200.parallel import gather_blobs, shard_range
+    n_t, a_t = int(500_000 * args.scale), int(5_000_000 * args.scale)
+    t = synth.random_graph_transducer(n_t, a_t, 5000, seed=5)
+    rng = np.random.default_rng(77)
+    t["finals"] = np.where(rng.random(n_t) < 0.5, rng.integers(0, 640, size=n_t) / 64.0, np.inf).astype(np.float32)
+    ht = synth.to_vector_fst(t)
+    lo, hi = shard_range(args.batch, rank, world)
+    accs = [synth.to_vector_fst(synth.linear_acceptor(synth.sample_path_labels(t, 200, seed=100 + i), seed=100 + i))
+            for i in range(lo, hi)]
+
+    def step(gather):
+        results, st = R.compose_batch(accs, ht)
+        blobs = None
+        if gather and dist is not None:
+            packed = []
+            for r in results:
+                o, a, f, _ = r.to_csr()
+                packed.append(o.tobytes() + a.tobytes() + f.tobytes())
+            blobs = gather_blobs(packed, dist, device=torch.device("cuda", local_rank))
+        return results, st, blobs
+
+    for _ in range(args.warmup):
+        step(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    arcs, launches, waves = 0, 0, 0
+    for _ in range(args.steps):
+        results, st, blobs = step(True)
+        arcs += st["arcs_out"]; launches += st["kernel_launches"]; waves += st["waves"]
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    total_arcs = sum_over_ranks(float(arcs))
+    if rank == 0:
+        line = {"metric": "composed_arcs_per_sec", "value": total_arcs / (ms * 1e-3), "unit": "arcs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C5: {args.batch} linear acceptors (200 arcs) o {n_t}-state/{len(t['arcs'])}-arc "
+                                       "transducer, sharded by acceptor, results gathered on rank 0 over NCCL",
+                           "parallelism": f"acceptor shards x{world}, transducer replicated",
+                           "waves_per_step": waves // max(1, args.steps)},
+                "e2e": {"value": total_arcs / (ms * 1e-3), "unit": "arcs/s", "api": "b200_compose_batch on host handles",
+                        "h2d_bytes_per_step": int(csr_bytes(t) + (hi - lo) * (201 * 8 + 200 * 16 + 4)),
+                        "d2h_bytes_per_step": int(arcs // max(1, args.steps) * 16)},
+                "gpu_launches": int(launches)}
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -141,7 +204,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C3", choices=["C3", "C2"])
+    ap.add_argument("--workload", default="C3", choices=["C3", "C2", "C5"])
+    ap.add_argument("--batch", type=int, default=8192, help="C5: number of linear acceptors")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; full size = 1.0)")
     ap.add_argument("--no-sssp", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -189,6 +253,12 @@ def main():
         return float(t.item())
 
     peak_gbs, peak_src = measured_peak_gbs()
+
+    if args.workload == "C5":
+        run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     # ------------------------------------------------------------------ compose leg
     a1, a2 = gen_compose_workload(args.workload, args.scale, rank)

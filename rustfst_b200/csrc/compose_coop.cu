@@ -50,7 +50,8 @@ struct CoopParams {
   // per-wave scratch, indexed by frontier-local state
   uint32_t* item_loc;     // slice-local exclusive item offset | side bit
   uint32_t* st_arc_loc;   // slice-local emission index of the state's first arc
-  uint8_t* st_flags;      // alleps1 | noeps1<<1 | alleps2<<2 | noeps2<<3
+  uint8_t* st_flags;      // alleps1 | noeps1<<1 | alleps2<<2 | noeps2<<3 | fs<<4
+  uint4* st_off;          // arc ranges of the two component states: alo, ahi, blo, bhi
   // per-wave scratch, indexed by item (active items compacted in place inside each CTA's slice)
   uint4* recs;            // x = first match, y = count|flags, z = frontier-local state, w = iterated arc (abs) or ~0
   uint32_t* arc_loc;      // slice-local emission index of the record's first arc
@@ -82,8 +83,9 @@ constexpr uint32_t kTile = kCoopThreads;
 __global__ void __launch_bounds__(kCoopThreads, 4)
 k_compose_coop(CoopParams P) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ uint32_t s_warp[kCoopThreads / 32];
+  __shared__ uint32_t s_warp[2 * (kCoopThreads / 32)];
   __shared__ uint32_t s_seg[kTile + 2];
+  __shared__ uint32_t s_side[kTile + 2];
   __shared__ uint32_t s_misc[4];
   extern __shared__ uint32_t s_dyn[];          // two prefix arrays of gridDim + 1 entries
   uint32_t* s_pref_a = s_dyn;                  // items (A1/B) then new-state counts (D)
@@ -111,14 +113,16 @@ k_compose_coop(CoopParams P) {
         if (i < s_end) {
           uint32_t fs, s1, s2;
           unpack_key(__ldcg(&P.tuples[lo + i]), fs, s1, s2);
-          const uint32_t d1 = P.a.off[s1 + 1] - P.a.off[s1], d2 = P.b.off[s2 + 1] - P.b.off[s2];
+          const uint32_t alo = P.a.off[s1], ahi = P.a.off[s1 + 1], blo = P.b.off[s2], bhi = P.b.off[s2 + 1];
+          const uint32_t d1 = ahi - alo, d2 = bhi - blo;
+          P.st_off[i] = make_uint4(alo, ahi, blo, bhi);
           const bool mi = P.side == kMatchInput || (P.side == kMatchBoth && d1 <= d2);
           nitems = 1u + (mi ? d1 : d2);
           side = mi ? kSideBit : 0u;
           const float f1 = P.a.fin[s1], f2 = P.b.fin[s2];
           const uint32_t ne1 = P.a.neps ? P.a.neps[s1] : 0u, ne2 = P.b.neps ? P.b.neps[s2] : 0u;
           const uint8_t fl = (uint8_t)(((d1 == ne1 && f1 == w_zero()) ? 1 : 0) | ((ne1 == 0) ? 2 : 0) |
-                                       ((d2 == ne2 && f2 == w_zero()) ? 4 : 0) | ((ne2 == 0) ? 8 : 0));
+                                       ((d2 == ne2 && f2 == w_zero()) ? 4 : 0) | ((ne2 == 0) ? 8 : 0) | (fs << 4));
           P.st_flags[i] = fl;
           const float fw = w_times(f1, f2);  // compose_fst_op.rs:420-449
           P.out_finals[lo + i] = w_is_zero(fw) ? w_zero() : fw;
@@ -159,7 +163,9 @@ k_compose_coop(CoopParams P) {
         // window of item start offsets for states i_cur .. i_cur + 256
         for (uint32_t k = tid; k < kTile + 1; k += kCoopThreads) {
           const uint32_t i = i_cur + k;
-          s_seg[k] = i < F ? s_pref_a[i / sc] + (__ldcg(&P.item_loc[i]) & ~kSideBit) : T;
+          const uint32_t il = i < F ? __ldcg(&P.item_loc[i]) : 0u;
+          s_seg[k] = i < F ? s_pref_a[i / sc] + (il & ~kSideBit) : T;
+          s_side[k] = il & kSideBit;
         }
         __syncthreads();
         const uint32_t t = t0 + tid;
@@ -168,13 +174,13 @@ k_compose_coop(CoopParams P) {
         if (t < it_end) {
           const uint32_t k = smem_segment(s_seg, kTile + 1, t);
           const uint32_t i = i_cur + k, j = t - s_seg[k];
-          uint32_t fs, s1, s2;
-          unpack_key(__ldcg(&P.tuples[lo + i]), fs, s1, s2);
-          const bool match_input = (__ldcg(&P.item_loc[i]) & kSideBit) != 0;
+          const bool match_input = s_side[k] != 0;
           const uint8_t fl = __ldcg(&P.st_flags[i]);
+          const uint32_t fs = fl >> 4;
           FsFlags ff;
           ff.alleps1 = fl & 1; ff.noeps1 = fl & 2; ff.alleps2 = fl & 4; ff.noeps2 = fl & 8;
-          const uint32_t alo = P.a.off[s1], ahi = P.a.off[s1 + 1], blo = P.b.off[s2], bhi = P.b.off[s2 + 1];
+          const uint4 so = __ldcg(&P.st_off[i]);
+          const uint32_t alo = so.x, ahi = so.y, blo = so.z, bhi = so.w;
           Label label;
           uint32_t it_idx = 0xFFFFFFFFu;  // absolute index of the iterated arc; all ones = implicit epsilon loop
           if (j == 0) label = kNoLabel;
@@ -202,10 +208,9 @@ k_compose_coop(CoopParams P) {
           rec = make_uint4(pos, (real_ok ? cnt : 0u) | (loop_ok ? 1u << 26 : 0u) | ((fs_loop & 3u) << 27) |
                                     ((fs_real & 3u) << 29) | (match_input ? 1u << 31 : 0u), i, it_idx);
         }
-        uint32_t tile_active, tile_arcs;
+        uint32_t tile_active, tile_arcs, ex_act, ex_arcs;
         const uint32_t act = cnt_out ? 1u : 0u;
-        const uint32_t ex_act = cta_exclusive_scan(act, s_warp, tile_active);
-        const uint32_t ex_arcs = cta_exclusive_scan(cnt_out, s_warp, tile_arcs);
+        cta_exclusive_scan2(act, cnt_out, s_warp, ex_act, ex_arcs, tile_active, tile_arcs);
         if (t < it_end) {
           if (rec.w == 0xFFFFFFFFu) P.st_arc_loc[rec.z] = my_arcs + ex_arcs;  // first arc of state rec.z (slice-local)
           if (act) {
@@ -474,6 +479,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   DevBuf<uint4> recs(s, items_cap);
   DevBuf<uint32_t> arc_loc(s, items_cap), item_loc(s, states_cap), st_arc_loc(s, states_cap), parts(s, 3 * 2048), ctl(s, 8);
   DevBuf<uint8_t> st_flags(s, states_cap);
+  DevBuf<uint4> st_off(s, states_cap);
   const uint32_t wave_cap = 1u << 20;
   DevBuf<uint32_t> wave_lo(s, wave_cap);
   B200_CUDA(cudaMemsetAsync(slots.p, 0xFF, table_cap * sizeof(Slot), s));
@@ -481,7 +487,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   P.tuples = tuples.p; P.states_cap = (uint32_t)states_cap;
   P.out_offsets = out.offsets.p; P.out_finals = out.finals.p; P.out_arcs = out.arcs.p; P.arcs_cap = (uint32_t)arcs_cap;
   P.slots = slots.p; P.mask = (uint32_t)table_cap - 1; P.table_cap = (uint32_t)table_cap;
-  P.item_loc = item_loc.p; P.st_arc_loc = st_arc_loc.p; P.st_flags = st_flags.p;
+  P.item_loc = item_loc.p; P.st_arc_loc = st_arc_loc.p; P.st_flags = st_flags.p; P.st_off = st_off.p;
   P.recs = recs.p; P.arc_loc = arc_loc.p; P.items_cap = (uint32_t)std::min<size_t>(items_cap, 0xFFFFFFF0ull);
   P.part_arcs = parts.p; P.part_items = parts.p + 2048; P.part_new = parts.p + 4096;
   P.ctl = ctl.p; P.stats = dstats.p;

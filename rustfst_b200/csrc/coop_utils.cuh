@@ -32,6 +32,28 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_w
   total = tot;
   return before + incl - v;
 }
+// Two independent exclusive scans sharing the shuffles and barriers of one (s_warp2 holds 2 x 8 words).
+__device__ __forceinline__ void cta_exclusive_scan2(uint32_t a, uint32_t b, uint32_t* s_warp2, uint32_t& ex_a,
+                                                    uint32_t& ex_b, uint32_t& tot_a, uint32_t& tot_b) {
+  const uint32_t wl = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t ia = a, ib = b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t ua = __shfl_up_sync(0xFFFFFFFFu, ia, o), ub = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+    if ((int)wl >= o) { ia += ua; ib += ub; }
+  }
+  __syncthreads();
+  if (wl == 31) { s_warp2[wid] = ia; s_warp2[kCoopThreads / 32 + wid] = ib; }
+  __syncthreads();
+  uint32_t ba = 0, bb = 0, ta = 0, tb = 0;
+#pragma unroll
+  for (int w = 0; w < kCoopThreads / 32; w++) {
+    uint32_t ca = s_warp2[w], cb = s_warp2[kCoopThreads / 32 + w];
+    if (w < (int)wid) { ba += ca; bb += cb; }
+    ta += ca; tb += cb;
+  }
+  ex_a = ba + ia - a; ex_b = bb + ib - b; tot_a = ta; tot_b = tb;
+}
 // s_out[0..n] = exclusive prefix of src[0..n) (n <= 2048), computed by the whole CTA; s_out[n] = total.
 __device__ __forceinline__ void cta_prefix_to_smem(const uint32_t* __restrict__ src, uint32_t n, uint32_t* s_out,
                                                    uint32_t* s_warp) {

@@ -80,7 +80,8 @@ constexpr uint32_t kTile = kCoopThreads;
 //   C  rank     : contiguous arc slices; ballot/popc ranks of first emissions published through slot.id
 //   D  resolve  : CTA prefix -> ids; nextstate patch; tuple publication
 // Five grid barriers per wave; every size is recomputed identically by every CTA from per-CTA partial arrays.
-__global__ void __launch_bounds__(kCoopThreads, 4)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kCoopThreads, kMinBlocks)
 k_compose_coop(CoopParams P) {
   cg::grid_group grid = cg::this_grid();
   __shared__ uint32_t s_warp[2 * (kCoopThreads / 32)];
@@ -403,9 +404,16 @@ void launch_unpack_s1(const unsigned long long* tuples, uint32_t n, uint32_t* s1
 
 float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   CoopParams P = P0;
+  // resident CTAs per SM the kernel is compiled for (register budget): 4 -> 64 regs, 5 -> 48, 6 -> 40
+  int minb = 4;
+  if (const char* e = std::getenv("B200_COOP_MINBLOCKS")) minb = std::atoi(e);
+  void* kern = (void*)k_compose_coop<4>;
+  if (minb == 5) kern = (void*)k_compose_coop<5>;
+  else if (minb == 6) kern = (void*)k_compose_coop<6>;
+  else if (minb == 3) kern = (void*)k_compose_coop<3>;
   int per_sm = 0;
   size_t dyn = 2 * 2049 * sizeof(uint32_t);
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compose_coop, kCoopThreads, dyn));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoopThreads, dyn));
   if (per_sm < 1) throw FstError("cooperative compose kernel does not fit on the device");
   int grid = sms * per_sm;
   if (grid > 2047) grid = 2047;  // CTA index must fit 11 bits next to the 20-bit local rank; prefix arrays hold 2048
@@ -415,7 +423,7 @@ float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   float ms = 0;
   B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
   B200_CUDA(cudaEventRecord(e0, s));
-  B200_CUDA(cudaLaunchCooperativeKernel((void*)k_compose_coop, dim3(grid), dim3(kCoopThreads), args, dyn, s));
+  B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kCoopThreads), args, dyn, s));
   B200_CUDA(cudaEventRecord(e1, s));
   B200_CUDA(cudaStreamSynchronize(s));
   B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));

@@ -23,6 +23,7 @@
 // The backtrace runs on the device as well; only the shortest path itself (a few hundred bytes) returns to the host.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "algos.h"
@@ -102,15 +103,21 @@ k_relax(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, const uin
 }
 
 // Persistent variant: the whole relaxation (all waves) in one cooperative launch.  kG lanes share a frontier state
-// and stride over its arcs (coalesced 128-bit loads); three frontier counters rotate so that no reset races with a
-// read: wave w consumes cnt[w % 3] (filled during wave w-1), fills cnt[(w+1) % 3] and clears cnt[(w+2) % 3].
-// out[0] = waves, out[1] = overflow/non-convergence flag, out64[0] = arcs relaxed, out64[1] = states settled.
+// and stride over its arcs (128-bit loads).  Newly improved states are first collected in a per-CTA shared-memory
+// queue and flushed to the next frontier with ONE global atomic per CTA and wave (a single global counter hit by
+// every warp serialises in the L2 atomic unit: ~30k same-address atomics per wave on C4).  Three frontier counters
+// rotate so that no reset races with a read: wave w consumes cnt[w % 3] (filled during wave w-1), fills
+// cnt[(w+1) % 3] and clears cnt[(w+2) % 3].
+// out[0] = waves, out[1] = non-convergence flag, out64[0] = arcs relaxed, out64[1] = states settled.
+constexpr uint32_t kQueueCap = 2048;
 template <int kG>
 __global__ void __launch_bounds__(kThreads)
 k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t* __restrict__ dist,
              uint32_t* __restrict__ stamp, uint32_t* __restrict__ fr_a, uint32_t* __restrict__ fr_b,
              uint32_t* __restrict__ cnt /*3*/, uint32_t* __restrict__ out, unsigned long long* __restrict__ out64) {
   cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t s_q[kQueueCap];
+  __shared__ uint32_t s_qn, s_gbase;
   const uint32_t lane = threadIdx.x % kG;
   const uint32_t groups = gridDim.x * (kThreads / kG);
   const uint32_t gid = blockIdx.x * (kThreads / kG) + threadIdx.x / kG;
@@ -122,6 +129,8 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
     const uint32_t nf = __ldcg(&cnt[wave % 3]);
     if (nf == 0 || wave > n) break;
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt[(wave + 2) % 3] = 0;
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
     uint32_t* next_count = &cnt[(wave + 1) % 3];
     for (uint32_t i = gid; i < nf; i += groups) {
       const uint32_t s = __ldcg(&cur[i]);
@@ -144,9 +153,27 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
             }
           }
         }
-        warp_push(push, t, nxt, next_count);
+        // warp-aggregated append to the CTA queue; spill to the global list when the queue is full
+        const uint32_t active = __activemask();
+        const uint32_t m = __ballot_sync(active, push);
+        if (m) {
+          const uint32_t wl = threadIdx.x & 31, leader = __ffs(m) - 1;
+          uint32_t qb = 0;
+          if (wl == leader) qb = atomicAdd(&s_qn, __popc(m));
+          qb = __shfl_sync(active, qb, leader);
+          if (push) {
+            const uint32_t pos = qb + __popc(m & ((1u << wl) - 1u));
+            if (pos < kQueueCap) s_q[pos] = t;
+            else nxt[atomicAdd(next_count, 1u)] = t;
+          }
+        }
       }
     }
+    __syncthreads();
+    const uint32_t qn = min(s_qn, kQueueCap);
+    if (threadIdx.x == 0 && qn) s_gbase = atomicAdd(next_count, qn);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < qn; i += kThreads) nxt[s_gbase + i] = s_q[i];
     wave++;
     uint32_t* tmp = cur; cur = nxt; nxt = tmp;
     grid.sync();
@@ -471,8 +498,16 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
       B200_CUDA(cudaMemsetAsync(outw.p, 0, 8, s));
       B200_CUDA(cudaMemsetAsync(out64.p, 0, 16, s));
       B200_CUDA(cudaStreamSynchronize(s));
+      // lanes per frontier state: few lanes = more states in flight (the relaxation is latency-bound)
+      int lanes = 8;
+      if (const char* e = std::getenv("B200_RELAX_LANES")) lanes = std::atoi(e);
+      void* kern = (void*)k_relax_coop<8>;
+      if (lanes == 1) kern = (void*)k_relax_coop<1>;
+      else if (lanes == 2) kern = (void*)k_relax_coop<2>;
+      else if (lanes == 4) kern = (void*)k_relax_coop<4>;
+      else if (lanes == 16) kern = (void*)k_relax_coop<16>;
       int per_sm = 0;
-      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_relax_coop<8>, kThreads, 0));
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
       if (per_sm < 1) throw FstError("cooperative relaxation kernel does not fit on the device");
       int grid = sm_count() * per_sm;
       const uint32_t* a_off = f.offsets.p; const Tr* a_arcs = f.arcs.p;
@@ -483,7 +518,7 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
       cudaEvent_t ea, eb;
       B200_CUDA(cudaEventCreate(&ea)); B200_CUDA(cudaEventCreate(&eb));
       B200_CUDA(cudaEventRecord(ea, s));
-      B200_CUDA(cudaLaunchCooperativeKernel((void*)k_relax_coop<8>, dim3(grid), dim3(kThreads), args, 0, s));
+      B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
       B200_CUDA(cudaEventRecord(eb, s));
       relax_events.emplace_back(ea, eb);
       st.relax_launches++; st.kernel_launches++;

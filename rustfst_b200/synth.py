@@ -46,12 +46,15 @@ def _finish(n, offsets, arcs, finals, acceptor, sorted_i, sorted_o):
             "props": int(pr), "num_states": int(n)}
 
 
-def layered_acceptor(n_states, n_arcs, vocab, seed, levels=32):
-    """Random layered acceptor (ilabel == olabel), arcs sorted by label."""
+def layered_acceptor(n_states, n_arcs, vocab, seed, levels=32, start_fanout=False):
+    """Random layered acceptor (ilabel == olabel), arcs sorted by label.  With start_fanout the start state has one
+    arc to every state of level 1 (a wide lattice from the first wave on) instead of ~A/N arcs."""
     rng = np.random.default_rng(seed)
     n, w, base = _level_layout(n_states, levels)
     n_src = n - w  # states of the last level have no arcs
     deg = _degrees(rng, n_src, n_arcs)
+    if start_fanout:
+        deg[0] = w
     offsets = np.zeros(n + 1, dtype=np.int64)
     offsets[1:n_src + 1] = np.cumsum(deg)
     offsets[n_src + 1:] = offsets[n_src]
@@ -60,6 +63,8 @@ def layered_acceptor(n_states, n_arcs, vocab, seed, levels=32):
     level = np.where(src == 0, 0, 1 + (src - 1) // w)
     label = rng.integers(1, vocab + 1, size=total, dtype=np.int64)
     target = base[level + 1] + rng.integers(0, w, size=total, dtype=np.int64)
+    if start_fanout:
+        target[:w] = base[1] + np.arange(w)
     weight = rng.integers(0, 640, size=total).astype(np.float32) / np.float32(64.0)
     order = np.lexsort((label, src))  # stable: by src, then label
     arcs = np.zeros(total, dtype=TR_DTYPE)
@@ -70,13 +75,16 @@ def layered_acceptor(n_states, n_arcs, vocab, seed, levels=32):
     return _finish(n, offsets, arcs, finals, True, True, True)
 
 
-def bigram_transducer(n_states, n_arcs, vocab, seed, levels=32, out_vocab=None):
-    """Layered transducer whose arc target is a function of the input label (LM-like); ilabel-sorted."""
+def bigram_transducer(n_states, n_arcs, vocab, seed, levels=32, out_vocab=None, start_fanout=False):
+    """Layered transducer whose arc target is a function of the input label (LM-like); ilabel-sorted.
+    With start_fanout the start state carries every input label once."""
     rng = np.random.default_rng(seed)
     out_vocab = out_vocab or vocab
     n, w, base = _level_layout(n_states, levels)
     n_src = n - w
     deg = np.minimum(_degrees(rng, n_src, n_arcs), vocab)
+    if start_fanout:
+        deg[0] = vocab
     offsets = np.zeros(n + 1, dtype=np.int64)
     offsets[1:n_src + 1] = np.cumsum(deg)
     offsets[n_src + 1:] = offsets[n_src]
@@ -85,6 +93,8 @@ def bigram_transducer(n_states, n_arcs, vocab, seed, levels=32, out_vocab=None):
     level = np.where(src == 0, 0, 1 + (src - 1) // w)
     ilabel = rng.integers(1, vocab + 1, size=total, dtype=np.int64)
     olabel = rng.integers(1, out_vocab + 1, size=total, dtype=np.int64)
+    if start_fanout:
+        ilabel[:vocab] = np.arange(1, vocab + 1)
     # a per-level rotation keeps consecutive levels from using the same slots for the same label
     target = base[level + 1] + (ilabel - 1 + 7919 * level) % w
     weight = rng.integers(0, 640, size=total).astype(np.float32) / np.float32(64.0)

@@ -16,13 +16,18 @@ ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--levels", type=int, default=50)
 ap.add_argument("--sssp", action="store_true")
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--fanout", action="store_true")
+ap.add_argument("--vocab", type=int, default=32)
+ap.add_argument("--no-compose", action="store_true")
 args = ap.parse_args()
 
 n, a = int(1_000_000 * args.scale), int(10_000_000 * args.scale)
-a1 = synth.layered_acceptor(n, a, 32, 3, args.levels)
-a2 = synth.bigram_transducer(n, a, 32, 4, args.levels, out_vocab=20000)
+a1 = synth.layered_acceptor(n, a, args.vocab, 3, args.levels, start_fanout=args.fanout)
+a2 = synth.bigram_transducer(n, a, args.vocab, 4, args.levels, out_vocab=20000, start_fanout=args.fanout)
 d1, d2 = R.DeviceFst.upload(synth.to_vector_fst(a1)), R.DeviceFst.upload(synth.to_vector_fst(a2))
-for _ in range(args.reps):
+out = None
+for _ in range(0 if args.no_compose else args.reps):
+    del out  # release the previous result first: the stream-ordered pool then reuses its blocks
     out, st = R.device_compose(d1, d2)
     print({k: st[k] for k in ("states_expanded", "arcs_emitted", "waves", "kernel_launches", "ms_expand", "ms_connect",
                               "ms_emit_kernel", "ms_phase_match", "ms_phase_emit", "ms_phase_rank", "ms_phase_resolve")})

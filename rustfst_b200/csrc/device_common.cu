@@ -1,4 +1,5 @@
 // device_common.cu — device discovery and host<->HBM marshalling of CSR FSTs.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
@@ -143,6 +144,16 @@ void exclusive_sum_u32(const uint32_t* in, uint32_t* out, size_t n, DevBuf<uint8
   B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int64_t)n, s));
   temp.reserve_discard(bytes);
   B200_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, bytes, in, out, (int64_t)n, s));
+}
+
+// Stable LSD radix sort of (key, value) pairs (CUB DeviceRadixSort); results land in keys_out / vals_out.
+void sort_pairs_u64_u32(const unsigned long long* keys_in, unsigned long long* keys_out, const uint32_t* vals_in,
+                        uint32_t* vals_out, size_t n, int end_bit, DevBuf<uint8_t>& temp, cudaStream_t s) {
+  if (n == 0) return;
+  size_t bytes = 0;
+  B200_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, (int64_t)n, 0, end_bit, s));
+  temp.reserve_discard(bytes);
+  B200_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, bytes, keys_in, keys_out, vals_in, vals_out, (int64_t)n, 0, end_bit, s));
 }
 
 }  // namespace b200

@@ -109,6 +109,10 @@ CsrFst download(const DevFst& d, cudaStream_t s);
 // Exclusive prefix sum of n uint32 values (CUB DeviceScan; compiled once in device_common.cu); out may alias in.
 void exclusive_sum_u32(const uint32_t* in, uint32_t* out, size_t n, DevBuf<uint8_t>& temp, cudaStream_t s);
 
+// Stable radix sort of (u64 key, u32 value) pairs on key bits [0, end_bit) (CUB; compiled once in device_common.cu).
+void sort_pairs_u64_u32(const unsigned long long* keys_in, unsigned long long* keys_out, const uint32_t* vals_in,
+                        uint32_t* vals_out, size_t n, int end_bit, DevBuf<uint8_t>& temp, cudaStream_t s);
+
 inline uint32_t read_u32(const uint32_t* dptr, cudaStream_t s) {
   uint32_t v = 0;
   B200_CUDA(cudaMemcpyAsync(&v, dptr, 4, cudaMemcpyDeviceToHost, s));

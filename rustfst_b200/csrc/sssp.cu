@@ -415,6 +415,127 @@ __global__ void k_serial_sssp(SerialArgs a) {
   a.meta[1] = L;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Order-faithful PARALLEL path for DAGs processed in a topological order (used when the certificate fails, i.e. for
+// weights with near-ties).  The reference dequeues states in `order`; when state t is dequeued every predecessor is
+// final, so the value t ends up with is a pure function of its in-arcs: the sequential fold, in (order[src], arc
+// position) order, of  d <- (d != min(d, c)) ? min(d, c) : d  with the approximate != of semiring.rs:159-168.
+// That fold is replayed verbatim by one thread per state over a reverse CSR whose in-arc lists are sorted by
+// (order[src], position) (one stable radix sort); states are scheduled level by level (Kahn), one grid barrier per
+// level.  Exact for any weights; falls back to the serial kernel if the graph turns out to be cyclic.
+__global__ void k_of_keys(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n,
+                          const uint32_t* __restrict__ order, unsigned long long* __restrict__ keys,
+                          uint32_t* __restrict__ vals, uint32_t* __restrict__ src_of, uint32_t* __restrict__ indeg) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const unsigned long long o = order ? order[s] : s;
+  for (uint32_t e = off[s]; e < off[s + 1]; e++) {
+    const uint32_t t = __ldg(&arcs[e].nextstate);
+    keys[e] = ((unsigned long long)t << 32) | o;
+    vals[e] = e;
+    src_of[e] = s;
+    atomicAdd(&indeg[t], 1u);
+  }
+}
+__global__ void k_of_roots(const uint32_t* __restrict__ indeg, uint32_t n, uint32_t* __restrict__ topo,
+                           uint32_t* __restrict__ cursor) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  warp_push(s < n && indeg[s] == 0, s, topo, cursor);
+}
+// ctl: [0] append cursor into topo (starts at #roots), [1] levels, [2] states processed
+__global__ void __launch_bounds__(kThreads)
+k_of_fold(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t source,
+          const uint32_t* __restrict__ roff, const uint32_t* __restrict__ in_arc /* sorted arc ids */,
+          const uint32_t* __restrict__ src_of, uint32_t* __restrict__ indeg, uint32_t* __restrict__ topo,
+          float* __restrict__ dist, uint32_t* __restrict__ pstate, uint32_t* __restrict__ ppos,
+          uint32_t* __restrict__ ctl, uint32_t n_roots) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t s_q[kQueueCap];
+  __shared__ uint32_t s_qn, s_gbase;
+  const uint32_t gsize = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t lo = 0, hi = n_roots, levels = 0;
+  while (lo < hi) {
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
+    for (uint32_t i = lo + gtid; i < hi; i += gsize) {
+      const uint32_t t = __ldcg(&topo[i]);
+      // ---- the reference's relaxation of all in-arcs of t, in its processing order (shortest_path.rs:222-236)
+      float d = (t == source) ? 0.0f : w_zero();
+      uint32_t ps = kNoState, pp = 0;
+      for (uint32_t k = roff[t]; k < roff[t + 1]; k++) {
+        const uint32_t e = in_arc[k], src = src_of[e];
+        const float c = w_times(__ldcg(&dist[src]), __ldg(&arcs[e].weight));
+        const float p = w_plus(d, c);
+        if (!w_approx_eq(d, p)) { d = p; ps = src; pp = e - off[src]; }
+      }
+      dist[t] = d; pstate[t] = ps; ppos[t] = pp;
+      // ---- Kahn: release the successors
+      for (uint32_t e = off[t]; e < off[t + 1]; e++) {
+        const uint32_t u = __ldg(&arcs[e].nextstate);
+        if (atomicSub(&indeg[u], 1u) == 1u) {
+          const uint32_t pos = atomicAdd(&s_qn, 1u);
+          if (pos < kQueueCap) s_q[pos] = u;
+          else topo[atomicAdd(&ctl[0], 1u)] = u;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t qn = min(s_qn, kQueueCap);
+    if (threadIdx.x == 0 && qn) s_gbase = atomicAdd(&ctl[0], qn);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < qn; i += kThreads) topo[s_gbase + i] = s_q[i];
+    levels++;
+    grid.sync();
+    lo = hi;
+    hi = __ldcg(&ctl[0]);
+  }
+  if (gtid == 0) { ctl[1] = levels; ctl[2] = hi; }
+}
+// Final-state fold in processing order + backtrace (one thread; the candidates are contiguous and sorted).
+__global__ void k_of_finish(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, const float* __restrict__ fin,
+                            const float* __restrict__ dist, const uint32_t* __restrict__ finals_sorted, uint32_t n_fin,
+                            const uint32_t* __restrict__ pstate, const uint32_t* __restrict__ ppos,
+                            Tr* __restrict__ out_arcs, uint32_t cap, uint32_t* __restrict__ meta) {
+  if (blockIdx.x || threadIdx.x) return;
+  float f = w_zero();
+  bool has = false;
+  uint32_t fp = 0;
+  for (uint32_t i = 0; i < n_fin; i++) {  // shortest_path.rs:214-220
+    const uint32_t s = finals_sorted[i];
+    const float p = w_plus(f, w_times(dist[s], fin[s]));
+    if (!w_approx_eq(f, p)) { f = p; fp = s; has = true; }
+  }
+  meta[0] = has ? 1u : 0u; meta[1] = 0; meta[2] = fp; meta[3] = 0;
+  if (!has) return;
+  uint32_t state = fp, L = 0;
+  while (pstate[state] != kNoState) {
+    const uint32_t src = pstate[state];
+    if (L >= cap) { meta[3] = 1; break; }
+    Tr tr = arcs[off[src] + ppos[state]];
+    tr.nextstate = L;
+    out_arcs[L++] = tr;
+    state = src;
+  }
+  meta[1] = L;
+}
+__global__ void k_of_final_keys(const float* __restrict__ fin, uint32_t n, const uint32_t* __restrict__ order,
+                                unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+                                uint32_t* __restrict__ count) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool f = s < n && fin[s] != w_zero();
+  uint32_t active = __activemask();
+  uint32_t m = __ballot_sync(active, f);
+  if (!m) return;
+  uint32_t lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+  if (lane == leader) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(active, base, leader);
+  if (f) {
+    const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
+    keys[p] = order ? order[s] : s;
+    vals[p] = s;
+  }
+}
+
 // Rebuild the output FST on the host from the path arcs, replaying the reference's mutation sequence so the
 // property word comes out identical (add_state; add_tr | set_final; ...; set_start; shortest_path_properties).
 CsrFst build_path_fst(bool found, const std::vector<Tr>& path, float final_w) {
@@ -546,6 +667,56 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
       B200_CUDA(cudaMemcpyAsync(hmeta, meta.p, 16, cudaMemcpyDeviceToHost, s));
       B200_CUDA(cudaStreamSynchronize(s));
       st.path = 0;
+      done = true;
+    }
+  }
+
+  if (!done && parallel_ok) {  // certificate failed: order-faithful parallel fold over a sorted reverse CSR
+    const uint32_t A = f.num_arcs;
+    DevBuf<unsigned long long> k_in(s, A ? A : 1), k_out(s, A ? A : 1), fk_in(s, n), fk_out(s, n);
+    DevBuf<uint32_t> v_in(s, A ? A : 1), in_arc(s, A ? A : 1), src_of(s, A ? A : 1), indeg(s, n), roff(s, (size_t)n + 1),
+        topo(s, n), ctl(s, 4), fv_in(s, n), fv_out(s, n), pstate(s, n), ppos(s, n);
+    DevBuf<float> distf(s, n);
+    DevBuf<uint8_t> tmp(s);
+    B200_CUDA(cudaMemsetAsync(indeg.p, 0, (size_t)n * 4, s));
+    B200_CUDA(cudaMemsetAsync(ctl.p, 0, 16, s));
+    k_of_keys<<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, order_p, k_in.p, v_in.p, src_of.p, indeg.p);
+    B200_CUDA(cudaMemcpyAsync(roff.p, indeg.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    B200_CUDA(cudaMemsetAsync(roff.p + n, 0, 4, s));
+    exclusive_sum_u32(roff.p, roff.p, (size_t)n + 1, tmp, s);
+    sort_pairs_u64_u32(k_in.p, k_out.p, v_in.p, in_arc.p, A, 64, tmp, s);
+    k_of_roots<<<blocks_for(n), kThreads, 0, s>>>(indeg.p, n, topo.p, ctl.p);
+    uint32_t n_roots = read_u32(ctl.p, s);
+    st.kernel_launches += 2;
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_of_fold, kThreads, 0));
+    if (per_sm < 1) throw FstError("cooperative fold kernel does not fit on the device");
+    int grid = sm_count() * per_sm;
+    const uint32_t* a_off = f.offsets.p; const Tr* a_arcs = f.arcs.p; uint32_t nn = n, src0 = f.start;
+    const uint32_t* a_roff = roff.p; const uint32_t* a_in = in_arc.p; const uint32_t* a_src = src_of.p;
+    uint32_t* a_indeg = indeg.p; uint32_t* a_topo = topo.p; float* a_dist = distf.p;
+    uint32_t* a_ps = pstate.p; uint32_t* a_pp = ppos.p; uint32_t* a_ctl = ctl.p;
+    void* args[] = {&a_off, &a_arcs, &nn, &src0, &a_roff, &a_in, &a_src, &a_indeg, &a_topo, &a_dist, &a_ps, &a_pp,
+                    &a_ctl, &n_roots};
+    B200_CUDA(cudaLaunchCooperativeKernel((void*)k_of_fold, dim3(grid), dim3(kThreads), args, 0, s));
+    st.kernel_launches++;
+    uint32_t hctl[4];
+    B200_CUDA(cudaMemcpyAsync(hctl, ctl.p, 16, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    if (hctl[2] == n) {  // every state was scheduled: the graph is a DAG
+      // final states in processing order
+      B200_CUDA(cudaMemsetAsync(ctl.p + 3, 0, 4, s));
+      k_of_final_keys<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, order_p, fk_in.p, fv_in.p, ctl.p + 3);
+      uint32_t n_fin = read_u32(ctl.p + 3, s);
+      sort_pairs_u64_u32(fk_in.p, fk_out.p, fv_in.p, fv_out.p, n_fin, 32, tmp, s);
+      k_of_finish<<<1, 32, 0, s>>>(f.offsets.p, f.arcs.p, f.finals.p, distf.p, fv_out.p, n_fin, pstate.p, ppos.p,
+                                   out_arcs.p, cap, meta.p);
+      st.kernel_launches += 2;
+      B200_CUDA(cudaMemcpyAsync(hmeta, meta.p, 16, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      st.waves = hctl[1];
+      st.arcs_relaxed = A; st.states_settled = n;
+      st.path = 2;
       done = true;
     }
   }

@@ -34,6 +34,13 @@ def _degrees(rng, n_src, n_arcs):
     return deg
 
 
+def _weights(rng, size, continuous):
+    """Dyadic grid k/64 (every path sum exact in f32, ties exact) or continuous U[0, 10) (near-ties within KDELTA)."""
+    if continuous:
+        return (rng.random(size) * 10.0).astype(np.float32)
+    return rng.integers(0, 640, size=size).astype(np.float32) / np.float32(64.0)
+
+
 def _finish(n, offsets, arcs, finals, acceptor, sorted_i, sorted_o):
     pr = (P.ACYCLIC | P.INITIAL_ACYCLIC | P.TOP_SORTED | P.NO_EPSILONS | P.NO_I_EPSILONS | P.NO_O_EPSILONS |
           P.WEIGHTED | P.ACCESSIBLE | P.UNWEIGHTED_CYCLES | P.NOT_STRING)
@@ -46,7 +53,7 @@ def _finish(n, offsets, arcs, finals, acceptor, sorted_i, sorted_o):
             "props": int(pr), "num_states": int(n)}
 
 
-def layered_acceptor(n_states, n_arcs, vocab, seed, levels=32, start_fanout=False):
+def layered_acceptor(n_states, n_arcs, vocab, seed, levels=32, start_fanout=False, continuous=False):
     """Random layered acceptor (ilabel == olabel), arcs sorted by label.  With start_fanout the start state has one
     arc to every state of level 1 (a wide lattice from the first wave on) instead of ~A/N arcs."""
     rng = np.random.default_rng(seed)
@@ -65,17 +72,18 @@ def layered_acceptor(n_states, n_arcs, vocab, seed, levels=32, start_fanout=Fals
     target = base[level + 1] + rng.integers(0, w, size=total, dtype=np.int64)
     if start_fanout:
         target[:w] = base[1] + np.arange(w)
-    weight = rng.integers(0, 640, size=total).astype(np.float32) / np.float32(64.0)
+    weight = _weights(rng, total, continuous)
     order = np.lexsort((label, src))  # stable: by src, then label
     arcs = np.zeros(total, dtype=TR_DTYPE)
     arcs["ilabel"] = label[order]; arcs["olabel"] = label[order]
     arcs["weight"] = weight[order]; arcs["nextstate"] = target[order]
     finals = np.full(n, np.inf, dtype=np.float32)
-    finals[n - w:] = rng.integers(0, 640, size=w).astype(np.float32) / np.float32(64.0)
+    finals[n - w:] = _weights(rng, w, continuous)
     return _finish(n, offsets, arcs, finals, True, True, True)
 
 
-def bigram_transducer(n_states, n_arcs, vocab, seed, levels=32, out_vocab=None, start_fanout=False):
+def bigram_transducer(n_states, n_arcs, vocab, seed, levels=32, out_vocab=None, start_fanout=False,
+                      continuous=False):
     """Layered transducer whose arc target is a function of the input label (LM-like); ilabel-sorted.
     With start_fanout the start state carries every input label once."""
     rng = np.random.default_rng(seed)
@@ -97,13 +105,13 @@ def bigram_transducer(n_states, n_arcs, vocab, seed, levels=32, out_vocab=None, 
         ilabel[:vocab] = np.arange(1, vocab + 1)
     # a per-level rotation keeps consecutive levels from using the same slots for the same label
     target = base[level + 1] + (ilabel - 1 + 7919 * level) % w
-    weight = rng.integers(0, 640, size=total).astype(np.float32) / np.float32(64.0)
+    weight = _weights(rng, total, continuous)
     order = np.lexsort((olabel, ilabel, src))
     arcs = np.zeros(total, dtype=TR_DTYPE)
     arcs["ilabel"] = ilabel[order]; arcs["olabel"] = olabel[order]
     arcs["weight"] = weight[order]; arcs["nextstate"] = target[order]
     finals = np.full(n, np.inf, dtype=np.float32)
-    finals[n - w:] = rng.integers(0, 640, size=w).astype(np.float32) / np.float32(64.0)
+    finals[n - w:] = _weights(rng, w, continuous)
     return _finish(n, offsets, arcs, finals, False, True, False)
 
 

@@ -254,3 +254,31 @@ def test_batched_compose_heterogeneous_falls_back():
     results, _ = R.compose_batch([p for p, _ in pairs], pb)
     for (p, o), r in zip(pairs, results):
         assert_same(r, O.compose(o, ob), "heterogeneous batch")
+
+
+def test_shortest_path_with_near_ties_uses_the_order_faithful_parallel_path():
+    """Continuous weights produce candidates within KDELTA of each other, so the certificate of the atomicMin path
+    fails; the order-faithful parallel fold must then reproduce the reference's approximate relaxation exactly
+    (shortest_path.rs:222-236), for both topological queue kinds."""
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    # (1) TOP_SORTED lattice -> StateOrderQueue
+    g = synth.layered_acceptor(200_000, 2_000_000, 1000, 6, 40, continuous=True)
+    p, o = both_from_dict(g)
+    got, st = R.shortestpath_with_stats(p)
+    assert st["queue_kind"] == 0 and st["path"] == 2, st
+    assert_same(got, O.shortest_path(o), "continuous weights, state order")
+    # (2) composed lattice: ACYCLIC known, TOP_SORTED unknown -> TopOrderQueue over the DFS order
+    a = synth.layered_acceptor(20_000, 200_000, 32, 1, 20, continuous=True)
+    b = synth.bigram_transducer(20_000, 200_000, 32, 2, 20, out_vocab=500, continuous=True)
+    pa, oa = both_from_dict(a)
+    pb, ob = both_from_dict(b)
+    pc, oc = pa.compose(pb), O.compose(oa, ob)
+    assert_same(pc, oc, "continuous weights compose")
+    got, st = R.shortestpath_with_stats(pc)
+    assert st["queue_kind"] == 1 and st["path"] in (0, 2), st
+    assert_same(got, O.shortest_path(oc), f"continuous weights, top order (path={st['path']})")
+    # the serial replay agrees as well
+    got2, st2 = R.shortestpath_with_stats(pc, force_serial=True)
+    assert st2["path"] == 1
+    assert_same(got2, O.shortest_path(oc), "continuous weights, serial replay")

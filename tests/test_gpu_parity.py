@@ -282,3 +282,66 @@ def test_shortest_path_with_near_ties_uses_the_order_faithful_parallel_path():
     got2, st2 = R.shortestpath_with_stats(pc, force_serial=True)
     assert st2["path"] == 1
     assert_same(got2, O.shortest_path(oc), "continuous weights, serial replay")
+
+
+def test_dense_product_overflows_presized_buffers_and_falls_back():
+    """Single-label complete machines: the product has (n1*n2) states and (n1*n2)^2-ish arcs, far beyond the
+    persistent kernel's pre-sized buffers (4 x input arcs) -> it must stop cleanly and the growing multi-kernel back
+    end must produce the same FST as the oracle (also exercises table rehash and buffer growth)."""
+    import rustfst_b200 as R
+    from rustfst_b200.fst import TR_DTYPE
+    from rustfst_b200 import props as P
+
+    def complete(n, seed):
+        rng = np.random.default_rng(seed)
+        arcs = np.zeros(n * n, dtype=TR_DTYPE)
+        arcs["ilabel"] = 1; arcs["olabel"] = 1
+        arcs["weight"] = rng.integers(0, 64, size=n * n) / 8.0
+        arcs["nextstate"] = np.tile(np.arange(n), n)
+        finals = np.full(n, np.inf, dtype=np.float32); finals[n - 1] = 0.5
+        d = {"offsets": (np.arange(n + 1) * n).astype(np.uint32), "arcs": arcs, "finals": finals, "start": 0,
+             "props": 0, "num_states": n}
+        o = O.OFst.from_csr(d["offsets"].astype(np.uint64), arcs, finals, 0, 0)
+        o.compute_props()
+        d["props"] = o.props
+        return d
+
+    pa, oa = both_from_dict(complete(40, 1))
+    pb, ob = both_from_dict(complete(45, 2))
+    got, st = R.compose_with_stats(pa, pb)
+    assert st["emit_launches"] > 1, "expected the fallback (multi-kernel) back end"
+    assert st["arcs_emitted"] == (40 * 45) * (40 * 45)
+    assert_same(got, O.compose(oa, ob), "dense product")
+
+
+def test_hub_state_with_long_label_runs():
+    """Degree / run-length skew: one state with 20 000 arcs over 5 labels on each side (runs of ~4000 equal labels),
+    so single items expand to thousands of arcs and single states to 20 001 items."""
+    import rustfst_b200 as R
+    from rustfst_b200.fst import TR_DTYPE
+    rng = np.random.default_rng(3)
+
+    def hub(n_leaf, deg, labels, by, seed):
+        r = np.random.default_rng(seed)
+        lab = np.sort(r.integers(1, labels + 1, size=deg))
+        arcs = np.zeros(deg + n_leaf, dtype=TR_DTYPE)
+        other = r.integers(1, labels + 1, size=deg)
+        arcs["ilabel"][:deg] = lab if by == "ilabel" else other
+        arcs["olabel"][:deg] = lab if by == "olabel" else other
+        arcs["weight"][:deg] = r.integers(0, 64, size=deg) / 8.0
+        arcs["nextstate"][:deg] = r.integers(1, n_leaf + 1, size=deg)
+        # leaves loop back to the hub with one arc each
+        arcs["ilabel"][deg:] = 1; arcs["olabel"][deg:] = 1; arcs["weight"][deg:] = 0.25; arcs["nextstate"][deg:] = 0
+        offsets = np.concatenate([[0, deg], deg + 1 + np.arange(n_leaf)]).astype(np.uint32)
+        finals = np.full(n_leaf + 1, np.inf, dtype=np.float32); finals[1] = 1.0
+        d = {"offsets": offsets, "arcs": arcs, "finals": finals, "start": 0, "props": 0, "num_states": n_leaf + 1}
+        o = O.OFst.from_csr(offsets.astype(np.uint64), arcs, finals, 0, 0)
+        o.compute_props()
+        d["props"] = o.props
+        return d
+
+    pa, oa = both_from_dict(hub(30, 20000, 5, "olabel", 10))
+    pb, ob = both_from_dict(hub(30, 600, 5, "ilabel", 11))
+    for connect in (False, True):
+        got = R.compose_with_config(pa, pb, R.ComposeConfig(R.ComposeFilter.AUTOFILTER, connect))
+        assert_same(got, O.compose(oa, ob, connect=connect), f"hub connect={connect}")

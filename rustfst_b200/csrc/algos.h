@@ -66,6 +66,9 @@ struct TrimExtras {  // optional per-state payload carried through the compactio
 DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_t n_waves, uint64_t* launches,
                             cudaStream_t s, const TrimExtras* extras = nullptr);
 
+// Stable per-state arc sort by input or output label, in place on the device (algorithms/tr_sort.rs:51-62).
+void tr_sort_device(DevFst& f, bool ilabel, cudaStream_t s);
+
 // ---- shortest path (n = 1)
 enum QueueKind : int { kStateOrderQueue = 0, kTopOrderQueue = 1, kLifoQueue = 2, kSccQueue = 3 };
 

@@ -208,7 +208,22 @@ RUSTFST_FFI_RESULT fst_connect(CFst* ptr) {
   });
 }
 RUSTFST_FFI_RESULT fst_tr_sort(CFst* ptr, bool ilabel_comp) {
-  return wrap([&] { nn(ptr, "fst")->fst.tr_sort(ilabel_comp); });
+  return wrap([&] {
+    nn(ptr, "fst");
+    // Large machines are sorted on the device (one radix sort + gather); small ones, and any machine on a box
+    // without a GPU, by the host container (same stable order either way; tr_sort is not part of the hot path).
+    int ndev = 0;
+    const CsrFst& h = ptr->fst.freeze();
+    if (h.arcs.size() >= (1u << 16) && h.inf_finals.empty() && cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+      Stream st;
+      DevFst d = upload(h, st.s);
+      tr_sort_device(d, ilabel_comp, st.s);
+      ptr->fst.replace(download(d, st.s));
+      return;
+    }
+    cudaGetLastError();
+    ptr->fst.tr_sort(ilabel_comp);
+  });
 }
 
 // ---------------------------------------------------------------- Fst accessors

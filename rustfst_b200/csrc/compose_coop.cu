@@ -61,6 +61,7 @@ struct CoopParams {
   uint32_t* part_new;     // gridDim entries: first emissions found in each CTA's arc slice
   uint32_t* ctl;          // [1] overflow flags, [2] #states, [3] #arcs
   uint32_t* wave_lo; uint32_t wave_cap;  // first product id of every BFS wave (+ one-past-the-end sentinel)
+  unsigned int* barrier;  // arrival counter of grid_barrier (zero-initialised)
   uint32_t n_starts;      // initial frontier = product ids [0, n_starts) (1 for a plain compose, batch size otherwise)
   unsigned long long* stats;  // states_expanded, arcs_iterated, arcs_emitted, waves, ns phase A, B, C, D
 };
@@ -93,6 +94,7 @@ k_compose_coop(CoopParams P) {
   uint32_t* s_pref_b = s_dyn + gridDim.x + 1;  // arcs (B)
 
   const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
+  unsigned int bar_epoch = 0;
   uint32_t lo = 0, hi = P.n_starts, base = 0;  // uniform across the grid by construction
   unsigned long long n_states_exp = 0, n_items = 0, n_arcs = 0, n_waves = 0;
   unsigned long long t_a = 0, t_b = 0, t_c = 0, t_d = 0;
@@ -135,7 +137,7 @@ k_compose_coop(CoopParams P) {
       }
       if (tid == 0) P.part_items[c] = run;
     }
-    grid.sync();
+    grid_barrier(P.barrier, bar_epoch);
 
     // ------------------------------------------------------------------ A1: per-item matching
     cta_prefix_to_smem(P.part_items, G, s_pref_a, s_warp);
@@ -230,7 +232,7 @@ k_compose_coop(CoopParams P) {
       }
     }
     if (tid == 0) P.part_arcs[c] = my_arcs;
-    grid.sync();
+    grid_barrier(P.barrier, bar_epoch);
     unsigned long long tp1 = globaltimer_ns();
 
     // ------------------------------------------------------------------ B: emit
@@ -306,7 +308,7 @@ k_compose_coop(CoopParams P) {
         P.out_offsets[lo + i] = base + s_pref_b[t_first / ic] + __ldcg(&P.st_arc_loc[i]);
       }
     }
-    grid.sync();
+    grid_barrier(P.barrier, bar_epoch);
     unsigned long long tp2 = globaltimer_ns();
 
     // ------------------------------------------------------------------ C: rank first emissions
@@ -329,7 +331,7 @@ k_compose_coop(CoopParams P) {
       }
       if (tid == 0) P.part_new[c] = cta_new;
     }
-    grid.sync();
+    grid_barrier(P.barrier, bar_epoch);
     unsigned long long tp3 = globaltimer_ns();
 
     // ------------------------------------------------------------------ D: resolve
@@ -359,7 +361,7 @@ k_compose_coop(CoopParams P) {
     base += E;
     lo = hi;
     hi += n_new;
-    grid.sync();
+    grid_barrier(P.barrier, bar_epoch);
     unsigned long long tp4 = globaltimer_ns();
     t_a += tp1 - tp0; t_b += tp2 - tp1; t_c += tp3 - tp2; t_d += tp4 - tp3;
   }
@@ -381,7 +383,7 @@ __global__ void k_coop_init(Slot* slots, uint32_t mask, unsigned long long* tupl
                             const uint32_t* __restrict__ starts1, uint32_t single_start1, uint32_t start2,
                             uint32_t n_starts, uint32_t* ctl) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { ctl[0] = ctl[1] = ctl[2] = ctl[3] = 0; }
+  if (i == 0) { for (int k = 0; k < 8; k++) ctl[k] = 0; }
   if (i >= n_starts) return;
   const unsigned long long key = pack_key(start_fs, starts1 ? starts1[i] : single_start1, start2);
   uint32_t h = hash_key(key) & mask;
@@ -499,6 +501,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   P.recs = recs.p; P.arc_loc = arc_loc.p; P.items_cap = (uint32_t)std::min<size_t>(items_cap, 0xFFFFFFF0ull);
   P.part_arcs = parts.p; P.part_items = parts.p + 2048; P.part_new = parts.p + 4096;
   P.ctl = ctl.p; P.stats = dstats.p;
+  P.barrier = ctl.p + 6;
   P.wave_lo = wave_lo.p; P.wave_cap = wave_cap;
   uint32_t start_fs = (kind == kNullFilter || kind == kTrivialFilter || kind == kNoMatchFilter) ? 1u : 0u;
   P.n_starts = n_starts;

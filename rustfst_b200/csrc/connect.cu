@@ -367,4 +367,42 @@ DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_
   return out;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// tr_sort on the device (rustfst/src/algorithms/tr_sort.rs:51-62: stable per-state sort by ilabel or olabel).
+// One stable LSD radix sort of (state << 32 | label) over all arcs + one gather; state order and, inside equal
+// labels, the original arc order are preserved exactly as Vec::sort_by does.
+namespace {
+__global__ void k_sort_keys(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, int by_ilabel,
+                            unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  for (uint32_t e = off[s]; e < off[s + 1]; e++) {
+    const Label l = by_ilabel ? __ldg(&arcs[e].ilabel) : __ldg(&arcs[e].olabel);
+    keys[e] = ((unsigned long long)s << 32) | l;
+    vals[e] = e;
+  }
+}
+__global__ void k_gather_arcs(const Tr* __restrict__ in, const uint32_t* __restrict__ perm, uint32_t a,
+                              Tr* __restrict__ out) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a) return;
+  *reinterpret_cast<int4*>(&out[e]) = __ldg(reinterpret_cast<const int4*>(&in[perm[e]]));
+}
+}  // namespace
+
+void tr_sort_device(DevFst& f, bool ilabel, cudaStream_t s) {
+  const uint32_t n = f.num_states, a = f.num_arcs;
+  if (a == 0) return;
+  DevBuf<unsigned long long> k_in(s, a), k_out(s, a);
+  DevBuf<uint32_t> v_in(s, a), perm(s, a);
+  DevBuf<Tr> sorted(s, a);
+  DevBuf<uint8_t> tmp(s);
+  k_sort_keys<<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, ilabel ? 1 : 0, k_in.p, v_in.p);
+  sort_pairs_u64_u32(k_in.p, k_out.p, v_in.p, perm.p, a, 64, tmp, s);
+  k_gather_arcs<<<blocks_for(a), kThreads, 0, s>>>(f.arcs.p, perm.p, a, sorted.p);
+  f.arcs = std::move(sorted);
+  f.props = props::after_tr_sort(f.props, ilabel) & props::kTrinary;
+  B200_CUDA(cudaStreamSynchronize(s));
+}
+
 }  // namespace b200

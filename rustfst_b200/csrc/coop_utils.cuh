@@ -17,6 +17,25 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// Grid-wide barrier on a monotonically increasing arrival counter (no reset, so no second phase): the k-th barrier
+// completes when the counter reaches k * gridDim.x.  Requires all CTAs to be co-resident (cooperative launch).
+// Lighter than cg::grid_group::sync(): one release atomic and acquire-load polling by one thread per CTA, no L1
+// invalidation inside the spin.  Cross-CTA data read after the barrier must bypass L1 (__ldcg / volatile / atomics).
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __syncthreads();
+  epoch++;
+  if (threadIdx.x == 0) {
+    const unsigned int target = epoch * gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - target) < 0);
+  }
+  __syncthreads();
+}
+
 // Exclusive scan of one value per thread over the CTA (256 threads); returns the exclusive prefix, total in `total`.
 __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_warp /*8*/, uint32_t& total) {
   const uint32_t wl = threadIdx.x & 31, wid = threadIdx.x >> 5;

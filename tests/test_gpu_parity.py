@@ -345,3 +345,14 @@ def test_hub_state_with_long_label_runs():
     for connect in (False, True):
         got = R.compose_with_config(pa, pb, R.ComposeConfig(R.ComposeFilter.AUTOFILTER, connect))
         assert_same(got, O.compose(oa, ob, connect=connect), f"hub connect={connect}")
+
+
+def test_tr_sort_on_device_is_stable():
+    """fst_tr_sort of a large machine runs on the device (radix sort + gather) and must order arcs exactly like
+    the reference's stable per-state sort (algorithms/tr_sort.rs:51-62)."""
+    rng = np.random.default_rng(21)
+    d = random_fst(rng, 20000, 12, 6, eps_prob=0.1)   # ~120k arcs: above the device threshold; many equal labels
+    for ilabel in (True, False):
+        p, o = both_from_dict(d)
+        p.tr_sort(ilabel); o.tr_sort(ilabel)
+        assert_same(p, o, f"device tr_sort ilabel={ilabel}")

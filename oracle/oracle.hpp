@@ -620,19 +620,66 @@ struct StateTable {
   }
 };
 
+// matchers/sigma_matcher.rs: SigmaMatcherConfig {sigma_label, rewrite_mode, sigma_allowed_matches}
+struct SigmaConfig {
+  bool enabled = false;
+  Label sigma_label = NO_LABEL;
+  int rewrite_mode = 0;  // 0 Auto (rewrite both iff ACCEPTOR), 1 Always, 2 Never  (matchers/mod.rs:69-75)
+  bool has_allowed = false;
+  std::unordered_set<Label> allowed;
+};
+
 struct ComposeConfig {
   int filter = AUTO;
   bool connect = true;
+  SigmaConfig sigma1, sigma2;  // matcher1_config / matcher2_config (compose_static.rs:80-97)
 };
 
 struct ComposeStats {
   uint64_t states_expanded = 0, arcs_iterated = 0, arcs_emitted = 0;
 };
 
+// SortedMatcher lookup of `label` among the arcs of one state on the matched side: [pos, end) run.
+// by_olabel selects the field (MatchOutput on fst1) — sorted_matcher.rs:124-184.
+inline void sorted_run(const std::vector<Tr>& trs, bool by_olabel, Label ml, size_t* pos, size_t* end) {
+  size_t p = std::lower_bound(trs.begin(), trs.end(), ml, [by_olabel](const Tr& x, Label l) {
+               return (by_olabel ? x.olabel : x.ilabel) < l; }) - trs.begin();
+  size_t e = p;
+  while (e < trs.size() && (by_olabel ? trs[e].olabel : trs[e].ilabel) == ml) e++;
+  *pos = p; *end = e;
+}
+// has_sigma (sigma_matcher.rs:33-45): the inner sorted matcher finds at least one arc labelled sigma
+inline bool state_has_sigma(const std::vector<Tr>& trs, bool by_olabel, const SigmaConfig& sc) {
+  if (!sc.enabled || sc.sigma_label == NO_LABEL) return false;
+  if (sc.sigma_label == EPS_LABEL) return true;  // (never constructed: SigmaMatcher::new rejects it)
+  size_t p, e;
+  sorted_run(trs, by_olabel, sc.sigma_label, &p, &e);
+  return e > p;
+}
+
 // compose_static.rs:198-298 + compose_fst_op.rs + lazy_fst.rs:226-269
 inline Fst compose(const Fst& fst1, const Fst& fst2, const ComposeConfig& cfg, ComposeStats* stats = nullptr) {
   int kind = cfg.filter == AUTO ? SEQUENCE : cfg.filter;  // compose_fst.rs:58-92 (new_auto = Sequence filter)
   if (kind < NULLF || kind > NO_MATCH) throw std::runtime_error("EnumConversionError");
+
+  // compose_static.rs:219-223
+  if (cfg.filter == AUTO && (cfg.sigma1.enabled || cfg.sigma2.enabled))
+    throw std::runtime_error("Custom MatcherConfig not supported with AutoFilter");
+  // SigmaMatcher::new (sigma_matcher.rs:55-84)
+  for (const SigmaConfig* sc : {&cfg.sigma1, &cfg.sigma2}) {
+    if (!sc->enabled) continue;
+    if (sc->rewrite_mode < 0 || sc->rewrite_mode > 2) throw std::runtime_error("EnumConversionError");
+    if (sc->sigma_label == EPS_LABEL) throw std::runtime_error("SigmaMatcher: 0 cannot be used as sigma_label");
+  }
+  const bool rewrite_both1 = cfg.sigma1.rewrite_mode == 1 || (cfg.sigma1.rewrite_mode == 0 && (fst1.props & P::ACCEPTOR));
+  const bool rewrite_both2 = cfg.sigma2.rewrite_mode == 1 || (cfg.sigma2.rewrite_mode == 0 && (fst2.props & P::ACCEPTOR));
+  // compose_fst_op.rs:170-179: a sigma matcher carries REQUIRE_MATCH (sigma_matcher.rs:126-132)
+  if (cfg.sigma1.enabled && cfg.sigma1.sigma_label != NO_LABEL &&
+      sorted_match_type(fst1, MatchOutput, true) != MatchOutput)
+    throw std::runtime_error("ComposeFst: 1st argument cannot perform required matching (sort?)");
+  if (cfg.sigma2.enabled && cfg.sigma2.sigma_label != NO_LABEL &&
+      sorted_match_type(fst2, MatchInput, true) != MatchInput)
+    throw std::runtime_error("ComposeFst: 2nd argument cannot perform required matching (sort?)");
 
   // compose_fst_op.rs:169-197 match_type (SortedMatcher flags are empty => REQUIRE_MATCH tests are no-ops)
   MatchType type1 = sorted_match_type(fst1, MatchOutput, false);
@@ -687,7 +734,14 @@ inline Fst compose(const Fst& fst1, const Fst& fst2, const ComposeConfig& cfg, C
     bool match_input;
     if (mt == MatchInput) match_input = true;
     else if (mt == MatchOutput) match_input = false;
-    else match_input = st1.trs.size() <= st2.trs.size();
+    else {
+      // SigmaMatcher::priority (sigma_matcher.rs:134-146): REQUIRE_PRIORITY when the state has a sigma arc
+      const bool req1 = state_has_sigma(st1.trs, true, cfg.sigma1), req2 = state_has_sigma(st2.trs, false, cfg.sigma2);
+      if (req1 && req2) throw std::runtime_error("Both sides can't require match");
+      if (req1) match_input = false;
+      else if (req2) match_input = true;
+      else match_input = st1.trs.size() <= st2.trs.size();
+    }
 
     std::vector<Tr> trs;
     // ordered_expand: compose_fst_op.rs:221-265; match_tr:324-353; match_tr_selected:287-322
@@ -710,6 +764,26 @@ inline Fst compose(const Fst& fst1, const Fst& fst2, const ComposeConfig& cfg, C
           pos = std::lower_bound(st2.trs.begin(), st2.trs.end(), ml,
                                  [](const Tr& x, Label l) { return x.ilabel < l; }) - st2.trs.begin();
         }
+        if (cfg.sigma2.enabled) {  // IteratorSigmaMatcher::new (sigma_matcher.rs:196-246) over matcher2
+          const SigmaConfig& sc = cfg.sigma2;
+          if (label == sc.sigma_label && sc.sigma_label != NO_LABEL)
+            throw std::runtime_error("SigmaMatcher::Find: bad label (sigma)");
+          const bool normal_nonempty = current_loop || (pos < st2.trs.size() && st2.trs[pos].ilabel == ml);
+          if (!normal_nonempty) {
+            if (state_has_sigma(st2.trs, false, sc) && label != EPS_LABEL && label != NO_LABEL &&
+                (!sc.has_allowed || sc.allowed.count(label))) {
+              size_t sp, se;
+              sorted_run(st2.trs, false, sc.sigma_label, &sp, &se);
+              for (size_t q = sp; q < se; q++) {  // value_openfst (sigma_matcher.rs:249-276): relabel sigma -> label
+                Tr t = st2.trs[q];
+                if (rewrite_both2) { if (t.ilabel == sc.sigma_label) t.ilabel = label; if (t.olabel == sc.sigma_label) t.olabel = label; }
+                else t.ilabel = label;
+                emit(a1, t);
+              }
+            }
+            return;  // next_openfst never switches from normal to sigma matches (r.is_none() is never true there)
+          }
+        }
         if (current_loop) {  // IterItemMatcher::EpsLoop -> matchers/mod.rs:98-105 (MatchInput)
           Tr loop2{NO_LABEL, EPS_LABEL, W_ONE, s2};
           emit(a1, loop2);
@@ -729,6 +803,26 @@ inline Fst compose(const Fst& fst1, const Fst& fst2, const ComposeConfig& cfg, C
         if (!current_loop) {
           pos = std::lower_bound(st1.trs.begin(), st1.trs.end(), ml,
                                  [](const Tr& x, Label l) { return x.olabel < l; }) - st1.trs.begin();
+        }
+        if (cfg.sigma1.enabled) {  // sigma matcher on fst1 (MatchOutput)
+          const SigmaConfig& sc = cfg.sigma1;
+          if (label == sc.sigma_label && sc.sigma_label != NO_LABEL)
+            throw std::runtime_error("SigmaMatcher::Find: bad label (sigma)");
+          const bool normal_nonempty = current_loop || (pos < st1.trs.size() && st1.trs[pos].olabel == ml);
+          if (!normal_nonempty) {
+            if (state_has_sigma(st1.trs, true, sc) && label != EPS_LABEL && label != NO_LABEL &&
+                (!sc.has_allowed || sc.allowed.count(label))) {
+              size_t sp, se;
+              sorted_run(st1.trs, true, sc.sigma_label, &sp, &se);
+              for (size_t q = sp; q < se; q++) {
+                Tr t = st1.trs[q];
+                if (rewrite_both1) { if (t.ilabel == sc.sigma_label) t.ilabel = label; if (t.olabel == sc.sigma_label) t.olabel = label; }
+                else t.olabel = label;
+                emit(t, a2);
+              }
+            }
+            return;
+          }
         }
         if (current_loop) {  // eps_loop(MatchOutput)
           Tr loop1{EPS_LABEL, NO_LABEL, W_ONE, s1};

@@ -75,7 +75,57 @@ int oracle_fst_from_csr(uint64_t nstates, const uint64_t* offsets, const Tr* arc
   });
 }
 
+// sigma: optional 2 x {enabled, sigma_label, rewrite_mode, n_allowed, allowed...} flattened; NULL = no sigma matcher
+static void fill_sigma(SigmaConfig& sc, const uint32_t*& p) {
+  sc.enabled = *p++ != 0;
+  sc.sigma_label = *p++;
+  sc.rewrite_mode = (int)*p++;
+  uint32_t n = *p++;
+  sc.has_allowed = n > 0;
+  for (uint32_t i = 0; i < n; i++) sc.allowed.insert(*p++);
+}
 // stats: [states_expanded, arcs_iterated, arcs_emitted]; seconds: wall time of the algorithm only
+int oracle_compose_sigma(void* a, void* b, int filter, int do_connect, const uint32_t* sigma, void** out) {
+  GUARD({
+    ComposeConfig cfg; cfg.filter = filter; cfg.connect = do_connect != 0;
+    const uint32_t* p = sigma;
+    fill_sigma(cfg.sigma1, p);
+    fill_sigma(cfg.sigma2, p);
+    *out = new Fst(compose(*(Fst*)a, *(Fst*)b, cfg, nullptr));
+  });
+}
+// number of successful paths of an acyclic FST (fst_traits/paths_iterator.rs semantics: start -> any final state)
+int oracle_count_paths(void* fp, uint64_t* count) {
+  try {
+    Fst& f = *(Fst*)fp;
+    *count = 0;
+    if (!f.has_start) return 0;
+    std::vector<uint64_t> memo(f.num_states(), ~0ull);
+    std::vector<std::pair<StateId, size_t>> stack;
+    std::vector<uint8_t> onstack(f.num_states(), 0);
+    // iterative post-order DP; throws on cycles
+    stack.push_back({f.start, 0});
+    onstack[f.start] = 1;
+    std::vector<uint64_t> acc(f.num_states(), 0);
+    while (!stack.empty()) {
+      auto& fr = stack.back();
+      StateId s = fr.first;
+      if (fr.second < f.states[s].trs.size()) {
+        StateId t = f.states[s].trs[fr.second].nextstate;
+        if (memo[t] != ~0ull) { acc[s] += memo[t]; fr.second++; }
+        else if (onstack[t]) throw std::runtime_error("cyclic");
+        else { onstack[t] = 1; stack.push_back({t, 0}); }
+      } else {
+        memo[s] = acc[s] + (f.states[s].has_final ? 1 : 0);
+        onstack[s] = 0;
+        stack.pop_back();
+        if (!stack.empty()) { acc[stack.back().first] += memo[s]; stack.back().second++; }
+      }
+    }
+    *count = memo[f.start];
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
 int oracle_compose(void* a, void* b, int filter, int do_connect, void** out, uint64_t* stats, double* seconds) {
   GUARD({
     ComposeConfig cfg; cfg.filter = filter; cfg.connect = do_connect != 0;

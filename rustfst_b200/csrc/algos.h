@@ -1,5 +1,7 @@
 // algos.h — device algorithms behind fst_compose* / fst_connect / fst_shortest_path* (see include/rustfst_b200.h).
 #pragma once
+#include <vector>
+
 #include "device_common.cuh"
 
 namespace b200 {
@@ -10,9 +12,18 @@ enum ComposeFilter : int {
   kMatchFilter = 5, kNoMatchFilter = 6
 };
 
+// rustfst/src/algorithms/compose/matchers/sigma_matcher.rs + compose_static.rs:34-58 (MatcherConfig)
+struct SigmaSpec {
+  bool enabled = false;
+  uint32_t sigma_label = kNoLabel;
+  int rewrite_mode = 0;            // 0 Auto (rewrite both labels iff the FST is an acceptor), 1 Always, 2 Never
+  std::vector<uint32_t> allowed;   // empty = every label may match sigma
+};
+
 struct ComposeOptions {  // rustfst/src/algorithms/compose/compose_static.rs:80-97
   int filter = kAutoFilter;
   bool connect = true;
+  SigmaSpec sigma1, sigma2;        // matcher1_config (fst1, MatchOutput) / matcher2_config (fst2, MatchInput)
 };
 
 struct ComposeStats {

@@ -1,5 +1,6 @@
 // capi.cu — the extern "C" surface declared in include/rustfst_b200.h.
 // Error convention and handle ownership follow rustfst-ffi/src/lib.rs:29-85 and rustfst-ffi/src/fst/mod.rs.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -71,11 +72,15 @@ ComposeOptions to_options(const CComposeConfig* c) {
   if (c->filter > 6) throw FstError("EnumConversionError");
   o.filter = (int)c->filter;
   o.connect = c->connect;
-  if (c->has_m1 || c->has_m2) {
-    if (o.filter == kAutoFilter)  // compose_static.rs:219-223
-      throw FstError("Custom MatcherConfig not supported with AutoFilter");
-    throw FstError("SigmaMatcher configurations are not supported by this build of librustfst_b200");
-  }
+  auto conv = [](const CMatcherConfig& m, SigmaSpec& sp) {
+    if (m.rewrite_mode > 2) throw FstError("EnumConversionError");
+    sp.enabled = true; sp.sigma_label = m.sigma_label; sp.rewrite_mode = (int)m.rewrite_mode; sp.allowed = m.allowed;
+    std::sort(sp.allowed.begin(), sp.allowed.end());
+  };
+  if (c->has_m1) conv(c->m1, o.sigma1);
+  if (c->has_m2) conv(c->m2, o.sigma2);
+  if ((c->has_m1 || c->has_m2) && o.filter == kAutoFilter)  // compose_static.rs:219-223
+    throw FstError("Custom MatcherConfig not supported with AutoFilter");
   return o;
 }
 void fill(B200ComposeStats* out, const ComposeStats& st, float h2d, float d2h) {

@@ -251,6 +251,9 @@ DevFst compose_device_waves(const DevFst& fa, const DevFst& fb, const ComposeOpt
   int kind = opt.filter == kAutoFilter ? kSequenceFilter : opt.filter;  // compose_fst.rs:58-92
   if (kind < kNullFilter || kind > kNoMatchFilter) throw FstError("EnumConversionError");
 
+  if (opt.sigma1.enabled || opt.sigma2.enabled)
+    throw FstError("sigma matcher configurations are only supported by the persistent compose back end "
+                   "(the result exceeded its pre-sized buffers)");
   int side = resolve_match_side(fa.props, fb.props);
   if (fa.num_states >= 0x7FFFFFFFu || fb.num_states >= 0x7FFFFFFFu)
     throw FstError("compose: operands with >= 2^31 states are not supported");

@@ -38,7 +38,14 @@ using namespace coop;
 constexpr uint32_t kTempFlag = 0x80000000u;   // slot.id holds (cta << 20 | local rank) between phases C and D
 constexpr uint32_t kLocalRankBits = 20;
 
-enum Overflow : uint32_t { kOvArcs = 1, kOvStates = 2, kOvTable = 4, kOvScratch = 8, kOvChunk = 16, kOvWaves = 32 };
+enum Overflow : uint32_t { kOvArcs = 1, kOvStates = 2, kOvTable = 4, kOvScratch = 8, kOvChunk = 16, kOvWaves = 32,
+                           kErrBothRequire = 0x100, kErrBadSigmaLabel = 0x200 };
+
+// Device view of one SigmaMatcher (sigma_matcher.rs): arcs labelled sigma_label on the matched side match any
+// (allowed) label that has no ordinary match at the state; the matched arc is relabelled.
+struct SigmaDev {
+  uint32_t enabled; uint32_t label; uint32_t rewrite_both; const uint32_t* allowed; uint32_t n_allowed;
+};
 
 struct CoopParams {
   FstView a, b;
@@ -62,10 +69,26 @@ struct CoopParams {
   uint32_t* ctl;          // [1] overflow flags, [2] #states, [3] #arcs
   uint32_t* wave_lo; uint32_t wave_cap;  // first product id of every BFS wave (+ one-past-the-end sentinel)
   unsigned int* barrier;  // arrival counter of grid_barrier (zero-initialised)
+  SigmaDev sig1, sig2;    // sigma matcher on fst1 (olabel side) / fst2 (ilabel side)
   uint32_t n_starts;      // initial frontier = product ids [0, n_starts) (1 for a plain compose, batch size otherwise)
   unsigned long long* stats;  // states_expanded, arcs_iterated, arcs_emitted, waves, ns phase A, B, C, D
 };
 
+
+// does state [lo, hi) of the matched side carry an arc labelled sigma? (has_sigma, sigma_matcher.rs:33-45)
+template <bool kByOlabel>
+__device__ __forceinline__ bool dev_has_sigma(const SigmaDev& sg, const Tr* arcs, uint32_t lo, uint32_t hi) {
+  if (!sg.enabled || sg.label == kNoLabel) return false;
+  const uint32_t p = lower_bound_label<kByOlabel>(arcs, lo, hi, sg.label);
+  if (p >= hi) return false;
+  return (kByOlabel ? __ldg(&arcs[p].olabel) : __ldg(&arcs[p].ilabel)) == sg.label;
+}
+__device__ __forceinline__ bool dev_sigma_allowed(const SigmaDev& sg, Label l) {
+  if (!sg.n_allowed) return true;
+  uint32_t lo = 0, hi = sg.n_allowed;
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (__ldg(&sg.allowed[mid]) < l) lo = mid + 1; else hi = mid; }
+  return lo < sg.n_allowed && __ldg(&sg.allowed[lo]) == l;
+}
 
 constexpr uint32_t kSideBit = 0x80000000u;
 constexpr uint32_t kTile = kCoopThreads;
@@ -119,13 +142,22 @@ k_compose_coop(CoopParams P) {
           const uint32_t alo = P.a.off[s1], ahi = P.a.off[s1 + 1], blo = P.b.off[s2], bhi = P.b.off[s2 + 1];
           const uint32_t d1 = ahi - alo, d2 = bhi - blo;
           P.st_off[i] = make_uint4(alo, ahi, blo, bhi);
-          const bool mi = P.side == kMatchInput || (P.side == kMatchBoth && d1 <= d2);
+          bool mi = P.side == kMatchInput || (P.side == kMatchBoth && d1 <= d2);
+          bool hs1 = false, hs2 = false;
+          if (P.sig1.enabled) hs1 = dev_has_sigma<true>(P.sig1, P.a.arcs, alo, ahi);
+          if (P.sig2.enabled) hs2 = dev_has_sigma<false>(P.sig2, P.b.arcs, blo, bhi);
+          if (P.side == kMatchBoth && (hs1 || hs2)) {  // SigmaMatcher::priority = REQUIRE_PRIORITY (compose_fst_op.rs:199-219)
+            if (hs1 && hs2) atomicOr(&P.ctl[1], (uint32_t)kErrBothRequire);
+            mi = hs2;
+          }
+          const bool hs_searched = mi ? hs2 : hs1;
           nitems = 1u + (mi ? d1 : d2);
           side = mi ? kSideBit : 0u;
           const float f1 = P.a.fin[s1], f2 = P.b.fin[s2];
           const uint32_t ne1 = P.a.neps ? P.a.neps[s1] : 0u, ne2 = P.b.neps ? P.b.neps[s2] : 0u;
           const uint8_t fl = (uint8_t)(((d1 == ne1 && f1 == w_zero()) ? 1 : 0) | ((ne1 == 0) ? 2 : 0) |
-                                       ((d2 == ne2 && f2 == w_zero()) ? 4 : 0) | ((ne2 == 0) ? 8 : 0) | (fs << 4));
+                                       ((d2 == ne2 && f2 == w_zero()) ? 4 : 0) | ((ne2 == 0) ? 8 : 0) | (fs << 4) |
+                                       (hs_searched ? 64 : 0));
           P.st_flags[i] = fl;
           const float fw = w_times(f1, f2);  // compose_fst_op.rs:420-449
           P.out_finals[lo + i] = w_is_zero(fw) ? w_zero() : fw;
@@ -179,7 +211,8 @@ k_compose_coop(CoopParams P) {
           const uint32_t i = i_cur + k, j = t - s_seg[k];
           const bool match_input = s_side[k] != 0;
           const uint8_t fl = __ldcg(&P.st_flags[i]);
-          const uint32_t fs = fl >> 4;
+          const uint32_t fs = (fl >> 4) & 3u;
+          const bool hs_searched = (fl & 64) != 0;
           FsFlags ff;
           ff.alleps1 = fl & 1; ff.noeps1 = fl & 2; ff.alleps2 = fl & 4; ff.noeps2 = fl & 8;
           const uint4 so = __ldcg(&P.st_off[i]);
@@ -203,12 +236,25 @@ k_compose_coop(CoopParams P) {
             fs_loop = has_loop ? filter_eval(P.kind, fs, ff, kNoLabel, label) : kNoFs;
             fs_real = filter_eval(P.kind, fs, ff, key, label);
           }
-          const uint32_t cnt = end - pos;
+          uint32_t cnt = end - pos;
+          bool sigma_mode = false;
+          const SigmaDev& sg = match_input ? P.sig2 : P.sig1;  // matcher of the searched side
+          if (sg.enabled) {  // IteratorSigmaMatcher::new (sigma_matcher.rs:196-246)
+            if (label == sg.label && sg.label != kNoLabel) atomicOr(&P.ctl[1], (uint32_t)kErrBadSigmaLabel);
+            if (!has_loop && cnt == 0 && hs_searched && label != kEps && label != kNoLabel &&
+                dev_sigma_allowed(sg, label)) {
+              if (match_input) { pos = lower_bound_label<false>(P.b.arcs, blo, bhi, sg.label); end = run_end<false>(P.b.arcs, pos, bhi, sg.label); }
+              else { pos = lower_bound_label<true>(P.a.arcs, alo, ahi, sg.label); end = run_end<true>(P.a.arcs, pos, ahi, sg.label); }
+              cnt = end - pos;
+              sigma_mode = true;  // the filter sees the relabelled arc: (label, label), i.e. fs_real as computed
+            }
+          }
           const bool loop_ok = has_loop && fs_loop != kNoFs;
           const bool real_ok = fs_real != kNoFs && cnt > 0;
           cnt_out = (loop_ok ? 1u : 0u) + (real_ok ? cnt : 0u);
-          // y: emitted real matches (26 bits) | loop_ok | fs_loop(2) | fs_real(2) | match_input
-          rec = make_uint4(pos, (real_ok ? cnt : 0u) | (loop_ok ? 1u << 26 : 0u) | ((fs_loop & 3u) << 27) |
+          // y: emitted real matches (25 bits) | sigma | loop_ok | fs_loop(2) | fs_real(2) | match_input
+          rec = make_uint4(pos, (real_ok ? (cnt & 0x01FFFFFFu) : 0u) | (sigma_mode ? 1u << 25 : 0u) |
+                                    (loop_ok ? 1u << 26 : 0u) | ((fs_loop & 3u) << 27) |
                                     ((fs_real & 3u) << 29) | (match_input ? 1u << 31 : 0u), i, it_idx);
         }
         uint32_t tile_active, tile_arcs, ex_act, ex_arcs;
@@ -238,6 +284,7 @@ k_compose_coop(CoopParams P) {
     // ------------------------------------------------------------------ B: emit
     cta_prefix_to_smem(P.part_arcs, G, s_pref_b, s_warp);
     const uint32_t E = s_pref_b[G];
+    overflow |= __ldcg(&P.ctl[1]);
     if ((unsigned long long)base + E > P.arcs_cap) overflow |= kOvArcs;
     if (((unsigned long long)hi + E) * 2ull > P.table_cap) overflow |= kOvTable;
     const uint32_t arc_chunk = ((E + G - 1) / G + 31u) & ~31u;
@@ -273,6 +320,13 @@ k_compose_coop(CoopParams P) {
             const uint32_t idx = rec.x + kk - (loop_ok ? 1u : 0u);
             cand = match_input ? load_tr(&P.b.arcs[idx]) : load_tr(&P.a.arcs[idx]);
             fsn = (rec.y >> 29) & 3u;
+            if ((rec.y >> 25) & 1u) {  // sigma match: relabel (value_openfst, sigma_matcher.rs:249-276)
+              const SigmaDev& sg = match_input ? P.sig2 : P.sig1;
+              const Label l = match_input ? it.olabel : it.ilabel;
+              if (sg.rewrite_both) { if (cand.ilabel == sg.label) cand.ilabel = l; if (cand.olabel == sg.label) cand.olabel = l; }
+              else if (match_input) cand.ilabel = l;
+              else cand.olabel = l;
+            }
           }
           const Tr& arc1 = match_input ? it : cand;
           const Tr& arc2 = match_input ? cand : it;
@@ -439,9 +493,32 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
                          cudaStream_t s, DevFst* result, const BatchStarts* batch) {
   int kind = opt.filter == kAutoFilter ? kSequenceFilter : opt.filter;
   if (kind < kNullFilter || kind > kNoMatchFilter) throw FstError("EnumConversionError");
+  // ---- sigma matcher configs: construction and REQUIRE_MATCH checks (sigma_matcher.rs:55-84,126-132,
+  // compose_fst_op.rs:170-179, compose_static.rs:219-223)
+  if (opt.filter == kAutoFilter && (opt.sigma1.enabled || opt.sigma2.enabled))
+    throw FstError("Custom MatcherConfig not supported with AutoFilter");
+  for (const SigmaSpec* sp : {&opt.sigma1, &opt.sigma2}) {
+    if (!sp->enabled) continue;
+    if (sp->rewrite_mode < 0 || sp->rewrite_mode > 2) throw FstError("EnumConversionError");
+    if (sp->sigma_label == kEps) throw FstError("SigmaMatcher: 0 cannot be used as sigma_label");
+  }
+  auto require_sorted = [](uint64_t p, uint64_t yes, uint64_t no, const char* which, const char* known) {
+    if (!(p & (yes | no))) throw FstError(std::string("Properties are not known : ") + known);
+    if (!(p & yes)) throw FstError(std::string("ComposeFst: ") + which + " argument cannot perform required matching (sort?)");
+  };
+  if (opt.sigma1.enabled && opt.sigma1.sigma_label != kNoLabel)
+    require_sorted(fa.props, props::kOLabelSorted, props::kNotOLabelSorted, "1st", "O_LABEL_SORTED | NOT_O_LABEL_SORTED");
+  if (opt.sigma2.enabled && opt.sigma2.sigma_label != kNoLabel)
+    require_sorted(fb.props, props::kILabelSorted, props::kNotILabelSorted, "2nd", "I_LABEL_SORTED | NOT_I_LABEL_SORTED");
   int side = resolve_match_side(fa.props, fb.props);
   if (fa.num_states >= 0x7FFFFFFFu || fb.num_states >= 0x7FFFFFFFu)
     throw FstError("compose: operands with >= 2^31 states are not supported");
+  if ((opt.sigma1.enabled || opt.sigma2.enabled) && !batch && (!fa.has_start || !fb.has_start)) {
+    // empty result; the multi-kernel back end (which handles the no-start case) does not take sigma configs
+    ComposeOptions plain = opt; plain.sigma1 = SigmaSpec(); plain.sigma2 = SigmaSpec();
+    *result = compose_device_waves(fa, fb, plain, stats, s);
+    return true;
+  }
   if (!batch && (!fa.has_start || !fb.has_start)) return false;  // trivial case: multi-kernel back end
   if (batch && (!fb.has_start || batch->n == 0)) throw FstError("batched compose needs a start state on both sides");
   const uint32_t n_starts = batch ? batch->n : 1u;
@@ -469,6 +546,23 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
     P.b.neps = neps2.p; st.kernel_launches++;
   }
   P.kind = kind; P.side = side;
+  DevBuf<uint32_t> allowed1(s), allowed2(s);
+  auto mk_sigma = [&](const SigmaSpec& sp, uint64_t fprops, DevBuf<uint32_t>& buf) {
+    SigmaDev d{};
+    if (!sp.enabled) return d;
+    d.enabled = 1; d.label = sp.sigma_label;
+    d.rewrite_both = sp.rewrite_mode == 1 || (sp.rewrite_mode == 0 && (fprops & props::kAcceptor));
+    d.n_allowed = (uint32_t)sp.allowed.size();
+    if (d.n_allowed) {
+      buf.reserve_discard(d.n_allowed);
+      B200_CUDA(cudaMemcpyAsync(buf.p, sp.allowed.data(), (size_t)d.n_allowed * 4, cudaMemcpyHostToDevice, s));
+      d.allowed = buf.p;
+    }
+    return d;
+  };
+  P.sig1 = mk_sigma(opt.sigma1, fa.props, allowed1);
+  P.sig2 = mk_sigma(opt.sigma2, fb.props, allowed2);
+  B200_CUDA(cudaStreamSynchronize(s));  // the allowed lists are host temporaries
 
   // ---- pre-sized buffers (HBM is plentiful: 180 GB); an overflow falls back to the growing back end
   const size_t sum_states = (size_t)fa.num_states + fb.num_states, sum_arcs = (size_t)fa.num_arcs + fb.num_arcs;
@@ -517,9 +611,11 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   B200_CUDA(cudaMemcpyAsync(hctl, ctl.p, 16, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaMemcpyAsync(hstats, dstats.p, 64, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
-  if (hctl[1] != 0) {  // a pre-sized buffer was too small
+  if (hctl[1] != 0) {
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
-    return false;
+    if (hctl[1] & kErrBothRequire) throw FstError("Both sides can't require match");           // compose_fst_op.rs:207-209
+    if (hctl[1] & kErrBadSigmaLabel) throw FstError("SigmaMatcher::Find: bad label (sigma)");  // sigma_matcher.rs:205-207
+    return false;  // a pre-sized buffer was too small
   }
   st.states_expanded = hstats[0]; st.arcs_iterated = hstats[1]; st.arcs_emitted = hstats[2]; st.waves = hstats[3];
   st.ms_emit_kernel = ms_kernel;

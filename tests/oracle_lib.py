@@ -51,6 +51,8 @@ def lib():
                                           C.POINTER(C.c_void_p)]
         L.oracle_compose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        L.oracle_compose_sigma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.oracle_count_paths.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_shortest_path.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_void_p]
         _LIB = L
@@ -175,6 +177,28 @@ def compose(a, b, filter=0, connect=True, want_stats=False):
         return r, {"states_expanded": stats[0], "arcs_iterated": stats[1], "arcs_emitted": stats[2],
                    "seconds": secs.value}
     return r
+
+
+def _flat_sigma(cfg):
+    if cfg is None:
+        return [0, 0, 0, 0]
+    label, mode, allowed = cfg
+    allowed = list(allowed or [])
+    return [1, label, mode, len(allowed)] + allowed
+
+
+def compose_sigma(a, b, filter, connect, sigma1=None, sigma2=None):
+    """sigma1 / sigma2 = (sigma_label, rewrite_mode, allowed list or None) for matcher1 / matcher2."""
+    flat = np.array(_flat_sigma(sigma1) + _flat_sigma(sigma2), dtype=np.uint32)
+    out = C.c_void_p()
+    _check(lib().oracle_compose_sigma(a.ptr, b.ptr, int(filter), 1 if connect else 0, flat.ctypes.data, C.byref(out)))
+    return OFst(out)
+
+
+def count_paths(a):
+    n = C.c_uint64()
+    _check(lib().oracle_count_paths(a.ptr, C.byref(n)))
+    return n.value
 
 
 def shortest_path(a, nshortest=1, unique=False, delta=1e-6, want_stats=False, want_distance=False):

@@ -356,3 +356,89 @@ def test_tr_sort_on_device_is_stable():
         p, o = both_from_dict(d)
         p.tr_sort(ilabel); o.tr_sort(ilabel)
         assert_same(p, o, f"device tr_sort ilabel={ilabel}")
+
+
+# ------------------------------------------------------------------------------------------------ sigma matcher
+def _acceptor(labels):
+    """rustfst-python `acceptor()` shape: linear chain, weight one, last state final."""
+    from rustfst_b200 import Tr, VectorFst
+    f = VectorFst()
+    states = [f.add_state() for _ in range(len(labels) + 1)]
+    f.set_start(states[0])
+    f.set_final(states[-1])
+    for i, l in enumerate(labels):
+        f.add_tr(states[i], Tr(l, l, None, states[i + 1]))
+    return f
+
+
+def test_sigma_compose_python_kats():
+    """rustfst-python/tests/algorithms/test_compose.py:157-214 with the mirrored API."""
+    from rustfst_b200 import ComposeConfig, ComposeFilter, MatcherConfig, MatcherRewriteMode, compose_with_config
+    # symt: <eps> play david queen please <sigma>  ->  1 play, 3 queen, 4 please, 5 <sigma>
+    query_fst, sigma_fst = _acceptor([1, 3, 4]), _acceptor([1, 5, 4])
+    cfg = ComposeConfig(compose_filter=ComposeFilter.SEQUENCEFILTER, connect=True,
+                        matcher2_config=MatcherConfig(sigma_label=5, rewrite_mode=MatcherRewriteMode.AUTO))
+    assert compose_with_config(query_fst, sigma_fst, cfg) == query_fst
+    # allowlist: symt <eps> play bowie queen radiohead please <sigma>
+    sigma_fst = _acceptor([1, 6, 5])
+    cfg = ComposeConfig(compose_filter=ComposeFilter.SEQUENCEFILTER, connect=True,
+                        matcher2_config=MatcherConfig(sigma_label=6, rewrite_mode=MatcherRewriteMode.AUTO,
+                                                      sigma_allowed_matches=[3, 2]))
+    for artist, ok in ((3, True), (2, True), (4, False)):
+        q = _acceptor([1, artist, 5])
+        assert (compose_with_config(q, sigma_fst, cfg) == q) is ok
+    # AutoFilter + custom matcher config is an error (compose_static.rs:219-223)
+    bad = ComposeConfig(compose_filter=ComposeFilter.AUTOFILTER, connect=True,
+                        matcher2_config=MatcherConfig(sigma_label=6))
+    with pytest.raises(ValueError, match="AutoFilter"):
+        compose_with_config(_acceptor([1, 2, 5]), sigma_fst, bad)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_sigma_compose_fuzz(seed):
+    """Random machines where label 9 plays sigma on fst2 (seed even) or on fst1 (seed odd), all rewrite modes,
+    optional allow-lists, every non-auto filter — against the oracle's restatement of sigma_matcher.rs."""
+    import rustfst_b200 as R
+    rng = np.random.default_rng(4000 + seed)
+    SIG = 9
+    on_right = seed % 2 == 0
+
+    def with_sigma(d, field):
+        arcs = d["arcs"].copy()
+        pick = rng.random(len(arcs)) < 0.25
+        arcs[field][pick] = SIG
+        if rng.random() < 0.5:   # acceptor-like sigma arcs exercise rewrite_both
+            other = "olabel" if field == "ilabel" else "ilabel"
+            arcs[other][pick] = SIG
+        d = dict(d); d["arcs"] = arcs
+        o = O.OFst.from_csr(d["offsets"].astype(np.uint64), arcs, d["finals"], d["start"], 0)
+        o.tr_sort(ilabel=(field == "ilabel"))
+        o.compute_props()
+        off, a, f = o.to_csr()
+        return {"offsets": off.astype(np.uint32), "arcs": a, "finals": f, "start": d["start"], "props": o.props,
+                "num_states": d["num_states"]}
+
+    da = random_fst(rng, int(rng.integers(2, 25)), 5, 6, eps_prob=0.15, sort="olabel")
+    db = random_fst(rng, int(rng.integers(2, 25)), 5, 6, eps_prob=0.15, sort="ilabel")
+    if on_right:
+        db = with_sigma(db, "ilabel")
+    else:
+        da = with_sigma(da, "olabel")
+    pa, oa = both_from_dict(da)
+    pb, ob = both_from_dict(db)
+    for mode in (0, 1, 2):
+        for allowed in (None, [1, 3, 5]):
+            spec = (SIG, mode, allowed)
+            mcfg = R.MatcherConfig(SIG, R.MatcherRewriteMode(mode), allowed)
+            for filt in (1, 2, 3, 4, 5, 6):
+                for connect in (False, True):
+                    kw = {"matcher2_config": mcfg} if on_right else {"matcher1_config": mcfg}
+                    cfg = R.ComposeConfig(R.ComposeFilter(filt), connect, **kw)
+                    try:
+                        expected = O.compose_sigma(oa, ob, filt, connect, **({"sigma2": spec} if on_right else {"sigma1": spec}))
+                    except O.OracleError as e:
+                        with pytest.raises(ValueError):
+                            R.compose_with_config(pa, pb, cfg)
+                        continue
+                    got = R.compose_with_config(pa, pb, cfg)
+                    assert_same(got, expected, f"sigma fuzz seed={seed} mode={mode} allowed={allowed} filt={filt} c={connect}")

@@ -83,8 +83,9 @@ RUSTFST_FFI_RESULT fst_compose_with_config(const CFst* fst_1, const CFst* fst_2,
 RUSTFST_FFI_RESULT fst_compose_config_new(size_t compose_filter, bool connect, const CMatcherConfig* matcher1_config,
                                           const CMatcherConfig* matcher2_config, const CComposeConfig** config);
 RUSTFST_FFI_RESULT fst_compose_config_destroy(CComposeConfig* ptr);         /* compose.rs:290-302 */
-/* rustfst-ffi/src/algorithms/compose.rs:191-223 (sigma matcher; configs are accepted and stored, composing with
- * one returns KO "not supported" in this build — SURVEY.md §8(f) rank 4) */
+/* rustfst-ffi/src/algorithms/compose.rs:191-223: sigma matcher config (sigma_label, rewrite_mode 0 Auto / 1 Always /
+ * 2 Never, allow-list; empty = any label).  Supported by the persistent compose back end; semantics follow
+ * rustfst/src/algorithms/compose/matchers/sigma_matcher.rs (incl. REQUIRE_MATCH / REQUIRE_PRIORITY and its errors). */
 RUSTFST_FFI_RESULT fst_matcher_config_new(size_t sigma_label, size_t rewrite_mode, CIntArray sigma_allowed_matches,
                                           const CMatcherConfig** config);
 RUSTFST_FFI_RESULT fst_matcher_config_destroy(CMatcherConfig* ptr);         /* compose.rs:274-286 */
@@ -233,6 +234,12 @@ RUSTFST_FFI_RESULT b200_device_shortest_path(const B200DeviceFst* dfst, const CF
 RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, const CFst* transducer,
                                       const CComposeConfig* config, const CFst** results /* n slots */,
                                       B200ComposeStats* total_stats);
+
+/* The queue discipline rustfst's AutoQueue would pick for `fst` from its stored property bits (host logic, no GPU):
+ * kind 0 StateOrder, 1 TopOrder, 2 Lifo, 3 Scc.  order_or_scc (num_states entries, may be NULL) receives order[state]
+ * for TopOrder and scc[state] for Scc; scc_is_fifo (num_states entries, may be NULL) the per-component queue type. */
+RUSTFST_FFI_RESULT b200_shortest_path_queue_plan(const CFst* fst, int32_t* kind, uint32_t* order_or_scc,
+                                                 uint8_t* scc_is_fifo, uint32_t* n_scc);
 
 /* Device management for one-process-per-GPU launches. */
 RUSTFST_FFI_RESULT b200_set_device(int device);

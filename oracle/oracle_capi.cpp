@@ -138,6 +138,25 @@ int oracle_compose(void* a, void* b, int filter, int do_connect, void** out, uin
     *out = new Fst(std::move(r));
   });
 }
+// The queue AutoQueue::new builds for `a` (auto_queue.rs:23-99): kind 0 StateOrder, 1 TopOrder, 2 Lifo, 3 Scc;
+// order_or_scc[n] = order[state] (TopOrder) or scc[state] (Scc); is_fifo[n_scc].
+int oracle_queue_plan(void* a, int32_t* kind, uint32_t* order_or_scc, uint8_t* is_fifo, uint32_t* n_scc) {
+  GUARD({
+    Fst& f = *(Fst*)a;
+    QueueKind k;
+    std::unique_ptr<Queue> q = make_auto_queue(f, &k);
+    *kind = (int32_t)k; *n_scc = 0;
+    if (k == QK_TOP_ORDER) {
+      auto* t = dynamic_cast<TopOrderQueue*>(q.get());
+      for (size_t i = 0; i < t->order.size(); i++) order_or_scc[i] = t->order[i];
+    } else if (k == QK_SCC) {
+      auto* sq = dynamic_cast<SccQueue*>(q.get());
+      for (size_t i = 0; i < sq->sccs.size(); i++) order_or_scc[i] = sq->sccs[i];
+      *n_scc = (uint32_t)sq->queues.size();
+      for (size_t c = 0; c < sq->queues.size(); c++) is_fifo[c] = dynamic_cast<FifoQueue*>(sq->queues[c].get()) ? 1 : 0;
+    }
+  });
+}
 // stats: [arcs_relaxed, states_dequeued]; distance (optional, N floats)
 int oracle_shortest_path(void* a, uint64_t nshortest, int unique, float delta, void** out, uint64_t* stats,
                          double* seconds, float* distance) {

@@ -1,7 +1,7 @@
 """Builds librustfst_b200.so (CUDA kernels + C-ABI) in-tree with nvcc for sm_100a.
 
-    python -m rustfst_b200.build            # incremental
-    python -m rustfst_b200.build --force
+    python rustfst_b200/build.py            # incremental (run as a script: importing the package dlopens the library)
+    python rustfst_b200/build.py --force
 
 The library links the CUDA runtime statically and has no torch dependency; it loads on a CPU-only box (the
 container, for the symbol/ABI tests) and reports "no CUDA device" from the compute entry points there.

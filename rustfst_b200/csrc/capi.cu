@@ -638,6 +638,19 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
     if (total) *total = acc;
   });
 }
+RUSTFST_FFI_RESULT b200_shortest_path_queue_plan(const CFst* fst, int32_t* kind, uint32_t* order_or_scc,
+                                                 uint8_t* scc_is_fifo, uint32_t* n_scc) {
+  return wrap([&] {
+    QueuePlan plan = build_queue_plan(nn(fst, "fst")->fst.freeze());
+    if (kind) *kind = (int32_t)plan.kind;
+    if (n_scc) *n_scc = (uint32_t)plan.scc_is_fifo.size();
+    if (order_or_scc) {
+      const std::vector<uint32_t>& v = plan.kind == kTopOrderQueue ? plan.order : plan.scc;
+      if (!v.empty()) std::memcpy(order_or_scc, v.data(), v.size() * 4);
+    }
+    if (scc_is_fifo && !plan.scc_is_fifo.empty()) std::memcpy(scc_is_fifo, plan.scc_is_fifo.data(), plan.scc_is_fifo.size());
+  });
+}
 RUSTFST_FFI_RESULT b200_set_device(int device) {
   return wrap([&] {
     require_device();

@@ -1,6 +1,6 @@
 """ctypes loader for librustfst_b200.so — the host-side mirror of rustfst-python/rustfst/ffi_utils.py:16-52.
 
-The library is the product: if it is missing the import fails loudly (build it with `python -m rustfst_b200.build`).
+The library is the product: if it is missing the import fails loudly (build it with `python rustfst_b200/build.py`).
 """
 import ctypes as C
 import os
@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "librustfst_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"Could not find compiled library {LIB_PATH}; build it with `python -m rustfst_b200.build` "
+        f"Could not find compiled library {LIB_PATH}; build it with `python rustfst_b200/build.py` "
         "(nvcc, sm_100a). There is no pure-Python or CPU fallback.")
 
 lib = C.CDLL(LIB_PATH)
@@ -149,6 +149,7 @@ _sig("b200_device_fst_destroy", _P)
 _sig("b200_device_compose", _P, _P, _P, _PP, C.POINTER(ComposeStats))
 _sig("b200_device_shortest_path", _P, _P, _PP, C.POINTER(SsspStats), C.c_bool)
 _sig("b200_compose_batch", C.POINTER(C.c_void_p), C.c_size_t, _P, _P, C.POINTER(C.c_void_p), C.POINTER(ComposeStats))
+_sig("b200_shortest_path_queue_plan", _P, C.POINTER(C.c_int32), _P, _P, C.POINTER(C.c_uint32))
 _sig("b200_set_device", C.c_int)
 _sig("b200_device_count", C.POINTER(C.c_int))
 _sig("b200_device_synchronize")

@@ -52,6 +52,7 @@ def lib():
         L.oracle_compose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         L.oracle_compose_sigma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.oracle_queue_plan.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         L.oracle_count_paths.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.oracle_shortest_path.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.c_void_p]
@@ -193,6 +194,15 @@ def compose_sigma(a, b, filter, connect, sigma1=None, sigma2=None):
     out = C.c_void_p()
     _check(lib().oracle_compose_sigma(a.ptr, b.ptr, int(filter), 1 if connect else 0, flat.ctypes.data, C.byref(out)))
     return OFst(out)
+
+
+def queue_plan(a):
+    n = a.num_states
+    kind, n_scc = C.c_int32(), C.c_uint32()
+    order = np.zeros(max(1, n), dtype=np.uint32)
+    fifo = np.zeros(max(1, n), dtype=np.uint8)
+    _check(lib().oracle_queue_plan(a.ptr, C.byref(kind), order.ctypes.data, fifo.ctypes.data, C.byref(n_scc)))
+    return kind.value, order[:n], fifo[:n_scc.value]
 
 
 def count_paths(a):

@@ -155,3 +155,46 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
         a.shortest_path()
     with pytest.raises(ValueError, match="no CUDA device"):
         a.connect()
+
+
+def _product_queue_plan(p):
+    n = p.num_states()
+    kind, n_scc = C.c_int32(), C.c_uint32()
+    order = np.zeros(max(1, n), dtype=np.uint32)
+    fifo = np.zeros(max(1, n), dtype=np.uint8)
+    assert lib.b200_shortest_path_queue_plan(p.ptr, C.byref(kind), order.ctypes.data, fifo.ctypes.data,
+                                             C.byref(n_scc)) == 0
+    return kind.value, order[:n], fifo[:n_scc.value]
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_queue_plan_matches_auto_queue_on_fixtures(name):
+    """AutoQueue selection + DFS orders (auto_queue.rs:23-99, top_sort.rs, scc_visitors.rs) are host logic: the
+    product's plan must equal the oracle's restatement on every fixture machine (cyclic, epsilon-rich)."""
+    for which in ("raw", "compose"):
+        p, o = R.VectorFst.read(golden_path(name, which)), O.OFst.from_path(golden_path(name, which))
+        pk, po, pf = _product_queue_plan(p)
+        ok, oo, of = O.queue_plan(o)
+        assert pk == ok, f"{name}/{which}: kind {pk} != {ok}"
+        if ok in (1, 3):
+            assert np.array_equal(po, oo), f"{name}/{which}: order/scc differ"
+        if ok == 3:
+            assert np.array_equal(pf, of)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_queue_plan_fuzz(seed):
+    rng = np.random.default_rng(5000 + seed)
+    d = random_fst(rng, int(rng.integers(1, 80)), 5, 6, eps_prob=0.1, cyclic=(seed % 3 != 0),
+                   weight_grid=(seed % 4 != 1))
+    if seed % 5 == 0:   # unknown properties force the SCC branch
+        d["props"] = 0
+    p = R.VectorFst.from_csr(d["offsets"], d["arcs"], d["finals"], d["start"], d["props"])
+    o = O.OFst.from_csr(d["offsets"].astype(np.uint64), d["arcs"], d["finals"], d["start"], d["props"])
+    pk, po, pf = _product_queue_plan(p)
+    ok, oo, of = O.queue_plan(o)
+    assert pk == ok
+    if ok in (1, 3):
+        assert np.array_equal(po, oo)
+    if ok == 3:
+        assert np.array_equal(pf, of)

@@ -183,6 +183,22 @@ def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_ove
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     total_arcs = sum_over_ranks(float(arcs))
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from tests import oracle_lib as O
+        ot = O.OFst.from_csr(t["offsets"].astype(np.uint64), t["arcs"], t["finals"], t["start"], t["props"])
+        n_sample = min(args.batch, 2048)
+        oaccs = []
+        for i in range(n_sample):
+            d = synth.linear_acceptor(synth.sample_path_labels(t, 200, seed=100 + i), seed=100 + i)
+            oaccs.append(O.OFst.from_csr(d["offsets"].astype(np.uint64), d["arcs"], d["finals"], d["start"], d["props"]))
+        secs, oarcs = 0.0, 0
+        for oa in oaccs:
+            r, ost = O.compose(oa, ot, want_stats=True)
+            secs += ost["seconds"]; oarcs += r.num_trs
+        cpu = {"value": oarcs / secs, "unit": "arcs/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+               "sample": f"the first {n_sample} acceptors of the batch composed one by one with the same transducer "
+                         f"({oarcs} result arcs in {secs:.2f} s), oracle port, 1 thread"}
     if rank == 0:
         line = {"metric": "composed_arcs_per_sec", "value": total_arcs / (ms * 1e-3), "unit": "arcs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -194,7 +210,7 @@ def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_ove
                 "e2e": {"value": total_arcs / (ms * 1e-3), "unit": "arcs/s", "api": "b200_compose_batch on host handles",
                         "h2d_bytes_per_step": int(csr_bytes(t) + (hi - lo) * (201 * 8 + 200 * 16 + 4)),
                         "d2h_bytes_per_step": int(arcs // max(1, args.steps) * 16)},
-                "gpu_launches": int(launches)}
+                "cpu_baseline": cpu, "gpu_launches": int(launches)}
         print(json.dumps(line), flush=True)
 
 

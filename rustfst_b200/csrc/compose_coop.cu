@@ -22,6 +22,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 
@@ -121,6 +122,7 @@ k_compose_coop(CoopParams P) {
   uint32_t lo = 0, hi = P.n_starts, base = 0;  // uniform across the grid by construction
   unsigned long long n_states_exp = 0, n_items = 0, n_arcs = 0, n_waves = 0;
   unsigned long long t_a = 0, t_b = 0, t_c = 0, t_d = 0;
+  unsigned long long busy[5] = {0, 0, 0, 0, 0};  // this CTA's own work time per phase (A0, A1, B, C, D), barriers excluded
   uint32_t overflow = 0;
 
   while (lo < hi) {
@@ -169,7 +171,9 @@ k_compose_coop(CoopParams P) {
       }
       if (tid == 0) P.part_items[c] = run;
     }
+    { unsigned long long tb = globaltimer_ns(); busy[0] += tb - tp0; }
     grid_barrier(P.barrier, bar_epoch);
+    unsigned long long ts1 = globaltimer_ns();
 
     // ------------------------------------------------------------------ A1: per-item matching
     cta_prefix_to_smem(P.part_items, G, s_pref_a, s_warp);
@@ -278,6 +282,7 @@ k_compose_coop(CoopParams P) {
       }
     }
     if (tid == 0) P.part_arcs[c] = my_arcs;
+    busy[1] += globaltimer_ns() - ts1;
     grid_barrier(P.barrier, bar_epoch);
     unsigned long long tp1 = globaltimer_ns();
 
@@ -362,6 +367,7 @@ k_compose_coop(CoopParams P) {
         P.out_offsets[lo + i] = base + s_pref_b[t_first / ic] + __ldcg(&P.st_arc_loc[i]);
       }
     }
+    busy[2] += globaltimer_ns() - tp1;
     grid_barrier(P.barrier, bar_epoch);
     unsigned long long tp2 = globaltimer_ns();
 
@@ -385,6 +391,7 @@ k_compose_coop(CoopParams P) {
       }
       if (tid == 0) P.part_new[c] = cta_new;
     }
+    busy[3] += globaltimer_ns() - tp2;
     grid_barrier(P.barrier, bar_epoch);
     unsigned long long tp3 = globaltimer_ns();
 
@@ -415,11 +422,15 @@ k_compose_coop(CoopParams P) {
     base += E;
     lo = hi;
     hi += n_new;
+    busy[4] += globaltimer_ns() - tp3;
     grid_barrier(P.barrier, bar_epoch);
     unsigned long long tp4 = globaltimer_ns();
     t_a += tp1 - tp0; t_b += tp2 - tp1; t_c += tp3 - tp2; t_d += tp4 - tp3;
   }
 
+  if (tid == 0) {
+    for (int k = 0; k < 5; k++) { atomicAdd(&P.stats[8 + k], busy[k]); atomicMax(&P.stats[13 + k], busy[k]); }
+  }
   if (c == 0 && tid == 0) {
     P.ctl[1] = overflow;
     P.ctl[2] = hi;    // number of product states
@@ -458,21 +469,24 @@ void launch_unpack_s1(const unsigned long long* tuples, uint32_t n, uint32_t* s1
   if (m) k_unpack_s1<<<blocks_for(m), kThreads, 0, s>>>(tuples, n, s1_out, n_starts, start_map);
 }
 
+static int grid_used = 1;
 float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   CoopParams P = P0;
   // resident CTAs per SM the kernel is compiled for (register budget): 4 -> 64 regs, 5 -> 48, 6 -> 40
-  int minb = 4;
+  int minb = 6;  // measured best on C3 (40 registers, no spills, 6 x 256 threads per SM)
   if (const char* e = std::getenv("B200_COOP_MINBLOCKS")) minb = std::atoi(e);
-  void* kern = (void*)k_compose_coop<4>;
+  void* kern = (void*)k_compose_coop<6>;
   if (minb == 5) kern = (void*)k_compose_coop<5>;
-  else if (minb == 6) kern = (void*)k_compose_coop<6>;
+  else if (minb == 4) kern = (void*)k_compose_coop<4>;
   else if (minb == 3) kern = (void*)k_compose_coop<3>;
+  else if (minb == 8) kern = (void*)k_compose_coop<8>;
   int per_sm = 0;
   size_t dyn = 2 * 2049 * sizeof(uint32_t);
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoopThreads, dyn));
   if (per_sm < 1) throw FstError("cooperative compose kernel does not fit on the device");
   int grid = sms * per_sm;
   if (grid > 2047) grid = 2047;  // CTA index must fit 11 bits next to the 20-bit local rank; prefix arrays hold 2048
+  grid_used = grid;
   dyn = 2 * ((size_t)grid + 1) * sizeof(uint32_t);
   void* args[] = {(void*)&P};
   cudaEvent_t e0, e1;
@@ -578,7 +592,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   out.offsets.reserve_discard(states_cap + 1);
   out.finals.reserve_discard(states_cap);
   out.arcs.reserve_discard(arcs_cap);
-  DevBuf<unsigned long long> tuples(s, states_cap), dstats(s, 8);
+  DevBuf<unsigned long long> tuples(s, states_cap), dstats(s, 18);
   DevBuf<Slot> slots(s, table_cap);
   DevBuf<uint4> recs(s, items_cap);
   DevBuf<uint32_t> arc_loc(s, items_cap), item_loc(s, states_cap), st_arc_loc(s, states_cap), parts(s, 3 * 2048), ctl(s, 8);
@@ -587,7 +601,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   const uint32_t wave_cap = 1u << 20;
   DevBuf<uint32_t> wave_lo(s, wave_cap);
   B200_CUDA(cudaMemsetAsync(slots.p, 0xFF, table_cap * sizeof(Slot), s));
-  B200_CUDA(cudaMemsetAsync(dstats.p, 0, 8 * sizeof(unsigned long long), s));
+  B200_CUDA(cudaMemsetAsync(dstats.p, 0, 18 * sizeof(unsigned long long), s));
   P.tuples = tuples.p; P.states_cap = (uint32_t)states_cap;
   P.out_offsets = out.offsets.p; P.out_finals = out.finals.p; P.out_arcs = out.arcs.p; P.arcs_cap = (uint32_t)arcs_cap;
   P.slots = slots.p; P.mask = (uint32_t)table_cap - 1; P.table_cap = (uint32_t)table_cap;
@@ -607,9 +621,9 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   st.kernel_launches++; st.emit_launches = 1;
 
   uint32_t hctl[4];
-  unsigned long long hstats[8];
+  unsigned long long hstats[18];
   B200_CUDA(cudaMemcpyAsync(hctl, ctl.p, 16, cudaMemcpyDeviceToHost, s));
-  B200_CUDA(cudaMemcpyAsync(hstats, dstats.p, 64, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(hstats, dstats.p, 18 * 8, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
   if (hctl[1] != 0) {
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
@@ -621,6 +635,12 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   st.ms_emit_kernel = ms_kernel;
   st.ms_phase[0] = hstats[4] * 1e-6f; st.ms_phase[1] = hstats[5] * 1e-6f;
   st.ms_phase[2] = hstats[6] * 1e-6f; st.ms_phase[3] = hstats[7] * 1e-6f;
+  if (std::getenv("B200_COOP_TRACE")) {
+    const char* names[5] = {"A0", "A1", "B", "C", "D"};
+    for (int k = 0; k < 5; k++)
+      std::fprintf(stderr, "[coop] phase %s: CTA busy avg %.3f ms, max %.3f ms\n", names[k],
+                   hstats[8 + k] * 1e-6 / grid_used, hstats[13 + k] * 1e-6);
+  }
   out.num_states = hctl[2]; out.num_arcs = hctl[3];
   out.has_start = true; out.start = 0;
   out.props = props::of_compose(fa.props, fb.props);

@@ -46,7 +46,8 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML every 10 ms (the timed region of the
+    default run is ~50 ms), falling back to one nvidia-smi query per 200 ms when pynvml is unavailable."""
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
@@ -54,12 +55,32 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
+        self.source = None
         self._stop_evt = threading.Event()
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.gpu)
+        self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        self.source = "nvml"
+        while not self._stop_evt.is_set():
+            self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+            r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+            self._stop_evt.wait(0.01)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.source = "nvidia-smi"
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
@@ -75,12 +96,18 @@ class ClockSampler(threading.Thread):
                 pass
             self._stop_evt.wait(0.2)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples), "window": "compose warm-up + timed region"}
+                "samples": len(self.samples), "source": self.source, "window": "compose warm-up + timed region"}
 
 
 def gen_compose_workload(name, scale, rank):

@@ -19,6 +19,7 @@ HEADERS = ["algos.h", "compose_common.cuh", "device_common.cuh", "fst_types.h", 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--cudart", "static",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("B200_EXTRA_NVCC_FLAGS", "").split()  # e.g. -DB200_COOP_PROFILE for the in-kernel timeline
 
 
 def _newer(a, b):

@@ -50,6 +50,7 @@ struct SigmaDev {
 
 struct CoopParams {
   FstView a, b;
+  const uint32_t* lab1; const uint32_t* lab2;  // fst1 olabels / fst2 ilabels as dense arrays (padded)
   int kind, side;
   unsigned long long* tuples; uint32_t states_cap;
   uint32_t* out_offsets; float* out_finals;
@@ -58,19 +59,21 @@ struct CoopParams {
   // per-wave scratch, indexed by frontier-local state
   uint32_t* item_loc;     // slice-local exclusive item offset | side bit
   uint32_t* st_arc_loc;   // slice-local emission index of the state's first arc
-  uint8_t* st_flags;      // alleps1 | noeps1<<1 | alleps2<<2 | noeps2<<3 | fs<<4
+  uint32_t* st_meta;      // alleps1 | noeps1<<1 | alleps2<<2 | noeps2<<3 | fs<<4 | searched side has sigma<<6 | owner CTA<<8
   uint4* st_off;          // arc ranges of the two component states: alo, ahi, blo, bhi
   // per-wave scratch, indexed by item (active items compacted in place inside each CTA's slice)
   uint4* recs;            // x = first match, y = count|flags, z = frontier-local state, w = iterated arc (abs) or ~0
   uint32_t* arc_loc;      // slice-local emission index of the record's first arc
   uint32_t items_cap;
-  uint32_t* part_items;   // gridDim entries: items of each CTA's state slice
-  uint32_t* part_arcs;    // gridDim entries: arcs emitted by each CTA's item slice
-  uint32_t* part_new;     // gridDim entries: first emissions found in each CTA's arc slice
-  uint32_t* ctl;          // [1] overflow flags, [2] #states, [3] #arcs
+  // epoch-tagged count exchanges (coop_utils.cuh), gridDim entries each
+  unsigned long long* part_items;   // items of each CTA's state slice
+  unsigned long long* part_arcs;    // arcs emitted by each CTA's item slice
+  unsigned long long* part_new;     // first emissions found in each CTA's arc slice
+  uint32_t* ctl;          // [1] overflow / error flags, [2] #states, [3] #arcs, [4] errors raised while matching
   uint32_t* wave_lo; uint32_t wave_cap;  // first product id of every BFS wave (+ one-past-the-end sentinel)
   unsigned int* barrier;  // arrival counter of grid_barrier (zero-initialised)
   SigmaDev sig1, sig2;    // sigma matcher on fst1 (olabel side) / fst2 (ilabel side)
+  uint32_t poll_ns;       // back-off between polls of a count word that is not there yet (0 = spin)
   uint32_t n_starts;      // initial frontier = product ids [0, n_starts) (1 for a plain compose, batch size otherwise)
   unsigned long long* stats;  // states_expanded, arcs_iterated, arcs_emitted, waves, ns phase A, B, C, D
 };
@@ -94,163 +97,305 @@ __device__ __forceinline__ bool dev_sigma_allowed(const SigmaDev& sg, Label l) {
 constexpr uint32_t kSideBit = 0x80000000u;
 constexpr uint32_t kTile = kCoopThreads;
 
-// One persistent kernel = the whole BFS.  Per wave:
-//   A0 states   : CTA c owns a contiguous slice of the frontier; per state: #items (1 + degree of the iterated side),
-//                 which side is iterated, filter flags, final weight; CTA-local exclusive offsets + CTA total
-//   A1 items    : CTA c owns a contiguous slice of the ITEMS (load-balanced: states located through a 257-entry
-//                 shared-memory window per 256-item tile); per item: binary search of the sorted side + filter;
-//                 active items are compacted in place with CTA-local arc offsets; CTA total
-//   B  arcs     : CTA c emits the arcs of its own items, one thread per ARC (records located through a shared-
-//                 memory window again); 128-bit gathers, CAS insert, atomicMin(first emission), 128-bit store
+// Optional fine-grained timeline of thread 0 of every CTA (build with -DB200_COOP_PROFILE): SM cycles spent in the
+// sub-steps of the A1 and B tiles, summed over the run and averaged over the CTAs by the host.
+#ifdef B200_COOP_PROFILE
+#define PROF_DECL long long prof_t = 0; unsigned long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_START() do { prof_t = clock64(); } while (0)
+#define PROF_MARK(k) do { long long now_ = clock64(); prof[k] += (unsigned long long)(now_ - prof_t); prof_t = now_; } while (0)
+#define PROF_USE(x) asm volatile("" ::"r"(x) : "memory")
+#else
+#define PROF_DECL
+#define PROF_START() do { } while (0)
+#define PROF_MARK(k) do { } while (0)
+#define PROF_USE(x) do { } while (0)
+#endif
+
+// Lower bound + equal run of `key` in the label-sorted slice [lo, hi) with as few DEPENDENT loads as possible: the
+// kernel is latency-bound, so a 4-ary narrowing (3 independent probes per round) is followed by one round that loads
+// a 16-arc window at once and counts "< key" and "== key" (sorted_matcher.rs:141-142,166-184: lower_bound_by, then
+// iterate while the label matches).  from_lo = the epsilon-loop search, which starts at lo instead of bisecting.
+// The matcher compares fst1 output labels with fst2 input labels only, so both are kept once more as dense 4-byte
+// arrays (lab1[i] = fst1 arc i .olabel, lab2[i] = fst2 arc i .ilabel; padded by kLabelPad entries): the label of an
+// iterated arc is a coalesced 4-byte load, and the 16-label window of a search is five aligned 128-bit loads instead
+// of sixteen strided ones.  Lanes matching on different sides run the same instruction stream (pointer select).
+constexpr uint32_t kLabelPad = 32;
+__global__ void k_extract_labels(const Tr* __restrict__ arcs, uint32_t n, uint32_t n_padded, int olabel,
+                                 uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = olabel ? __ldg(&arcs[i].olabel) : __ldg(&arcs[i].ilabel);
+  else if (i < n_padded) out[i] = kNoLabel;
+}
+__device__ __forceinline__ uint32_t lower_bound_lab(const uint32_t* __restrict__ lab, uint32_t lo, uint32_t hi, Label key) {
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(&lab[mid]) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ uint32_t run_end_lab(const uint32_t* __restrict__ lab, uint32_t pos, uint32_t hi, Label key) {
+  uint32_t p = pos;
+  const uint32_t lim = pos + 8 < hi ? pos + 8 : hi;
+  while (p < lim) { if (__ldg(&lab[p]) != key) return p; p++; }
+  if (p == hi) return p;
+  return lower_bound_lab(lab, p, hi, key + 1);  // key + 1 cannot overflow: kNoLabel is never searched for
+}
+// Lower bound + equal run of `key` in the sorted label slice [lo, hi) with as few DEPENDENT loads as possible
+// (sorted_matcher.rs:141-142,166-184: lower_bound_by, then iterate while the label matches): 4-ary narrowing (three
+// independent probes per round) down to 16 labels, then one round that fetches the window and counts "< key" and
+// "== key".  from_lo = the epsilon-loop search, which starts at lo instead of bisecting.
+__device__ __forceinline__ void match_range(const uint32_t* __restrict__ lab, uint32_t lo, uint32_t hi, Label key,
+                                            bool from_lo, uint32_t& pos, uint32_t& end) {
+  uint32_t l = lo, h = hi;
+  if (!from_lo) {
+    while (h - l > 16) {  // invariant: labels below l are < key, labels from h on are >= key
+      const uint32_t q = (h - l) >> 2, m1 = l + q, m2 = m1 + q, m3 = m2 + q;
+      const Label x1 = __ldg(&lab[m1]), x2 = __ldg(&lab[m2]), x3 = __ldg(&lab[m3]);
+      if (x1 >= key) h = m1;
+      else if (x2 >= key) { l = m1 + 1; h = m2; }
+      else if (x3 >= key) { l = m2 + 1; h = m3; }
+      else l = m3 + 1;
+    }
+  }
+  // window [l, l + 16) lies inside the five aligned quads starting at l & ~3 (reads past hi hit the padding)
+  const uint32_t l4 = l & ~3u;
+  const uint4* __restrict__ q4 = reinterpret_cast<const uint4*>(lab + l4);
+  uint4 v[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) v[k] = __ldg(q4 + k);
+  uint32_t n_lt = 0, n_eq = 0;
+  const uint32_t w_end = min(hi, l + 16);
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const uint32_t xs[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t idx = l4 + 4 * k + u;
+      const bool valid = idx >= l && idx < w_end;
+      n_lt += (valid && xs[u] < key) ? 1u : 0u;
+      n_eq += (valid && xs[u] == key) ? 1u : 0u;
+    }
+  }
+  pos = l + n_lt;
+  end = pos + n_eq;
+  if (end == l + 16 && end < hi) end = run_end_lab(lab, end, hi, key);  // run leaves the window (rare)
+}
+
+// State table lookup-or-insert: linear probing, kW consecutive slots fetched per round.  Loaded non-empty keys are permanent (no deletions); loaded empties are confirmed by the CAS.  Returns the
+// id stored in the slot (kUnassigned for a tuple discovered in this wave) and the slot index in h.
+template <int kW>
+__device__ __forceinline__ uint32_t table_probe(Slot* slots, uint32_t mask, unsigned long long key, uint32_t& h) {
+  while (true) {
+    uint4 sv[kW];
+#pragma unroll
+    for (int q = 0; q < kW; q++) sv[q] = ld_volatile_u4(&slots[(h + q) & mask]);
+#pragma unroll
+    for (int q = 0; q < kW; q++) {
+      const unsigned long long curk = (unsigned long long)sv[q].x | ((unsigned long long)sv[q].y << 32);
+      const uint32_t hq = (h + q) & mask;
+      if (curk == key) { h = hq; return sv[q].z; }
+      if (curk == kEmptyKey) {
+        const unsigned long long prev = atomicCAS(&slots[hq].key, kEmptyKey, key);
+        if (prev == kEmptyKey) { h = hq; return kUnassigned; }  // fresh insert: discovered in this wave
+        if (prev == key) { h = hq; return *reinterpret_cast<volatile uint32_t*>(&slots[hq].id); }
+      }
+    }
+    h = (h + kW) & mask;
+  }
+}
+
+// Per-state setup of a product state that joins the next frontier (compose_fst_op.rs:199-219 match side,
+// :420-449 final weight; filter flags as in compose_common.cuh): writes the state's scratch records and returns
+// (#items | side bit).  i = frontier-local index, id = product state id, c = CTA that owns the state's slice.
+__device__ __forceinline__ uint32_t setup_state(const CoopParams& P, unsigned long long key, uint32_t i, uint32_t id,
+                                                uint32_t c) {
+  uint32_t fs, s1, s2;
+  unpack_key(key, fs, s1, s2);
+  const uint32_t alo = __ldg(&P.a.off[s1]), ahi = __ldg(&P.a.off[s1 + 1]);
+  const uint32_t blo = __ldg(&P.b.off[s2]), bhi = __ldg(&P.b.off[s2 + 1]);
+  const float f1 = __ldg(&P.a.fin[s1]), f2 = __ldg(&P.b.fin[s2]);
+  const uint32_t ne1 = P.a.neps ? __ldg(&P.a.neps[s1]) : 0u, ne2 = P.b.neps ? __ldg(&P.b.neps[s2]) : 0u;
+  const uint32_t d1 = ahi - alo, d2 = bhi - blo;
+  P.st_off[i] = make_uint4(alo, ahi, blo, bhi);
+  bool mi = P.side == kMatchInput || (P.side == kMatchBoth && d1 <= d2);
+  bool hs1 = false, hs2 = false;
+  if (P.sig1.enabled) hs1 = dev_has_sigma<true>(P.sig1, P.a.arcs, alo, ahi);
+  if (P.sig2.enabled) hs2 = dev_has_sigma<false>(P.sig2, P.b.arcs, blo, bhi);
+  if (P.side == kMatchBoth && (hs1 || hs2)) {  // SigmaMatcher::priority = REQUIRE_PRIORITY (compose_fst_op.rs:199-219)
+    if (hs1 && hs2) atomicOr(&P.ctl[1], (uint32_t)kErrBothRequire);
+    mi = hs2;
+  }
+  const bool hs_searched = mi ? hs2 : hs1;
+  const uint32_t fl = ((d1 == ne1 && f1 == w_zero()) ? 1u : 0u) | ((ne1 == 0) ? 2u : 0u) |
+                      ((d2 == ne2 && f2 == w_zero()) ? 4u : 0u) | ((ne2 == 0) ? 8u : 0u) | (fs << 4) |
+                      (hs_searched ? 64u : 0u);
+  P.st_meta[i] = fl | (c << 8);
+  const float fw = w_times(f1, f2);
+  P.out_finals[id] = w_is_zero(fw) ? w_zero() : fw;
+  return (1u + (mi ? d1 : d2)) | (mi ? kSideBit : 0u);
+}
+
+// One persistent kernel = the whole BFS.  A frontier state belongs to the slice of the CTA that discovered it
+// (slice c = frontier-local ids [pref_new[c], pref_new[c+1])).  Per wave:
+//   A1 items    : CTA c owns a contiguous slice of the ITEMS (item 0 of a state = the implicit epsilon loop, item j =
+//                 j-th arc of the iterated side); load-balanced: the states of a 256-item tile are staged in a
+//                 257-entry shared-memory window (offsets, flags, arc ranges); per item: match_range on the sorted
+//                 side + filter; active items are compacted in place with CTA-local arc offsets
+//   B  arcs     : CTA c emits the arcs of its own items, one thread per ARC (records staged in shared memory);
+//                 128-bit gathers, one 128-bit probe of the state table (CAS insert), atomicMin(first emission),
+//                 128-bit store
 //   C  rank     : contiguous arc slices; ballot/popc ranks of first emissions published through slot.id
-//   D  resolve  : CTA prefix -> ids; nextstate patch; tuple publication
-// Five grid barriers per wave; every size is recomputed identically by every CTA from per-CTA partial arrays.
+//   D  resolve  : CTA prefix -> ids; nextstate patch; tuple publication; and the per-state setup of the NEXT
+//                 frontier (the first emitter holds the tuple already), slice-local item offsets
+// The three count exchanges (items, arcs, new states) are epoch-tagged per-CTA words: every CTA spins until all
+// gridDim words of the current epoch are there and builds the same exclusive prefix in shared memory, which is a
+// full grid barrier and the broadcast in one round trip.  Only B -> C (all atomicMin's must have landed) uses the
+// arrival-counter barrier.  Control flow stays uniform across the grid by construction.
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kCoopThreads, kMinBlocks)
 k_compose_coop(CoopParams P) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ uint32_t s_warp[2 * (kCoopThreads / 32)];
   __shared__ uint32_t s_seg[kTile + 2];
-  __shared__ uint32_t s_side[kTile + 2];
-  __shared__ uint32_t s_misc[4];
-  extern __shared__ uint32_t s_dyn[];          // two prefix arrays of gridDim + 1 entries
-  uint32_t* s_pref_a = s_dyn;                  // items (A1/B) then new-state counts (D)
-  uint32_t* s_pref_b = s_dyn + gridDim.x + 1;  // arcs (B)
-
+  __shared__ uint32_t s_wmeta[kTile + 2];
+  __shared__ uint4 s_wrec[kTile + 1];
+  extern __shared__ uint32_t s_dyn[];          // three prefix arrays of gridDim + 1 entries
   const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
+  uint32_t* s_pref_items = s_dyn;
+  uint32_t* s_pref_arcs = s_dyn + (G + 1);
+  uint32_t* s_pref_new = s_dyn + 2 * (G + 1);
+
   unsigned int bar_epoch = 0;
+  uint32_t tag = 1;                            // epoch of the tagged count exchanges
   uint32_t lo = 0, hi = P.n_starts, base = 0;  // uniform across the grid by construction
   unsigned long long n_states_exp = 0, n_items = 0, n_arcs = 0, n_waves = 0;
   unsigned long long t_a = 0, t_b = 0, t_c = 0, t_d = 0;
-  unsigned long long busy[5] = {0, 0, 0, 0, 0};  // this CTA's own work time per phase (A0, A1, B, C, D), barriers excluded
+  unsigned long long busy[5] = {0, 0, 0, 0, 0};  // this CTA's own work time per phase (setup, A1, B, C, D), waits excluded
   uint32_t overflow = 0;
+  PROF_DECL
+
+  // ---------------------------------------------------------------------- setup of the initial frontier [0, n_starts)
+  {
+    unsigned long long t0 = globaltimer_ns();
+    const uint32_t sc0 = (hi + G - 1) / G;
+    const uint32_t s_begin = min(hi, c * sc0), s_end = min(hi, s_begin + sc0);
+    uint32_t run = 0;
+    for (uint32_t i0 = s_begin; i0 < s_end; i0 += kTile) {
+      const uint32_t i = i0 + tid;
+      uint32_t r = 0;
+      if (i < s_end) r = setup_state(P, __ldcg(&P.tuples[i]), i, i, c);
+      uint32_t tile_total;
+      const uint32_t ex = cta_exclusive_scan(r & ~kSideBit, s_warp, tile_total);
+      if (i < s_end) P.item_loc[i] = (run + ex) | (r & kSideBit);
+      run += tile_total;
+    }
+    publish_count(P.part_new, c, tag, s_end - s_begin);
+    publish_count(P.part_items, c, tag, run);
+    cta_prefix_wait_to_smem(P.part_new, G, tag, s_pref_new, s_warp, P.poll_ns);
+    busy[0] += globaltimer_ns() - t0;
+  }
 
   while (lo < hi) {
     const uint32_t F = hi - lo;
     unsigned long long tp0 = globaltimer_ns();
     if (n_waves + 1 >= P.wave_cap) { overflow |= kOvWaves; break; }  // uniform
     if (c == 0 && tid == 0) P.wave_lo[n_waves] = lo;
-    // ------------------------------------------------------------------ A0: per-state setup
-    const uint32_t sc = (F + G - 1) / G;  // states per CTA slice
-    {
-      const uint32_t s_begin = min(F, c * sc), s_end = min(F, s_begin + sc);
-      uint32_t run = 0;
-      for (uint32_t i0 = s_begin; i0 < s_end; i0 += kTile) {
-        const uint32_t i = i0 + tid;
-        uint32_t nitems = 0, side = 0;
-        if (i < s_end) {
-          uint32_t fs, s1, s2;
-          unpack_key(__ldcg(&P.tuples[lo + i]), fs, s1, s2);
-          const uint32_t alo = P.a.off[s1], ahi = P.a.off[s1 + 1], blo = P.b.off[s2], bhi = P.b.off[s2 + 1];
-          const uint32_t d1 = ahi - alo, d2 = bhi - blo;
-          P.st_off[i] = make_uint4(alo, ahi, blo, bhi);
-          bool mi = P.side == kMatchInput || (P.side == kMatchBoth && d1 <= d2);
-          bool hs1 = false, hs2 = false;
-          if (P.sig1.enabled) hs1 = dev_has_sigma<true>(P.sig1, P.a.arcs, alo, ahi);
-          if (P.sig2.enabled) hs2 = dev_has_sigma<false>(P.sig2, P.b.arcs, blo, bhi);
-          if (P.side == kMatchBoth && (hs1 || hs2)) {  // SigmaMatcher::priority = REQUIRE_PRIORITY (compose_fst_op.rs:199-219)
-            if (hs1 && hs2) atomicOr(&P.ctl[1], (uint32_t)kErrBothRequire);
-            mi = hs2;
-          }
-          const bool hs_searched = mi ? hs2 : hs1;
-          nitems = 1u + (mi ? d1 : d2);
-          side = mi ? kSideBit : 0u;
-          const float f1 = P.a.fin[s1], f2 = P.b.fin[s2];
-          const uint32_t ne1 = P.a.neps ? P.a.neps[s1] : 0u, ne2 = P.b.neps ? P.b.neps[s2] : 0u;
-          const uint8_t fl = (uint8_t)(((d1 == ne1 && f1 == w_zero()) ? 1 : 0) | ((ne1 == 0) ? 2 : 0) |
-                                       ((d2 == ne2 && f2 == w_zero()) ? 4 : 0) | ((ne2 == 0) ? 8 : 0) | (fs << 4) |
-                                       (hs_searched ? 64 : 0));
-          P.st_flags[i] = fl;
-          const float fw = w_times(f1, f2);  // compose_fst_op.rs:420-449
-          P.out_finals[lo + i] = w_is_zero(fw) ? w_zero() : fw;
-        }
-        uint32_t tile_total;
-        const uint32_t ex = cta_exclusive_scan(nitems, s_warp, tile_total);
-        if (i < s_end) P.item_loc[i] = (run + ex) | side;
-        run += tile_total;
-      }
-      if (tid == 0) P.part_items[c] = run;
-    }
-    { unsigned long long tb = globaltimer_ns(); busy[0] += tb - tp0; }
-    grid_barrier(P.barrier, bar_epoch);
-    unsigned long long ts1 = globaltimer_ns();
 
     // ------------------------------------------------------------------ A1: per-item matching
-    cta_prefix_to_smem(P.part_items, G, s_pref_a, s_warp);
-    const uint32_t T = s_pref_a[G];
+    cta_prefix_wait_to_smem(P.part_items, G, tag, s_pref_items, s_warp, P.poll_ns);
+    unsigned long long ts1 = globaltimer_ns();
+    const uint32_t T = s_pref_items[G];
     overflow = __ldcg(&P.ctl[1]);
     if (T > P.items_cap) overflow |= kOvScratch;
     if (overflow) break;  // uniform
-    const uint32_t ic = (((T + G - 1) / G) + kTile - 1) / kTile * kTile;  // items per CTA slice (multiple of a tile)
+    const uint32_t ic = (((T + G - 1) / G) + 31u) & ~31u;  // items per CTA slice
     const uint32_t it_begin = min(T, c * ic), it_end = min(T, it_begin + ic);
     uint32_t my_active = 0, my_arcs = 0;
     if (it_begin < it_end) {
       // state containing my first item: producing CTA slice from the shared prefix, then bisect its local offsets
       if (tid == 0) {
-        const uint32_t p = smem_segment(s_pref_a, G, it_begin);
-        const uint32_t want = it_begin - s_pref_a[p];
-        uint32_t l = min(F, p * sc), h = min(F, l + sc);
+        const uint32_t p = smem_segment(s_pref_items, G, it_begin);
+        const uint32_t want = it_begin - s_pref_items[p];
+        uint32_t l = s_pref_new[p], h = s_pref_new[p + 1];
         while (h - l > 1) {
           const uint32_t mid = (l + h) >> 1;
           if ((__ldcg(&P.item_loc[mid]) & ~kSideBit) <= want) l = mid; else h = mid;
         }
-        s_misc[0] = l;
+        s_seg[kTile + 1] = l;
       }
       __syncthreads();
-      uint32_t i_cur = s_misc[0];
+      uint32_t i_cur = s_seg[kTile + 1];
+      __syncthreads();
+      // The window of a tile = states i_cur .. i_cur + 256 with their global item offsets, flags and arc ranges.  It is
+      // loaded into registers one tile ahead (the loads fly while the current tile is matched) and committed to shared
+      // memory at the top of the tile.  Entry 256 only bounds the search, so it carries no flags / ranges.
+      uint32_t w_il = 0, w_meta = 0, w_il2 = 0, w_meta2 = 0;
+      uint4 w_off = make_uint4(0, 0, 0, 0);
+      auto window_load = [&](uint32_t i_base) {
+        const uint32_t i = i_base + tid;
+        if (i < F) { w_il = __ldcg(&P.item_loc[i]); w_meta = __ldcg(&P.st_meta[i]); w_off = __ldcg(&P.st_off[i]); }
+        if (tid == 0 && i_base + kTile < F) { w_il2 = __ldcg(&P.item_loc[i_base + kTile]); w_meta2 = __ldcg(&P.st_meta[i_base + kTile]); }
+      };
+      window_load(i_cur);
       for (uint32_t t0 = it_begin; t0 < it_end; t0 += kTile) {
-        // window of item start offsets for states i_cur .. i_cur + 256
-        for (uint32_t k = tid; k < kTile + 1; k += kCoopThreads) {
-          const uint32_t i = i_cur + k;
-          const uint32_t il = i < F ? __ldcg(&P.item_loc[i]) : 0u;
-          s_seg[k] = i < F ? s_pref_a[i / sc] + (il & ~kSideBit) : T;
-          s_side[k] = il & kSideBit;
+        PROF_START();
+        if (i_cur + tid < F) {
+          s_wrec[tid] = w_off;
+          s_seg[tid] = s_pref_items[w_meta >> 8] + (w_il & ~kSideBit);
+          s_wmeta[tid] = (w_meta & 0xFFu) | (w_il & kSideBit);
+        } else {
+          s_seg[tid] = T;
         }
+        if (tid == 0) s_seg[kTile] = (i_cur + kTile < F) ? s_pref_items[w_meta2 >> 8] + (w_il2 & ~kSideBit) : T;
         __syncthreads();
+        PROF_MARK(0);
         const uint32_t t = t0 + tid;
         uint32_t cnt_out = 0;
         uint4 rec = make_uint4(0, 0, 0, 0);
         if (t < it_end) {
           const uint32_t k = smem_segment(s_seg, kTile + 1, t);
           const uint32_t i = i_cur + k, j = t - s_seg[k];
-          const bool match_input = s_side[k] != 0;
-          const uint8_t fl = __ldcg(&P.st_flags[i]);
+          // the thread on the tile's last item knows which state holds the first item of the next tile
+          if (tid == kTile - 1) s_seg[kTile + 1] = i + (s_seg[k + 1] <= t + 1 ? 1u : 0u);
+          const uint32_t fl = s_wmeta[k];
+          const bool match_input = (fl & kSideBit) != 0;
           const uint32_t fs = (fl >> 4) & 3u;
           const bool hs_searched = (fl & 64) != 0;
           FsFlags ff;
           ff.alleps1 = fl & 1; ff.noeps1 = fl & 2; ff.alleps2 = fl & 4; ff.noeps2 = fl & 8;
-          const uint4 so = __ldcg(&P.st_off[i]);
-          const uint32_t alo = so.x, ahi = so.y, blo = so.z, bhi = so.w;
-          Label label;
+          const uint4 so = s_wrec[k];
+          // iterated side / searched side, selected without branching (lanes of a warp sit on both sides)
+          const uint32_t* __restrict__ it_lab = match_input ? P.lab1 : P.lab2;
+          const uint32_t* __restrict__ se_lab = match_input ? P.lab2 : P.lab1;
+          const uint32_t it_lo = match_input ? so.x : so.z;
+          const uint32_t se_lo = match_input ? so.z : so.x, se_hi = match_input ? so.w : so.y;
+          Label label = kNoLabel;
           uint32_t it_idx = 0xFFFFFFFFu;  // absolute index of the iterated arc; all ones = implicit epsilon loop
-          if (j == 0) label = kNoLabel;
-          else if (match_input) { it_idx = alo + j - 1; label = __ldg(&P.a.arcs[it_idx].olabel); }
-          else { it_idx = blo + j - 1; label = __ldg(&P.b.arcs[it_idx].ilabel); }
+          if (j != 0) { it_idx = it_lo + j - 1; label = __ldg(&it_lab[it_idx]); }
+          PROF_USE(label);
+          PROF_MARK(1);
           const bool has_loop = (label == kEps);
           const Label key = (label == kNoLabel) ? kEps : label;
-          uint32_t pos, end, fs_loop, fs_real;
-          if (match_input) {
-            pos = has_loop ? blo : lower_bound_label<false>(P.b.arcs, blo, bhi, key);
-            end = run_end<false>(P.b.arcs, pos, bhi, key);
-            fs_loop = has_loop ? filter_eval(P.kind, fs, ff, label, kNoLabel) : kNoFs;
-            fs_real = filter_eval(P.kind, fs, ff, label, key);
-          } else {
-            pos = has_loop ? alo : lower_bound_label<true>(P.a.arcs, alo, ahi, key);
-            end = run_end<true>(P.a.arcs, pos, ahi, key);
-            fs_loop = has_loop ? filter_eval(P.kind, fs, ff, kNoLabel, label) : kNoFs;
-            fs_real = filter_eval(P.kind, fs, ff, key, label);
-          }
+          uint32_t pos, end;
+          match_range(se_lab, se_lo, se_hi, key, has_loop, pos, end);
           uint32_t cnt = end - pos;
+          PROF_USE(cnt);
+          PROF_MARK(2);
+          // filter_tr sees (arc1.olabel, arc2.ilabel): the iterated arc's label on its own side, the match on the other
+          const uint32_t fs_loop = !has_loop ? kNoFs
+                                   : filter_eval(P.kind, fs, ff, match_input ? label : kNoLabel, match_input ? kNoLabel : label);
+          const uint32_t fs_real = filter_eval(P.kind, fs, ff, match_input ? label : key, match_input ? key : label);
           bool sigma_mode = false;
-          const SigmaDev& sg = match_input ? P.sig2 : P.sig1;  // matcher of the searched side
-          if (sg.enabled) {  // IteratorSigmaMatcher::new (sigma_matcher.rs:196-246)
-            if (label == sg.label && sg.label != kNoLabel) atomicOr(&P.ctl[1], (uint32_t)kErrBadSigmaLabel);
-            if (!has_loop && cnt == 0 && hs_searched && label != kEps && label != kNoLabel &&
-                dev_sigma_allowed(sg, label)) {
-              if (match_input) { pos = lower_bound_label<false>(P.b.arcs, blo, bhi, sg.label); end = run_end<false>(P.b.arcs, pos, bhi, sg.label); }
-              else { pos = lower_bound_label<true>(P.a.arcs, alo, ahi, sg.label); end = run_end<true>(P.a.arcs, pos, ahi, sg.label); }
-              cnt = end - pos;
-              sigma_mode = true;  // the filter sees the relabelled arc: (label, label), i.e. fs_real as computed
+          if (P.sig1.enabled | P.sig2.enabled) {
+            const SigmaDev& sg = match_input ? P.sig2 : P.sig1;  // matcher of the searched side
+            if (sg.enabled) {  // IteratorSigmaMatcher::new (sigma_matcher.rs:196-246)
+              if (label == sg.label && sg.label != kNoLabel) atomicOr(&P.ctl[4], (uint32_t)kErrBadSigmaLabel);
+              if (!has_loop && cnt == 0 && hs_searched && label != kEps && label != kNoLabel &&
+                  dev_sigma_allowed(sg, label)) {
+                pos = lower_bound_lab(se_lab, se_lo, se_hi, sg.label);
+                end = run_end_lab(se_lab, pos, se_hi, sg.label);
+                cnt = end - pos;
+                sigma_mode = true;  // the filter sees the relabelled arc: (label, label), i.e. fs_real as computed
+              }
             }
           }
           const bool loop_ok = has_loop && fs_loop != kNoFs;
@@ -262,8 +407,13 @@ k_compose_coop(CoopParams P) {
                                     ((fs_real & 3u) << 29) | (match_input ? 1u << 31 : 0u), i, it_idx);
         }
         uint32_t tile_active, tile_arcs, ex_act, ex_arcs;
-        const uint32_t act = cnt_out ? 1u : 0u;
-        cta_exclusive_scan2(act, cnt_out, s_warp, ex_act, ex_arcs, tile_active, tile_arcs);
+        const bool act = cnt_out != 0;
+        PROF_MARK(3);
+        cta_exclusive_scan_flag_count(act, cnt_out, s_warp, ex_act, ex_arcs, tile_active, tile_arcs);
+        PROF_MARK(4);
+        // (the scan's barriers make the last thread's note visible) request the next tile's window now
+        const uint32_t i_next = s_seg[kTile + 1];
+        if (t0 + kTile < it_end) window_load(i_next);
         if (t < it_end) {
           if (rec.w == 0xFFFFFFFFu) P.st_arc_loc[rec.z] = my_arcs + ex_arcs;  // first arc of state rec.z (slice-local)
           if (act) {
@@ -273,57 +423,64 @@ k_compose_coop(CoopParams P) {
           }
         }
         my_active += tile_active; my_arcs += tile_arcs;
-        // advance the state window to the state that contains the first item of the next tile
-        const uint32_t nxt = t0 + kTile;
-        __syncthreads();
-        if (tid == 0) s_misc[0] = i_cur + smem_segment(s_seg, kTile + 1, min(nxt, T - 1));
-        __syncthreads();
-        i_cur = s_misc[0];
+        i_cur = i_next;
+        __syncthreads();  // the window is overwritten at the top of the next tile
+        PROF_MARK(5);
       }
     }
-    if (tid == 0) P.part_arcs[c] = my_arcs;
+    publish_count(P.part_arcs, c, tag, my_arcs);
     busy[1] += globaltimer_ns() - ts1;
-    grid_barrier(P.barrier, bar_epoch);
-    unsigned long long tp1 = globaltimer_ns();
 
     // ------------------------------------------------------------------ B: emit
-    cta_prefix_to_smem(P.part_arcs, G, s_pref_b, s_warp);
-    const uint32_t E = s_pref_b[G];
-    overflow |= __ldcg(&P.ctl[1]);
+    cta_prefix_wait_to_smem(P.part_arcs, G, tag, s_pref_arcs, s_warp, P.poll_ns);
+    unsigned long long tp1 = globaltimer_ns();
+    const uint32_t E = s_pref_arcs[G];
+    overflow |= __ldcg(&P.ctl[4]);  // raised during A1 only, so every CTA reads the same value here
     if ((unsigned long long)base + E > P.arcs_cap) overflow |= kOvArcs;
     if (((unsigned long long)hi + E) * 2ull > P.table_cap) overflow |= kOvTable;
     const uint32_t arc_chunk = ((E + G - 1) / G + 31u) & ~31u;
     if (arc_chunk > (1u << kLocalRankBits)) overflow |= kOvChunk;
     if (overflow) break;  // uniform
     {
-      const uint32_t cta_off = s_pref_b[c];
+      const uint32_t cta_off = s_pref_arcs[c];
       Tr* __restrict__ wave_arcs = P.out_arcs + base;
       uint32_t cursor = 0;  // first record (slice-local) that can contain the next tile's first arc
+      // record window of a tile (first-arc offsets + records), loaded one tile ahead like the state window of A1
+      uint32_t w_loc = 0, w_loc2 = 0;
+      uint4 w_rec = make_uint4(0, 0, 0, 0);
+      auto window_load = [&](uint32_t cur) {
+        if (cur + tid < my_active) { w_loc = P.arc_loc[it_begin + cur + tid]; w_rec = P.recs[it_begin + cur + tid]; }
+        if (tid == 0 && cur + kTile < my_active) w_loc2 = P.arc_loc[it_begin + cur + kTile];
+      };
+      if (my_arcs) window_load(0);
       for (uint32_t e0 = 0; e0 < my_arcs; e0 += kTile) {
-        for (uint32_t k = tid; k < kTile + 1; k += kCoopThreads)
-          s_seg[k] = (cursor + k) < my_active ? P.arc_loc[it_begin + cursor + k] : my_arcs;
+        PROF_START();
+        if (cursor + tid < my_active) { s_seg[tid] = w_loc; s_wrec[tid] = w_rec; }
+        else s_seg[tid] = my_arcs;
+        if (tid == 0) s_seg[kTile] = (cursor + kTile < my_active) ? w_loc2 : my_arcs;
         __syncthreads();
+        PROF_MARK(6);
         const uint32_t el = e0 + tid;
         if (el < my_arcs) {
           const uint32_t k = smem_segment(s_seg, kTile + 1, el);
-          const uint4 rec = P.recs[it_begin + cursor + k];
+          const uint4 rec = s_wrec[k];
           const uint32_t kk = el - s_seg[k];
+          // the thread on the tile's last arc knows which record holds the first arc of the next tile
+          if (tid == kTile - 1) s_seg[kTile + 1] = cursor + k + (s_seg[k + 1] <= el + 1 ? 1u : 0u);
           const bool loop_ok = (rec.y >> 26) & 1u;
           const bool match_input = rec.y >> 31;
+          const bool it_is_loop = rec.w == 0xFFFFFFFFu, cand_is_loop = loop_ok && kk == 0;
+          const Tr* __restrict__ it_arcs = match_input ? P.a.arcs : P.b.arcs;
+          const Tr* __restrict__ cd_arcs = match_input ? P.b.arcs : P.a.arcs;
           uint32_t s1 = 0, s2 = 0;
-          const bool need_tuple = (rec.w == 0xFFFFFFFFu) || (loop_ok && kk == 0);
-          if (need_tuple) { uint32_t fs; unpack_key(__ldcg(&P.tuples[lo + rec.z]), fs, s1, s2); }
-          Tr it;
-          if (rec.w == 0xFFFFFFFFu) it = match_input ? Tr{kEps, kNoLabel, 0.0f, s1} : Tr{kNoLabel, kEps, 0.0f, s2};
-          else it = match_input ? load_tr(&P.a.arcs[rec.w]) : load_tr(&P.b.arcs[rec.w]);
-          Tr cand;
-          uint32_t fsn;
-          if (loop_ok && kk == 0) {
-            cand = match_input ? Tr{kNoLabel, kEps, 0.0f, s2} : Tr{kEps, kNoLabel, 0.0f, s1};
-            fsn = (rec.y >> 27) & 3u;
-          } else {
-            const uint32_t idx = rec.x + kk - (loop_ok ? 1u : 0u);
-            cand = match_input ? load_tr(&P.b.arcs[idx]) : load_tr(&P.a.arcs[idx]);
+          if (it_is_loop || cand_is_loop) { uint32_t fs; unpack_key(__ldcg(&P.tuples[lo + rec.z]), fs, s1, s2); }
+          // implicit epsilon loops (matcher.rs: eps_loop): (0, NO_LABEL) / (NO_LABEL, 0) staying in the same state
+          Tr it = match_input ? Tr{kEps, kNoLabel, 0.0f, s1} : Tr{kNoLabel, kEps, 0.0f, s2};
+          Tr cand = match_input ? Tr{kNoLabel, kEps, 0.0f, s2} : Tr{kEps, kNoLabel, 0.0f, s1};
+          if (!it_is_loop) it = load_tr(&it_arcs[rec.w]);
+          if (!cand_is_loop) cand = load_tr(&cd_arcs[rec.x + kk - (loop_ok ? 1u : 0u)]);
+          uint32_t fsn = (rec.y >> 27) & 3u;
+          if (!cand_is_loop) {
             fsn = (rec.y >> 29) & 3u;
             if ((rec.y >> 25) & 1u) {  // sigma match: relabel (value_openfst, sigma_matcher.rs:249-276)
               const SigmaDev& sg = match_input ? P.sig2 : P.sig1;
@@ -333,38 +490,36 @@ k_compose_coop(CoopParams P) {
               else cand.olabel = l;
             }
           }
-          const Tr& arc1 = match_input ? it : cand;
-          const Tr& arc2 = match_input ? cand : it;
           Tr out;
-          out.ilabel = arc1.ilabel;
-          out.olabel = arc2.olabel;
-          out.weight = w_times(arc1.weight, arc2.weight);
-          const unsigned long long key = pack_key(fsn, arc1.nextstate, arc2.nextstate);
+          out.ilabel = match_input ? it.ilabel : cand.ilabel;   // arc1 = the fst1 arc, arc2 = the fst2 arc
+          out.olabel = match_input ? cand.olabel : it.olabel;
+          out.weight = w_times(it.weight, cand.weight);
+          PROF_USE(__float_as_uint(out.weight));
+          PROF_MARK(7);
+          const unsigned long long key = pack_key(fsn, match_input ? it.nextstate : cand.nextstate,
+                                                  match_input ? cand.nextstate : it.nextstate);
           const uint32_t e = cta_off + el;  // canonical wave-local emission index
+          // state table: linear probing, four consecutive slots fetched per round (one latency for the usual chain);
+          // loaded non-empty keys are permanent (no deletions), loaded empties are confirmed by the CAS
           uint32_t h = hash_key(key) & P.mask;
-          while (true) {
-            unsigned long long curk = *reinterpret_cast<volatile unsigned long long*>(&P.slots[h].key);
-            if (curk == key) break;
-            if (curk == kEmptyKey) {
-              unsigned long long prev = atomicCAS(&P.slots[h].key, kEmptyKey, key);
-              if (prev == kEmptyKey || prev == key) break;
-            }
-            h = (h + 1) & P.mask;
-          }
-          const uint32_t id = *reinterpret_cast<volatile uint32_t*>(&P.slots[h].id);
+          // one slot per round: wider rounds (2 / 4 slots fetched together) were measured slower on C3 (B busy time
+          // 1.00 / 1.17 / 1.60 ms): the phase is bound by the number of memory requests, not by the probe chain
+          const uint32_t id = table_probe<1>(P.slots, P.mask, key, h);
+          PROF_USE(id);
+          PROF_MARK(8);
           if (id != kUnassigned) out.nextstate = id;
           else { atomicMin(&P.slots[h].emin, e); out.nextstate = kPendingBit | h; }
           store_tr(&wave_arcs[e], out);
         }
         __syncthreads();
-        if (tid == 0) s_misc[1] = cursor + smem_segment(s_seg, kTile + 1, min(e0 + kTile, my_arcs - 1));
-        __syncthreads();
-        cursor = s_misc[1];
+        if (e0 + kTile < my_arcs) { cursor = s_seg[kTile + 1]; window_load(cursor); }
+        PROF_MARK(9);
       }
-      // state -> first arc (CSR offsets of the result): slice of the arc owner = slice that processed item 0 of the state
-      for (uint32_t i = c * sc + tid; i < min(F, (c + 1) * sc); i += kCoopThreads) {
-        const uint32_t t_first = s_pref_a[i / sc] + (__ldcg(&P.item_loc[i]) & ~kSideBit);
-        P.out_offsets[lo + i] = base + s_pref_b[t_first / ic] + __ldcg(&P.st_arc_loc[i]);
+      // state -> first arc (CSR offsets of the result) for the states of my slice: the CTA that processed item 0 of
+      // the state knows the slice-local emission index of its first arc
+      for (uint32_t i = s_pref_new[c] + tid; i < s_pref_new[c + 1]; i += kCoopThreads) {
+        const uint32_t t_first = s_pref_items[c] + (__ldcg(&P.item_loc[i]) & ~kSideBit);
+        P.out_offsets[lo + i] = base + s_pref_arcs[t_first / ic] + __ldcg(&P.st_arc_loc[i]);
       }
     }
     busy[2] += globaltimer_ns() - tp1;
@@ -373,9 +528,9 @@ k_compose_coop(CoopParams P) {
 
     // ------------------------------------------------------------------ C: rank first emissions
     const uint32_t e_begin = min(E, c * arc_chunk), e_end = min(E, e_begin + arc_chunk);
+    uint32_t cta_new = 0;
     {
       const Tr* __restrict__ wave_arcs = P.out_arcs + base;
-      uint32_t cta_new = 0;
       for (uint32_t t0 = e_begin; t0 < e_end; t0 += kCoopThreads) {
         const uint32_t e = t0 + tid;
         bool owner = false;
@@ -389,47 +544,64 @@ k_compose_coop(CoopParams P) {
         if (owner) P.slots[h].id = kTempFlag | (c << kLocalRankBits) | (cta_new + ex);
         cta_new += tile_total;
       }
-      if (tid == 0) P.part_new[c] = cta_new;
     }
+    tag++;
+    publish_count(P.part_new, c, tag, cta_new);
     busy[3] += globaltimer_ns() - tp2;
-    grid_barrier(P.barrier, bar_epoch);
-    unsigned long long tp3 = globaltimer_ns();
 
-    // ------------------------------------------------------------------ D: resolve
-    cta_prefix_to_smem(P.part_new, G, s_pref_a, s_warp);
-    const uint32_t n_new = s_pref_a[G];
+    // ------------------------------------------------------------------ D: resolve + setup of the next frontier
+    cta_prefix_wait_to_smem(P.part_new, G, tag, s_pref_new, s_warp, P.poll_ns);
+    unsigned long long tp3 = globaltimer_ns();
+    const uint32_t n_new = s_pref_new[G];
     if ((unsigned long long)hi + n_new > P.states_cap || (unsigned long long)hi + n_new >= 0x7FFFFFFFull) {
       overflow |= kOvStates;
       break;  // uniform
     }
     {
       Tr* __restrict__ wave_arcs = P.out_arcs + base;
-      for (uint32_t e = e_begin + tid; e < e_end; e += kCoopThreads) {
-        const uint32_t ns = __ldcg(&wave_arcs[e].nextstate);
-        if (!(ns & kPendingBit)) continue;
-        const uint32_t h = ns & ~kPendingBit;
-        const uint32_t v = *reinterpret_cast<volatile uint32_t*>(&P.slots[h].id);
-        uint32_t id = v;
-        if (v & kTempFlag) id = hi + s_pref_a[(v & ~kTempFlag) >> kLocalRankBits] + (v & ((1u << kLocalRankBits) - 1u));
-        wave_arcs[e].nextstate = id;
-        if (__ldcg(&P.slots[h].emin) == e) {  // first emitter: publish
-          P.slots[h].id = id;
-          P.tuples[id] = __ldcg(&P.slots[h].key);
+      uint32_t run = 0;
+      for (uint32_t t0 = e_begin; t0 < e_end; t0 += kCoopThreads) {
+        const uint32_t e = t0 + tid;
+        uint32_t r = 0, i_new = 0;
+        if (e < e_end) {
+          const uint32_t ns = __ldcg(&wave_arcs[e].nextstate);
+          if (ns & kPendingBit) {
+            const uint32_t h = ns & ~kPendingBit;
+            const uint4 sv = ld_volatile_u4(&P.slots[h]);
+            const uint32_t v = sv.z;
+            uint32_t id = v;
+            if (v & kTempFlag) id = hi + s_pref_new[(v & ~kTempFlag) >> kLocalRankBits] + (v & ((1u << kLocalRankBits) - 1u));
+            wave_arcs[e].nextstate = id;
+            if (sv.w == e) {  // first emitter: publish, and set the state up for the next wave
+              P.slots[h].id = id;
+              const unsigned long long key = (unsigned long long)sv.x | ((unsigned long long)sv.y << 32);
+              P.tuples[id] = key;
+              i_new = id - hi;
+              r = setup_state(P, key, i_new, id, c);
+            }
+          }
         }
+        uint32_t tile_total;
+        const uint32_t ex = cta_exclusive_scan(r & ~kSideBit, s_warp, tile_total);
+        if (r) P.item_loc[i_new] = (run + ex) | (r & kSideBit);
+        run += tile_total;
       }
+      publish_count(P.part_items, c, tag, run);
     }
     n_states_exp += F; n_items += T; n_arcs += E; n_waves++;
     base += E;
     lo = hi;
     hi += n_new;
-    busy[4] += globaltimer_ns() - tp3;
-    grid_barrier(P.barrier, bar_epoch);
     unsigned long long tp4 = globaltimer_ns();
+    busy[4] += tp4 - tp3;
     t_a += tp1 - tp0; t_b += tp2 - tp1; t_c += tp3 - tp2; t_d += tp4 - tp3;
   }
 
   if (tid == 0) {
     for (int k = 0; k < 5; k++) { atomicAdd(&P.stats[8 + k], busy[k]); atomicMax(&P.stats[13 + k], busy[k]); }
+#ifdef B200_COOP_PROFILE
+    for (int k = 0; k < 12; k++) atomicAdd(&P.stats[18 + k], prof[k]);
+#endif
   }
   if (c == 0 && tid == 0) {
     P.ctl[1] = overflow;
@@ -473,21 +645,21 @@ static int grid_used = 1;
 float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   CoopParams P = P0;
   // resident CTAs per SM the kernel is compiled for (register budget): 4 -> 64 regs, 5 -> 48, 6 -> 40
-  int minb = 6;  // measured best on C3 (40 registers, no spills, 6 x 256 threads per SM)
+  int minb = 4;  // measured best on C3 (64 registers: the 16 window loads of match_range stay in flight together)
   if (const char* e = std::getenv("B200_COOP_MINBLOCKS")) minb = std::atoi(e);
-  void* kern = (void*)k_compose_coop<6>;
+  void* kern = (void*)k_compose_coop<4>;
   if (minb == 5) kern = (void*)k_compose_coop<5>;
-  else if (minb == 4) kern = (void*)k_compose_coop<4>;
+  else if (minb == 6) kern = (void*)k_compose_coop<6>;
   else if (minb == 3) kern = (void*)k_compose_coop<3>;
   else if (minb == 8) kern = (void*)k_compose_coop<8>;
   int per_sm = 0;
-  size_t dyn = 2 * 2049 * sizeof(uint32_t);
+  size_t dyn = 3 * 2049 * sizeof(uint32_t);
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoopThreads, dyn));
   if (per_sm < 1) throw FstError("cooperative compose kernel does not fit on the device");
   int grid = sms * per_sm;
   if (grid > 2047) grid = 2047;  // CTA index must fit 11 bits next to the 20-bit local rank; prefix arrays hold 2048
   grid_used = grid;
-  dyn = 2 * ((size_t)grid + 1) * sizeof(uint32_t);
+  dyn = 3 * ((size_t)grid + 1) * sizeof(uint32_t);
   void* args[] = {(void*)&P};
   cudaEvent_t e0, e1;
   float ms = 0;
@@ -560,6 +732,10 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
     P.b.neps = neps2.p; st.kernel_launches++;
   }
   P.kind = kind; P.side = side;
+  DevBuf<uint32_t> lab1(s, (size_t)fa.num_arcs + kLabelPad), lab2(s, (size_t)fb.num_arcs + kLabelPad);
+  k_extract_labels<<<blocks_for((size_t)fa.num_arcs + kLabelPad), kThreads, 0, s>>>(fa.arcs.p, fa.num_arcs, fa.num_arcs + kLabelPad, 1, lab1.p);
+  k_extract_labels<<<blocks_for((size_t)fb.num_arcs + kLabelPad), kThreads, 0, s>>>(fb.arcs.p, fb.num_arcs, fb.num_arcs + kLabelPad, 0, lab2.p);
+  P.lab1 = lab1.p; P.lab2 = lab2.p; st.kernel_launches += 2;
   DevBuf<uint32_t> allowed1(s), allowed2(s);
   auto mk_sigma = [&](const SigmaSpec& sp, uint64_t fprops, DevBuf<uint32_t>& buf) {
     SigmaDev d{};
@@ -592,20 +768,21 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   out.offsets.reserve_discard(states_cap + 1);
   out.finals.reserve_discard(states_cap);
   out.arcs.reserve_discard(arcs_cap);
-  DevBuf<unsigned long long> tuples(s, states_cap), dstats(s, 18);
+  DevBuf<unsigned long long> tuples(s, states_cap), dstats(s, 30);
   DevBuf<Slot> slots(s, table_cap);
   DevBuf<uint4> recs(s, items_cap);
-  DevBuf<uint32_t> arc_loc(s, items_cap), item_loc(s, states_cap), st_arc_loc(s, states_cap), parts(s, 3 * 2048), ctl(s, 8);
-  DevBuf<uint8_t> st_flags(s, states_cap);
+  DevBuf<uint32_t> arc_loc(s, items_cap), item_loc(s, states_cap), st_arc_loc(s, states_cap), st_meta(s, states_cap), ctl(s, 8);
+  DevBuf<unsigned long long> parts(s, 3 * 2048);
   DevBuf<uint4> st_off(s, states_cap);
   const uint32_t wave_cap = 1u << 20;
   DevBuf<uint32_t> wave_lo(s, wave_cap);
   B200_CUDA(cudaMemsetAsync(slots.p, 0xFF, table_cap * sizeof(Slot), s));
-  B200_CUDA(cudaMemsetAsync(dstats.p, 0, 18 * sizeof(unsigned long long), s));
+  B200_CUDA(cudaMemsetAsync(dstats.p, 0, 30 * sizeof(unsigned long long), s));
+  B200_CUDA(cudaMemsetAsync(parts.p, 0, 3 * 2048 * sizeof(unsigned long long), s));  // tag 0 = nothing published yet
   P.tuples = tuples.p; P.states_cap = (uint32_t)states_cap;
   P.out_offsets = out.offsets.p; P.out_finals = out.finals.p; P.out_arcs = out.arcs.p; P.arcs_cap = (uint32_t)arcs_cap;
   P.slots = slots.p; P.mask = (uint32_t)table_cap - 1; P.table_cap = (uint32_t)table_cap;
-  P.item_loc = item_loc.p; P.st_arc_loc = st_arc_loc.p; P.st_flags = st_flags.p; P.st_off = st_off.p;
+  P.item_loc = item_loc.p; P.st_arc_loc = st_arc_loc.p; P.st_meta = st_meta.p; P.st_off = st_off.p;
   P.recs = recs.p; P.arc_loc = arc_loc.p; P.items_cap = (uint32_t)std::min<size_t>(items_cap, 0xFFFFFFF0ull);
   P.part_arcs = parts.p; P.part_items = parts.p + 2048; P.part_new = parts.p + 4096;
   P.ctl = ctl.p; P.stats = dstats.p;
@@ -613,6 +790,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   P.wave_lo = wave_lo.p; P.wave_cap = wave_cap;
   uint32_t start_fs = (kind == kNullFilter || kind == kTrivialFilter || kind == kNoMatchFilter) ? 1u : 0u;
   P.n_starts = n_starts;
+  if (const char* e = std::getenv("B200_POLL_NS")) P.poll_ns = (uint32_t)std::atoi(e);
   k_coop_init<<<blocks_for(n_starts), kThreads, 0, s>>>(slots.p, P.mask, tuples.p, start_fs,
                                                         batch ? batch->d_starts1 : nullptr, fa.start, fb.start, n_starts, ctl.p);
   st.kernel_launches++;
@@ -621,9 +799,9 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   st.kernel_launches++; st.emit_launches = 1;
 
   uint32_t hctl[4];
-  unsigned long long hstats[18];
+  unsigned long long hstats[30];
   B200_CUDA(cudaMemcpyAsync(hctl, ctl.p, 16, cudaMemcpyDeviceToHost, s));
-  B200_CUDA(cudaMemcpyAsync(hstats, dstats.p, 18 * 8, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(hstats, dstats.p, 30 * 8, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
   if (hctl[1] != 0) {
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
@@ -636,10 +814,16 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   st.ms_phase[0] = hstats[4] * 1e-6f; st.ms_phase[1] = hstats[5] * 1e-6f;
   st.ms_phase[2] = hstats[6] * 1e-6f; st.ms_phase[3] = hstats[7] * 1e-6f;
   if (std::getenv("B200_COOP_TRACE")) {
-    const char* names[5] = {"A0", "A1", "B", "C", "D"};
+    const char* names[5] = {"init", "A1", "B", "C", "D+setup"};
     for (int k = 0; k < 5; k++)
       std::fprintf(stderr, "[coop] phase %s: CTA busy avg %.3f ms, max %.3f ms\n", names[k],
                    hstats[8 + k] * 1e-6 / grid_used, hstats[13 + k] * 1e-6);
+#ifdef B200_COOP_PROFILE
+    const char* pn[12] = {"A1 window fill", "A1 segment+label", "A1 match_range", "A1 filter", "A1 scan", "A1 store+advance",
+                          "B window fill", "B segment+gathers", "B table probe", "B store+advance", "-", "-"};
+    for (int k = 0; k < 10; k++)
+      std::fprintf(stderr, "[coop-prof] %-18s %.1f kcycles per CTA\n", pn[k], hstats[18 + k] * 1e-3 / grid_used);
+#endif
   }
   out.num_states = hctl[2]; out.num_arcs = hctl[3];
   out.has_start = true; out.start = 0;

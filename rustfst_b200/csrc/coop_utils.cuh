@@ -11,6 +11,7 @@ namespace coop {
 
 constexpr int kCoopThreads = 256;
 
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -73,6 +74,27 @@ __device__ __forceinline__ void cta_exclusive_scan2(uint32_t a, uint32_t b, uint
   }
   ex_a = ba + ia - a; ex_b = bb + ib - b; tot_a = ta; tot_b = tb;
 }
+// Exclusive scans of a 0/1 flag (ballot + popc) and of a count (shuffles) over the CTA, sharing the two barriers.
+__device__ __forceinline__ void cta_exclusive_scan_flag_count(bool flag, uint32_t b, uint32_t* s_warp2, uint32_t& ex_a,
+                                                              uint32_t& ex_b, uint32_t& tot_a, uint32_t& tot_b) {
+  const uint32_t wl = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, flag);
+  const uint32_t ia_ex = __popc(bal & ((1u << wl) - 1u));
+  uint32_t ib = b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t ub = __shfl_up_sync(0xFFFFFFFFu, ib, o); if ((int)wl >= o) ib += ub; }
+  __syncthreads();
+  if (wl == 31) { s_warp2[wid] = __popc(bal); s_warp2[kCoopThreads / 32 + wid] = ib; }
+  __syncthreads();
+  uint32_t ba = 0, bb = 0, ta = 0, tb = 0;
+#pragma unroll
+  for (int w = 0; w < kCoopThreads / 32; w++) {
+    uint32_t ca = s_warp2[w], cb = s_warp2[kCoopThreads / 32 + w];
+    if (w < (int)wid) { ba += ca; bb += cb; }
+    ta += ca; tb += cb;
+  }
+  ex_a = ba + ia_ex; ex_b = bb + ib - b; tot_a = ta; tot_b = tb;
+}
 // s_out[0..n] = exclusive prefix of src[0..n) (n <= 2048), computed by the whole CTA; s_out[n] = total.
 __device__ __forceinline__ void cta_prefix_to_smem(const uint32_t* __restrict__ src, uint32_t n, uint32_t* s_out,
                                                    uint32_t* s_warp) {
@@ -86,6 +108,50 @@ __device__ __forceinline__ void cta_prefix_to_smem(const uint32_t* __restrict__ 
   if (threadIdx.x == 0) s_out[n] = total;
   __syncthreads();
 }
+// ---- epoch-tagged count exchange: a grid barrier and a broadcast in one round trip.
+// Each CTA publishes one word (tag << 32 | count) after its writes of the phase; every CTA then spins until all
+// gridDim words carry the current tag and builds the exclusive prefix in shared memory.  Because every CTA waits for
+// every other CTA's word, passing the wait is a full grid barrier (release: fence + store by thread 0 after a CTA
+// barrier; acquire: relaxed polling + fence + CTA barrier).  Requires co-resident CTAs (cooperative launch) and a
+// zero-initialised array; tags start at 1 and only grow.
+__device__ __forceinline__ void publish_count(unsigned long long* part, uint32_t c, uint32_t tag, uint32_t count) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long v = ((unsigned long long)tag << 32) | count;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(part + c), "l"(v) : "memory");
+  }
+}
+__device__ __forceinline__ void cta_prefix_wait_to_smem(const unsigned long long* part, uint32_t n, uint32_t tag,
+                                                        uint32_t* s_out, uint32_t* s_warp, uint32_t poll_ns = 0) {
+  for (uint32_t i = threadIdx.x; i < n; i += kCoopThreads) {
+    unsigned long long v;
+    while (true) {
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(part + i) : "memory");
+      if ((uint32_t)(v >> 32) == tag) break;
+      if (poll_ns) __nanosleep(poll_ns);
+    }
+    s_out[i] = (uint32_t)v;
+  }
+  __threadfence();
+  __syncthreads();
+  uint32_t v[8], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { uint32_t i = threadIdx.x * 8 + k; v[k] = i < n ? s_out[i] : 0u; sum += v[k]; }
+  uint32_t total;
+  uint32_t run = cta_exclusive_scan(sum, s_warp, total);
+#pragma unroll
+  for (int k = 0; k < 8; k++) { uint32_t i = threadIdx.x * 8 + k; if (i < n) s_out[i] = run; run += v[k]; }
+  if (threadIdx.x == 0) s_out[n] = total;
+  __syncthreads();
+}
+// 128-bit load of a 16-byte record that other CTAs update concurrently (bypasses L1; one transaction)
+__device__ __forceinline__ uint4 ld_volatile_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // largest k in [0, m) with s[k] <= x   (s non-decreasing, s[0] <= x)
 __device__ __forceinline__ uint32_t smem_segment(const uint32_t* s, uint32_t m, uint32_t x) {
   uint32_t lo = 0, hi = m;

@@ -25,6 +25,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "compose_common.cuh"
 #include "coop_utils.cuh"
@@ -63,7 +65,8 @@ struct CoopParams {
   uint4* st_off;          // arc ranges of the two component states: alo, ahi, blo, bhi
   // per-wave scratch, indexed by item (active items compacted in place inside each CTA's slice)
   uint4* recs;            // x = first match, y = count|flags, z = frontier-local state, w = iterated arc (abs) or ~0
-  uint32_t* arc_loc;      // slice-local emission index of the record's first arc
+  uint32_t* arc_loc;      // warp-local emission index of the record's first arc
+  uint32_t* wpref_arcs;   // per warp (CTA * 8 + warp): arcs emitted by the lower warps of the same CTA in this wave
   uint32_t items_cap;
   // epoch-tagged count exchanges (coop_utils.cuh), gridDim entries each
   unsigned long long* part_items;   // items of each CTA's state slice
@@ -75,6 +78,7 @@ struct CoopParams {
   SigmaDev sig1, sig2;    // sigma matcher on fst1 (olabel side) / fst2 (ilabel side)
   uint32_t poll_ns;       // back-off between polls of a count word that is not there yet (0 = spin)
   uint32_t n_starts;      // initial frontier = product ids [0, n_starts) (1 for a plain compose, batch size otherwise)
+  unsigned long long* cta_trace;  // optional (B200_COOP_TRACE): per CTA {smid, busy A1, B, C, D} ; may be null
   unsigned long long* stats;  // states_expanded, arcs_iterated, arcs_emitted, waves, ns phase A, B, C, D
 };
 
@@ -96,6 +100,7 @@ __device__ __forceinline__ bool dev_sigma_allowed(const SigmaDev& sg, Label l) {
 
 constexpr uint32_t kSideBit = 0x80000000u;
 constexpr uint32_t kTile = kCoopThreads;
+constexpr uint32_t kWarps = kCoopThreads / 32;
 
 // Optional fine-grained timeline of thread 0 of every CTA (build with -DB200_COOP_PROFILE): SM cycles spent in the
 // sub-steps of the A1 and B tiles, summed over the run and averaged over the CTAs by the host.
@@ -255,11 +260,11 @@ template <int kMinBlocks>
 __global__ void __launch_bounds__(kCoopThreads, kMinBlocks)
 k_compose_coop(CoopParams P) {
   __shared__ uint32_t s_warp[2 * (kCoopThreads / 32)];
-  __shared__ uint32_t s_seg[kTile + 2];
-  __shared__ uint32_t s_wmeta[kTile + 2];
-  __shared__ uint4 s_wrec[kTile + 1];
+  __shared__ uint32_t s_wseg[kWarps][36];   // per-warp tile windows (A1: states, B: records)
+  __shared__ uint32_t s_wmeta8[kWarps][36];
+  __shared__ uint4 s_wrec8[kWarps][33];
   extern __shared__ uint32_t s_dyn[];          // three prefix arrays of gridDim + 1 entries
-  const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
+  const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   uint32_t* s_pref_items = s_dyn;
   uint32_t* s_pref_arcs = s_dyn + (G + 1);
   uint32_t* s_pref_new = s_dyn + 2 * (G + 1);
@@ -307,62 +312,77 @@ k_compose_coop(CoopParams P) {
     overflow = __ldcg(&P.ctl[1]);
     if (T > P.items_cap) overflow |= kOvScratch;
     if (overflow) break;  // uniform
-    const uint32_t ic = (((T + G - 1) / G) + 31u) & ~31u;  // items per CTA slice
-    const uint32_t it_begin = min(T, c * ic), it_end = min(T, it_begin + ic);
-    uint32_t my_active = 0, my_arcs = 0;
-    if (it_begin < it_end) {
-      // state containing my first item: producing CTA slice from the shared prefix, then bisect its local offsets
-      if (tid == 0) {
-        const uint32_t p = smem_segment(s_pref_items, G, it_begin);
-        const uint32_t want = it_begin - s_pref_items[p];
+    // Every WARP owns a contiguous run of wc items (CTA c = warps 8c .. 8c+7) and walks it in 32-item tiles without
+    // any CTA-wide barrier: the kernel is bound by latency and synchronisation, not by bandwidth, and a CTA barrier per
+    // 256-item tile made all eight warps wait for the slowest one several times per tile.
+    const uint32_t wc = (T + G * kWarps - 1) / (G * kWarps);  // items per warp
+    const uint32_t ic = wc * kWarps;                          // items per CTA
+    const uint32_t wb = min(T, c * ic + wid * wc), we = min(T, wb + wc);
+    uint32_t w_active = 0, w_arcs = 0;  // active records / emitted arcs of this warp (lane-uniform)
+    if (wb < we) {
+      uint32_t* const win_seg = s_wseg[wid];
+      uint32_t* const win_meta = s_wmeta8[wid];
+      uint4* const win_rec = s_wrec8[wid];
+      // state containing my first item: producing CTA slice from the shared prefix, then a 32-ary search (one probe per
+      // lane and round) over that slice's local item offsets
+      uint32_t i_cur;
+      {
+        const uint32_t p = smem_segment(s_pref_items, G, wb);
+        const uint32_t want = wb - s_pref_items[p];
         uint32_t l = s_pref_new[p], h = s_pref_new[p + 1];
-        while (h - l > 1) {
-          const uint32_t mid = (l + h) >> 1;
-          if ((__ldcg(&P.item_loc[mid]) & ~kSideBit) <= want) l = mid; else h = mid;
+        while (h - l > 1) {  // invariant: item_loc[l] <= want < item_loc[h] (or h = end of the slice)
+          const uint32_t step = (h - l + 31u) >> 5, idx = l + lane * step;
+          const bool ok = idx < h && (__ldcg(&P.item_loc[idx]) & ~kSideBit) <= want;
+          const uint32_t n_ok = __popc(__ballot_sync(0xFFFFFFFFu, ok));  // ok lanes form a prefix, lane 0 is always ok
+          l += (n_ok - 1u) * step;
+          h = min(h, l + step);
         }
-        s_seg[kTile + 1] = l;
+        i_cur = l;
       }
-      __syncthreads();
-      uint32_t i_cur = s_seg[kTile + 1];
-      __syncthreads();
-      // The window of a tile = states i_cur .. i_cur + 256 with their global item offsets, flags and arc ranges.  It is
-      // loaded into registers one tile ahead (the loads fly while the current tile is matched) and committed to shared
-      // memory at the top of the tile.  Entry 256 only bounds the search, so it carries no flags / ranges.
+      // The window of a tile = states i_cur .. i_cur + 32 with their global item offsets, flags and arc ranges.  It is
+      // loaded into registers one tile ahead (the loads fly while the current tile is matched) and committed to the
+      // warp's shared-memory window at the top of the tile.  Entry 32 only bounds the search.
       uint32_t w_il = 0, w_meta = 0, w_il2 = 0, w_meta2 = 0;
       uint4 w_off = make_uint4(0, 0, 0, 0);
       auto window_load = [&](uint32_t i_base) {
-        const uint32_t i = i_base + tid;
+        const uint32_t i = i_base + lane;
         if (i < F) { w_il = __ldcg(&P.item_loc[i]); w_meta = __ldcg(&P.st_meta[i]); w_off = __ldcg(&P.st_off[i]); }
-        if (tid == 0 && i_base + kTile < F) { w_il2 = __ldcg(&P.item_loc[i_base + kTile]); w_meta2 = __ldcg(&P.st_meta[i_base + kTile]); }
+        if (lane == 0 && i_base + 32 < F) { w_il2 = __ldcg(&P.item_loc[i_base + 32]); w_meta2 = __ldcg(&P.st_meta[i_base + 32]); }
       };
       window_load(i_cur);
-      for (uint32_t t0 = it_begin; t0 < it_end; t0 += kTile) {
+      for (uint32_t t0 = wb; t0 < we; t0 += 32) {
         PROF_START();
-        if (i_cur + tid < F) {
-          s_wrec[tid] = w_off;
-          s_seg[tid] = s_pref_items[w_meta >> 8] + (w_il & ~kSideBit);
-          s_wmeta[tid] = (w_meta & 0xFFu) | (w_il & kSideBit);
+        if (i_cur + lane < F) {
+          win_rec[lane] = w_off;
+          win_seg[lane] = s_pref_items[w_meta >> 8] + (w_il & ~kSideBit);
+          win_meta[lane] = (w_meta & 0xFFu) | (w_il & kSideBit);
         } else {
-          s_seg[tid] = T;
+          win_seg[lane] = T;
         }
-        if (tid == 0) s_seg[kTile] = (i_cur + kTile < F) ? s_pref_items[w_meta2 >> 8] + (w_il2 & ~kSideBit) : T;
-        __syncthreads();
+        if (lane == 0) win_seg[32] = (i_cur + 32 < F) ? s_pref_items[w_meta2 >> 8] + (w_il2 & ~kSideBit) : T;
+        __syncwarp();
         PROF_MARK(0);
-        const uint32_t t = t0 + tid;
-        uint32_t cnt_out = 0;
+        const uint32_t t = t0 + lane;
+        uint32_t cnt_out = 0, next_note = 0;
         uint4 rec = make_uint4(0, 0, 0, 0);
-        if (t < it_end) {
-          const uint32_t k = smem_segment(s_seg, kTile + 1, t);
-          const uint32_t i = i_cur + k, j = t - s_seg[k];
-          // the thread on the tile's last item knows which state holds the first item of the next tile
-          if (tid == kTile - 1) s_seg[kTile + 1] = i + (s_seg[k + 1] <= t + 1 ? 1u : 0u);
-          const uint32_t fl = s_wmeta[k];
+        const bool valid = t < we;
+        uint32_t k = 0;
+        if (valid) {
+          k = smem_segment(win_seg, 33, t);
+          // the lane on the tile's last item knows which state holds the first item of the next tile
+          next_note = i_cur + k + (win_seg[k + 1] <= t + 1 ? 1u : 0u);
+        }
+        const uint32_t i_next = __shfl_sync(0xFFFFFFFFu, next_note, 31);
+        if (t0 + 32 < we) window_load(i_next);
+        if (valid) {
+          const uint32_t i = i_cur + k, j = t - win_seg[k];
+          const uint32_t fl = win_meta[k];
           const bool match_input = (fl & kSideBit) != 0;
           const uint32_t fs = (fl >> 4) & 3u;
           const bool hs_searched = (fl & 64) != 0;
           FsFlags ff;
           ff.alleps1 = fl & 1; ff.noeps1 = fl & 2; ff.alleps2 = fl & 4; ff.noeps2 = fl & 8;
-          const uint4 so = s_wrec[k];
+          const uint4 so = win_rec[k];
           // iterated side / searched side, selected without branching (lanes of a warp sit on both sides)
           const uint32_t* __restrict__ it_lab = match_input ? P.lab1 : P.lab2;
           const uint32_t* __restrict__ se_lab = match_input ? P.lab2 : P.lab1;
@@ -406,28 +426,39 @@ k_compose_coop(CoopParams P) {
                                     (loop_ok ? 1u << 26 : 0u) | ((fs_loop & 3u) << 27) |
                                     ((fs_real & 3u) << 29) | (match_input ? 1u << 31 : 0u), i, it_idx);
         }
-        uint32_t tile_active, tile_arcs, ex_act, ex_arcs;
-        const bool act = cnt_out != 0;
         PROF_MARK(3);
-        cta_exclusive_scan_flag_count(act, cnt_out, s_warp, ex_act, ex_arcs, tile_active, tile_arcs);
+        // warp scans: active records by ballot, arcs by shuffles
+        const bool act = cnt_out != 0;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, act);
+        const uint32_t ex_act = __popc(bal & ((1u << lane) - 1u));
+        uint32_t inc = cnt_out;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += u; }
+        const uint32_t ex_arcs = inc - cnt_out;
+        const uint32_t tile_arcs = __shfl_sync(0xFFFFFFFFu, inc, 31);
         PROF_MARK(4);
-        // (the scan's barriers make the last thread's note visible) request the next tile's window now
-        const uint32_t i_next = s_seg[kTile + 1];
-        if (t0 + kTile < it_end) window_load(i_next);
-        if (t < it_end) {
-          if (rec.w == 0xFFFFFFFFu) P.st_arc_loc[rec.z] = my_arcs + ex_arcs;  // first arc of state rec.z (slice-local)
+        if (valid) {
+          if (rec.w == 0xFFFFFFFFu) P.st_arc_loc[rec.z] = w_arcs + ex_arcs;  // first arc of state rec.z (warp-local)
           if (act) {
-            const uint32_t r = it_begin + my_active + ex_act;  // in-place compaction inside my own item slice
+            const uint32_t r = wb + w_active + ex_act;  // in-place compaction inside the warp's own item run
             P.recs[r] = rec;
-            P.arc_loc[r] = my_arcs + ex_arcs;
+            P.arc_loc[r] = w_arcs + ex_arcs;
           }
         }
-        my_active += tile_active; my_arcs += tile_arcs;
+        w_active += __popc(bal); w_arcs += tile_arcs;
         i_cur = i_next;
-        __syncthreads();  // the window is overwritten at the top of the next tile
+        __syncwarp();  // the window is overwritten at the top of the next tile
         PROF_MARK(5);
       }
     }
+    // warp totals -> CTA total and the warps' exclusive arc offsets inside the CTA
+    __syncthreads();
+    if (lane == 0) s_warp[wid] = w_arcs;
+    __syncthreads();
+    uint32_t my_arcs = 0, w_pref = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kWarps; w++) { const uint32_t v = s_warp[w]; if (w < wid) w_pref += v; my_arcs += v; }
+    if (lane == 0) P.wpref_arcs[c * kWarps + wid] = w_pref;  // read by the CTAs that own the states (CSR offsets)
     publish_count(P.part_arcs, c, tag, my_arcs);
     busy[1] += globaltimer_ns() - ts1;
 
@@ -442,31 +473,39 @@ k_compose_coop(CoopParams P) {
     if (arc_chunk > (1u << kLocalRankBits)) overflow |= kOvChunk;
     if (overflow) break;  // uniform
     {
-      const uint32_t cta_off = s_pref_arcs[c];
+      // every warp emits the arcs of its own records, 32 arcs per tile, again without CTA barriers
+      const uint32_t e_off = s_pref_arcs[c] + w_pref;  // canonical wave-local emission index of the warp's first arc
       Tr* __restrict__ wave_arcs = P.out_arcs + base;
-      uint32_t cursor = 0;  // first record (slice-local) that can contain the next tile's first arc
-      // record window of a tile (first-arc offsets + records), loaded one tile ahead like the state window of A1
+      uint32_t* const win_seg = s_wseg[wid];
+      uint4* const win_rec = s_wrec8[wid];
+      uint32_t cursor = 0;  // first record (warp-local) that can contain the next tile's first arc
       uint32_t w_loc = 0, w_loc2 = 0;
       uint4 w_rec = make_uint4(0, 0, 0, 0);
       auto window_load = [&](uint32_t cur) {
-        if (cur + tid < my_active) { w_loc = P.arc_loc[it_begin + cur + tid]; w_rec = P.recs[it_begin + cur + tid]; }
-        if (tid == 0 && cur + kTile < my_active) w_loc2 = P.arc_loc[it_begin + cur + kTile];
+        if (cur + lane < w_active) { w_loc = P.arc_loc[wb + cur + lane]; w_rec = P.recs[wb + cur + lane]; }
+        if (lane == 0 && cur + 32 < w_active) w_loc2 = P.arc_loc[wb + cur + 32];
       };
-      if (my_arcs) window_load(0);
-      for (uint32_t e0 = 0; e0 < my_arcs; e0 += kTile) {
+      if (w_arcs) window_load(0);
+      for (uint32_t e0 = 0; e0 < w_arcs; e0 += 32) {
         PROF_START();
-        if (cursor + tid < my_active) { s_seg[tid] = w_loc; s_wrec[tid] = w_rec; }
-        else s_seg[tid] = my_arcs;
-        if (tid == 0) s_seg[kTile] = (cursor + kTile < my_active) ? w_loc2 : my_arcs;
-        __syncthreads();
+        if (cursor + lane < w_active) { win_seg[lane] = w_loc; win_rec[lane] = w_rec; }
+        else win_seg[lane] = w_arcs;
+        if (lane == 0) win_seg[32] = (cursor + 32 < w_active) ? w_loc2 : w_arcs;
+        __syncwarp();
         PROF_MARK(6);
-        const uint32_t el = e0 + tid;
-        if (el < my_arcs) {
-          const uint32_t k = smem_segment(s_seg, kTile + 1, el);
-          const uint4 rec = s_wrec[k];
-          const uint32_t kk = el - s_seg[k];
-          // the thread on the tile's last arc knows which record holds the first arc of the next tile
-          if (tid == kTile - 1) s_seg[kTile + 1] = cursor + k + (s_seg[k + 1] <= el + 1 ? 1u : 0u);
+        const uint32_t el = e0 + lane;
+        const bool valid = el < w_arcs;
+        uint32_t k = 0, next_note = 0;
+        if (valid) {
+          k = smem_segment(win_seg, 33, el);
+          // the lane on the tile's last arc knows which record holds the first arc of the next tile
+          next_note = cursor + k + (win_seg[k + 1] <= el + 1 ? 1u : 0u);
+        }
+        const uint32_t cursor_next = __shfl_sync(0xFFFFFFFFu, next_note, 31);
+        if (e0 + 32 < w_arcs) window_load(cursor_next);
+        if (valid) {
+          const uint4 rec = win_rec[k];
+          const uint32_t kk = el - win_seg[k];
           const bool loop_ok = (rec.y >> 26) & 1u;
           const bool match_input = rec.y >> 31;
           const bool it_is_loop = rec.w == 0xFFFFFFFFu, cand_is_loop = loop_ok && kk == 0;
@@ -498,9 +537,7 @@ k_compose_coop(CoopParams P) {
           PROF_MARK(7);
           const unsigned long long key = pack_key(fsn, match_input ? it.nextstate : cand.nextstate,
                                                   match_input ? cand.nextstate : it.nextstate);
-          const uint32_t e = cta_off + el;  // canonical wave-local emission index
-          // state table: linear probing, four consecutive slots fetched per round (one latency for the usual chain);
-          // loaded non-empty keys are permanent (no deletions), loaded empties are confirmed by the CAS
+          const uint32_t e = e_off + el;  // canonical wave-local emission index
           uint32_t h = hash_key(key) & P.mask;
           // one slot per round: wider rounds (2 / 4 slots fetched together) were measured slower on C3 (B busy time
           // 1.00 / 1.17 / 1.60 ms): the phase is bound by the number of memory requests, not by the probe chain
@@ -511,15 +548,16 @@ k_compose_coop(CoopParams P) {
           else { atomicMin(&P.slots[h].emin, e); out.nextstate = kPendingBit | h; }
           store_tr(&wave_arcs[e], out);
         }
-        __syncthreads();
-        if (e0 + kTile < my_arcs) { cursor = s_seg[kTile + 1]; window_load(cursor); }
+        cursor = cursor_next;
+        __syncwarp();
         PROF_MARK(9);
       }
-      // state -> first arc (CSR offsets of the result) for the states of my slice: the CTA that processed item 0 of
-      // the state knows the slice-local emission index of its first arc
+      // state -> first arc (CSR offsets of the result) for the states of my slice: the warp that processed item 0 of
+      // the state recorded the warp-local emission index of its first arc
       for (uint32_t i = s_pref_new[c] + tid; i < s_pref_new[c + 1]; i += kCoopThreads) {
         const uint32_t t_first = s_pref_items[c] + (__ldcg(&P.item_loc[i]) & ~kSideBit);
-        P.out_offsets[lo + i] = base + s_pref_arcs[t_first / ic] + __ldcg(&P.st_arc_loc[i]);
+        const uint32_t cw = t_first / wc;  // global warp index = CTA * 8 + warp
+        P.out_offsets[lo + i] = base + s_pref_arcs[cw / kWarps] + __ldcg(&P.wpref_arcs[cw]) + __ldcg(&P.st_arc_loc[i]);
       }
     }
     busy[2] += globaltimer_ns() - tp1;
@@ -599,6 +637,12 @@ k_compose_coop(CoopParams P) {
 
   if (tid == 0) {
     for (int k = 0; k < 5; k++) { atomicAdd(&P.stats[8 + k], busy[k]); atomicMax(&P.stats[13 + k], busy[k]); }
+    if (P.cta_trace) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      P.cta_trace[5 * c] = smid;
+      for (int k = 1; k < 5; k++) P.cta_trace[5 * c + k] = busy[k];
+    }
 #ifdef B200_COOP_PROFILE
     for (int k = 0; k < 12; k++) atomicAdd(&P.stats[18 + k], prof[k]);
 #endif
@@ -645,17 +689,21 @@ static int grid_used = 1;
 float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   CoopParams P = P0;
   // resident CTAs per SM the kernel is compiled for (register budget): 4 -> 64 regs, 5 -> 48, 6 -> 40
-  int minb = 4;  // measured best on C3 (64 registers: the 16 window loads of match_range stay in flight together)
+  int minb = 3;  // measured best on C3: 1 / 2 / 3 / 4 / 5 CTAs per SM -> 7.31 / 5.09 / 4.92 / 5.23 / 5.51 ms (more CTAs shorten
+                 // the phases but lengthen the count exchanges)
   if (const char* e = std::getenv("B200_COOP_MINBLOCKS")) minb = std::atoi(e);
-  void* kern = (void*)k_compose_coop<4>;
+  void* kern = (void*)k_compose_coop<3>;
   if (minb == 5) kern = (void*)k_compose_coop<5>;
   else if (minb == 6) kern = (void*)k_compose_coop<6>;
-  else if (minb == 3) kern = (void*)k_compose_coop<3>;
+  else if (minb == 4) kern = (void*)k_compose_coop<4>;
+  else if (minb == 2) kern = (void*)k_compose_coop<2>;
+  else if (minb == 1) kern = (void*)k_compose_coop<1>;
   else if (minb == 8) kern = (void*)k_compose_coop<8>;
   int per_sm = 0;
   size_t dyn = 3 * 2049 * sizeof(uint32_t);
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoopThreads, dyn));
   if (per_sm < 1) throw FstError("cooperative compose kernel does not fit on the device");
+  if (per_sm > minb) per_sm = minb;
   int grid = sms * per_sm;
   if (grid > 2047) grid = 2047;  // CTA index must fit 11 bits next to the 20-bit local rank; prefix arrays hold 2048
   grid_used = grid;
@@ -773,6 +821,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   DevBuf<uint4> recs(s, items_cap);
   DevBuf<uint32_t> arc_loc(s, items_cap), item_loc(s, states_cap), st_arc_loc(s, states_cap), st_meta(s, states_cap), ctl(s, 8);
   DevBuf<unsigned long long> parts(s, 3 * 2048);
+  DevBuf<uint32_t> wpref_arcs(s, 2048 * 8);
   DevBuf<uint4> st_off(s, states_cap);
   const uint32_t wave_cap = 1u << 20;
   DevBuf<uint32_t> wave_lo(s, wave_cap);
@@ -783,7 +832,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   P.out_offsets = out.offsets.p; P.out_finals = out.finals.p; P.out_arcs = out.arcs.p; P.arcs_cap = (uint32_t)arcs_cap;
   P.slots = slots.p; P.mask = (uint32_t)table_cap - 1; P.table_cap = (uint32_t)table_cap;
   P.item_loc = item_loc.p; P.st_arc_loc = st_arc_loc.p; P.st_meta = st_meta.p; P.st_off = st_off.p;
-  P.recs = recs.p; P.arc_loc = arc_loc.p; P.items_cap = (uint32_t)std::min<size_t>(items_cap, 0xFFFFFFF0ull);
+  P.recs = recs.p; P.arc_loc = arc_loc.p; P.wpref_arcs = wpref_arcs.p; P.items_cap = (uint32_t)std::min<size_t>(items_cap, 0xFFFFFFF0ull);
   P.part_arcs = parts.p; P.part_items = parts.p + 2048; P.part_new = parts.p + 4096;
   P.ctl = ctl.p; P.stats = dstats.p;
   P.barrier = ctl.p + 6;
@@ -795,6 +844,9 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
                                                         batch ? batch->d_starts1 : nullptr, fa.start, fb.start, n_starts, ctl.p);
   st.kernel_launches++;
 
+  DevBuf<unsigned long long> cta_trace(s);
+  const bool trace = std::getenv("B200_COOP_TRACE") != nullptr;
+  if (trace) { cta_trace.reserve_discard(5 * 2048); P.cta_trace = cta_trace.p; }
   float ms_kernel = run_coop(P, sm_count(), s);
   st.kernel_launches++; st.emit_launches = 1;
 
@@ -818,6 +870,20 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
     for (int k = 0; k < 5; k++)
       std::fprintf(stderr, "[coop] phase %s: CTA busy avg %.3f ms, max %.3f ms\n", names[k],
                    hstats[8 + k] * 1e-6 / grid_used, hstats[13 + k] * 1e-6);
+    {
+      // The warp schedulers favour the oldest warps, so on every SM the CTA that was launched first finishes a phase
+      // first and the youngest last: per-CTA busy time grows with the CTA index although the work is equal.  The time
+      // an SM needs for a phase is the busy time of its slowest CTA.
+      std::vector<unsigned long long> tr(5 * (size_t)grid_used);
+      B200_CUDA(cudaMemcpy(tr.data(), cta_trace.p, tr.size() * 8, cudaMemcpyDeviceToHost));
+      for (int ph = 1; ph <= 4; ph++) {
+        std::vector<double> sm_max(256, 0.0);
+        for (int c = 0; c < grid_used; c++) sm_max[tr[5 * c] & 255] = std::max(sm_max[tr[5 * c] & 255], tr[5 * c + ph] * 1e-6);
+        double sum = 0, mx = 0; int n = 0;
+        for (int m = 0; m < 256; m++) if (sm_max[m] > 0) { sum += sm_max[m]; mx = std::max(mx, sm_max[m]); n++; }
+        std::fprintf(stderr, "[coop] phase %s: slowest CTA per SM avg %.3f ms, max %.3f ms over %d SMs\n", names[ph], sum / n, mx, n);
+      }
+    }
 #ifdef B200_COOP_PROFILE
     const char* pn[12] = {"A1 window fill", "A1 segment+label", "A1 match_range", "A1 filter", "A1 scan", "A1 store+advance",
                           "B window fill", "B segment+gathers", "B table probe", "B store+advance", "-", "-"};

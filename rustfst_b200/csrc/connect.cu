@@ -115,11 +115,14 @@ struct TrimParams {
   uint32_t* ctl;         // [0] changed flag per sweep, [1] back-arc seen, [2] n_keep, [3] a_keep, [4] sweeps
   const unsigned long long* tuples; uint32_t* ntag;   // optional: s1 component of the packed tuple, gathered
   uint32_t n_starts; uint32_t* start_map;             // optional: new ids of input states 0..n_starts-1
+  uint32_t light_barrier;  // 1: arrival-counter barrier of coop_utils.cuh on ctl[5] instead of cg::grid_group::sync()
 };
 
+#define TRIM_SYNC() do { if (P.light_barrier) grid_barrier(P.ctl + 5, bar_epoch); else grid.sync(); } while (0)
 __global__ void __launch_bounds__(kCoopThreads)
 k_trim_coop(TrimParams P) {
   cg::grid_group grid = cg::this_grid();
+  unsigned int bar_epoch = 0;
   __shared__ uint32_t s_warp[kCoopThreads / 32];
   extern __shared__ uint32_t s_dyn[];
   uint32_t* s_pref_id = s_dyn;
@@ -128,6 +131,7 @@ k_trim_coop(TrimParams P) {
   const uint32_t gsize = G * kCoopThreads, gtid = c * kCoopThreads + tid;
 
   // ---- coaccessibility: reverse sweeps over the BFS waves
+  const unsigned long long t_start = globaltimer_ns();
   uint32_t sweeps = 0;
   while (true) {
     for (uint32_t k = P.n_waves; k-- > 0;) {
@@ -146,17 +150,18 @@ k_trim_coop(TrimParams P) {
           else if (back) P.ctl[1] = 1;
         }
       }
-      grid.sync();
+      TRIM_SYNC();
     }
     sweeps++;
     // another sweep is needed only if some undecided state has an arc that was looked at too early
     const uint32_t back_seen = __ldcg(&P.ctl[1]), changed = __ldcg(&P.ctl[0]);
-    grid.sync();
+    TRIM_SYNC();
     if (!back_seen || (sweeps > 1 && !changed)) break;
     if (c == 0 && tid == 0) { P.ctl[0] = 0; P.ctl[1] = 0; }
-    grid.sync();
+    TRIM_SYNC();
   }
 
+  const unsigned long long t_sweep = globaltimer_ns();
   // ---- new state ids: slice-local exclusive scan of the keep flags
   const uint32_t sc = ((P.n + G - 1) / G + kCoopThreads - 1) / kCoopThreads * kCoopThreads;
   const uint32_t s_begin = min(P.n, c * sc), s_end = min(P.n, s_begin + sc);
@@ -167,15 +172,16 @@ k_trim_coop(TrimParams P) {
       const uint32_t keep = (s < s_end) ? (uint32_t)__ldcg(&P.coacc[s]) : 0u;
       uint32_t tot;
       const uint32_t ex = cta_exclusive_scan(keep, s_warp, tot);
-      if (s < s_end) P.id_loc[s] = run + ex;
+      if (s < s_end) P.id_loc[s] = keep ? run + ex : 0xFFFFFFFFu;  // all ones = state is dropped
       run += tot;
     }
     if (tid == 0) P.part_keep[c] = run;
   }
-  grid.sync();
+  TRIM_SYNC();
   cta_prefix_to_smem(P.part_keep, G, s_pref_id, s_warp);
   const uint32_t n_keep = s_pref_id[G];
 
+  const unsigned long long t_ids = globaltimer_ns();
   // ---- surviving out-degrees: slice-local scan, indexed by old state id
   {
     uint32_t run = 0;
@@ -183,7 +189,16 @@ k_trim_coop(TrimParams P) {
       const uint32_t s = s0 + tid;
       uint32_t d = 0;
       if (s < s_end && __ldcg(&P.coacc[s])) {
-        for (uint32_t i = P.off[s]; i < P.off[s + 1]; i++) d += __ldcg(&P.coacc[__ldg(&P.arcs[i].nextstate)]);
+        const uint32_t a_lo = P.off[s], a_hi = P.off[s + 1];
+        for (uint32_t i = a_lo; i < a_hi; i += 4) {  // four arcs per round: the target look-ups fly together
+          uint32_t t[4], x[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) t[q] = __ldg(&P.arcs[min(i + q, a_hi - 1)].nextstate);
+#pragma unroll
+          for (int q = 0; q < 4; q++) x[q] = __ldcg(&P.id_loc[t[q]]);
+#pragma unroll
+          for (int q = 0; q < 4; q++) d += (i + q < a_hi && x[q] != 0xFFFFFFFFu) ? 1u : 0u;
+        }
       }
       uint32_t tot;
       const uint32_t ex = cta_exclusive_scan(d, s_warp, tot);
@@ -192,10 +207,11 @@ k_trim_coop(TrimParams P) {
     }
     if (tid == 0) P.part_deg[c] = run;
   }
-  grid.sync();
+  TRIM_SYNC();
   cta_prefix_to_smem(P.part_deg, G, s_pref_deg, s_warp);
   const uint32_t a_keep = s_pref_deg[G];
 
+  const unsigned long long t_deg = globaltimer_ns();
   // ---- gather (mutable_fst.rs:132-189: survivors keep their relative order, arcs into deleted states are dropped)
   for (uint32_t s = s_begin + tid; s < s_end; s += kCoopThreads) {
     if (!__ldcg(&P.coacc[s])) continue;
@@ -204,21 +220,35 @@ k_trim_coop(TrimParams P) {
     P.nfin[ns] = P.fin[s];
     P.noff[ns] = o;
     if (P.ntag) P.ntag[ns] = (uint32_t)(P.tuples[s] & 0x7FFFFFFFull);
-    for (uint32_t i = P.off[s]; i < P.off[s + 1]; i++) {
-      int4 v = __ldg(reinterpret_cast<const int4*>(&P.arcs[i]));
-      const uint32_t t = (uint32_t)v.w;
-      if (__ldcg(&P.coacc[t])) {
-        v.w = (int)(s_pref_id[t / sc] + __ldcg(&P.id_loc[t]));
-        *reinterpret_cast<int4*>(&P.narcs[o++]) = v;
+    const uint32_t a_lo = P.off[s], a_hi = P.off[s + 1];
+    for (uint32_t i = a_lo; i < a_hi; i += 4) {
+      int4 v[4];
+      uint32_t x[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[q] = __ldg(reinterpret_cast<const int4*>(&P.arcs[min(i + q, a_hi - 1)]));
+#pragma unroll
+      for (int q = 0; q < 4; q++) x[q] = __ldcg(&P.id_loc[(uint32_t)v[q].w]);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (i + q < a_hi && x[q] != 0xFFFFFFFFu) {
+          v[q].w = (int)(s_pref_id[(uint32_t)v[q].w / sc] + x[q]);
+          *reinterpret_cast<int4*>(&P.narcs[o++]) = v[q];
+        }
       }
     }
   }
   if (P.start_map)
     for (uint32_t i = gtid; i < P.n_starts; i += gsize)
       P.start_map[i] = __ldcg(&P.coacc[i]) ? s_pref_id[i / sc] + __ldcg(&P.id_loc[i]) : 0xFFFFFFFFu;
-  if (c == 0 && tid == 0) { P.noff[n_keep] = a_keep; P.ctl[2] = n_keep; P.ctl[3] = a_keep; P.ctl[4] = sweeps; }
+  if (c == 0 && tid == 0) {
+    P.noff[n_keep] = a_keep; P.ctl[2] = n_keep; P.ctl[3] = a_keep; P.ctl[4] = sweeps;
+    // phase times of CTA 0 in microseconds: sweep, ids, degrees, gather (its own share only)
+    P.ctl[8] = (uint32_t)((t_sweep - t_start) / 1000); P.ctl[9] = (uint32_t)((t_ids - t_sweep) / 1000);
+    P.ctl[10] = (uint32_t)((t_deg - t_ids) / 1000); P.ctl[11] = (uint32_t)((globaltimer_ns() - t_deg) / 1000);
+  }
 }
 
+#undef TRIM_SYNC
 }  // namespace
 
 DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launches, cudaStream_t s) {
@@ -327,9 +357,9 @@ DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_
     return out;
   }
   DevBuf<uint8_t> coacc(s, n);
-  DevBuf<uint32_t> id_loc(s, n), deg_loc(s, n), parts(s, 2 * 2049), ctl(s, 8);
+  DevBuf<uint32_t> id_loc(s, n), deg_loc(s, n), parts(s, 2 * 2049), ctl(s, 12);
   B200_CUDA(cudaMemsetAsync(coacc.p, 0, n, s));
-  B200_CUDA(cudaMemsetAsync(ctl.p, 0, 32, s));
+  B200_CUDA(cudaMemsetAsync(ctl.p, 0, 48, s));
   out.offsets.reserve_discard((size_t)n + 1);
   out.finals.reserve_discard(n);
   out.arcs.reserve_discard(in.num_arcs ? in.num_arcs : 1);
@@ -339,6 +369,7 @@ DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_
   P.coacc = coacc.p; P.id_loc = id_loc.p; P.deg_loc = deg_loc.p;
   P.part_keep = parts.p; P.part_deg = parts.p + 2049;
   P.noff = out.offsets.p; P.narcs = out.arcs.p; P.nfin = out.finals.p; P.ctl = ctl.p;
+  P.light_barrier = std::getenv("B200_TRIM_CG") ? 0u : 1u;
   if (extras && extras->out_tag) {
     extras->out_tag->reserve_discard(n);
     extras->out_start_map->reserve_discard(extras->n_starts);
@@ -354,9 +385,12 @@ DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_
   void* args[] = {(void*)&P};
   B200_CUDA(cudaLaunchCooperativeKernel((void*)k_trim_coop, dim3(grid), dim3(kCoopThreads), args, dyn, s));
   if (launches) *launches = 1;
-  uint32_t h[5];
-  B200_CUDA(cudaMemcpyAsync(h, ctl.p, 20, cudaMemcpyDeviceToHost, s));
+  uint32_t h[12];
+  B200_CUDA(cudaMemcpyAsync(h, ctl.p, 48, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
+  if (std::getenv("B200_COOP_TRACE"))
+    std::fprintf(stderr, "[trim] %d CTAs, %u sweeps: sweep %u us, ids %u us, degrees %u us, gather %u us\n", grid, h[4], h[8],
+                 h[9], h[10], h[11]);
   out.num_states = h[2]; out.num_arcs = h[3];
   // start remap (mutable_fst.rs:176-183): the start state is id 0 of the composed FST
   uint8_t keep0 = 0;

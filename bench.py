@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--workload", default="C3", choices=["C3", "C2", "C5"])
     ap.add_argument("--batch", type=int, default=8192, help="C5: number of linear acceptors")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; full size = 1.0)")
+    ap.add_argument("--callers", type=int, default=3, help="host threads of the supplementary concurrent e2e figure (1 = skip)")
     ap.add_argument("--no-sssp", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -385,6 +386,29 @@ def main():
     e2e = {"value": sum_over_ranks(float(e2e_arcs)) / (e2e_ms * 1e-3), "unit": "arcs/s",
            "h2d_bytes_per_step": csr_bytes(a1) + csr_bytes(a2), "d2h_bytes_per_step": int(d2h),
            "api": "fst_compose (b200_compose_with_stats) on host VectorFst handles"}
+    # Same calls issued by several host threads at once (the C-ABI is re-entrant, every call owns a stream): the PCIe
+    # link is full duplex, so one caller's upload overlaps another's kernels and download.  Supplementary figure; the
+    # headline `value` above is the single-caller number.
+    if args.callers > 1:
+        import threading
+        done = [0] * args.callers
+
+        def worker(k):
+            for _ in range(steps):
+                r, s = R.compose_with_stats(h1, h2)
+                done[k] += s["arcs_emitted"]
+                del r
+        barrier()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(args.callers)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        check_ffi_error(lib.b200_device_synchronize(), "sync")
+        dt = time.perf_counter() - t0
+        e2e["concurrent_callers"] = {"callers": args.callers, "value": float(sum(done)) / dt, "unit": "arcs/s",
+                                     "ms_per_compose": dt * 1e3 / (steps * args.callers), "timer": "host wall clock"}
     del d1, d2
 
     # ------------------------------------------------------------------ SSSP leg (C4)

@@ -101,6 +101,7 @@ __device__ __forceinline__ bool dev_sigma_allowed(const SigmaDev& sg, Label l) {
 constexpr uint32_t kSideBit = 0x80000000u;
 constexpr uint32_t kTile = kCoopThreads;
 constexpr uint32_t kWarps = kCoopThreads / 32;
+constexpr int kArcsPerThread = 4;  // rank / resolve phases: consecutive arcs per thread and round
 
 // Optional fine-grained timeline of thread 0 of every CTA (build with -DB200_COOP_PROFILE): SM cycles spent in the
 // sub-steps of the A1 and B tiles, summed over the run and averaged over the CTAs by the host.
@@ -565,22 +566,29 @@ k_compose_coop(CoopParams P) {
     unsigned long long tp2 = globaltimer_ns();
 
     // ------------------------------------------------------------------ C: rank first emissions
+    // Four consecutive arcs per thread and round (1024 arcs per CTA round): the loads of a round fly together and one
+    // CTA scan serves four arcs; a chunk is usually a single round.
     const uint32_t e_begin = min(E, c * arc_chunk), e_end = min(E, e_begin + arc_chunk);
     uint32_t cta_new = 0;
     {
       const Tr* __restrict__ wave_arcs = P.out_arcs + base;
-      for (uint32_t t0 = e_begin; t0 < e_end; t0 += kCoopThreads) {
-        const uint32_t e = t0 + tid;
-        bool owner = false;
-        uint32_t h = 0;
-        if (e < e_end) {
-          const uint32_t ns = __ldcg(&wave_arcs[e].nextstate);
-          if (ns & kPendingBit) { h = ns & ~kPendingBit; owner = (__ldcg(&P.slots[h].emin) == e); }
-        }
-        uint32_t tile_total;
-        const uint32_t ex = cta_exclusive_scan(owner ? 1u : 0u, s_warp, tile_total);
-        if (owner) P.slots[h].id = kTempFlag | (c << kLocalRankBits) | (cta_new + ex);
-        cta_new += tile_total;
+      for (uint32_t r0 = e_begin; r0 < e_end; r0 += kArcsPerThread * kCoopThreads) {
+        const uint32_t eb = r0 + kArcsPerThread * tid;
+        uint32_t ns[kArcsPerThread], em[kArcsPerThread];
+#pragma unroll
+        for (int q = 0; q < kArcsPerThread; q++) ns[q] = (eb + q < e_end) ? __ldcg(&wave_arcs[eb + q].nextstate) : 0u;
+#pragma unroll
+        for (int q = 0; q < kArcsPerThread; q++)
+          em[q] = (ns[q] & kPendingBit) ? __ldcg(&P.slots[ns[q] & ~kPendingBit].emin) : 0xFFFFFFFFu;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int q = 0; q < kArcsPerThread; q++) cnt += (em[q] == eb + q) ? 1u : 0u;  // first emitter of a new tuple
+        uint32_t round_total;
+        uint32_t r = cta_new + cta_exclusive_scan(cnt, s_warp, round_total);
+#pragma unroll
+        for (int q = 0; q < kArcsPerThread; q++)
+          if (em[q] == eb + q) { P.slots[ns[q] & ~kPendingBit].id = kTempFlag | (c << kLocalRankBits) | r; r++; }
+        cta_new += round_total;
       }
     }
     tag++;
@@ -598,31 +606,40 @@ k_compose_coop(CoopParams P) {
     {
       Tr* __restrict__ wave_arcs = P.out_arcs + base;
       uint32_t run = 0;
-      for (uint32_t t0 = e_begin; t0 < e_end; t0 += kCoopThreads) {
-        const uint32_t e = t0 + tid;
-        uint32_t r = 0, i_new = 0;
-        if (e < e_end) {
-          const uint32_t ns = __ldcg(&wave_arcs[e].nextstate);
-          if (ns & kPendingBit) {
-            const uint32_t h = ns & ~kPendingBit;
-            const uint4 sv = ld_volatile_u4(&P.slots[h]);
-            const uint32_t v = sv.z;
+      for (uint32_t r0 = e_begin; r0 < e_end; r0 += kArcsPerThread * kCoopThreads) {
+        const uint32_t eb = r0 + kArcsPerThread * tid;
+        uint32_t ns[kArcsPerThread], nit[kArcsPerThread], inew[kArcsPerThread];
+        uint4 sv[kArcsPerThread];
+#pragma unroll
+        for (int q = 0; q < kArcsPerThread; q++) ns[q] = (eb + q < e_end) ? __ldcg(&wave_arcs[eb + q].nextstate) : 0u;
+#pragma unroll
+        for (int q = 0; q < kArcsPerThread; q++)
+          sv[q] = (ns[q] & kPendingBit) ? ld_volatile_u4(&P.slots[ns[q] & ~kPendingBit]) : make_uint4(0, 0, 0, 0xFFFFFFFFu);
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < kArcsPerThread; q++) {
+          nit[q] = 0; inew[q] = 0;
+          if (ns[q] & kPendingBit) {
+            const uint32_t v = sv[q].z;
             uint32_t id = v;
             if (v & kTempFlag) id = hi + s_pref_new[(v & ~kTempFlag) >> kLocalRankBits] + (v & ((1u << kLocalRankBits) - 1u));
-            wave_arcs[e].nextstate = id;
-            if (sv.w == e) {  // first emitter: publish, and set the state up for the next wave
-              P.slots[h].id = id;
-              const unsigned long long key = (unsigned long long)sv.x | ((unsigned long long)sv.y << 32);
+            wave_arcs[eb + q].nextstate = id;
+            if (sv[q].w == eb + q) {  // first emitter: publish, and set the state up for the next wave
+              P.slots[ns[q] & ~kPendingBit].id = id;
+              const unsigned long long key = (unsigned long long)sv[q].x | ((unsigned long long)sv[q].y << 32);
               P.tuples[id] = key;
-              i_new = id - hi;
-              r = setup_state(P, key, i_new, id, c);
+              inew[q] = id - hi;
+              nit[q] = setup_state(P, key, inew[q], id, c);
+              sum += nit[q] & ~kSideBit;
             }
           }
         }
-        uint32_t tile_total;
-        const uint32_t ex = cta_exclusive_scan(r & ~kSideBit, s_warp, tile_total);
-        if (r) P.item_loc[i_new] = (run + ex) | (r & kSideBit);
-        run += tile_total;
+        uint32_t round_total;
+        uint32_t off = run + cta_exclusive_scan(sum, s_warp, round_total);
+#pragma unroll
+        for (int q = 0; q < kArcsPerThread; q++)
+          if (nit[q]) { P.item_loc[inew[q]] = off | (nit[q] & kSideBit); off += nit[q] & ~kSideBit; }
+        run += round_total;
       }
       publish_count(P.part_items, c, tag, run);
     }

@@ -28,6 +28,8 @@
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
+#include <functional>
+#include <cmath>
 #include <algorithm>
 #include <fstream>
 
@@ -1055,11 +1057,195 @@ inline uint64_t shortest_path_properties(uint64_t props, bool tree) {
   return out;
 }
 
-// shortest_path.rs:107-133 (nshortest <= 1), :173-239 single_shortest_path, :241-282 backtrace
+// ---- n > 1: shortest_distance + reverse + heap n-best -------------------------------------------------------
+// semirings/utils_float.rs:1-3 via TropicalWeight::approx_equal (tropical_weight.rs:72-74).  NOT the KDELTA `==`:
+// |inf - inf| is NaN, so two infinite weights are *not* approx_equal (the relaxation below relies on it verbatim).
+inline bool w_approx_equal(float w1, float w2, float delta) { return std::fabs(w1 - w2) <= delta; }
+
+// algorithms/shortest_distance.rs:153-237 with reverse = false (:318-323), AnyTrFilter, first_path = false,
+// retain = false.  The returned vector grows on demand (ensure_distance_index_is_valid, :137-144): its length is
+// 1 + the largest state index touched, not num_states().
+inline std::vector<float> shortest_distance(const Fst& fst, float delta) {
+  std::vector<float> distance, adder, radder;
+  std::vector<uint8_t> enqueued;
+  if (!fst.has_start) return distance;  // :158-161
+  std::unique_ptr<Queue> queue = make_auto_queue(fst);  // :319
+  auto ensure = [&](size_t index) {
+    while (distance.size() <= index) {
+      distance.push_back(W_ZERO); enqueued.push_back(0); adder.push_back(W_ZERO); radder.push_back(W_ZERO);
+    }
+  };
+  queue->clear();
+  size_t source = fst.start;
+  ensure(source);
+  distance[source] = W_ONE; adder[source] = W_ONE; radder[source] = W_ONE;
+  enqueued[source] = 1;
+  queue->enqueue((StateId)source);
+  StateId st;
+  while (queue->dequeue(&st)) {
+    size_t state = st;
+    enqueued[state] = 0;
+    float r = radder[state];
+    radder[state] = W_ZERO;
+    for (const Tr& tr : fst.states[state].trs) {
+      size_t nextstate = tr.nextstate;
+      ensure(nextstate);
+      float weight = w_times(r, tr.weight);
+      if (!w_approx_equal(distance[nextstate], w_plus(distance[nextstate], weight), delta)) {  // :217
+        adder[nextstate] = w_plus(adder[nextstate], weight);
+        distance[nextstate] = adder[nextstate];
+        radder[nextstate] = w_plus(radder[nextstate], weight);
+        if (!enqueued[state]) {  // :224 — tests `state`, not `nextstate` (reference quirk, kept)
+          queue->enqueue((StateId)nextstate);
+          enqueued[nextstate] = 1;
+        } else {
+          queue->update((StateId)nextstate);
+        }
+      }
+    }
+  }
+  return distance;
+}
+
+// algorithms/reverse.rs:33-87 (TropicalWeight: reverse() is the identity).  The property word written at :78-83
+// (reverse_properties) is never read on the shortest-path route and is not restated: props are what the mutations
+// leave.
+inline Fst reverse(const Fst& ifst) {
+  Fst ofst;
+  StateId ostart = ofst.add_state();
+  ofst.add_states(ifst.num_states());
+  std::vector<std::vector<Tr>> states_trs(ifst.num_states() + 1);
+  for (size_t is = 0; is < ifst.num_states(); is++) {
+    StateId os = (StateId)is + 1;
+    if (ifst.has_start && ifst.start == is) ofst.set_final(os, W_ONE);
+    const State& st = ifst.states[is];
+    if (st.has_final) states_trs[0].push_back(Tr{EPS_LABEL, EPS_LABEL, st.final_weight, os});
+    for (const Tr& itr : st.trs) states_trs[itr.nextstate + 1].push_back(Tr{itr.ilabel, itr.olabel, itr.weight, os});
+  }
+  for (size_t s = 0; s < states_trs.size(); s++) ofst.set_trs_unchecked((StateId)s, std::move(states_trs[s]));
+  ofst.set_start(ostart);
+  return ofst;
+}
+
+inline bool natural_less(float w1, float w2) {  // shortest_path.rs:284-286 (`==`/`!=` are the KDELTA-approximate ones)
+  return w_eq(w_plus(w1, w2), w1) && !w_eq(w1, w2);
+}
+
+// shortest_path.rs:409-518 n_shortest_path over the reversed machine, with ShortestPathCompare (:288-339) and the
+// hand-rolled binary heap (:341-407) restated verbatim (the pop order among ties decides state numbering).
+inline Fst n_shortest_path(const Fst& ifst, const std::vector<float>& distance, size_t nshortest, float delta) {
+  Fst ofst;
+  if (nshortest == 0) return ofst;
+  if (!ifst.has_start || distance.size() <= ifst.start || w_is_zero(distance[ifst.start])) return ofst;  // :427-434
+  StateId istart = ifst.start;
+  StateId ostart = ofst.add_state();
+  ofst.set_start(ostart);
+  StateId final_state = ofst.add_state();
+  ofst.set_final(final_state, W_ONE);
+  struct Pair { bool some; StateId state; float w; };
+  std::vector<Pair> pairs(final_state + 1, Pair{false, 0, W_ZERO});
+  pairs[final_state] = Pair{true, istart, W_ONE};
+
+  auto pweight = [&](const Pair& p) -> float {  // :309-321
+    if (p.some) return p.state < distance.size() ? distance[p.state] : W_ZERO;
+    return W_ONE;
+  };
+  auto compare = [&](StateId x, StateId y) -> bool {  // :323-338
+    const Pair& px = pairs[x];
+    const Pair& py = pairs[y];
+    float wx = w_times(pweight(px), px.w);
+    float wy = w_times(pweight(py), py.w);
+    if (!px.some && py.some) return natural_less(wy, wx) || w_approx_equal(wx, wy, delta);
+    if (px.some && !py.some) return natural_less(wy, wx) && !w_approx_equal(wx, wy, delta);
+    return natural_less(wy, wx);
+  };
+  std::vector<StateId> heap;
+  std::function<void(size_t)> sift_up = [&](size_t idx) {  // :361-369
+    if (idx > 0) {
+      size_t parent_idx = (idx - 1) / 2;
+      if (compare(heap[parent_idx], heap[idx])) { std::swap(heap[idx], heap[parent_idx]); sift_up(parent_idx); }
+    }
+  };
+  std::function<void(size_t)> sift_down = [&](size_t idx) {  // :374-392
+    StateId cur_val = heap[idx];
+    size_t c1 = 2 * idx + 1, c2 = 2 * idx + 2, big;
+    if (c1 >= heap.size() && c2 >= heap.size()) return;
+    else if (c1 < heap.size() && c2 >= heap.size()) big = c1;
+    else if (compare(heap[c1], heap[c2])) big = c2;
+    else big = c1;
+    if (!compare(heap[big], cur_val)) { std::swap(heap[idx], heap[big]); sift_down(big); }
+  };
+  auto push = [&](StateId v) { heap.push_back(v); sift_up(heap.size() - 1); };
+  auto pop = [&]() -> StateId {  // :393-402
+    StateId top = heap[0];
+    if (heap.size() == 1) heap.clear();
+    else { heap[0] = heap.back(); heap.pop_back(); sift_down(0); }
+    return top;
+  };
+  push(final_state);
+  float limit = w_times(distance[istart], W_ZERO);  // weight_threshold = zero (:448-449)
+  std::vector<size_t> r;
+  while (!heap.empty()) {
+    StateId state = pop();
+    Pair p = pairs[state];
+    size_t p_first_real = p.some ? (size_t)p.state + 1 : 0;
+    float d = p.some ? (p.state < distance.size() ? distance[p.state] : W_ZERO) : W_ONE;
+    if (natural_less(limit, w_times(d, p.w))) continue;
+    while (r.size() <= p_first_real) r.push_back(0);
+    r[p_first_real] += 1;
+    if (!p.some) ofst.add_tr(ofst.start, Tr{0, 0, W_ONE, state});
+    if (!p.some && r[p_first_real] == nshortest) break;
+    if (r[p_first_real] > nshortest) continue;
+    if (!p.some) continue;
+    for (const Tr& rarc : ifst.states[p.state].trs) {
+      Tr tr{rarc.ilabel, rarc.olabel, rarc.weight, rarc.nextstate};
+      float weight = w_times(p.w, tr.weight);
+      StateId next = ofst.add_state();
+      pairs.push_back(Pair{true, tr.nextstate, weight});
+      tr.nextstate = state;
+      ofst.add_tr(next, tr);
+      push(next);
+    }
+    const State& ist = ifst.states[p.state];
+    if (ist.has_final && !w_is_zero(ist.final_weight)) {
+      float weight = w_times(p.w, ist.final_weight);
+      StateId next = ofst.add_state();
+      pairs.push_back(Pair{false, 0, weight});
+      ofst.add_tr(next, Tr{0, 0, ist.final_weight, state});
+      push(next);
+    }
+  }
+  connect(ofst);
+  ofst.set_properties_with_mask(shortest_path_properties(ofst.props, false), P::ALL);
+  return ofst;
+}
+
+// shortest_path.rs:107-171 (dispatch), :173-239 single_shortest_path, :241-282 backtrace
 inline Fst shortest_path(const Fst& ifst, const ShortestPathConfig& cfg, SsspStats* stats = nullptr,
                          std::vector<float>* distance_out = nullptr) {
   if (cfg.nshortest == 0) return Fst();
-  if (cfg.nshortest != 1) throw std::runtime_error("oracle: nshortest > 1 is not restated (out of first scope)");
+  if (cfg.nshortest != 1) {  // :135-170
+    std::vector<float> distance = shortest_distance(ifst, cfg.delta);
+    Fst rfst = reverse(ifst);
+    float d = W_ZERO;
+    for (const Tr& rarc : rfst.states[0].trs) {
+      size_t state = rarc.nextstate - 1;
+      if (state < distance.size()) d = w_plus(d, w_times(rarc.weight, distance[state]));
+    }
+    std::vector<float> distance_2;
+    distance_2.reserve(distance.size() + 1);
+    distance_2.push_back(d);
+    distance_2.insert(distance_2.end(), distance.begin(), distance.end());
+    if (distance_out) *distance_out = distance;
+    if (cfg.unique)
+      // determinize_with_distance (determinize_fsa_op.rs:154-165) rebuilds each weighted subset from
+      // `HashMap::values()` of a RandomState map: element order, hence subset identity, state numbering and even
+      // the number of states, change from process to process in the reference itself.  There is no reproducible
+      // answer to restate.
+      throw std::runtime_error("oracle: unique n-shortest paths are not restated (reference output is "
+                               "process-dependent: HashMap iteration order in determinize_fsa_op.rs:154-165)");
+    return n_shortest_path(rfst, distance_2, cfg.nshortest, cfg.delta);
+  }
 
   std::vector<float> distance;
   std::vector<int64_t> parent_state;  // -1 = None

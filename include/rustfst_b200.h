@@ -92,7 +92,9 @@ RUSTFST_FFI_RESULT fst_matcher_config_destroy(CMatcherConfig* ptr);         /* c
 
 /* rustfst-ffi/src/algorithms/shortest_path.rs:44-57 (ShortestPathConfig::default(): nshortest = 1) */
 RUSTFST_FFI_RESULT fst_shortest_path(const CFst* ptr, const CFst** res_fst);
-/* rustfst-ffi/src/algorithms/shortest_path.rs:62-83 (nshortest 0 and 1; > 1 returns KO in this build) */
+/* rustfst-ffi/src/algorithms/shortest_path.rs:62-83.  nshortest > 1 with unique = true returns KO: the reference
+ * determinizes through a RandomState HashMap iteration (determinize_fsa_op.rs:154-165), so its own output differs from
+ * process to process and there is no answer to be identical to. */
 RUSTFST_FFI_RESULT fst_shortest_path_with_config(const CFst* ptr, const CShortestPathConfig* config,
                                                  const CFst** res_fst);
 /* rustfst-ffi/src/algorithms/shortest_path.rs:22-39 */
@@ -203,7 +205,8 @@ typedef struct B200ComposeStats {
 } B200ComposeStats;
 typedef struct B200SsspStats {
   uint64_t arcs_relaxed, states_settled, waves, kernel_launches, relax_launches;
-  int32_t path;      /* 0 parallel relaxation + certificate, 1 order-faithful serial kernel */
+  int32_t path;      /* 0 parallel relaxation + certificate, 1 order-faithful serial kernel, 2 order-faithful
+                        parallel fold; for nshortest > 1: the path the forward-distance pass took */
   int32_t queue_kind; /* 0 StateOrder, 1 TopOrder, 2 Lifo, 3 Scc */
   float ms_device, ms_relax_kernel;
   float ms_h2d;

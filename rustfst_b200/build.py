@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librustfst_b200.so")
-SOURCES = ["capi.cu", "compose.cu", "compose_coop.cu", "connect.cu", "sssp.cu", "device_common.cu", "queue_plan.cpp"]
+SOURCES = ["capi.cu", "compose.cu", "compose_coop.cu", "connect.cu", "sssp.cu", "nshortest.cu", "device_common.cu", "queue_plan.cpp"]
 HEADERS = ["algos.h", "compose_common.cuh", "device_common.cuh", "fst_types.h", "host_fst.h", os.path.join("..", "..", "include", "rustfst_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--cudart", "static",

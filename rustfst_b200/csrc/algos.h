@@ -111,4 +111,27 @@ struct SsspStats {
 CsrFst shortest_path_device(const DevFst& fst, const QueuePlan& plan, SsspStats* stats, cudaStream_t s,
                             bool force_serial = false);
 
+// Forward shortest distances from the start state with the semantics of shortest_distance_with_config(fst, false,
+// delta) (rustfst/src/algorithms/shortest_distance.rs:153-237,312-323): out[s] for s < num_states, +inf = unreached
+// (the reference's vector may be shorter; missing entries read as zero() everywhere it is used).
+void shortest_distance_device(const DevFst& fst, const QueuePlan& plan, float delta, DevBuf<float>& out,
+                              SsspStats* stats, cudaStream_t s, bool force_serial = false);
+
+// reverse() of rustfst/src/algorithms/reverse.rs:33-87 as a device CSR: state 0 = superinitial with one epsilon arc
+// per final state (in state order, weight = final weight), state t + 1 = in-arcs of t in (source state, arc
+// position) order with nextstate = source + 1; final: start + 1 with weight one().
+DevFst reverse_device(const DevFst& fst, cudaStream_t s, uint64_t* launches = nullptr);
+
+// n > 1 shortest paths (shortest_path.rs:135-170 with unique = false, n_shortest_path :409-518): distances and the
+// reversed machine are built on the device, the n-best heap search runs on the host over rows fetched on demand,
+// the result tree is trimmed on the device.  inf_finals = states that are final with weight +inf (host-only notion).
+struct NShortestStats {
+  SsspStats distance;
+  uint64_t heap_pops = 0, rows_fetched = 0, arcs_fetched = 0, states_before_trim = 0;
+  float ms_distance = 0, ms_reverse = 0, ms_search_host = 0, ms_total = 0;
+};
+CsrFst n_shortest_paths_device(const DevFst& fst, const std::vector<StateId>& inf_finals, const QueuePlan& plan,
+                               size_t nshortest, float delta, NShortestStats* stats, cudaStream_t s,
+                               bool force_serial = false);
+
 }  // namespace b200

@@ -125,14 +125,25 @@ CFst* shortest_path_host(const CFst* in, const CShortestPathConfig* cfg, B200Sss
     if (stats) std::memset(stats, 0, sizeof(*stats));
     return new CFst{};
   }
-  if (nshortest != 1)
-    throw FstError("shortest_path with nshortest > 1 is not supported by this build of librustfst_b200");
+  if (nshortest != 1 && cfg->unique)
+    // shortest_path.rs:156-165 determinizes the reversed machine; determinize_fsa_op.rs:154-165 rebuilds every
+    // weighted subset from HashMap::values() of a RandomState map, so the reference's own answer (subset identity,
+    // state numbering, even the number of states) changes from process to process: nothing to be identical to.
+    throw FstError("shortest_path with nshortest > 1 and unique = true is not supported by this build of "
+                   "librustfst_b200 (the reference result is process-dependent; use unique = false)");
   const CsrFst& h = nn(in, "fst")->fst.freeze();
   QueuePlan plan = build_queue_plan(h);
   Stream st;
   double t0 = now_ms();
   DevFst d = upload(h, st.s);
   double t1 = now_ms();
+  if (nshortest != 1) {  // shortest_path.rs:135-170
+    NShortestStats ns;
+    CsrFst r = n_shortest_paths_device(d, h.inf_finals, plan, nshortest, cfg->delta, &ns, st.s, force_serial);
+    ns.distance.ms_device = ns.ms_total;
+    fill(stats, ns.distance, (int)plan.kind, (float)(t1 - t0));
+    return new CFst{HostFst(std::move(r))};
+  }
   SsspStats ss;
   CsrFst r = shortest_path_device(d, plan, &ss, st.s, force_serial);
   fill(stats, ss, (int)plan.kind, (float)(t1 - t0));

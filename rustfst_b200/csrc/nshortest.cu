@@ -1,0 +1,283 @@
+// nshortest.cu — n > 1 shortest paths over the tropical semiring on B200.
+//
+// Replaces (paths relative to /root/reference):
+//   rustfst/src/algorithms/shortest_path.rs:135-170   the nshortest > 1 branch of shortest_path_with_config
+//   rustfst/src/algorithms/reverse.rs:33-87           reverse (superinitial state, stable in-arc order)
+//   rustfst/src/algorithms/shortest_path.rs:288-518   ShortestPathCompare, Heap, n_shortest_path
+//
+// Work split.  The two passes over the whole machine are data parallel and run on the device:
+//   * forward distances (sssp.cu: shortest_distance_device);
+//   * the reversed machine: ONE stable radix sort of (reversed-row id) over a list holding first the N "final weight"
+//     pseudo-arcs and then the A arcs in CSR order, followed by one gather.  A stable sort keeps CSR order inside a
+//     row, which is exactly the (source state, arc position) push order of reverse.rs:62-71, and puts the
+//     superinitial state's arcs (row 0) in state order (reverse.rs:57-60).
+// The n-best search itself is a best-first search driven by a binary heap whose pop order (ties included) decides
+// the numbering of the result states: inherently sequential, O(n * path length * degree) steps that touch a few
+// thousand arcs.  It runs on the host (as SURVEY.md §8f ranks it) over rows of the reversed machine fetched on
+// demand from HBM — the reversed machine never leaves the device.  The search tree is trimmed by connect_device.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <vector>
+
+#include "algos.h"
+
+namespace b200 {
+namespace {
+
+// keys[0..n)   : row of the final-weight pseudo arc of state s (0 = superinitial row, n + 1 = "none" sentinel row)
+// keys[n..n+A) : row of arc e = nextstate + 1
+// vals[i] = i; src_of[e] = source state of arc e; rows[r] += 1 (row sizes; rows has n + 2 entries, zeroed)
+__global__ void __launch_bounds__(kThreads)
+k_rev_keys(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, const float* __restrict__ fin, uint32_t n,
+           unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ src_of,
+           uint32_t* __restrict__ rows) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool is_final = s < n && fin[s] != w_zero();
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_final);
+  if (m && (threadIdx.x & 31) == (uint32_t)(__ffs(m) - 1)) atomicAdd(&rows[0], (uint32_t)__popc(m));
+  if (s >= n) return;
+  keys[s] = is_final ? 0ull : (unsigned long long)n + 1ull;
+  vals[s] = s;
+  for (uint32_t e = off[s]; e < off[s + 1]; e++) {
+    const uint32_t t = __ldg(&arcs[e].nextstate);
+    keys[(size_t)n + e] = (unsigned long long)t + 1ull;
+    vals[(size_t)n + e] = n + e;
+    src_of[e] = s;
+    atomicAdd(&rows[t + 1], 1u);
+  }
+}
+
+// out[k] = the k-th entry of the sorted list, rewritten as an arc of the reversed machine.
+__global__ void __launch_bounds__(kThreads)
+k_rev_gather(const Tr* __restrict__ arcs, const float* __restrict__ fin, uint32_t n,
+             const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ src_of, uint32_t count,
+             Tr* __restrict__ out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const uint32_t i = sorted[k];
+  Tr tr;
+  if (i < n) {  // reverse.rs:57-60
+    tr.ilabel = kEps; tr.olabel = kEps; tr.weight = fin[i]; tr.nextstate = i + 1;
+  } else {      // reverse.rs:62-67
+    const uint32_t e = i - n;
+    const int4 v = __ldg(reinterpret_cast<const int4*>(&arcs[e]));
+    tr.ilabel = (uint32_t)v.x; tr.olabel = (uint32_t)v.y; tr.weight = __int_as_float(v.z);
+    tr.nextstate = src_of[e] + 1;
+  }
+  *reinterpret_cast<int4*>(&out[k]) = *reinterpret_cast<const int4*>(&tr);
+}
+
+__global__ void k_rev_finals(float* __restrict__ fin, uint32_t n1, uint32_t final_state, bool has_final) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n1) fin[s] = (has_final && s == final_state) ? 0.0f : w_zero();
+}
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// shortest_path.rs:284-286; `==` / `!=` on TropicalWeight are the KDELTA-approximate ones (semiring.rs:159-168)
+inline bool natural_less(float w1, float w2) { return w_approx_eq(w_plus(w1, w2), w1) && !w_approx_eq(w1, w2); }
+// TropicalWeight::approx_equal(.., delta) (tropical_weight.rs:72-74, utils_float.rs:1-3)
+inline bool approx_equal(float a, float b, float delta) { return std::fabs(a - b) <= delta; }
+
+}  // namespace
+
+DevFst reverse_device(const DevFst& f, cudaStream_t s, uint64_t* launches) {
+  const uint32_t n = f.num_states, A = f.num_arcs;
+  if ((size_t)n + A >= 0xFFFFFFF0ull) throw FstError("reverse: machine too large for 32-bit arc ids");
+  DevFst r(s);
+  r.num_states = n + 1;
+  r.has_start = true; r.start = 0;
+  const size_t total = (size_t)n + A;
+  DevBuf<unsigned long long> k_in(s, total ? total : 1), k_out(s, total ? total : 1);
+  DevBuf<uint32_t> v_in(s, total ? total : 1), v_out(s, total ? total : 1), src_of(s, A ? A : 1);
+  DevBuf<uint8_t> tmp(s);
+  r.offsets.reserve_discard((size_t)n + 3);  // rows 0 .. n (+ the sentinel row n + 1 during construction)
+  B200_CUDA(cudaMemsetAsync(r.offsets.p, 0, ((size_t)n + 3) * 4, s));
+  uint64_t nl = 0;
+  if (n) {
+    k_rev_keys<<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, f.finals.p, n, k_in.p, v_in.p, src_of.p,
+                                                  r.offsets.p);
+    nl++;
+  }
+  exclusive_sum_u32(r.offsets.p, r.offsets.p, (size_t)n + 2, tmp, s);  // offsets[n + 1] = #real arcs
+  int bits = 1;
+  while (((unsigned long long)n + 1ull) >> bits) bits++;
+  if (total) sort_pairs_u64_u32(k_in.p, k_out.p, v_in.p, v_out.p, total, bits, tmp, s);
+  uint32_t count = read_u32(r.offsets.p + n + 1, s);
+  r.num_arcs = count;
+  r.arcs.reserve_discard(count ? count : 1);
+  if (count) {
+    k_rev_gather<<<blocks_for(count), kThreads, 0, s>>>(f.arcs.p, f.finals.p, n, v_out.p, src_of.p, count, r.arcs.p);
+    nl++;
+  }
+  r.finals.reserve_discard((size_t)n + 1);
+  k_rev_finals<<<blocks_for((size_t)n + 1), kThreads, 0, s>>>(r.finals.p, n + 1, f.start + 1, f.has_start);
+  nl++;
+  r.props = 0;  // reverse_properties (reverse.rs:78-83) is never read on this route
+  if (launches) *launches += nl + 2;  // + scan + sort (library passes counted once each)
+  return r;
+}
+
+CsrFst n_shortest_paths_device(const DevFst& f, const std::vector<StateId>& inf_finals, const QueuePlan& plan,
+                               size_t nshortest, float delta, NShortestStats* stats, cudaStream_t s,
+                               bool force_serial) {
+  NShortestStats local;
+  NShortestStats& st = stats ? *stats : local;
+  st = NShortestStats();
+  const double t_begin = now_ms();
+  CsrFst empty;  // FO::new(): shortest_path.rs:419-434 return the untouched new FST (null_properties)
+  if (nshortest == 0) return empty;
+  const uint32_t n = f.num_states;
+
+  // ---- device: forward distances (shortest_path.rs:139-140) and the reversed machine (:142)
+  DevBuf<float> d_dist(s);
+  double t0 = now_ms();
+  shortest_distance_device(f, plan, delta, d_dist, &st.distance, s, force_serial);
+  B200_CUDA(cudaStreamSynchronize(s));
+  st.ms_distance = (float)(now_ms() - t0);
+  t0 = now_ms();
+  DevFst r = reverse_device(f, s, &st.distance.kernel_launches);
+  std::vector<float> dist((size_t)n, w_zero());
+  std::vector<uint32_t> roff((size_t)n + 2, 0);
+  if (n && f.has_start) B200_CUDA(cudaMemcpyAsync(dist.data(), d_dist.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(roff.data(), r.offsets.p, ((size_t)n + 2) * 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  st.ms_reverse = (float)(now_ms() - t0);
+  t0 = now_ms();
+
+  // A row of the reversed machine, fetched from HBM.  Row 0 also receives the `Some(+inf)` finals, which the
+  // device representation (+inf = not final) cannot tell from non-final states; they are merged by state id.
+  std::vector<Tr> row;
+  auto fetch_row = [&](uint32_t q) {
+    const uint32_t b = roff[q], e = roff[q + 1];
+    row.resize(e - b);
+    if (e > b) {
+      B200_CUDA(cudaMemcpyAsync(row.data(), r.arcs.p + b, (size_t)(e - b) * 16, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+    }
+    st.rows_fetched++; st.arcs_fetched += e - b;
+    if (q == 0 && !inf_finals.empty()) {
+      std::vector<Tr> merged;
+      merged.reserve(row.size() + inf_finals.size());
+      size_t i = 0;
+      for (StateId fs : inf_finals) {
+        while (i < row.size() && row[i].nextstate < fs + 1) merged.push_back(row[i++]);
+        merged.push_back(Tr{kEps, kEps, w_zero(), fs + 1});
+      }
+      while (i < row.size()) merged.push_back(row[i++]);
+      row.swap(merged);
+    }
+  };
+  // distance_2 of shortest_path.rs:153-154: index 0 = the superinitial state, index q = distance[q - 1]
+  float d0 = w_zero();
+  fetch_row(0);
+  const std::vector<Tr> row0 = row;
+  for (const Tr& rarc : row0) {  // :144-150
+    const size_t state = rarc.nextstate - 1;
+    if (state < dist.size()) d0 = w_plus(d0, w_times(rarc.weight, dist[state]));
+  }
+  auto distance2 = [&](uint32_t q) -> float { return q == 0 ? d0 : (q - 1 < dist.size() ? dist[q - 1] : w_zero()); };
+
+  // ---- host: n_shortest_path (shortest_path.rs:409-518) over the reversed machine
+  if (w_is_zero(d0)) { st.ms_total = (float)(now_ms() - t_begin); return empty; }  // :427-434 (istart = 0 always exists)
+  HostFst ofst;
+  const StateId ostart = ofst.add_state();
+  ofst.set_start(ostart);
+  const StateId final_state = ofst.add_state();
+  ofst.set_final(final_state, 0.0f);
+  struct Pair { bool some; uint32_t state; float w; };
+  std::vector<Pair> pairs(final_state + 1, Pair{false, 0, w_zero()});
+  pairs[final_state] = Pair{true, 0, 0.0f};
+  // Keys of ShortestPathCompare (:323-338) are pure functions of a pair, fixed at push time: cache them.
+  struct Key { float w; bool some; };
+  std::vector<Key> keys(pairs.size());
+  auto key_of = [&](const Pair& p) { return Key{w_times(p.some ? distance2(p.state) : 0.0f, p.w), p.some}; };
+  keys[final_state] = key_of(pairs[final_state]);
+  auto compare = [&](StateId x, StateId y) -> bool {
+    const Key &kx = keys[x], &ky = keys[y];
+    if (!kx.some && ky.some) return natural_less(ky.w, kx.w) || approx_equal(kx.w, ky.w, delta);
+    if (kx.some && !ky.some) return natural_less(ky.w, kx.w) && !approx_equal(kx.w, ky.w, delta);
+    return natural_less(ky.w, kx.w);
+  };
+  std::vector<StateId> heap;  // Heap of :341-407, restated (iteratively) with the same comparisons in the same order
+  auto sift_up = [&](size_t idx) {
+    while (idx > 0) {
+      const size_t parent = (idx - 1) / 2;
+      if (!compare(heap[parent], heap[idx])) break;
+      std::swap(heap[idx], heap[parent]);
+      idx = parent;
+    }
+  };
+  auto sift_down = [&](size_t idx) {
+    while (true) {
+      const StateId cur = heap[idx];
+      const size_t c1 = 2 * idx + 1, c2 = 2 * idx + 2;
+      size_t big;
+      if (c1 >= heap.size() && c2 >= heap.size()) return;
+      else if (c1 < heap.size() && c2 >= heap.size()) big = c1;
+      else if (compare(heap[c1], heap[c2])) big = c2;
+      else big = c1;
+      if (compare(heap[big], cur)) return;
+      std::swap(heap[idx], heap[big]);
+      idx = big;
+    }
+  };
+  auto push = [&](StateId v) { heap.push_back(v); sift_up(heap.size() - 1); };
+  auto pop = [&]() -> StateId {
+    const StateId top = heap[0];
+    if (heap.size() == 1) heap.clear();
+    else { heap[0] = heap.back(); heap.pop_back(); sift_down(0); }
+    return top;
+  };
+  push(final_state);
+  const float limit = w_times(d0, w_zero());  // weight_threshold = zero(): :448-449
+  std::vector<size_t> seen;                    // r of :451
+  const uint32_t rfinal = f.has_start ? f.start + 1 : kNoState;
+  while (!heap.empty()) {
+    const StateId state = pop();
+    st.heap_pops++;
+    const Pair p = pairs[state];
+    const size_t first_real = p.some ? (size_t)p.state + 1 : 0;
+    const float d = p.some ? distance2(p.state) : 0.0f;
+    if (natural_less(limit, w_times(d, p.w))) continue;
+    if (seen.size() <= first_real) seen.resize(first_real + 1, 0);
+    seen[first_real] += 1;
+    if (!p.some) ofst.add_tr(ostart, Tr{0, 0, 0.0f, state});
+    if (!p.some && seen[first_real] == nshortest) break;
+    if (seen[first_real] > nshortest) continue;
+    if (!p.some) continue;
+    if (p.state == 0) row = row0; else fetch_row(p.state);
+    for (const Tr& rarc : row) {
+      const float weight = w_times(p.w, rarc.weight);
+      const StateId next = ofst.add_state();
+      pairs.push_back(Pair{true, rarc.nextstate, weight});
+      keys.push_back(key_of(pairs.back()));
+      ofst.add_tr(next, Tr{rarc.ilabel, rarc.olabel, rarc.weight, state});
+      push(next);
+    }
+    if (p.state == rfinal) {  // the only final state of the reversed machine, weight one(): reverse.rs:54-56
+      const float weight = w_times(p.w, 0.0f);
+      const StateId next = ofst.add_state();
+      pairs.push_back(Pair{false, 0, weight});
+      keys.push_back(key_of(pairs.back()));
+      ofst.add_tr(next, Tr{0, 0, 0.0f, state});
+      push(next);
+    }
+  }
+  st.ms_search_host = (float)(now_ms() - t0);
+  st.states_before_trim = ofst.num_states();
+
+  // ---- device: connect (:511) + shortest_path_properties(.., false) (:512-515)
+  const CsrFst& ho = ofst.freeze();
+  DevFst dofst = upload(ho, s);
+  DevFst trimmed = connect_device(dofst, false, &st.distance.kernel_launches, s);
+  CsrFst out = download(trimmed, s);
+  out.props = props::of_shortest_path(out.props, false) & props::kTrinary;
+  st.ms_total = (float)(now_ms() - t_begin);
+  return out;
+}
+
+}  // namespace b200

@@ -189,10 +189,14 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
 }
 
 // Parent selection + certificate over all arcs of reached states.  flags[0] = certificate violations.
+// kAbs selects the approximate test the caller's reference loop uses: false = the KDELTA `==` of
+// semiring.rs:159-168 (single_shortest_path), true = approx_equal(.., delta) = |a - b| <= delta
+// (utils_float.rs:1-3, shortest_distance.rs:217).  pkey may be null (distances only).
+template <bool kAbs>
 __global__ void __launch_bounds__(kThreads)
 k_parents(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n,
           const uint32_t* __restrict__ dist, const uint32_t* __restrict__ order,
-          unsigned long long* __restrict__ pkey, uint32_t* __restrict__ flags) {
+          unsigned long long* __restrict__ pkey, uint32_t* __restrict__ flags, float delta) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   uint32_t es = dist[s];
@@ -207,10 +211,14 @@ k_parents(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_
     if (c == w_zero()) continue;
     uint32_t t = (uint32_t)v.w;
     float m = dec_f32(dist[t]);
-    if (c == m) atomicMin(&pkey[t], hi | (k - b));
-    else if (!(c > m + kDelta)) bad = true;
+    if (c == m) { if (pkey) atomicMin(&pkey[t], hi | (k - b)); }
+    else if (kAbs ? (fabsf(c - m) <= delta) : !(c > m + delta)) bad = true;
   }
   if (bad) atomicAdd(&flags[0], 1u);
+}
+__global__ void k_decode_dist(const uint32_t* __restrict__ enc, uint32_t n, float* __restrict__ out) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) out[s] = dec_f32(enc[s]);
 }
 
 // Best final state: key = (enc(d[s] (x) rho(s)) << 32) | order[s]   (shortest_path.rs:214-220)
@@ -281,12 +289,19 @@ struct SerialArgs {
   int32_t* slot;      // StateOrder: presence flag per state; TopOrder: state stored at order position (-1 none)
   uint32_t* stack;    // Lifo storage / Scc ring storage
   uint32_t* qhead; uint32_t* qlen;  // per component ring head / length (Trivial uses length 0/1)
+  // shortest_distance only (queues may hold duplicates): radder, FIFO components as linked lists over a node pool
+  // (stack[node] = state, pool_next[node] = next node, qhead/qtail = first/last node of the component)
+  float* radder; uint32_t* pool_next; uint32_t* qtail; uint32_t pool_cap;
   // out
   Tr* out_arcs; uint32_t cap; uint32_t* meta; unsigned long long* counters;
 };
 
+template <bool kDup>
 struct SerialQueue {
   const SerialArgs& a;
+  // kDup: node pool bookkeeping + overflow flag
+  uint32_t pool_used = 0, free_head = 0xFFFFFFFFu;
+  bool overflow = false;
   // StateOrder / TopOrder
   uint32_t front = 0, back = 0; bool has_back = false;
   // Lifo
@@ -307,12 +322,31 @@ struct SerialQueue {
         a.slot[o] = a.kind == kTopOrderQueue ? (int32_t)s : 1;
         break;
       }
-      case kLifoQueue: a.stack[sp++] = s; break;  // lifo_queue.rs
+      case kLifoQueue:  // lifo_queue.rs
+        if (kDup && sp >= a.pool_cap) { overflow = true; break; }
+        a.stack[sp++] = s;
+        break;
       default: {  // scc_queue.rs:34-45
         long long c = a.scc[s];
         if (sfront > sback) { sfront = c; sback = c; }
         else if (c > sback) sback = c;
         else if (c < sfront) sfront = c;
+        if (kDup) {
+          if (a.scc_fifo[c]) {  // FifoQueue with duplicates: append a pool node to the component's list
+            uint32_t node;
+            if (free_head != 0xFFFFFFFFu) { node = free_head; free_head = a.pool_next[node]; }
+            else if (pool_used < a.pool_cap) node = pool_used++;
+            else { overflow = true; break; }
+            a.stack[node] = s; a.pool_next[node] = 0xFFFFFFFFu;
+            if (a.qlen[c] == 0) a.qhead[c] = node; else a.pool_next[a.qtail[c]] = node;
+            a.qtail[c] = node;
+            a.qlen[c]++;
+          } else {              // TrivialQueue: enqueue overwrites (trivial_queue.rs); the state lives in qhead
+            a.qhead[c] = s;
+            a.qlen[c] = 1;
+          }
+          break;
+        }
         uint32_t size = a.scc_base[c + 1] - a.scc_base[c];
         if (a.scc_fifo[c]) {  // FifoQueue (ring sized to the component: a state is enqueued at most once at a time)
           a.stack[a.scc_base[c] + (a.qhead[c] + a.qlen[c]) % size] = s;
@@ -352,6 +386,18 @@ struct SerialQueue {
         while (sfront <= sback && scc_q_empty((uint32_t)sfront)) sfront++;
         uint32_t c = (uint32_t)sfront;
         if (a.qlen[c] == 0) return false;
+        if (kDup) {
+          if (a.scc_fifo[c]) {
+            uint32_t node = a.qhead[c];
+            *out = a.stack[node];
+            a.qhead[c] = a.pool_next[node];
+            a.pool_next[node] = free_head; free_head = node;
+          } else {
+            *out = a.qhead[c];
+          }
+          a.qlen[c]--;
+          return true;
+        }
         uint32_t size = a.scc_base[c + 1] - a.scc_base[c];
         *out = a.stack[a.scc_base[c] + a.qhead[c]];
         if (a.scc_fifo[c]) a.qhead[c] = (a.qhead[c] + 1) % size;
@@ -368,7 +414,7 @@ __global__ void k_serial_sssp(SerialArgs a) {
   for (uint32_t s = 0; s < a.n; s++) { a.dist[s] = inf; a.pstate[s] = kNoState; a.ppos[s] = 0; a.enq[s] = 0; }
   if (a.kind == kStateOrderQueue) for (uint32_t s = 0; s < a.n; s++) a.slot[s] = 0;
   if (a.kind == kTopOrderQueue) for (uint32_t s = 0; s < a.n; s++) a.slot[s] = -1;
-  SerialQueue q(a);
+  SerialQueue<false> q(a);
   float f_distance = inf;
   bool has_f_parent = false;
   uint32_t f_parent = 0;
@@ -416,6 +462,44 @@ __global__ void k_serial_sssp(SerialArgs a) {
   a.meta[1] = L;
 }
 
+// The loop of shortest_distance.rs:176-233, one thread, verbatim (tropical: adder == distance at all times, so
+// only distance and radder are kept).  meta[3] = queue pool overflow (the host retries with a larger pool).
+__global__ void k_serial_sdist(SerialArgs a, float delta) {
+  if (blockIdx.x || threadIdx.x) return;
+  const float inf = w_zero();
+  for (uint32_t s = 0; s < a.n; s++) { a.dist[s] = inf; a.radder[s] = inf; a.enq[s] = 0; }
+  if (a.kind == kStateOrderQueue) for (uint32_t s = 0; s < a.n; s++) a.slot[s] = 0;
+  if (a.kind == kTopOrderQueue) for (uint32_t s = 0; s < a.n; s++) a.slot[s] = -1;
+  SerialQueue<true> q(a);
+  unsigned long long relaxed = 0, dequeued = 0;
+  a.dist[a.start] = 0.0f;
+  a.radder[a.start] = 0.0f;
+  a.enq[a.start] = 1;
+  q.enqueue(a.start);
+  uint32_t s;
+  while (!q.overflow && q.dequeue(&s)) {
+    a.enq[s] = 0;
+    const float r = a.radder[s];
+    a.radder[s] = inf;
+    dequeued++;
+    const uint32_t b = a.off[s], e = a.off[s + 1];
+    relaxed += e - b;
+    for (uint32_t k = b; k < e; k++) {
+      const Tr tr = a.arcs[k];
+      const float nd = a.dist[tr.nextstate];
+      const float w = w_times(r, tr.weight);
+      const float p = w_plus(nd, w);
+      if (!(fabsf(nd - p) <= delta)) {  // :217 — NaN (inf - inf) counts as "not equal", as in the reference
+        a.dist[tr.nextstate] = p;
+        a.radder[tr.nextstate] = w_plus(a.radder[tr.nextstate], w);
+        if (!a.enq[s]) { q.enqueue(tr.nextstate); a.enq[tr.nextstate] = 1; }  // :224 tests `state` (sic)
+      }
+    }
+  }
+  a.counters[0] = relaxed; a.counters[1] = dequeued;
+  a.meta[0] = a.meta[1] = a.meta[2] = 0; a.meta[3] = q.overflow ? 1u : 0u;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Order-faithful PARALLEL path for DAGs processed in a topological order (used when the certificate fails, i.e. for
 // weights with near-ties).  The reference dequeues states in `order`; when state t is dequeued every predecessor is
@@ -444,12 +528,13 @@ __global__ void k_of_roots(const uint32_t* __restrict__ indeg, uint32_t n, uint3
   warp_push(s < n && indeg[s] == 0, s, topo, cursor);
 }
 // ctl: [0] append cursor into topo (starts at #roots), [1] levels, [2] states processed
+template <bool kAbs>
 __global__ void __launch_bounds__(kThreads)
 k_of_fold(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t source,
           const uint32_t* __restrict__ roff, const uint32_t* __restrict__ in_arc /* sorted arc ids */,
           const uint32_t* __restrict__ src_of, uint32_t* __restrict__ indeg, uint32_t* __restrict__ topo,
           float* __restrict__ dist, uint32_t* __restrict__ pstate, uint32_t* __restrict__ ppos,
-          uint32_t* __restrict__ ctl, uint32_t n_roots) {
+          uint32_t* __restrict__ ctl, uint32_t n_roots, float delta) {
   unsigned int bar_epoch = 0;  // ctl[3] = arrival counter of the grid barrier (zero-initialised)
   __shared__ uint32_t s_q[kQueueCap];
   __shared__ uint32_t s_qn, s_gbase;
@@ -467,7 +552,9 @@ k_of_fold(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_
         const uint32_t e = in_arc[k], src = src_of[e];
         const float c = w_times(__ldcg(&dist[src]), __ldg(&arcs[e].weight));
         const float p = w_plus(d, c);
-        if (!w_approx_eq(d, p)) { d = p; ps = src; pp = e - off[src]; }
+        // kAbs: |inf - inf| is NaN, i.e. "not approx_equal": the update then rewrites inf with inf (harmless)
+        const bool same = kAbs ? (fabsf(d - p) <= delta) : w_approx_eq(d, p);
+        if (!same) { d = p; ps = src; pp = e - off[src]; }
       }
       dist[t] = d; pstate[t] = ps; ppos[t] = pp;
       // ---- Kahn: release the successors
@@ -566,6 +653,130 @@ CsrFst build_path_fst(bool found, const std::vector<Tr>& path, float final_w) {
   return o;
 }
 
+
+using EventPairs = std::vector<std::pair<cudaEvent_t, cudaEvent_t>>;
+
+// Exact minima from f.start by frontier relaxation waves: one cooperative launch of k_relax_coop.
+// dist receives the order-preserving integer images (kEncInf = unreached).
+void run_relax_coop(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, EventPairs& relax_events, cudaStream_t s) {
+  const uint32_t n = f.num_states;
+  DevBuf<uint32_t> stamp(s, n), fr_a(s, n), fr_b(s, n), cnt(s, 3), outw(s, 3);
+  DevBuf<unsigned long long> out64(s, 2);
+  dist.reserve_discard(n);
+  k_fill_u32<<<blocks_for(n), kThreads, 0, s>>>(dist.p, kEncInf, n);
+  B200_CUDA(cudaMemsetAsync(stamp.p, 0xFF, (size_t)n * 4, s));
+  uint32_t zero_enc = enc_f32(0.0f), src = f.start;
+  uint32_t init_cnt[3] = {1, 0, 0};
+  B200_CUDA(cudaMemcpyAsync(dist.p + src, &zero_enc, 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(fr_a.p, &src, 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(cnt.p, init_cnt, 12, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemsetAsync(outw.p, 0, 12, s));
+  B200_CUDA(cudaMemsetAsync(out64.p, 0, 16, s));
+  B200_CUDA(cudaStreamSynchronize(s));  // the sources of the small copies are host temporaries
+  st.kernel_launches += 1;
+  // lanes per frontier state: few lanes = more states in flight (the relaxation is latency-bound)
+  int lanes = 8;
+  if (const char* e = std::getenv("B200_RELAX_LANES")) lanes = std::atoi(e);
+  void* kern = (void*)k_relax_coop<8>;
+  if (lanes == 1) kern = (void*)k_relax_coop<1>;
+  else if (lanes == 2) kern = (void*)k_relax_coop<2>;
+  else if (lanes == 4) kern = (void*)k_relax_coop<4>;
+  else if (lanes == 16) kern = (void*)k_relax_coop<16>;
+  int per_sm = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+  if (per_sm < 1) throw FstError("cooperative relaxation kernel does not fit on the device");
+  int grid = sm_count() * per_sm;
+  const uint32_t* a_off = f.offsets.p; const Tr* a_arcs = f.arcs.p;
+  uint32_t nn = n;
+  uint32_t* a_dist = dist.p; uint32_t* a_stamp = stamp.p; uint32_t* a_fa = fr_a.p; uint32_t* a_fb = fr_b.p;
+  uint32_t* a_cnt = cnt.p; uint32_t* a_out = outw.p; unsigned long long* a_out64 = out64.p;
+  void* args[] = {&a_off, &a_arcs, &nn, &a_dist, &a_stamp, &a_fa, &a_fb, &a_cnt, &a_out, &a_out64};
+  cudaEvent_t ea, eb;
+  B200_CUDA(cudaEventCreate(&ea)); B200_CUDA(cudaEventCreate(&eb));
+  B200_CUDA(cudaEventRecord(ea, s));
+  B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
+  B200_CUDA(cudaEventRecord(eb, s));
+  relax_events.emplace_back(ea, eb);
+  st.relax_launches++; st.kernel_launches++;
+  uint32_t hw[2]; unsigned long long h64[2];
+  B200_CUDA(cudaMemcpyAsync(hw, outw.p, 8, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(h64, out64.p, 16, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  if (hw[1]) throw FstError("shortest_path: relaxation did not converge (negative cycle?)");
+  st.waves = hw[0]; st.arcs_relaxed = h64[0]; st.states_settled = h64[1];
+}
+
+// Order-faithful parallel fold (see k_of_fold).  Returns false when the graph turned out to be cyclic.
+struct FoldOut {
+  DevBuf<float> dist;
+  DevBuf<uint32_t> pstate, ppos;
+  explicit FoldOut(cudaStream_t s) : dist(s), pstate(s), ppos(s) {}
+};
+bool run_order_faithful_fold(const DevFst& f, const uint32_t* order_p, bool abs_form, float delta, FoldOut& out,
+                             SsspStats& st, cudaStream_t s) {
+  const uint32_t n = f.num_states, A = f.num_arcs;
+  DevBuf<unsigned long long> k_in(s, A ? A : 1), k_out(s, A ? A : 1);
+  DevBuf<uint32_t> v_in(s, A ? A : 1), in_arc(s, A ? A : 1), src_of(s, A ? A : 1), indeg(s, n), roff(s, (size_t)n + 1),
+      topo(s, n), ctl(s, 4);
+  DevBuf<uint8_t> tmp(s);
+  out.dist.reserve_discard(n); out.pstate.reserve_discard(n); out.ppos.reserve_discard(n);
+  B200_CUDA(cudaMemsetAsync(indeg.p, 0, (size_t)n * 4, s));
+  B200_CUDA(cudaMemsetAsync(ctl.p, 0, 16, s));
+  k_of_keys<<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, order_p, k_in.p, v_in.p, src_of.p, indeg.p);
+  B200_CUDA(cudaMemcpyAsync(roff.p, indeg.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  B200_CUDA(cudaMemsetAsync(roff.p + n, 0, 4, s));
+  exclusive_sum_u32(roff.p, roff.p, (size_t)n + 1, tmp, s);
+  sort_pairs_u64_u32(k_in.p, k_out.p, v_in.p, in_arc.p, A, 64, tmp, s);
+  k_of_roots<<<blocks_for(n), kThreads, 0, s>>>(indeg.p, n, topo.p, ctl.p);
+  uint32_t n_roots = read_u32(ctl.p, s);
+  st.kernel_launches += 2;
+  void* kern = abs_form ? (void*)k_of_fold<true> : (void*)k_of_fold<false>;
+  int per_sm = 0;
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+  if (per_sm < 1) throw FstError("cooperative fold kernel does not fit on the device");
+  int grid = sm_count() * per_sm;
+  const uint32_t* a_off = f.offsets.p; const Tr* a_arcs = f.arcs.p; uint32_t nn = n, src0 = f.start;
+  const uint32_t* a_roff = roff.p; const uint32_t* a_in = in_arc.p; const uint32_t* a_src = src_of.p;
+  uint32_t* a_indeg = indeg.p; uint32_t* a_topo = topo.p; float* a_dist = out.dist.p;
+  uint32_t* a_ps = out.pstate.p; uint32_t* a_pp = out.ppos.p; uint32_t* a_ctl = ctl.p;
+  float a_delta = delta;
+  void* args[] = {&a_off, &a_arcs, &nn, &src0, &a_roff, &a_in, &a_src, &a_indeg, &a_topo, &a_dist, &a_ps, &a_pp,
+                  &a_ctl, &n_roots, &a_delta};
+  B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
+  st.kernel_launches++;
+  uint32_t hctl[4];
+  B200_CUDA(cudaMemcpyAsync(hctl, ctl.p, 16, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  if (hctl[2] != n) return false;  // not every state was scheduled: the graph has a cycle
+  st.waves = hctl[1];
+  st.arcs_relaxed = A; st.states_settled = n;
+  return true;
+}
+
+// Device copies of the queue plan for the serial kernels.
+struct SerialPlanBufs {
+  DevBuf<uint32_t> scc, base, qhead, qlen, qtail;
+  DevBuf<uint8_t> fifo;
+  explicit SerialPlanBufs(cudaStream_t s) : scc(s), base(s), qhead(s), qlen(s), qtail(s), fifo(s) {}
+};
+void upload_scc_plan(const QueuePlan& plan, uint32_t n, SerialPlanBufs& b, SerialArgs& a, cudaStream_t s) {
+  size_t nscc = plan.scc_is_fifo.size();
+  std::vector<uint32_t> base(nscc + 1, 0);
+  for (uint32_t c : plan.scc) base[c + 1]++;
+  for (size_t c = 0; c < nscc; c++) base[c + 1] += base[c];
+  b.scc.reserve_discard(n); b.base.reserve_discard(nscc + 1); b.fifo.reserve_discard(nscc);
+  b.qhead.reserve_discard(nscc); b.qlen.reserve_discard(nscc); b.qtail.reserve_discard(nscc);
+  B200_CUDA(cudaMemcpyAsync(b.scc.p, plan.scc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(b.base.p, base.data(), (nscc + 1) * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(b.fifo.p, plan.scc_is_fifo.data(), nscc, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemsetAsync(b.qhead.p, 0, nscc * 4, s));
+  B200_CUDA(cudaMemsetAsync(b.qlen.p, 0, nscc * 4, s));
+  B200_CUDA(cudaMemsetAsync(b.qtail.p, 0, nscc * 4, s));
+  B200_CUDA(cudaStreamSynchronize(s));  // base is a host temporary
+  a.scc = b.scc.p; a.scc_base = b.base.p; a.scc_fifo = b.fifo.p; a.qhead = b.qhead.p; a.qlen = b.qlen.p;
+  a.qtail = b.qtail.p;
+}
+
 }  // namespace
 
 CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* stats, cudaStream_t s,
@@ -580,7 +791,7 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
   cudaEvent_t ev0, ev1;
   B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1));
   B200_CUDA(cudaEventRecord(ev0, s));
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> relax_events;
+  EventPairs relax_events;
 
   const uint32_t cap = n;  // a shortest path visits each state at most once
   DevBuf<Tr> out_arcs(s, cap);
@@ -598,60 +809,15 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
   uint32_t hmeta[4] = {0, 0, 0, 0};
 
   if (parallel_ok) {
-    DevBuf<uint32_t> dist(s, n), stamp(s, n), fr_a(s, n), fr_b(s, n), counters(s, 4), flags(s, 1), inv(s);
+    DevBuf<uint32_t> dist(s), flags(s, 1), inv(s);
     DevBuf<unsigned long long> pkey(s, n), fkey(s, 1);
-    k_fill_u32<<<blocks_for(n), kThreads, 0, s>>>(dist.p, kEncInf, n);
-    B200_CUDA(cudaMemsetAsync(stamp.p, 0xFF, (size_t)n * 4, s));
     k_fill_u64<<<blocks_for(n), kThreads, 0, s>>>(pkey.p, kNoParent, n);
     B200_CUDA(cudaMemsetAsync(fkey.p, 0xFF, 8, s));
     B200_CUDA(cudaMemsetAsync(flags.p, 0, 4, s));
-    B200_CUDA(cudaMemsetAsync(counters.p, 0, 16, s));
-    uint32_t zero_enc = enc_f32(0.0f), src = f.start;
-    B200_CUDA(cudaMemcpyAsync(dist.p + src, &zero_enc, 4, cudaMemcpyHostToDevice, s));
-    B200_CUDA(cudaMemcpyAsync(fr_a.p, &src, 4, cudaMemcpyHostToDevice, s));
-    B200_CUDA(cudaStreamSynchronize(s));
-    st.kernel_launches += 2;
-    {
-      // one cooperative launch runs every relaxation wave
-      DevBuf<uint32_t> cnt(s, 3), outw(s, 3);
-      DevBuf<unsigned long long> out64(s, 2);
-      uint32_t init_cnt[3] = {1, 0, 0};
-      B200_CUDA(cudaMemcpyAsync(cnt.p, init_cnt, 12, cudaMemcpyHostToDevice, s));
-      B200_CUDA(cudaMemsetAsync(outw.p, 0, 12, s));
-      B200_CUDA(cudaMemsetAsync(out64.p, 0, 16, s));
-      B200_CUDA(cudaStreamSynchronize(s));
-      // lanes per frontier state: few lanes = more states in flight (the relaxation is latency-bound)
-      int lanes = 8;
-      if (const char* e = std::getenv("B200_RELAX_LANES")) lanes = std::atoi(e);
-      void* kern = (void*)k_relax_coop<8>;
-      if (lanes == 1) kern = (void*)k_relax_coop<1>;
-      else if (lanes == 2) kern = (void*)k_relax_coop<2>;
-      else if (lanes == 4) kern = (void*)k_relax_coop<4>;
-      else if (lanes == 16) kern = (void*)k_relax_coop<16>;
-      int per_sm = 0;
-      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
-      if (per_sm < 1) throw FstError("cooperative relaxation kernel does not fit on the device");
-      int grid = sm_count() * per_sm;
-      const uint32_t* a_off = f.offsets.p; const Tr* a_arcs = f.arcs.p;
-      uint32_t nn = n;
-      uint32_t* a_dist = dist.p; uint32_t* a_stamp = stamp.p; uint32_t* a_fa = fr_a.p; uint32_t* a_fb = fr_b.p;
-      uint32_t* a_cnt = cnt.p; uint32_t* a_out = outw.p; unsigned long long* a_out64 = out64.p;
-      void* args[] = {&a_off, &a_arcs, &nn, &a_dist, &a_stamp, &a_fa, &a_fb, &a_cnt, &a_out, &a_out64};
-      cudaEvent_t ea, eb;
-      B200_CUDA(cudaEventCreate(&ea)); B200_CUDA(cudaEventCreate(&eb));
-      B200_CUDA(cudaEventRecord(ea, s));
-      B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
-      B200_CUDA(cudaEventRecord(eb, s));
-      relax_events.emplace_back(ea, eb);
-      st.relax_launches++; st.kernel_launches++;
-      uint32_t hw[2]; unsigned long long h64[2];
-      B200_CUDA(cudaMemcpyAsync(hw, outw.p, 8, cudaMemcpyDeviceToHost, s));
-      B200_CUDA(cudaMemcpyAsync(h64, out64.p, 16, cudaMemcpyDeviceToHost, s));
-      B200_CUDA(cudaStreamSynchronize(s));
-      if (hw[1]) throw FstError("shortest_path: relaxation did not converge (negative cycle?)");
-      st.waves = hw[0]; st.arcs_relaxed = h64[0]; st.states_settled = h64[1];
-    }
-    k_parents<<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, dist.p, order_p, pkey.p, flags.p);
+    st.kernel_launches += 1;
+    run_relax_coop(f, dist, st, relax_events, s);  // one cooperative launch runs every relaxation wave
+    k_parents<false><<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, dist.p, order_p, pkey.p, flags.p,
+                                                        kDelta);
     k_final_min<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, dist.p, order_p, fkey.p);
     k_final_check<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, dist.p, fkey.p, flags.p);
     st.kernel_launches += 3;
@@ -673,50 +839,21 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
   }
 
   if (!done && parallel_ok) {  // certificate failed: order-faithful parallel fold over a sorted reverse CSR
-    const uint32_t A = f.num_arcs;
-    DevBuf<unsigned long long> k_in(s, A ? A : 1), k_out(s, A ? A : 1), fk_in(s, n), fk_out(s, n);
-    DevBuf<uint32_t> v_in(s, A ? A : 1), in_arc(s, A ? A : 1), src_of(s, A ? A : 1), indeg(s, n), roff(s, (size_t)n + 1),
-        topo(s, n), ctl(s, 4), fv_in(s, n), fv_out(s, n), pstate(s, n), ppos(s, n);
-    DevBuf<float> distf(s, n);
-    DevBuf<uint8_t> tmp(s);
-    B200_CUDA(cudaMemsetAsync(indeg.p, 0, (size_t)n * 4, s));
-    B200_CUDA(cudaMemsetAsync(ctl.p, 0, 16, s));
-    k_of_keys<<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, order_p, k_in.p, v_in.p, src_of.p, indeg.p);
-    B200_CUDA(cudaMemcpyAsync(roff.p, indeg.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
-    B200_CUDA(cudaMemsetAsync(roff.p + n, 0, 4, s));
-    exclusive_sum_u32(roff.p, roff.p, (size_t)n + 1, tmp, s);
-    sort_pairs_u64_u32(k_in.p, k_out.p, v_in.p, in_arc.p, A, 64, tmp, s);
-    k_of_roots<<<blocks_for(n), kThreads, 0, s>>>(indeg.p, n, topo.p, ctl.p);
-    uint32_t n_roots = read_u32(ctl.p, s);
-    st.kernel_launches += 2;
-    int per_sm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_of_fold, kThreads, 0));
-    if (per_sm < 1) throw FstError("cooperative fold kernel does not fit on the device");
-    int grid = sm_count() * per_sm;
-    const uint32_t* a_off = f.offsets.p; const Tr* a_arcs = f.arcs.p; uint32_t nn = n, src0 = f.start;
-    const uint32_t* a_roff = roff.p; const uint32_t* a_in = in_arc.p; const uint32_t* a_src = src_of.p;
-    uint32_t* a_indeg = indeg.p; uint32_t* a_topo = topo.p; float* a_dist = distf.p;
-    uint32_t* a_ps = pstate.p; uint32_t* a_pp = ppos.p; uint32_t* a_ctl = ctl.p;
-    void* args[] = {&a_off, &a_arcs, &nn, &src0, &a_roff, &a_in, &a_src, &a_indeg, &a_topo, &a_dist, &a_ps, &a_pp,
-                    &a_ctl, &n_roots};
-    B200_CUDA(cudaLaunchCooperativeKernel((void*)k_of_fold, dim3(grid), dim3(kThreads), args, 0, s));
-    st.kernel_launches++;
-    uint32_t hctl[4];
-    B200_CUDA(cudaMemcpyAsync(hctl, ctl.p, 16, cudaMemcpyDeviceToHost, s));
-    B200_CUDA(cudaStreamSynchronize(s));
-    if (hctl[2] == n) {  // every state was scheduled: the graph is a DAG
+    FoldOut fo(s);
+    if (run_order_faithful_fold(f, order_p, false, kDelta, fo, st, s)) {  // every state scheduled: a DAG
       // final states in processing order
-      B200_CUDA(cudaMemsetAsync(ctl.p + 3, 0, 4, s));
-      k_of_final_keys<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, order_p, fk_in.p, fv_in.p, ctl.p + 3);
-      uint32_t n_fin = read_u32(ctl.p + 3, s);
+      DevBuf<unsigned long long> fk_in(s, n), fk_out(s, n);
+      DevBuf<uint32_t> fv_in(s, n), fv_out(s, n), cnt(s, 1);
+      DevBuf<uint8_t> tmp(s);
+      B200_CUDA(cudaMemsetAsync(cnt.p, 0, 4, s));
+      k_of_final_keys<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, order_p, fk_in.p, fv_in.p, cnt.p);
+      uint32_t n_fin = read_u32(cnt.p, s);
       sort_pairs_u64_u32(fk_in.p, fk_out.p, fv_in.p, fv_out.p, n_fin, 32, tmp, s);
-      k_of_finish<<<1, 32, 0, s>>>(f.offsets.p, f.arcs.p, f.finals.p, distf.p, fv_out.p, n_fin, pstate.p, ppos.p,
-                                   out_arcs.p, cap, meta.p);
+      k_of_finish<<<1, 32, 0, s>>>(f.offsets.p, f.arcs.p, f.finals.p, fo.dist.p, fv_out.p, n_fin, fo.pstate.p,
+                                   fo.ppos.p, out_arcs.p, cap, meta.p);
       st.kernel_launches += 2;
       B200_CUDA(cudaMemcpyAsync(hmeta, meta.p, 16, cudaMemcpyDeviceToHost, s));
       B200_CUDA(cudaStreamSynchronize(s));
-      st.waves = hctl[1];
-      st.arcs_relaxed = A; st.states_settled = n;
       st.path = 2;
       done = true;
     }
@@ -725,28 +862,15 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
   if (!done) {  // order-faithful serial replay
     st.path = 1;
     DevBuf<float> dist(s, n);
-    DevBuf<uint32_t> pstate(s, n), ppos(s, n), stack(s, (size_t)n + 1), d_scc(s), d_base(s), qhead(s), qlen(s);
-    DevBuf<uint8_t> enq(s, n), d_fifo(s);
+    DevBuf<uint32_t> pstate(s, n), ppos(s, n), stack(s, (size_t)n + 1);
+    DevBuf<uint8_t> enq(s, n);
     DevBuf<int32_t> slot(s, n);
     DevBuf<unsigned long long> counters(s, 2);
+    SerialPlanBufs pb(s);
     SerialArgs a{};
     a.off = f.offsets.p; a.arcs = f.arcs.p; a.fin = f.finals.p; a.n = n; a.start = f.start;
     a.kind = plan.kind; a.order = order_p;
-    if (plan.kind == kSccQueue) {
-      size_t nscc = plan.scc_is_fifo.size();
-      std::vector<uint32_t> base(nscc + 1, 0);
-      for (uint32_t c : plan.scc) base[c + 1]++;
-      for (size_t c = 0; c < nscc; c++) base[c + 1] += base[c];
-      d_scc.reserve_discard(n); d_base.reserve_discard(nscc + 1); d_fifo.reserve_discard(nscc);
-      qhead.reserve_discard(nscc); qlen.reserve_discard(nscc);
-      B200_CUDA(cudaMemcpyAsync(d_scc.p, plan.scc.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-      B200_CUDA(cudaMemcpyAsync(d_base.p, base.data(), (nscc + 1) * 4, cudaMemcpyHostToDevice, s));
-      B200_CUDA(cudaMemcpyAsync(d_fifo.p, plan.scc_is_fifo.data(), nscc, cudaMemcpyHostToDevice, s));
-      B200_CUDA(cudaMemsetAsync(qhead.p, 0, nscc * 4, s));
-      B200_CUDA(cudaMemsetAsync(qlen.p, 0, nscc * 4, s));
-      B200_CUDA(cudaStreamSynchronize(s));  // base is a host temporary
-      a.scc = d_scc.p; a.scc_base = d_base.p; a.scc_fifo = d_fifo.p; a.qhead = qhead.p; a.qlen = qlen.p;
-    }
+    if (plan.kind == kSccQueue) upload_scc_plan(plan, n, pb, a, s);
     a.dist = dist.p; a.pstate = pstate.p; a.ppos = ppos.p; a.enq = enq.p; a.slot = slot.p; a.stack = stack.p;
     a.out_arcs = out_arcs.p; a.cap = cap; a.meta = meta.p; a.counters = counters.p;
     k_serial_sssp<<<1, 32, 0, s>>>(a);
@@ -776,6 +900,95 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
   }
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);
   return build_path_fst(hmeta[0] != 0, path, final_w);
+}
+
+// Forward shortest distances with the semantics of shortest_distance.rs:153-237 (see the header of this function in
+// algos.h).  Same three device paths as shortest_path_device, with approx_equal(.., delta) as the update test.
+void shortest_distance_device(const DevFst& f, const QueuePlan& plan, float delta, DevBuf<float>& out,
+                              SsspStats* stats, cudaStream_t s, bool force_serial) {
+  SsspStats local;
+  SsspStats& st = stats ? *stats : local;
+  st = SsspStats();
+  st.plan_host_ms = plan.host_ms;
+  const uint32_t n = f.num_states;
+  out.reserve_discard(n ? n : 1);
+  if (!f.has_start || n == 0) return;
+  EventPairs relax_events;
+  DevBuf<uint32_t> d_order(s);
+  const uint32_t* order_p = nullptr;
+  if (plan.kind == kTopOrderQueue) {
+    d_order.reserve_discard(n);
+    B200_CUDA(cudaMemcpyAsync(d_order.p, plan.order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    order_p = d_order.p;
+  }
+  const bool parallel_ok = !force_serial && (plan.kind == kStateOrderQueue || plan.kind == kTopOrderQueue);
+  bool done = false;
+  if (parallel_ok) {
+    // On a DAG processed in topological order every state is dequeued once, after all its predecessors, with
+    // r = radder[state] = distance[state] (both fold the same accepted candidates), so the reference computes the
+    // same per-state fold as single_shortest_path, only with |d - min(d, c)| <= delta as the "unchanged" test.
+    // Exact minima + the certificate "no candidate in (m, m + delta]" therefore reproduce it (see k_parents).
+    DevBuf<uint32_t> dist(s), flags(s, 1);
+    B200_CUDA(cudaMemsetAsync(flags.p, 0, 4, s));
+    run_relax_coop(f, dist, st, relax_events, s);
+    k_parents<true><<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, dist.p, order_p, nullptr, flags.p,
+                                                       delta);
+    st.kernel_launches++;
+    if (read_u32(flags.p, s) == 0) {
+      k_decode_dist<<<blocks_for(n), kThreads, 0, s>>>(dist.p, n, out.p);
+      st.kernel_launches++;
+      st.path = 0;
+      done = true;
+    }
+  }
+  if (!done && parallel_ok) {
+    FoldOut fo(s);
+    if (run_order_faithful_fold(f, order_p, true, delta, fo, st, s)) {
+      B200_CUDA(cudaMemcpyAsync(out.p, fo.dist.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+      st.path = 2;
+      done = true;
+    }
+  }
+  if (!done) {  // order-faithful serial replay with the queue discipline AutoQueue picks
+    st.path = 1;
+    // Unlike single_shortest_path, shortest_distance re-enqueues a state that is already queued
+    // (shortest_distance.rs:224 tests enqueued[state], not enqueued[nextstate]), so LIFO / FIFO queues hold
+    // duplicates and have no a-priori bound: pools are sized generously and grown on overflow.
+    size_t pool = 4 * ((size_t)n + f.num_arcs) + 1024;
+    for (int attempt = 0;; attempt++) {
+      DevBuf<float> radder(s, n);
+      DevBuf<uint32_t> stack(s, pool), pool_next(s, pool), meta(s, 4);
+      DevBuf<uint8_t> enq(s, n);
+      DevBuf<int32_t> slot(s, n);
+      DevBuf<unsigned long long> counters(s, 2);
+      SerialPlanBufs pb(s);
+      SerialArgs a{};
+      a.off = f.offsets.p; a.arcs = f.arcs.p; a.fin = f.finals.p; a.n = n; a.start = f.start;
+      a.kind = plan.kind; a.order = order_p;
+      if (plan.kind == kSccQueue) upload_scc_plan(plan, n, pb, a, s);
+      a.dist = out.p; a.radder = radder.p; a.enq = enq.p; a.slot = slot.p; a.stack = stack.p;
+      a.pool_next = pool_next.p; a.pool_cap = (uint32_t)std::min<size_t>(pool, 0xFFFFFFF0u);
+      a.meta = meta.p; a.counters = counters.p;
+      k_serial_sdist<<<1, 32, 0, s>>>(a, delta);
+      st.kernel_launches++;
+      uint32_t hmeta[4];
+      unsigned long long hc[2] = {0, 0};
+      B200_CUDA(cudaMemcpyAsync(hmeta, meta.p, 16, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaMemcpyAsync(hc, counters.p, 16, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      st.arcs_relaxed = hc[0]; st.states_settled = hc[1]; st.waves = 0;
+      if (!hmeta[3]) break;
+      if (attempt >= 4 || pool >= 0xFFFFFFF0u) throw FstError("shortest_distance: queue pool exhausted");
+      pool *= 8;
+    }
+  }
+  for (auto& pr : relax_events) {
+    float ms = 0;
+    B200_CUDA(cudaStreamSynchronize(s));
+    B200_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    st.ms_relax_kernel += ms;
+    cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+  }
 }
 
 }  // namespace b200

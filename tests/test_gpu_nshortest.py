@@ -1,0 +1,134 @@
+"""GPU parity for nshortest > 1 (fst_shortest_path_with_config): the device route (forward distances + reversed
+machine on the GPU, heap search over rows fetched from HBM, device trim) against the oracle's restatement of
+shortest_path.rs:135-170,409-518 — bit-exact state ids, arc order, weights and property words."""
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+from tests.parity_utils import FIXTURES, assert_same, both_from_dict, both_from_path, golden_path, random_fst
+
+pytestmark = pytest.mark.gpu
+
+NS = [2, 3, 5]
+
+
+def _both(p, o, n, delta=None, force_serial=False):
+    import rustfst_b200 as R
+    cfg = R.ShortestPathConfig(nshortest=n, unique=False, delta=delta)
+    got, st = R.shortestpath_with_stats(p, cfg, force_serial=force_serial)
+    exp = O.shortest_path(o, nshortest=n, delta=1e-6 if delta is None else delta)
+    return got, exp, st
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_fixture_nshortest(name):
+    """Every fixture input (cyclic, epsilon-rich: LIFO / SCC / TopOrder queue branches of shortest_distance, with the
+    re-enqueue quirk of shortest_distance.rs:224), n = 2, 3, 5 as rustfst-tests-data/main.cpp:423 sweeps."""
+    for which in ("raw", "compose"):
+        p, o = both_from_path(golden_path(name, which))
+        for n in NS:
+            got, exp, st = _both(p, o, n)
+            assert_same(got, exp, f"{name}/{which} n={n} (distance path={st['path']} queue={st['queue_kind']})")
+        got, exp, _ = _both(p, o, 3, force_serial=True)
+        assert_same(got, exp, f"{name}/{which} n=3 serial distances")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_nshortest_fuzz(seed):
+    rng = np.random.default_rng(7000 + seed)
+    cyclic = seed % 3 == 0
+    d = random_fst(rng, int(rng.integers(2, 80)), 5, 6, eps_prob=0.1, cyclic=cyclic, weight_grid=(seed % 4 < 2))
+    p, o = both_from_dict(d)
+    for n in (2, 4, 17):
+        got, exp, st = _both(p, o, n)
+        assert_same(got, exp, f"n-best fuzz seed={seed} n={n} path={st['path']}")
+    got, exp, _ = _both(p, o, 4, delta=0.25)
+    assert_same(got, exp, f"n-best fuzz seed={seed} delta=0.25")
+    got, exp, _ = _both(p, o, 4, force_serial=True)
+    assert_same(got, exp, f"n-best fuzz seed={seed} serial")
+
+
+def test_nshortest_python_style_kat():
+    """Two parallel paths (the n = 2 picture of shortest_path.rs:91-105): both come back, best first."""
+    import rustfst_b200 as R
+    f = R.VectorFst()
+    for _ in range(4):
+        f.add_state()
+    f.set_start(0)
+    f.set_final(3, 0.5)
+    f.add_tr(0, R.Tr(1, 1, 1.0, 1))
+    f.add_tr(0, R.Tr(2, 2, 3.0, 2))
+    f.add_tr(1, R.Tr(3, 3, 1.0, 3))
+    f.add_tr(2, R.Tr(4, 4, 0.25, 3))
+    r = f.shortest_path(R.ShortestPathConfig(nshortest=2))
+    off, arcs, fin, start = r.to_csr()
+    assert start == 0 and len(fin) == 8
+    assert int(off[1] - off[0]) == 2  # two paths leave the start state
+    # unique = true is refused with an explanation, never answered wrongly
+    with pytest.raises(ValueError, match="unique"):
+        f.shortest_path(R.ShortestPathConfig(nshortest=2, unique=True))
+    # degenerate inputs: shortest_path.rs:427-434
+    e = R.VectorFst()
+    assert e.shortest_path(R.ShortestPathConfig(nshortest=3)).num_states() == 0
+    e.add_state()
+    assert e.shortest_path(R.ShortestPathConfig(nshortest=3)).num_states() == 0
+    e.set_start(0)
+    assert e.shortest_path(R.ShortestPathConfig(nshortest=3)).num_states() == 0
+
+
+def test_nshortest_on_composed_lattices_all_distance_paths():
+    """BASELINE.json configs[1] generator, shrunk: compose, then the 10 best paths of the lattice.  Dyadic weights
+    take the parallel relaxation + certificate; continuous weights fail it and take the order-faithful fold."""
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    a, b = synth.workload("C2", scale=0.1)
+    pa, oa = both_from_dict(a)
+    pb, ob = both_from_dict(b)
+    pc, oc = pa.compose(pb), O.compose(oa, ob)
+    got, exp, st = _both(pc, oc, 10)
+    assert st["queue_kind"] == 1 and st["path"] == 0, st
+    assert_same(got, exp, "10 best of the C2 lattice")
+    got, exp, st = _both(pa, oa, 10)  # TOP_SORTED acceptor: StateOrderQueue
+    assert st["queue_kind"] == 0 and st["path"] == 0, st
+    assert_same(got, exp, "10 best of the acceptor")
+
+    g = synth.layered_acceptor(100_000, 1_000_000, 1000, 6, 40, continuous=True)
+    p, o = both_from_dict(g)
+    got, exp, st = _both(p, o, 8)
+    assert st["path"] in (0, 2), st
+    assert_same(got, exp, f"8 best, continuous weights (distance path={st['path']})")
+    got, exp, st = _both(p, o, 8, delta=0.05)  # a coarse delta makes near-ties common: fold path
+    assert st["path"] == 2, st
+    assert_same(got, exp, "8 best, continuous weights, delta=0.05")
+
+
+def test_reverse_device_matches_oracle_reverse_through_nbest_of_large_fanin():
+    """A hub with thousands of in-arcs and many final states: the rows of the reversed machine (in-arcs in (source,
+    position) order, superinitial arcs in state order) decide heap push order, hence result ids."""
+    from rustfst_b200 import props as P
+    from rustfst_b200.fst import TR_DTYPE
+    n_mid = 3000
+    n = n_mid + 2
+    rows, offsets = [], [0]
+    for k in range(n_mid):  # start -> mid_k
+        rows.append((1 + k % 7, 1 + k % 5, (k * 37 % 101) / 8.0, 1 + k))
+    offsets.append(len(rows))
+    for k in range(n_mid):  # mid_k -> hub (two parallel arcs each)
+        rows.append((2, 3, (k * 11 % 53) / 8.0, n - 1))
+        rows.append((4, 4, (k * 7 % 29) / 8.0, n - 1))
+        offsets.append(len(rows))
+    offsets.append(len(rows))
+    arr = np.zeros(len(rows), dtype=TR_DTYPE)
+    for i, r in enumerate(rows):
+        arr[i] = r
+    finals = np.full(n, np.inf, dtype=np.float32)
+    finals[n - 1] = 0.5
+    finals[1:n_mid:3] = 9.0
+    d = {"offsets": np.array(offsets, dtype=np.uint32), "arcs": arr, "finals": finals, "start": 0, "props": 0}
+    o = O.OFst.from_csr(d["offsets"].astype(np.uint64), arr, finals, 0, 0)
+    o.compute_props()
+    d["props"] = o.props
+    p, o = both_from_dict(d)
+    for nsh in (2, 50):
+        got, exp, st = _both(p, o, nsh)
+        assert_same(got, exp, f"hub n={nsh}")

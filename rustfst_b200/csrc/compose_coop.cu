@@ -709,6 +709,15 @@ float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   int minb = 3;  // measured best on C3: 1 / 2 / 3 / 4 / 5 CTAs per SM -> 7.31 / 5.09 / 4.92 / 5.23 / 5.51 ms (more CTAs shorten
                  // the phases but lengthen the count exchanges)
   if (const char* e = std::getenv("B200_COOP_MINBLOCKS")) minb = std::atoi(e);
+#if B200_COOP_THREADS > 512
+  minb = 1;
+  void* kern = (void*)k_compose_coop<1>;
+#elif B200_COOP_THREADS > 256
+  if (minb > 3) minb = 3;
+  void* kern = (void*)k_compose_coop<2>;
+  if (minb == 3) kern = (void*)k_compose_coop<3>;
+  else if (minb == 1) kern = (void*)k_compose_coop<1>;
+#else
   void* kern = (void*)k_compose_coop<3>;
   if (minb == 5) kern = (void*)k_compose_coop<5>;
   else if (minb == 6) kern = (void*)k_compose_coop<6>;
@@ -716,6 +725,7 @@ float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   else if (minb == 2) kern = (void*)k_compose_coop<2>;
   else if (minb == 1) kern = (void*)k_compose_coop<1>;
   else if (minb == 8) kern = (void*)k_compose_coop<8>;
+#endif
   int per_sm = 0;
   size_t dyn = 3 * 2049 * sizeof(uint32_t);
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoopThreads, dyn));

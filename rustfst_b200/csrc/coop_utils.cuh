@@ -9,7 +9,11 @@
 namespace b200 {
 namespace coop {
 
-constexpr int kCoopThreads = 256;
+// Threads per CTA of the persistent kernels (a build-time knob for experiments: -DB200_COOP_THREADS=512).
+#ifndef B200_COOP_THREADS
+#define B200_COOP_THREADS 256
+#endif
+constexpr int kCoopThreads = B200_COOP_THREADS;
 
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {

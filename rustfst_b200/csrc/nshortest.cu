@@ -18,6 +18,9 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "algos.h"
@@ -71,6 +74,22 @@ k_rev_gather(const Tr* __restrict__ arcs, const float* __restrict__ fin, uint32_
 __global__ void k_rev_finals(float* __restrict__ fin, uint32_t n1, uint32_t final_state, bool has_final) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n1) fin[s] = (has_final && s == final_state) ? 0.0f : w_zero();
+}
+
+// One row of the reversed machine, packed for the host search: out[0] = {#arcs, 0, 0, 0}; when the row fits `cap`,
+// out[1 + k] = arc k and dists[k] = forward distance of its source state (distance_2[nextstate], i.e. dist[nextstate
+// - 1]).  The host never holds the distance array or the row offsets of a multi-million-state machine.
+__global__ void __launch_bounds__(kThreads)
+k_fetch_row(const uint32_t* __restrict__ roff, const Tr* __restrict__ rarcs, const float* __restrict__ dist,
+            uint32_t n, uint32_t q, uint32_t cap, int4* __restrict__ out, float* __restrict__ dists) {
+  const uint32_t b = roff[q], deg = roff[q + 1] - b;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) out[0] = make_int4((int)deg, 0, 0, 0);
+  if (k >= deg || deg > cap) return;
+  const int4 v = __ldg(reinterpret_cast<const int4*>(&rarcs[b + k]));
+  out[1 + k] = v;
+  const uint32_t src = (uint32_t)v.w - 1u;  // rows never point at the superinitial state
+  dists[k] = (dist && src < n) ? dist[src] : w_zero();
 }
 
 double now_ms() {
@@ -140,62 +159,101 @@ CsrFst n_shortest_paths_device(const DevFst& f, const std::vector<StateId>& inf_
   st.ms_distance = (float)(now_ms() - t0);
   t0 = now_ms();
   DevFst r = reverse_device(f, s, &st.distance.kernel_launches);
-  std::vector<float> dist((size_t)n, w_zero());
-  std::vector<uint32_t> roff((size_t)n + 2, 0);
-  if (n && f.has_start) B200_CUDA(cudaMemcpyAsync(dist.data(), d_dist.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-  B200_CUDA(cudaMemcpyAsync(roff.data(), r.offsets.p, ((size_t)n + 2) * 4, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
   st.ms_reverse = (float)(now_ms() - t0);
   t0 = now_ms();
 
-  // A row of the reversed machine, fetched from HBM.  Row 0 also receives the `Some(+inf)` finals, which the
-  // device representation (+inf = not final) cannot tell from non-final states; they are merged by state id.
+  // Rows of the reversed machine are fetched on demand into a page-locked staging buffer: one small kernel gathers
+  // the row's arcs and the forward distances of their source states (k_fetch_row).  Row 0 also receives the
+  // `Some(+inf)` finals, which the device representation (+inf = not final) cannot tell from non-final states; they
+  // are merged by state id.
+  const float* d_dist_p = (n && f.has_start) ? d_dist.p : nullptr;
+  uint32_t cap = 1u << 12;
+  int4* h_row = nullptr;
+  float* h_rdist = nullptr;
+  DevBuf<int4> d_row(s, (size_t)cap + 1);
+  DevBuf<float> d_rdist(s, cap);
+  B200_CUDA(cudaMallocHost((void**)&h_row, ((size_t)cap + 1) * 16));
+  B200_CUDA(cudaMallocHost((void**)&h_rdist, (size_t)cap * 4));
+  struct HostStage {  // frees the staging buffers on every exit path
+    int4*& a; float*& b;
+    ~HostStage() { if (a) cudaFreeHost(a); if (b) cudaFreeHost(b); }
+  } stage_guard{h_row, h_rdist};
   std::vector<Tr> row;
+  std::vector<float> row_dist;
   auto fetch_row = [&](uint32_t q) {
-    const uint32_t b = roff[q], e = roff[q + 1];
-    row.resize(e - b);
-    if (e > b) {
-      B200_CUDA(cudaMemcpyAsync(row.data(), r.arcs.p + b, (size_t)(e - b) * 16, cudaMemcpyDeviceToHost, s));
+    while (true) {
+      k_fetch_row<<<blocks_for(cap), kThreads, 0, s>>>(r.offsets.p, r.arcs.p, d_dist_p, n, q, cap, d_row.p, d_rdist.p);
+      st.distance.kernel_launches++;
+      B200_CUDA(cudaMemcpyAsync(h_row, d_row.p, 16, cudaMemcpyDeviceToHost, s));
       B200_CUDA(cudaStreamSynchronize(s));
+      const uint32_t deg = (uint32_t)h_row[0].x;
+      if (deg <= cap) {
+        if (deg) {
+          B200_CUDA(cudaMemcpyAsync(h_row + 1, d_row.p + 1, (size_t)deg * 16, cudaMemcpyDeviceToHost, s));
+          B200_CUDA(cudaMemcpyAsync(h_rdist, d_rdist.p, (size_t)deg * 4, cudaMemcpyDeviceToHost, s));
+          B200_CUDA(cudaStreamSynchronize(s));
+        }
+        row.resize(deg); row_dist.resize(deg);
+        for (uint32_t k = 0; k < deg; k++) {
+          const int4 v = h_row[1 + k];
+          Tr tr; tr.ilabel = (uint32_t)v.x; tr.olabel = (uint32_t)v.y; tr.nextstate = (uint32_t)v.w;
+          std::memcpy(&tr.weight, &v.z, 4);
+          row[k] = tr; row_dist[k] = h_rdist[k];
+        }
+        break;
+      }
+      cap = deg;  // grow the staging buffers to the row and fetch again
+      cudaFreeHost(h_row); cudaFreeHost(h_rdist); h_row = nullptr; h_rdist = nullptr;
+      B200_CUDA(cudaMallocHost((void**)&h_row, ((size_t)cap + 1) * 16));
+      B200_CUDA(cudaMallocHost((void**)&h_rdist, (size_t)cap * 4));
+      d_row.reserve_discard((size_t)cap + 1);
+      d_rdist.reserve_discard(cap);
     }
-    st.rows_fetched++; st.arcs_fetched += e - b;
+    st.rows_fetched++; st.arcs_fetched += row.size();
     if (q == 0 && !inf_finals.empty()) {
-      std::vector<Tr> merged;
+      std::vector<Tr> merged; std::vector<float> merged_d;
       merged.reserve(row.size() + inf_finals.size());
       size_t i = 0;
-      for (StateId fs : inf_finals) {
-        while (i < row.size() && row[i].nextstate < fs + 1) merged.push_back(row[i++]);
-        merged.push_back(Tr{kEps, kEps, w_zero(), fs + 1});
+      std::vector<float> inf_d(inf_finals.size(), w_zero());
+      for (size_t k = 0; k < inf_finals.size(); k++)
+        if (d_dist_p) B200_CUDA(cudaMemcpyAsync(&inf_d[k], d_dist_p + inf_finals[k], 4, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      for (size_t k = 0; k < inf_finals.size(); k++) {
+        const StateId fs = inf_finals[k];
+        while (i < row.size() && row[i].nextstate < fs + 1) { merged.push_back(row[i]); merged_d.push_back(row_dist[i]); i++; }
+        merged.push_back(Tr{kEps, kEps, w_zero(), fs + 1}); merged_d.push_back(inf_d[k]);
       }
-      while (i < row.size()) merged.push_back(row[i++]);
-      row.swap(merged);
+      while (i < row.size()) { merged.push_back(row[i]); merged_d.push_back(row_dist[i]); i++; }
+      row.swap(merged); row_dist.swap(merged_d);
     }
   };
-  // distance_2 of shortest_path.rs:153-154: index 0 = the superinitial state, index q = distance[q - 1]
+  // distance_2 of shortest_path.rs:153-154: index 0 = the superinitial state (d0), index q = distance[q - 1]
   float d0 = w_zero();
   fetch_row(0);
   const std::vector<Tr> row0 = row;
-  for (const Tr& rarc : row0) {  // :144-150
-    const size_t state = rarc.nextstate - 1;
-    if (state < dist.size()) d0 = w_plus(d0, w_times(rarc.weight, dist[state]));
-  }
-  auto distance2 = [&](uint32_t q) -> float { return q == 0 ? d0 : (q - 1 < dist.size() ? dist[q - 1] : w_zero()); };
+  const std::vector<float> row0_dist = row_dist;
+  for (size_t k = 0; k < row0.size(); k++) d0 = w_plus(d0, w_times(row0[k].weight, row0_dist[k]));  // :144-150
 
   // ---- host: n_shortest_path (shortest_path.rs:409-518) over the reversed machine
   if (w_is_zero(d0)) { st.ms_total = (float)(now_ms() - t_begin); return empty; }  // :427-434 (istart = 0 always exists)
-  HostFst ofst;
-  const StateId ostart = ofst.add_state();
-  ofst.set_start(ostart);
-  const StateId final_state = ofst.add_state();
-  ofst.set_final(final_state, 0.0f);
+  // The result tree is written straight in CSR form: state 0 = start (arcs appended as complete paths are popped),
+  // state 1 = final, every later state carries exactly one arc; the property word replays the reference's mutation
+  // sequence (add_state / set_start / set_final / add_tr) in its order.
+  uint64_t pw = props::kNull;
+  pw = props::on_add_state(pw);                 // ostart
+  pw = props::on_set_start(pw);
+  pw = props::on_add_state(pw);                 // final_state
+  { const float one = 0.0f; pw = props::on_set_final(pw, nullptr, &one); }
+  const StateId ostart = 0, final_state = 1;
+  std::vector<Tr> start_arcs, single_arc;       // single_arc[i] = the arc of state i + 2
   struct Pair { bool some; uint32_t state; float w; };
   std::vector<Pair> pairs(final_state + 1, Pair{false, 0, w_zero()});
   pairs[final_state] = Pair{true, 0, 0.0f};
   // Keys of ShortestPathCompare (:323-338) are pure functions of a pair, fixed at push time: cache them.
   struct Key { float w; bool some; };
-  std::vector<Key> keys(pairs.size());
-  auto key_of = [&](const Pair& p) { return Key{w_times(p.some ? distance2(p.state) : 0.0f, p.w), p.some}; };
-  keys[final_state] = key_of(pairs[final_state]);
+  std::vector<Key> keys(pairs.size(), Key{w_zero(), false});
+  keys[final_state] = Key{w_times(d0, 0.0f), true};
   auto compare = [&](StateId x, StateId y) -> bool {
     const Key &kx = keys[x], &ky = keys[y];
     if (!kx.some && ky.some) return natural_less(ky.w, kx.w) || approx_equal(kx.w, ky.w, delta);
@@ -232,6 +290,15 @@ CsrFst n_shortest_paths_device(const DevFst& f, const std::vector<StateId>& inf_
     else { heap[0] = heap.back(); heap.pop_back(); sift_down(0); }
     return top;
   };
+  auto new_state = [&](const Tr& tr, const Pair& pr, float dist_of_pair_state) -> StateId {
+    const StateId next = (StateId)(single_arc.size() + 2);
+    pw = props::on_add_state(pw);
+    pairs.push_back(pr);
+    keys.push_back(Key{w_times(pr.some ? dist_of_pair_state : 0.0f, pr.w), pr.some});
+    single_arc.push_back(tr);
+    pw = props::on_add_tr(pw, next, tr, nullptr);
+    return next;
+  };
   push(final_state);
   const float limit = w_times(d0, w_zero());  // weight_threshold = zero(): :448-449
   std::vector<size_t> seen;                    // r of :451
@@ -241,42 +308,61 @@ CsrFst n_shortest_paths_device(const DevFst& f, const std::vector<StateId>& inf_
     st.heap_pops++;
     const Pair p = pairs[state];
     const size_t first_real = p.some ? (size_t)p.state + 1 : 0;
-    const float d = p.some ? distance2(p.state) : 0.0f;
-    if (natural_less(limit, w_times(d, p.w))) continue;
+    // d (x) p.1 of :463-474 is exactly the cached heap key
+    if (natural_less(limit, keys[state].w)) continue;
     if (seen.size() <= first_real) seen.resize(first_real + 1, 0);
     seen[first_real] += 1;
-    if (!p.some) ofst.add_tr(ostart, Tr{0, 0, 0.0f, state});
+    if (!p.some) {
+      const Tr tr{0, 0, 0.0f, state};
+      pw = props::on_add_tr(pw, ostart, tr, start_arcs.empty() ? nullptr : &start_arcs.back());
+      start_arcs.push_back(tr);
+    }
     if (!p.some && seen[first_real] == nshortest) break;
     if (seen[first_real] > nshortest) continue;
     if (!p.some) continue;
-    if (p.state == 0) row = row0; else fetch_row(p.state);
-    for (const Tr& rarc : row) {
-      const float weight = w_times(p.w, rarc.weight);
-      const StateId next = ofst.add_state();
-      pairs.push_back(Pair{true, rarc.nextstate, weight});
-      keys.push_back(key_of(pairs.back()));
-      ofst.add_tr(next, Tr{rarc.ilabel, rarc.olabel, rarc.weight, state});
+    const std::vector<Tr>* prow = &row0;
+    const std::vector<float>* pdist = &row0_dist;
+    if (p.state != 0) { fetch_row(p.state); prow = &row; pdist = &row_dist; }
+    for (size_t k = 0; k < prow->size(); k++) {
+      const Tr& rarc = (*prow)[k];
+      const StateId next = new_state(Tr{rarc.ilabel, rarc.olabel, rarc.weight, state},
+                                     Pair{true, rarc.nextstate, w_times(p.w, rarc.weight)}, (*pdist)[k]);
       push(next);
     }
     if (p.state == rfinal) {  // the only final state of the reversed machine, weight one(): reverse.rs:54-56
-      const float weight = w_times(p.w, 0.0f);
-      const StateId next = ofst.add_state();
-      pairs.push_back(Pair{false, 0, weight});
-      keys.push_back(key_of(pairs.back()));
-      ofst.add_tr(next, Tr{0, 0, 0.0f, state});
+      const StateId next = new_state(Tr{0, 0, 0.0f, state}, Pair{false, 0, w_times(p.w, 0.0f)}, 0.0f);
       push(next);
     }
   }
   st.ms_search_host = (float)(now_ms() - t0);
-  st.states_before_trim = ofst.num_states();
+  t0 = now_ms();
+  CsrFst ho;
+  const size_t ns = single_arc.size() + 2;
+  st.states_before_trim = ns;
+  ho.offsets.resize(ns + 1);
+  ho.arcs.resize(start_arcs.size() + single_arc.size());
+  ho.finals.assign(ns, w_zero());
+  ho.finals[final_state] = 0.0f;
+  std::copy(start_arcs.begin(), start_arcs.end(), ho.arcs.begin());
+  std::copy(single_arc.begin(), single_arc.end(), ho.arcs.begin() + start_arcs.size());
+  ho.offsets[0] = 0; ho.offsets[1] = (uint32_t)start_arcs.size(); ho.offsets[2] = (uint32_t)start_arcs.size();
+  for (size_t i = 2; i < ns; i++) ho.offsets[i + 1] = ho.offsets[i] + 1;
+  ho.has_start = true; ho.start = ostart;
+  ho.props = pw & props::kTrinary;
 
   // ---- device: connect (:511) + shortest_path_properties(.., false) (:512-515)
-  const CsrFst& ho = ofst.freeze();
   DevFst dofst = upload(ho, s);
   DevFst trimmed = connect_device(dofst, false, &st.distance.kernel_launches, s);
   CsrFst out = download(trimmed, s);
   out.props = props::of_shortest_path(out.props, false) & props::kTrinary;
+  const float ms_trim = (float)(now_ms() - t0);
   st.ms_total = (float)(now_ms() - t_begin);
+  if (std::getenv("B200_NSHORTEST_TRACE"))
+    std::fprintf(stderr, "[nshortest] n=%zu distance %.2f ms (path %d) reverse %.2f ms search %.2f ms (%llu pops, %llu rows, "
+                 "%llu arcs fetched, %llu tree states) trim %.2f ms total %.2f ms\n", nshortest, st.ms_distance,
+                 st.distance.path, st.ms_reverse, st.ms_search_host, (unsigned long long)st.heap_pops,
+                 (unsigned long long)st.rows_fetched, (unsigned long long)st.arcs_fetched,
+                 (unsigned long long)st.states_before_trim, ms_trim, st.ms_total);
   return out;
 }
 

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librustfst_b200.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(HERE, "librustfst_b200.so")  # B200_LIB: experimental builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

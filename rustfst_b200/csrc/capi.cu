@@ -139,7 +139,7 @@ CFst* shortest_path_host(const CFst* in, const CShortestPathConfig* cfg, B200Sss
   double t1 = now_ms();
   if (nshortest != 1) {  // shortest_path.rs:135-170
     NShortestStats ns;
-    CsrFst r = n_shortest_paths_device(d, h.inf_finals, plan, nshortest, cfg->delta, &ns, st.s, force_serial);
+    CsrFst r = n_shortest_paths_device(d, plan, nshortest, cfg->delta, &ns, st.s, force_serial);
     ns.distance.ms_device = ns.ms_total;
     fill(stats, ns.distance, (int)plan.kind, (float)(t1 - t0));
     return new CFst{HostFst(std::move(r))};

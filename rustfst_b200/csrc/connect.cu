@@ -47,18 +47,43 @@ __global__ void k_seed_finals(const float* __restrict__ fin, uint32_t n, uint32_
   basep = __shfl_sync(0xFFFFFFFFu, basep, leader);
   if (f) frontier[basep + __popc(m & ((1u << lane) - 1u))] = s;
 }
-// One BFS level.  kForward: neighbours are arcs[i].nextstate; otherwise adj[i] (reverse CSR sources).
+// One BFS level, one WARP per frontier vertex (lanes stride over its adjacency list).  kForward: neighbours are
+// arcs[i].nextstate; otherwise adj[i] (reverse CSR sources).  Vertices with more than kHeavyDegree neighbours (hub
+// states: superfinal states, the root of an n-best tree) are only listed; k_bfs_heavy then spreads each of them over
+// 64 CTAs.  count[0] = size of the next frontier, count[1] = number of heavy vertices of this level.
+constexpr uint32_t kHeavyDegree = 4096;
+constexpr uint32_t kHeavyCtas = 64;
 template <bool kForward>
-__global__ void k_bfs_level(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs,
-                            const uint32_t* __restrict__ adj, const uint32_t* __restrict__ fin_in, uint32_t n_in,
-                            uint32_t* __restrict__ mark, uint32_t* __restrict__ fout, uint32_t* __restrict__ count) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_in) return;
-  uint32_t v = fin_in[i];
-  for (uint32_t k = off[v]; k < off[v + 1]; k++) {
-    uint32_t u = kForward ? __ldg(&arcs[k].nextstate) : __ldg(&adj[k]);
-    if (mark[u] == 0 && atomicExch(&mark[u], 1u) == 0) fout[atomicAdd(count, 1u)] = u;
+__device__ __forceinline__ void bfs_visit(const Tr* __restrict__ arcs, const uint32_t* __restrict__ adj, uint32_t k,
+                                          uint32_t* __restrict__ mark, uint32_t* __restrict__ fout,
+                                          uint32_t* __restrict__ count) {
+  const uint32_t u = kForward ? __ldg(&arcs[k].nextstate) : __ldg(&adj[k]);
+  if (mark[u] == 0 && atomicExch(&mark[u], 1u) == 0) fout[atomicAdd(count, 1u)] = u;
+}
+template <bool kForward>
+__global__ void __launch_bounds__(kThreads)
+k_bfs_level(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, const uint32_t* __restrict__ adj,
+            const uint32_t* __restrict__ fin_in, uint32_t n_in, uint32_t* __restrict__ mark,
+            uint32_t* __restrict__ fout, uint32_t* __restrict__ count, uint32_t* __restrict__ heavy) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_in) return;
+  const uint32_t v = fin_in[w];
+  const uint32_t b = off[v], e = off[v + 1];
+  if (e - b > kHeavyDegree) {
+    if (lane == 0) heavy[atomicAdd(&count[1], 1u)] = v;
+    return;
   }
+  for (uint32_t k = b + lane; k < e; k += 32) bfs_visit<kForward>(arcs, adj, k, mark, fout, count);
+}
+template <bool kForward>
+__global__ void __launch_bounds__(kThreads)
+k_bfs_heavy(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, const uint32_t* __restrict__ adj,
+            const uint32_t* __restrict__ heavy, uint32_t* __restrict__ mark, uint32_t* __restrict__ fout,
+            uint32_t* __restrict__ count) {
+  const uint32_t v = heavy[blockIdx.y];
+  const uint32_t b = off[v], e = off[v + 1];
+  for (uint32_t k = b + blockIdx.x * blockDim.x + threadIdx.x; k < e; k += gridDim.x * blockDim.x)
+    bfs_visit<kForward>(arcs, adj, k, mark, fout, count);
 }
 __global__ void k_keep_flags(const uint32_t* __restrict__ access, const uint32_t* __restrict__ coaccess, uint32_t n,
                              uint32_t* __restrict__ keep) {
@@ -249,6 +274,26 @@ k_trim_coop(TrimParams P) {
 }
 
 #undef TRIM_SYNC
+// One BFS level from the host: launches the level kernel (+ the hub kernel when the level contains hub vertices) and
+// returns the size of the next frontier.
+template <bool kForward>
+uint32_t bfs_step(const uint32_t* off, const Tr* arcs, const uint32_t* adj, const uint32_t* fin_in, uint32_t nf,
+                  uint32_t* mark, uint32_t* fout, uint32_t* count, uint32_t* heavy, uint64_t* nl, cudaStream_t s) {
+  B200_CUDA(cudaMemsetAsync(count, 0, 8, s));
+  k_bfs_level<kForward><<<blocks_for((size_t)nf * 32), kThreads, 0, s>>>(off, arcs, adj, fin_in, nf, mark, fout, count, heavy);
+  (*nl)++;
+  uint32_t c[2];
+  B200_CUDA(cudaMemcpyAsync(c, count, 8, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  for (uint32_t h0 = 0; h0 < c[1]; h0 += 32768) {
+    const uint32_t nh = std::min<uint32_t>(32768, c[1] - h0);
+    k_bfs_heavy<kForward><<<dim3(kHeavyCtas, nh), kThreads, 0, s>>>(off, arcs, adj, heavy + h0, mark, fout, count);
+    (*nl)++;
+  }
+  if (c[1]) c[0] = read_u32(count, s);
+  return c[0];
+}
+
 }  // namespace
 
 DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launches, cudaStream_t s) {
@@ -260,11 +305,10 @@ DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launch
   if (n == 0 || !in.has_start) {
     out.offsets.reserve_discard(1);
     B200_CUDA(cudaMemsetAsync(out.offsets.p, 0, 4, s));
-    if (launches) *launches = 0;
     return out;
   }
   DevBuf<uint8_t> scan_tmp(s);
-  DevBuf<uint32_t> fa(s, n), fb(s, n), count(s, 1);
+  DevBuf<uint32_t> fa(s, n), fb(s, n), count(s, 2), heavy(s, n);
   uint32_t* fin_p = fa.p;
   uint32_t* fout_p = fb.p;
 
@@ -279,11 +323,7 @@ DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launch
     B200_CUDA(cudaStreamSynchronize(s));
     uint32_t nf = 1;
     while (nf) {
-      B200_CUDA(cudaMemsetAsync(count.p, 0, 4, s));
-      k_bfs_level<true><<<blocks_for(nf), kThreads, 0, s>>>(in.offsets.p, in.arcs.p, nullptr, fin_p, nf, access.p,
-                                                            fout_p, count.p);
-      nl++;
-      nf = read_u32(count.p, s);
+      nf = bfs_step<true>(in.offsets.p, in.arcs.p, nullptr, fin_p, nf, access.p, fout_p, count.p, heavy.p, &nl, s);
       std::swap(fin_p, fout_p);
     }
   }
@@ -300,11 +340,7 @@ DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launch
   nl += 4;
   uint32_t nf = read_u32(count.p, s);
   while (nf) {
-    B200_CUDA(cudaMemsetAsync(count.p, 0, 4, s));
-    k_bfs_level<false><<<blocks_for(nf), kThreads, 0, s>>>(roff.p, nullptr, rsrc.p, fin_p, nf, coaccess.p, fout_p,
-                                                           count.p);
-    nl++;
-    nf = read_u32(count.p, s);
+    nf = bfs_step<false>(roff.p, nullptr, rsrc.p, fin_p, nf, coaccess.p, fout_p, count.p, heavy.p, &nl, s);
     std::swap(fin_p, fout_p);
   }
 
@@ -335,7 +371,7 @@ DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launch
   B200_CUDA(cudaStreamSynchronize(s));
   out.has_start = kv[0] != 0;
   out.start = kv[0] ? kv[1] : 0;
-  if (launches) *launches = nl;
+  if (launches) *launches += nl;
   return out;
 }
 

@@ -83,13 +83,37 @@ __global__ void __launch_bounds__(kThreads)
 k_fetch_row(const uint32_t* __restrict__ roff, const Tr* __restrict__ rarcs, const float* __restrict__ dist,
             uint32_t n, uint32_t q, uint32_t cap, int4* __restrict__ out, float* __restrict__ dists) {
   const uint32_t b = roff[q], deg = roff[q + 1] - b;
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0) out[0] = make_int4((int)deg, 0, 0, 0);
-  if (k >= deg || deg > cap) return;
-  const int4 v = __ldg(reinterpret_cast<const int4*>(&rarcs[b + k]));
-  out[1 + k] = v;
-  const uint32_t src = (uint32_t)v.w - 1u;  // rows never point at the superinitial state
-  dists[k] = (dist && src < n) ? dist[src] : w_zero();
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0) out[0] = make_int4((int)deg, 0, 0, 0);
+  if (deg > cap) return;
+  for (uint32_t k = tid; k < deg; k += gridDim.x * blockDim.x) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(&rarcs[b + k]));
+    out[1 + k] = v;
+    const uint32_t src = (uint32_t)v.w - 1u;  // rows never point at the superinitial state
+    dists[k] = (dist && src < n) ? dist[src] : w_zero();
+  }
+}
+
+// Mapped page-locked staging area: [header + cap arcs as int4][cap distances].
+struct Staging {
+  void* base = nullptr;
+  size_t cap = 0;
+  int4* arcs() const { return static_cast<int4*>(base); }
+  float* dists() const { return reinterpret_cast<float*>(static_cast<char*>(base) + (cap + 1) * 16); }
+  void ensure(size_t want) {
+    if (want <= cap) return;
+    if (base) cudaFreeHost(base);
+    base = nullptr; cap = 0;
+    size_t c = 4096;
+    while (c < want) c <<= 1;
+    B200_CUDA(cudaHostAlloc(&base, (c + 1) * 16 + c * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+    cap = c;
+  }
+  ~Staging() { if (base) cudaFreeHost(base); }
+};
+Staging& thread_staging() {
+  thread_local Staging st;
+  return st;
 }
 
 double now_ms() {
@@ -140,7 +164,7 @@ DevFst reverse_device(const DevFst& f, cudaStream_t s, uint64_t* launches) {
   return r;
 }
 
-CsrFst n_shortest_paths_device(const DevFst& f, const std::vector<StateId>& inf_finals, const QueuePlan& plan,
+CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
                                size_t nshortest, float delta, NShortestStats* stats, cudaStream_t s,
                                bool force_serial) {
   NShortestStats local;
@@ -159,74 +183,39 @@ CsrFst n_shortest_paths_device(const DevFst& f, const std::vector<StateId>& inf_
   st.ms_distance = (float)(now_ms() - t0);
   t0 = now_ms();
   DevFst r = reverse_device(f, s, &st.distance.kernel_launches);
-  B200_CUDA(cudaStreamSynchronize(s));
+  const size_t r_row0_len = read_u32(r.offsets.p + 1, s);
   st.ms_reverse = (float)(now_ms() - t0);
   t0 = now_ms();
 
   // Rows of the reversed machine are fetched on demand into a page-locked staging buffer: one small kernel gathers
-  // the row's arcs and the forward distances of their source states (k_fetch_row).  Row 0 also receives the
-  // `Some(+inf)` finals, which the device representation (+inf = not final) cannot tell from non-final states; they
-  // are merged by state id.
+  // the row's arcs and the forward distances of their source states (k_fetch_row).
   const float* d_dist_p = (n && f.has_start) ? d_dist.p : nullptr;
-  uint32_t cap = 1u << 12;
-  int4* h_row = nullptr;
-  float* h_rdist = nullptr;
-  DevBuf<int4> d_row(s, (size_t)cap + 1);
-  DevBuf<float> d_rdist(s, cap);
-  B200_CUDA(cudaMallocHost((void**)&h_row, ((size_t)cap + 1) * 16));
-  B200_CUDA(cudaMallocHost((void**)&h_rdist, (size_t)cap * 4));
-  struct HostStage {  // frees the staging buffers on every exit path
-    int4*& a; float*& b;
-    ~HostStage() { if (a) cudaFreeHost(a); if (b) cudaFreeHost(b); }
-  } stage_guard{h_row, h_rdist};
+  // Staging buffer in mapped page-locked host memory, written by the kernel itself (zero copy): a row costs one
+  // launch and one stream synchronisation.  It is cached per host thread and sized to the longest row seen.
+  Staging& stage = thread_staging();
+  stage.ensure(std::max<size_t>(r_row0_len, 4096));
   std::vector<Tr> row;
   std::vector<float> row_dist;
   auto fetch_row = [&](uint32_t q) {
     while (true) {
-      k_fetch_row<<<blocks_for(cap), kThreads, 0, s>>>(r.offsets.p, r.arcs.p, d_dist_p, n, q, cap, d_row.p, d_rdist.p);
+      const uint32_t cap = (uint32_t)stage.cap;
+      const size_t hint = q == 0 ? std::max<size_t>(r_row0_len, 1) : 1024;  // rows are short; the kernel strides
+      k_fetch_row<<<blocks_for(std::min<size_t>(cap, hint)), kThreads, 0, s>>>(r.offsets.p, r.arcs.p, d_dist_p, n, q, cap, stage.arcs(),
+                                                       stage.dists());
       st.distance.kernel_launches++;
-      B200_CUDA(cudaMemcpyAsync(h_row, d_row.p, 16, cudaMemcpyDeviceToHost, s));
       B200_CUDA(cudaStreamSynchronize(s));
-      const uint32_t deg = (uint32_t)h_row[0].x;
+      const uint32_t deg = (uint32_t)stage.arcs()[0].x;
       if (deg <= cap) {
-        if (deg) {
-          B200_CUDA(cudaMemcpyAsync(h_row + 1, d_row.p + 1, (size_t)deg * 16, cudaMemcpyDeviceToHost, s));
-          B200_CUDA(cudaMemcpyAsync(h_rdist, d_rdist.p, (size_t)deg * 4, cudaMemcpyDeviceToHost, s));
-          B200_CUDA(cudaStreamSynchronize(s));
-        }
         row.resize(deg); row_dist.resize(deg);
-        for (uint32_t k = 0; k < deg; k++) {
-          const int4 v = h_row[1 + k];
-          Tr tr; tr.ilabel = (uint32_t)v.x; tr.olabel = (uint32_t)v.y; tr.nextstate = (uint32_t)v.w;
-          std::memcpy(&tr.weight, &v.z, 4);
-          row[k] = tr; row_dist[k] = h_rdist[k];
+        if (deg) {
+          std::memcpy(row.data(), stage.arcs() + 1, (size_t)deg * 16);
+          std::memcpy(row_dist.data(), stage.dists(), (size_t)deg * 4);
         }
         break;
       }
-      cap = deg;  // grow the staging buffers to the row and fetch again
-      cudaFreeHost(h_row); cudaFreeHost(h_rdist); h_row = nullptr; h_rdist = nullptr;
-      B200_CUDA(cudaMallocHost((void**)&h_row, ((size_t)cap + 1) * 16));
-      B200_CUDA(cudaMallocHost((void**)&h_rdist, (size_t)cap * 4));
-      d_row.reserve_discard((size_t)cap + 1);
-      d_rdist.reserve_discard(cap);
+      stage.ensure(deg);  // grow to the row and fetch again
     }
     st.rows_fetched++; st.arcs_fetched += row.size();
-    if (q == 0 && !inf_finals.empty()) {
-      std::vector<Tr> merged; std::vector<float> merged_d;
-      merged.reserve(row.size() + inf_finals.size());
-      size_t i = 0;
-      std::vector<float> inf_d(inf_finals.size(), w_zero());
-      for (size_t k = 0; k < inf_finals.size(); k++)
-        if (d_dist_p) B200_CUDA(cudaMemcpyAsync(&inf_d[k], d_dist_p + inf_finals[k], 4, cudaMemcpyDeviceToHost, s));
-      B200_CUDA(cudaStreamSynchronize(s));
-      for (size_t k = 0; k < inf_finals.size(); k++) {
-        const StateId fs = inf_finals[k];
-        while (i < row.size() && row[i].nextstate < fs + 1) { merged.push_back(row[i]); merged_d.push_back(row_dist[i]); i++; }
-        merged.push_back(Tr{kEps, kEps, w_zero(), fs + 1}); merged_d.push_back(inf_d[k]);
-      }
-      while (i < row.size()) { merged.push_back(row[i]); merged_d.push_back(row_dist[i]); i++; }
-      row.swap(merged); row_dist.swap(merged_d);
-    }
   };
   // distance_2 of shortest_path.rs:153-154: index 0 = the superinitial state (d0), index q = distance[q - 1]
   float d0 = w_zero();
@@ -352,7 +341,9 @@ CsrFst n_shortest_paths_device(const DevFst& f, const std::vector<StateId>& inf_
 
   // ---- device: connect (:511) + shortest_path_properties(.., false) (:512-515)
   DevFst dofst = upload(ho, s);
-  DevFst trimmed = connect_device(dofst, false, &st.distance.kernel_launches, s);
+  uint64_t trim_launches = 0;
+  DevFst trimmed = connect_device(dofst, false, &trim_launches, s);
+  st.distance.kernel_launches += trim_launches;
   CsrFst out = download(trimmed, s);
   out.props = props::of_shortest_path(out.props, false) & props::kTrinary;
   const float ms_trim = (float)(now_ms() - t0);

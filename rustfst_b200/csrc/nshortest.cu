@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "algos.h"
@@ -288,26 +289,29 @@ CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
     pw = props::on_add_tr(pw, next, tr, nullptr);
     return next;
   };
+  pairs.reserve(r_row0_len + 1024); keys.reserve(r_row0_len + 1024); single_arc.reserve(r_row0_len + 1024);
+  heap.reserve(r_row0_len + 1024);
   push(final_state);
   const float limit = w_times(d0, w_zero());  // weight_threshold = zero(): :448-449
-  std::vector<size_t> seen;                    // r of :451
+  // r of :451 — the reference grows a dense vector up to the largest popped state id (tens of MB on a multi-million-
+  // state lattice for a few hundred pops); a hash map holds the same counters
+  std::unordered_map<uint32_t, size_t> seen;
   const uint32_t rfinal = f.has_start ? f.start + 1 : kNoState;
   while (!heap.empty()) {
     const StateId state = pop();
     st.heap_pops++;
     const Pair p = pairs[state];
-    const size_t first_real = p.some ? (size_t)p.state + 1 : 0;
+    const uint32_t first_real = p.some ? p.state + 1 : 0;
     // d (x) p.1 of :463-474 is exactly the cached heap key
     if (natural_less(limit, keys[state].w)) continue;
-    if (seen.size() <= first_real) seen.resize(first_real + 1, 0);
-    seen[first_real] += 1;
+    const size_t n_seen = ++seen[first_real];
     if (!p.some) {
       const Tr tr{0, 0, 0.0f, state};
       pw = props::on_add_tr(pw, ostart, tr, start_arcs.empty() ? nullptr : &start_arcs.back());
       start_arcs.push_back(tr);
     }
-    if (!p.some && seen[first_real] == nshortest) break;
-    if (seen[first_real] > nshortest) continue;
+    if (!p.some && n_seen == nshortest) break;
+    if (n_seen > nshortest) continue;
     if (!p.some) continue;
     const std::vector<Tr>* prow = &row0;
     const std::vector<float>* pdist = &row0_dist;

@@ -166,22 +166,24 @@ __device__ __forceinline__ void match_range(const uint32_t* __restrict__ lab, ui
   // window [l, l + 16) lies inside the five aligned quads starting at l & ~3 (reads past hi hit the padding)
   const uint32_t l4 = l & ~3u;
   const uint4* __restrict__ q4 = reinterpret_cast<const uint4*>(lab + l4);
+  const uint32_t w_end = min(hi, l + 16);
   uint4 v[5];
 #pragma unroll
   for (int k = 0; k < 5; k++) v[k] = __ldg(q4 + k);
-  uint32_t n_lt = 0, n_eq = 0;
-  const uint32_t w_end = min(hi, l + 16);
+  // "< key" / "== key" collected as 20-bit masks (one compare + one predicated OR per label), cut to the valid window
+  // [l, w_end) once
+  uint32_t lt_m = 0, eq_m = 0;
 #pragma unroll
   for (int k = 0; k < 5; k++) {
     const uint32_t xs[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const uint32_t idx = l4 + 4 * k + u;
-      const bool valid = idx >= l && idx < w_end;
-      n_lt += (valid && xs[u] < key) ? 1u : 0u;
-      n_eq += (valid && xs[u] == key) ? 1u : 0u;
+      if (xs[u] < key) lt_m |= 1u << (4 * k + u);
+      if (xs[u] == key) eq_m |= 1u << (4 * k + u);
     }
   }
+  const uint32_t vm = ((1u << (w_end - l4)) - 1u) & ~((1u << (l - l4)) - 1u);
+  const uint32_t n_lt = __popc(lt_m & vm), n_eq = __popc(eq_m & vm);
   pos = l + n_lt;
   end = pos + n_eq;
   if (end == l + 16 && end < hi) end = run_end_lab(lab, end, hi, key);  // run leaves the window (rare)

@@ -139,6 +139,17 @@ __device__ __forceinline__ void cta_prefix_wait_to_smem(const unsigned long long
   }
   __threadfence();
   __syncthreads();
+  if (n <= 2 * kCoopThreads) {  // the usual grid (<= 512 CTAs): two entries per thread instead of eight
+    const uint32_t i0 = threadIdx.x * 2;
+    const uint32_t a = i0 < n ? s_out[i0] : 0u, b = i0 + 1 < n ? s_out[i0 + 1] : 0u;
+    uint32_t total;
+    const uint32_t run = cta_exclusive_scan(a + b, s_warp, total);
+    if (i0 < n) s_out[i0] = run;
+    if (i0 + 1 < n) s_out[i0 + 1] = run + a;
+    if (threadIdx.x == 0) s_out[n] = total;
+    __syncthreads();
+    return;
+  }
   uint32_t v[8], sum = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) { uint32_t i = threadIdx.x * 8 + k; v[k] = i < n ? s_out[i] : 0u; sum += v[k]; }

@@ -233,6 +233,11 @@ RUSTFST_FFI_RESULT b200_device_compose(const B200DeviceFst* fst_1, const B200Dev
 RUSTFST_FFI_RESULT b200_device_shortest_path(const B200DeviceFst* dfst, const CFst* plan_from, const CFst** res_fst,
                                              B200SsspStats* stats, bool force_serial);
 
+/* Same with a ShortestPathConfig (nshortest > 1: n-best over the device-resident machine; config may be NULL). */
+RUSTFST_FFI_RESULT b200_device_shortest_path_with_config(const B200DeviceFst* dfst, const CFst* plan_from,
+                                                         const CShortestPathConfig* config, const CFst** res_fst,
+                                                         B200SsspStats* stats, bool force_serial);
+
 /* Batched compose: acceptors[i] o transducer for i in [0, n) on the current device (transducer uploaded once). */
 RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, const CFst* transducer,
                                       const CComposeConfig* config, const CFst** results /* n slots */,

@@ -160,12 +160,17 @@ def device_compose(a: DeviceFst, b: DeviceFst, config: Optional[ComposeConfig] =
     return DeviceFst(out), st.as_dict()
 
 
-def device_shortest_path(d: DeviceFst, plan_from: Optional[VectorFst] = None, force_serial=False):
+def device_shortest_path(d: DeviceFst, plan_from: Optional[VectorFst] = None, force_serial=False,
+                         config: Optional[ShortestPathConfig] = None):
     host = plan_from or d.host
     out = C.c_void_p()
     st = SsspStats()
-    check_ffi_error(lib.b200_device_shortest_path(d.ptr, host.ptr, C.byref(out), C.byref(st), bool(force_serial)),
-                    "Error computing shortest path")
+    if config is None:
+        rc = lib.b200_device_shortest_path(d.ptr, host.ptr, C.byref(out), C.byref(st), bool(force_serial))
+    else:
+        rc = lib.b200_device_shortest_path_with_config(d.ptr, host.ptr, config.ptr, C.byref(out), C.byref(st),
+                                                       bool(force_serial))
+    check_ffi_error(rc, "Error computing shortest path")
     return VectorFst(out), st.as_dict()
 
 

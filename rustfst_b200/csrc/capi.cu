@@ -119,35 +119,45 @@ CFst* compose_host(const CFst* a, const CFst* b, const CComposeConfig* cfg, B200
   return new CFst{HostFst(std::move(hr))};
 }
 
-CFst* shortest_path_host(const CFst* in, const CShortestPathConfig* cfg, B200SsspStats* stats, bool force_serial) {
-  size_t nshortest = cfg ? cfg->nshortest : 1;  // shortest_path.rs:30-38 defaults
-  if (nshortest == 0) {                          // shortest_path.rs:120-122
-    if (stats) std::memset(stats, 0, sizeof(*stats));
-    return new CFst{};
-  }
-  if (nshortest != 1 && cfg->unique)
+// shortest_path_with_config (shortest_path.rs:107-171) on a device-resident machine: nshortest == 1 -> single
+// shortest path; > 1 -> distances + reversed machine + n-best search; unique is refused (see the message).
+void check_sp_config(const CShortestPathConfig* cfg) {
+  if (cfg && cfg->nshortest > 1 && cfg->unique)
     // shortest_path.rs:156-165 determinizes the reversed machine; determinize_fsa_op.rs:154-165 rebuilds every
     // weighted subset from HashMap::values() of a RandomState map, so the reference's own answer (subset identity,
     // state numbering, even the number of states) changes from process to process: nothing to be identical to.
     throw FstError("shortest_path with nshortest > 1 and unique = true is not supported by this build of "
                    "librustfst_b200 (the reference result is process-dependent; use unique = false)");
+}
+CsrFst shortest_path_dispatch(const DevFst& d, const QueuePlan& plan, const CShortestPathConfig* cfg,
+                              B200SsspStats* stats, float ms_h2d, cudaStream_t s, bool force_serial) {
+  const size_t nshortest = cfg ? cfg->nshortest : 1;  // shortest_path.rs:30-38 defaults
+  if (nshortest != 1) {                                // shortest_path.rs:135-170
+    NShortestStats ns;
+    CsrFst r = n_shortest_paths_device(d, plan, nshortest, cfg->delta, &ns, s, force_serial);
+    ns.distance.ms_device = ns.ms_total;
+    fill(stats, ns.distance, (int)plan.kind, ms_h2d);
+    return r;
+  }
+  SsspStats ss;
+  CsrFst r = shortest_path_device(d, plan, &ss, s, force_serial);
+  fill(stats, ss, (int)plan.kind, ms_h2d);
+  return r;
+}
+
+CFst* shortest_path_host(const CFst* in, const CShortestPathConfig* cfg, B200SsspStats* stats, bool force_serial) {
+  if (cfg && cfg->nshortest == 0) {  // shortest_path.rs:120-122
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    return new CFst{};
+  }
+  check_sp_config(cfg);
   const CsrFst& h = nn(in, "fst")->fst.freeze();
   QueuePlan plan = build_queue_plan(h);
   Stream st;
   double t0 = now_ms();
   DevFst d = upload(h, st.s);
   double t1 = now_ms();
-  if (nshortest != 1) {  // shortest_path.rs:135-170
-    NShortestStats ns;
-    CsrFst r = n_shortest_paths_device(d, plan, nshortest, cfg->delta, &ns, st.s, force_serial);
-    ns.distance.ms_device = ns.ms_total;
-    fill(stats, ns.distance, (int)plan.kind, (float)(t1 - t0));
-    return new CFst{HostFst(std::move(r))};
-  }
-  SsspStats ss;
-  CsrFst r = shortest_path_device(d, plan, &ss, st.s, force_serial);
-  fill(stats, ss, (int)plan.kind, (float)(t1 - t0));
-  return new CFst{HostFst(std::move(r))};
+  return new CFst{HostFst(shortest_path_dispatch(d, plan, cfg, stats, (float)(t1 - t0), st.s, force_serial))};
 }
 }  // namespace
 
@@ -520,6 +530,20 @@ RUSTFST_FFI_RESULT b200_device_shortest_path(const B200DeviceFst* d, const CFst*
     CsrFst r = shortest_path_device(nn(d, "dfst")->d, plan, &ss, d->stream.s, force_serial);
     fill(stats, ss, (int)plan.kind, 0.0f);
     *out = new CFst{HostFst(std::move(r))};
+  });
+}
+RUSTFST_FFI_RESULT b200_device_shortest_path_with_config(const B200DeviceFst* d, const CFst* plan_from,
+                                                         const CShortestPathConfig* cfg, const CFst** out,
+                                                         B200SsspStats* stats, bool force_serial) {
+  return wrap([&] {
+    if (cfg && cfg->nshortest == 0) {
+      if (stats) std::memset(stats, 0, sizeof(*stats));
+      *out = new CFst{};
+      return;
+    }
+    check_sp_config(cfg);
+    QueuePlan plan = build_queue_plan(nn(plan_from, "plan_from")->fst.freeze());
+    *out = new CFst{HostFst(shortest_path_dispatch(nn(d, "dfst")->d, plan, cfg, stats, 0.0f, d->stream.s, force_serial))};
   });
 }
 RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, const CFst* transducer,

@@ -102,6 +102,10 @@ constexpr uint32_t kSideBit = 0x80000000u;
 constexpr uint32_t kTile = kCoopThreads;
 constexpr uint32_t kWarps = kCoopThreads / 32;
 constexpr int kArcsPerThread = 4;  // rank / resolve phases: consecutive arcs per thread and round
+#ifndef B200_EMIT_ARCS_PER_LANE
+#define B200_EMIT_ARCS_PER_LANE 1
+#endif
+constexpr int kEmitArcs = B200_EMIT_ARCS_PER_LANE;  // emit phase: arcs per lane and round (32 * kEmitArcs per warp)
 
 // Optional fine-grained timeline of thread 0 of every CTA (build with -DB200_COOP_PROFILE): SM cycles spent in the
 // sub-steps of the A1 and B tiles, summed over the run and averaged over the CTAs by the host.
@@ -212,6 +216,23 @@ __device__ __forceinline__ uint32_t table_probe(Slot* slots, uint32_t mask, unsi
   }
 }
 
+// Same lookup-or-insert with the first slot already fetched (the emit phase issues the first probes of all the arcs of
+// a lane before it waits for any of them; with kEmitArcs = 1 this is the plain probe).
+__device__ __forceinline__ uint32_t table_probe_from(Slot* slots, uint32_t mask, unsigned long long key, uint32_t& h,
+                                                     uint4 sv) {
+  while (true) {
+    const unsigned long long curk = (unsigned long long)sv.x | ((unsigned long long)sv.y << 32);
+    if (curk == key) return sv.z;
+    if (curk == kEmptyKey) {
+      const unsigned long long prev = atomicCAS(&slots[h].key, kEmptyKey, key);
+      if (prev == kEmptyKey) return kUnassigned;  // fresh insert: discovered in this wave
+      if (prev == key) return *reinterpret_cast<volatile uint32_t*>(&slots[h].id);
+    }
+    h = (h + 1) & mask;
+    sv = ld_volatile_u4(&slots[h]);
+  }
+}
+
 // Per-state setup of a product state that joins the next frontier (compose_fst_op.rs:199-219 match side,
 // :420-449 final weight; filter flags as in compose_common.cuh): writes the state's scratch records and returns
 // (#items | side bit).  i = frontier-local index, id = product state id, c = CTA that owns the state's slice.
@@ -263,9 +284,9 @@ template <int kMinBlocks>
 __global__ void __launch_bounds__(kCoopThreads, kMinBlocks)
 k_compose_coop(CoopParams P) {
   __shared__ uint32_t s_warp[2 * (kCoopThreads / 32)];
-  __shared__ uint32_t s_wseg[kWarps][36];   // per-warp tile windows (A1: states, B: records)
+  __shared__ uint32_t s_wseg[kWarps][32 * kEmitArcs + 4];   // per-warp tile windows (A1: 32 states, B: records)
   __shared__ uint32_t s_wmeta8[kWarps][36];
-  __shared__ uint4 s_wrec8[kWarps][33];
+  __shared__ uint4 s_wrec8[kWarps][32 * kEmitArcs + 1];
   extern __shared__ uint32_t s_dyn[];          // three prefix arrays of gridDim + 1 entries
   const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   uint32_t* s_pref_items = s_dyn;
@@ -481,76 +502,105 @@ k_compose_coop(CoopParams P) {
       Tr* __restrict__ wave_arcs = P.out_arcs + base;
       uint32_t* const win_seg = s_wseg[wid];
       uint4* const win_rec = s_wrec8[wid];
-      uint32_t cursor = 0;  // first record (warp-local) that can contain the next tile's first arc
-      uint32_t w_loc = 0, w_loc2 = 0;
-      uint4 w_rec = make_uint4(0, 0, 0, 0);
+      // kEmitArcs arcs per lane and round: the gathers, and then the first table probes, of all the lane's arcs are
+      // issued before any of them is waited for.  Measured on C3 (emit phase, 768-thread CTAs): 1 arc per lane 1.39 ms,
+      // 2 arcs 1.47 ms; 512-thread CTAs: 2 arcs 1.63 ms, 4 arcs 1.74 ms — more requests in flight per warp make the
+      // phase slower, not faster (it is bound by memory-request throughput, not by the dependent chain), so the
+      // default stays 1.
+      constexpr uint32_t kBT = 32u * kEmitArcs;
+      uint32_t cursor = 0;  // first record (warp-local) that can contain the next round's first arc
+      uint32_t w_loc[kEmitArcs], w_loc2 = 0;
+      uint4 w_rec[kEmitArcs];
+#pragma unroll
+      for (int q = 0; q < kEmitArcs; q++) { w_loc[q] = 0; w_rec[q] = make_uint4(0, 0, 0, 0); }
       auto window_load = [&](uint32_t cur) {
-        if (cur + lane < w_active) { w_loc = P.arc_loc[wb + cur + lane]; w_rec = P.recs[wb + cur + lane]; }
-        if (lane == 0 && cur + 32 < w_active) w_loc2 = P.arc_loc[wb + cur + 32];
+#pragma unroll
+        for (int q = 0; q < kEmitArcs; q++) {
+          const uint32_t idx = cur + 32u * q + lane;
+          if (idx < w_active) { w_loc[q] = P.arc_loc[wb + idx]; w_rec[q] = P.recs[wb + idx]; }
+        }
+        if (lane == 0 && cur + kBT < w_active) w_loc2 = P.arc_loc[wb + cur + kBT];
       };
       if (w_arcs) window_load(0);
-      for (uint32_t e0 = 0; e0 < w_arcs; e0 += 32) {
+      for (uint32_t e0 = 0; e0 < w_arcs; e0 += kBT) {
         PROF_START();
-        if (cursor + lane < w_active) { win_seg[lane] = w_loc; win_rec[lane] = w_rec; }
-        else win_seg[lane] = w_arcs;
-        if (lane == 0) win_seg[32] = (cursor + 32 < w_active) ? w_loc2 : w_arcs;
+#pragma unroll
+        for (int q = 0; q < kEmitArcs; q++) {
+          const uint32_t idx = 32u * q + lane;
+          if (cursor + idx < w_active) { win_seg[idx] = w_loc[q]; win_rec[idx] = w_rec[q]; }
+          else win_seg[idx] = w_arcs;
+        }
+        if (lane == 0) win_seg[kBT] = (cursor + kBT < w_active) ? w_loc2 : w_arcs;
         __syncwarp();
         PROF_MARK(6);
-        const uint32_t el = e0 + lane;
-        const bool valid = el < w_arcs;
-        uint32_t k = 0, next_note = 0;
-        if (valid) {
-          k = smem_segment(win_seg, 33, el);
-          // the lane on the tile's last arc knows which record holds the first arc of the next tile
-          next_note = cursor + k + (win_seg[k + 1] <= el + 1 ? 1u : 0u);
+        uint32_t el[kEmitArcs], k[kEmitArcs];
+        bool valid[kEmitArcs];
+#pragma unroll
+        for (int q = 0; q < kEmitArcs; q++) {
+          el[q] = e0 + 32u * q + lane;
+          valid[q] = el[q] < w_arcs;
+          k[q] = valid[q] ? smem_segment(win_seg, kBT + 1, el[q]) : 0u;
         }
+        // the lane on the round's last arc knows which record holds the first arc of the next round
+        uint32_t next_note = 0;
+        if (valid[kEmitArcs - 1])
+          next_note = cursor + k[kEmitArcs - 1] + (win_seg[k[kEmitArcs - 1] + 1] <= el[kEmitArcs - 1] + 1 ? 1u : 0u);
         const uint32_t cursor_next = __shfl_sync(0xFFFFFFFFu, next_note, 31);
-        if (e0 + 32 < w_arcs) window_load(cursor_next);
-        if (valid) {
-          const uint4 rec = win_rec[k];
-          const uint32_t kk = el - win_seg[k];
-          const bool loop_ok = (rec.y >> 26) & 1u;
-          const bool match_input = rec.y >> 31;
-          const bool it_is_loop = rec.w == 0xFFFFFFFFu, cand_is_loop = loop_ok && kk == 0;
-          const Tr* __restrict__ it_arcs = match_input ? P.a.arcs : P.b.arcs;
-          const Tr* __restrict__ cd_arcs = match_input ? P.b.arcs : P.a.arcs;
-          uint32_t s1 = 0, s2 = 0;
-          if (it_is_loop || cand_is_loop) { uint32_t fs; unpack_key(__ldcg(&P.tuples[lo + rec.z]), fs, s1, s2); }
-          // implicit epsilon loops (matcher.rs: eps_loop): (0, NO_LABEL) / (NO_LABEL, 0) staying in the same state
-          Tr it = match_input ? Tr{kEps, kNoLabel, 0.0f, s1} : Tr{kNoLabel, kEps, 0.0f, s2};
-          Tr cand = match_input ? Tr{kNoLabel, kEps, 0.0f, s2} : Tr{kEps, kNoLabel, 0.0f, s1};
-          if (!it_is_loop) it = load_tr(&it_arcs[rec.w]);
-          if (!cand_is_loop) cand = load_tr(&cd_arcs[rec.x + kk - (loop_ok ? 1u : 0u)]);
-          uint32_t fsn = (rec.y >> 27) & 3u;
-          if (!cand_is_loop) {
-            fsn = (rec.y >> 29) & 3u;
-            if ((rec.y >> 25) & 1u) {  // sigma match: relabel (value_openfst, sigma_matcher.rs:249-276)
-              const SigmaDev& sg = match_input ? P.sig2 : P.sig1;
-              const Label l = match_input ? it.olabel : it.ilabel;
-              if (sg.rewrite_both) { if (cand.ilabel == sg.label) cand.ilabel = l; if (cand.olabel == sg.label) cand.olabel = l; }
-              else if (match_input) cand.ilabel = l;
-              else cand.olabel = l;
+        if (e0 + kBT < w_arcs) window_load(cursor_next);
+        Tr out[kEmitArcs];
+        unsigned long long key[kEmitArcs];
+        uint32_t h[kEmitArcs];
+        uint4 sv[kEmitArcs];
+#pragma unroll
+        for (int q = 0; q < kEmitArcs; q++) {
+          if (valid[q]) {
+            const uint4 rec = win_rec[k[q]];
+            const uint32_t kk = el[q] - win_seg[k[q]];
+            const bool loop_ok = (rec.y >> 26) & 1u;
+            const bool match_input = rec.y >> 31;
+            const bool it_is_loop = rec.w == 0xFFFFFFFFu, cand_is_loop = loop_ok && kk == 0;
+            const Tr* __restrict__ it_arcs = match_input ? P.a.arcs : P.b.arcs;
+            const Tr* __restrict__ cd_arcs = match_input ? P.b.arcs : P.a.arcs;
+            uint32_t s1 = 0, s2 = 0;
+            if (it_is_loop || cand_is_loop) { uint32_t fs; unpack_key(__ldcg(&P.tuples[lo + rec.z]), fs, s1, s2); }
+            // implicit epsilon loops (matcher.rs: eps_loop): (0, NO_LABEL) / (NO_LABEL, 0) staying in the same state
+            Tr it = match_input ? Tr{kEps, kNoLabel, 0.0f, s1} : Tr{kNoLabel, kEps, 0.0f, s2};
+            Tr cand = match_input ? Tr{kNoLabel, kEps, 0.0f, s2} : Tr{kEps, kNoLabel, 0.0f, s1};
+            if (!it_is_loop) it = load_tr(&it_arcs[rec.w]);
+            if (!cand_is_loop) cand = load_tr(&cd_arcs[rec.x + kk - (loop_ok ? 1u : 0u)]);
+            uint32_t fsn = (rec.y >> 27) & 3u;
+            if (!cand_is_loop) {
+              fsn = (rec.y >> 29) & 3u;
+              if ((rec.y >> 25) & 1u) {  // sigma match: relabel (value_openfst, sigma_matcher.rs:249-276)
+                const SigmaDev& sg = match_input ? P.sig2 : P.sig1;
+                const Label l = match_input ? it.olabel : it.ilabel;
+                if (sg.rewrite_both) { if (cand.ilabel == sg.label) cand.ilabel = l; if (cand.olabel == sg.label) cand.olabel = l; }
+                else if (match_input) cand.ilabel = l;
+                else cand.olabel = l;
+              }
             }
+            out[q].ilabel = match_input ? it.ilabel : cand.ilabel;   // arc1 = the fst1 arc, arc2 = the fst2 arc
+            out[q].olabel = match_input ? cand.olabel : it.olabel;
+            out[q].weight = w_times(it.weight, cand.weight);
+            key[q] = pack_key(fsn, match_input ? it.nextstate : cand.nextstate,
+                              match_input ? cand.nextstate : it.nextstate);
+            h[q] = hash_key(key[q]) & P.mask;
+            // one slot per probe round: wider rounds (2 / 4 slots fetched together) were measured slower on C3
+            sv[q] = ld_volatile_u4(&P.slots[h[q]]);
           }
-          Tr out;
-          out.ilabel = match_input ? it.ilabel : cand.ilabel;   // arc1 = the fst1 arc, arc2 = the fst2 arc
-          out.olabel = match_input ? cand.olabel : it.olabel;
-          out.weight = w_times(it.weight, cand.weight);
-          PROF_USE(__float_as_uint(out.weight));
-          PROF_MARK(7);
-          const unsigned long long key = pack_key(fsn, match_input ? it.nextstate : cand.nextstate,
-                                                  match_input ? cand.nextstate : it.nextstate);
-          const uint32_t e = e_off + el;  // canonical wave-local emission index
-          uint32_t h = hash_key(key) & P.mask;
-          // one slot per round: wider rounds (2 / 4 slots fetched together) were measured slower on C3 (B busy time
-          // 1.00 / 1.17 / 1.60 ms): the phase is bound by the number of memory requests, not by the probe chain
-          const uint32_t id = table_probe<1>(P.slots, P.mask, key, h);
-          PROF_USE(id);
-          PROF_MARK(8);
-          if (id != kUnassigned) out.nextstate = id;
-          else { atomicMin(&P.slots[h].emin, e); out.nextstate = kPendingBit | h; }
-          store_tr(&wave_arcs[e], out);
         }
+        PROF_MARK(7);
+#pragma unroll
+        for (int q = 0; q < kEmitArcs; q++) {
+          if (valid[q]) {
+            const uint32_t e = e_off + el[q];  // canonical wave-local emission index
+            const uint32_t id = table_probe_from(P.slots, P.mask, key[q], h[q], sv[q]);
+            if (id != kUnassigned) out[q].nextstate = id;
+            else { atomicMin(&P.slots[h[q]].emin, e); out[q].nextstate = kPendingBit | h[q]; }
+            store_tr(&wave_arcs[e], out[q]);
+          }
+        }
+        PROF_MARK(8);
         cursor = cursor_next;
         __syncwarp();
         PROF_MARK(9);
@@ -707,14 +757,14 @@ void launch_unpack_s1(const unsigned long long* tuples, uint32_t n, uint32_t* s1
 static int grid_used = 1;
 float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   CoopParams P = P0;
-  // resident CTAs per SM the kernel is compiled for (register budget): 4 -> 64 regs, 5 -> 48, 6 -> 40
-  int minb = 3;  // measured best on C3: 1 / 2 / 3 / 4 / 5 CTAs per SM -> 7.31 / 5.09 / 4.92 / 5.23 / 5.51 ms (more CTAs shorten
-                 // the phases but lengthen the count exchanges)
+  // resident CTAs per SM (only the 256-thread build has a choice; see coop_utils.cuh for the measured shapes)
+  int minb = 3;
   if (const char* e = std::getenv("B200_COOP_MINBLOCKS")) minb = std::atoi(e);
 #if B200_COOP_THREADS > 512
   minb = 1;
   void* kern = (void*)k_compose_coop<1>;
 #elif B200_COOP_THREADS > 256
+  if (!std::getenv("B200_COOP_MINBLOCKS")) minb = 1;
   if (minb > 3) minb = 3;
   void* kern = (void*)k_compose_coop<2>;
   if (minb == 3) kern = (void*)k_compose_coop<3>;
@@ -729,7 +779,7 @@ float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   else if (minb == 8) kern = (void*)k_compose_coop<8>;
 #endif
   int per_sm = 0;
-  size_t dyn = 3 * 2049 * sizeof(uint32_t);
+  size_t dyn = 3 * ((size_t)std::min(2047, sms * minb) + 1) * sizeof(uint32_t);
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoopThreads, dyn));
   if (per_sm < 1) throw FstError("cooperative compose kernel does not fit on the device");
   if (per_sm > minb) per_sm = minb;

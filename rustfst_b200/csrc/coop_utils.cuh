@@ -9,9 +9,12 @@
 namespace b200 {
 namespace coop {
 
-// Threads per CTA of the persistent kernels (a build-time knob for experiments: -DB200_COOP_THREADS=512).
+// Threads per CTA of the persistent kernels.  One 768-thread CTA per SM (148 CTAs) measured best for the compose
+// kernel on C3: 3 x 256 threads per SM 5.08 ms, 2 x 512 5.11, 1 x 512 5.19, 1 x 768 4.78 (same warps per SM as
+// 3 x 256, but a third of the words in every count exchange and no scheduling skew between co-resident CTAs).
+// -DB200_COOP_THREADS=256|512|640 rebuilds the other shapes.
 #ifndef B200_COOP_THREADS
-#define B200_COOP_THREADS 256
+#define B200_COOP_THREADS 768
 #endif
 constexpr int kCoopThreads = B200_COOP_THREADS;
 

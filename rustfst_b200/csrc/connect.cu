@@ -144,10 +144,7 @@ struct TrimParams {
 };
 
 #define TRIM_SYNC() do { if (P.light_barrier) grid_barrier(P.ctl + 5, bar_epoch); else grid.sync(); } while (0)
-#ifndef B200_TRIM_MINBLOCKS
-#define B200_TRIM_MINBLOCKS 2
-#endif
-__global__ void __launch_bounds__(kCoopThreads, B200_TRIM_MINBLOCKS)
+__global__ void __launch_bounds__(kCoopThreads, 2)
 k_trim_coop(TrimParams P) {
   cg::grid_group grid = cg::this_grid();
   unsigned int bar_epoch = 0;

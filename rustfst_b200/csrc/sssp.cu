@@ -111,17 +111,18 @@ k_relax(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, const uin
 // cnt[(w+1) % 3] and clears cnt[(w+2) % 3].
 // out[0] = waves, out[1] = non-convergence flag, out64[0] = arcs relaxed, out64[1] = states settled.
 constexpr uint32_t kQueueCap = 2048;
-template <int kG>
-__global__ void __launch_bounds__(kThreads)
+template <int kG, int kT, bool kPreTest, int kS>
+__global__ void __launch_bounds__(kT)
 k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t* __restrict__ dist,
              uint32_t* __restrict__ stamp, uint32_t* __restrict__ fr_a, uint32_t* __restrict__ fr_b,
              uint32_t* __restrict__ cnt /*3*/, uint32_t* __restrict__ out, unsigned long long* __restrict__ out64) {
   unsigned int bar_epoch = 0;  // out[2] = arrival counter of the grid barrier (zero-initialised)
-  __shared__ uint32_t s_q[kQueueCap];
+  constexpr uint32_t kQCap = kQueueCap * (kT / 256);
+  __shared__ uint32_t s_q[kQCap];
   __shared__ uint32_t s_qn, s_gbase;
   const uint32_t lane = threadIdx.x % kG;
-  const uint32_t groups = gridDim.x * (kThreads / kG);
-  const uint32_t gid = blockIdx.x * (kThreads / kG) + threadIdx.x / kG;
+  const uint32_t groups = gridDim.x * (kT / kG);
+  const uint32_t gid = blockIdx.x * (kT / kG) + threadIdx.x / kG;
   uint32_t* cur = fr_a;
   uint32_t* nxt = fr_b;
   unsigned long long relaxed = 0, settled = 0;
@@ -133,48 +134,75 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
     if (threadIdx.x == 0) s_qn = 0;
     __syncthreads();
     uint32_t* next_count = &cnt[(wave + 1) % 3];
-    for (uint32_t i = gid; i < nf; i += groups) {
-      const uint32_t s = __ldcg(&cur[i]);
-      const float ds = dec_f32(__ldcg(&dist[s]));
-      const uint32_t b = off[s], e = off[s + 1];
-      if (lane == 0) { relaxed += e - b; settled++; }
-      for (uint32_t k0 = b; k0 < e; k0 += kG) {
-        const uint32_t k = k0 + lane;
-        bool push = false;
-        uint32_t t = 0;
-        if (k < e) {
-          int4 v = __ldg(reinterpret_cast<const int4*>(&arcs[k]));
-          float c = w_times(ds, __int_as_float(v.z));
-          t = (uint32_t)v.w;
-          if (c != w_zero()) {
-            uint32_t ec = enc_f32(c);
-            if (ec < __ldcg(&dist[t])) {
-              uint32_t old = atomicMin(&dist[t], ec);
-              if (ec < old) push = atomicExch(&stamp[t], wave) != wave;
+    // kS frontier states per group and round: their loads, and then their atomics, are issued together (the kernel is
+    // bound by the chain frontier entry -> distance / offsets -> arcs -> atomicMin -> stamp, not by bandwidth)
+    for (uint32_t i = gid; i < nf; i += groups * kS) {
+      uint32_t b[kS], e[kS];
+      float ds[kS];
+      {
+        uint32_t st[kS];
+#pragma unroll
+        for (int q = 0; q < kS; q++) st[q] = (i + q * groups < nf) ? __ldcg(&cur[i + q * groups]) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < kS; q++) {
+          b[q] = 0; e[q] = 0; ds[q] = 0.0f;
+          if (st[q] != 0xFFFFFFFFu) { ds[q] = dec_f32(__ldcg(&dist[st[q]])); b[q] = off[st[q]]; e[q] = off[st[q] + 1]; }
+        }
+#pragma unroll
+        for (int q = 0; q < kS; q++)
+          if (lane == 0 && st[q] != 0xFFFFFFFFu) { relaxed += e[q] - b[q]; settled++; }
+      }
+      for (uint32_t r = 0;; r += kG) {
+        bool any = false;
+        int4 v[kS];
+        bool has[kS];
+#pragma unroll
+        for (int q = 0; q < kS; q++) {
+          any |= b[q] + r < e[q];
+          has[q] = b[q] + r + lane < e[q];
+          if (has[q]) v[q] = __ldg(reinterpret_cast<const int4*>(&arcs[b[q] + r + lane]));
+        }
+        if (!any) break;
+        uint32_t ec[kS], old[kS];
+#pragma unroll
+        for (int q = 0; q < kS; q++) {
+          old[q] = 0; ec[q] = kEncInf;
+          if (has[q]) {
+            const float c = w_times(ds[q], __int_as_float(v[q].z));
+            if (c != w_zero()) {
+              ec[q] = enc_f32(c);
+              // kPreTest: a plain load filters most candidates before the atomic
+              if (!kPreTest || ec[q] < __ldcg(&dist[(uint32_t)v[q].w])) old[q] = atomicMin(&dist[(uint32_t)v[q].w], ec[q]);
             }
           }
         }
-        // warp-aggregated append to the CTA queue; spill to the global list when the queue is full
-        const uint32_t active = __activemask();
-        const uint32_t m = __ballot_sync(active, push);
-        if (m) {
-          const uint32_t wl = threadIdx.x & 31, leader = __ffs(m) - 1;
-          uint32_t qb = 0;
-          if (wl == leader) qb = atomicAdd(&s_qn, __popc(m));
-          qb = __shfl_sync(active, qb, leader);
-          if (push) {
-            const uint32_t pos = qb + __popc(m & ((1u << wl) - 1u));
-            if (pos < kQueueCap) s_q[pos] = t;
-            else nxt[atomicAdd(next_count, 1u)] = t;
+#pragma unroll
+        for (int q = 0; q < kS; q++) {
+          const uint32_t t = (uint32_t)v[q].w;
+          bool push = false;
+          if (has[q] && ec[q] < old[q]) push = atomicExch(&stamp[t], wave) != wave;
+          // warp-aggregated append to the CTA queue; spill to the global list when the queue is full
+          const uint32_t active = __activemask();
+          const uint32_t m = __ballot_sync(active, push);
+          if (m) {
+            const uint32_t wl = threadIdx.x & 31, leader = __ffs(m) - 1;
+            uint32_t qb = 0;
+            if (wl == leader) qb = atomicAdd(&s_qn, __popc(m));
+            qb = __shfl_sync(active, qb, leader);
+            if (push) {
+              const uint32_t pos = qb + __popc(m & ((1u << wl) - 1u));
+              if (pos < kQCap) s_q[pos] = t;
+              else nxt[atomicAdd(next_count, 1u)] = t;
+            }
           }
         }
       }
     }
     __syncthreads();
-    const uint32_t qn = min(s_qn, kQueueCap);
+    const uint32_t qn = min(s_qn, kQCap);
     if (threadIdx.x == 0 && qn) s_gbase = atomicAdd(next_count, qn);
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < qn; i += kThreads) nxt[s_gbase + i] = s_q[i];
+    for (uint32_t i = threadIdx.x; i < qn; i += kT) nxt[s_gbase + i] = s_q[i];
     wave++;
     uint32_t* tmp = cur; cur = nxt; nxt = tmp;
     coop::grid_barrier(&out[2], bar_epoch);  // lighter than cg::grid_group::sync() (measured 3.4 us less per barrier)
@@ -675,16 +703,27 @@ void run_relax_coop(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, Even
   B200_CUDA(cudaStreamSynchronize(s));  // the sources of the small copies are host temporaries
   st.kernel_launches += 1;
   // lanes per frontier state: few lanes = more states in flight (the relaxation is latency-bound)
-  int lanes = 8;
+  // shape of the persistent relaxation kernel (measured on C4, ms of the kernel): 256 threads x 6 CTAs/SM with the
+  // pre-test 1.25; 1024 x 2 1.19; without the pre-test 1.09 / 1.02; see BENCH_NOTES.md for the sweep
+  int lanes = 8, threads = 1024, pre = 0, ilp = 1;
   if (const char* e = std::getenv("B200_RELAX_LANES")) lanes = std::atoi(e);
-  void* kern = (void*)k_relax_coop<8>;
-  if (lanes == 1) kern = (void*)k_relax_coop<1>;
-  else if (lanes == 2) kern = (void*)k_relax_coop<2>;
-  else if (lanes == 4) kern = (void*)k_relax_coop<4>;
-  else if (lanes == 16) kern = (void*)k_relax_coop<16>;
+  if (const char* e = std::getenv("B200_RELAX_THREADS")) threads = std::atoi(e);
+  if (const char* e = std::getenv("B200_RELAX_PRETEST")) pre = std::atoi(e);
+  if (const char* e = std::getenv("B200_RELAX_ILP")) ilp = std::atoi(e);
+  void* kern = nullptr;
+#define B200_RELAX_PICK(G, T, P, S) if (!kern && lanes == G && threads == T && pre == P && ilp == S) kern = (void*)k_relax_coop<G, T, P != 0, S>;
+  B200_RELAX_PICK(8, 1024, 0, 1) B200_RELAX_PICK(8, 1024, 0, 2) B200_RELAX_PICK(8, 1024, 0, 4)
+  B200_RELAX_PICK(8, 1024, 1, 1) B200_RELAX_PICK(8, 1024, 1, 2)
+  B200_RELAX_PICK(8, 512, 0, 1) B200_RELAX_PICK(8, 512, 0, 2) B200_RELAX_PICK(8, 512, 0, 4)
+  B200_RELAX_PICK(8, 256, 0, 1) B200_RELAX_PICK(8, 256, 1, 1) B200_RELAX_PICK(8, 256, 0, 2)
+  B200_RELAX_PICK(4, 1024, 0, 1) B200_RELAX_PICK(4, 1024, 0, 2) B200_RELAX_PICK(16, 1024, 0, 1) B200_RELAX_PICK(16, 1024, 0, 2)
+  B200_RELAX_PICK(1, 256, 1, 1) B200_RELAX_PICK(2, 256, 1, 1) B200_RELAX_PICK(4, 256, 1, 1) B200_RELAX_PICK(16, 256, 1, 1)
+#undef B200_RELAX_PICK
+  if (!kern) { kern = (void*)k_relax_coop<8, 1024, false, 1>; threads = 1024; }
   int per_sm = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0));
+  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
   if (per_sm < 1) throw FstError("cooperative relaxation kernel does not fit on the device");
+  if (const char* e = std::getenv("B200_RELAX_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, std::atoi(e)));
   int grid = sm_count() * per_sm;
   const uint32_t* a_off = f.offsets.p; const Tr* a_arcs = f.arcs.p;
   uint32_t nn = n;
@@ -694,7 +733,7 @@ void run_relax_coop(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, Even
   cudaEvent_t ea, eb;
   B200_CUDA(cudaEventCreate(&ea)); B200_CUDA(cudaEventCreate(&eb));
   B200_CUDA(cudaEventRecord(ea, s));
-  B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kThreads), args, 0, s));
+  B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(threads), args, 0, s));
   B200_CUDA(cudaEventRecord(eb, s));
   relax_events.emplace_back(ea, eb);
   st.relax_launches++; st.kernel_launches++;

@@ -458,6 +458,24 @@ def main():
         barrier()
         sssp["e2e"] = {"value": e2e_edges / (time.perf_counter() - t0), "unit": "edges/s",
                        "h2d_bytes_per_step": csr_bytes(g), "d2h_bytes_per_step": 16 * 64}
+        # SURVEY.md §8d asks for the lattice "with props as compose would leave them" as well: ACYCLIC known, TOP_SORTED
+        # unknown -> AutoQueue picks TopOrderQueue, whose order comes from the reference's sequential DFS (run on the
+        # host, exactly as the reference does; its time is reported next to the device time)
+        from rustfst_b200 import props as PR
+        hg_top = synth.to_vector_fst(dict(g, props=g["props"] & ~(PR.TOP_SORTED | PR.NOT_TOP_SORTED)))
+        dg_top = R.DeviceFst.upload(hg_top)
+        R.device_shortest_path(dg_top)
+        barrier()
+        t0 = time.perf_counter()
+        top_steps = min(steps, 2)
+        for _ in range(top_steps):
+            _, tst = R.device_shortest_path(dg_top)
+        barrier()
+        sssp["top_order_variant"] = {
+            "workload": "same lattice, ACYCLIC known / TOP_SORTED unknown (TopOrderQueue)", "queue_kind": tst["queue_kind"],
+            "ms_per_call_wall": (time.perf_counter() - t0) * 1e3 / top_steps, "ms_device": tst["ms_device"],
+            "ms_queue_plan_host_dfs": tst["ms_queue_plan_host"], "device_path": tst["path"]}
+        del dg_top, hg_top
         # n-best on the same device-resident lattice (fst_shortest_path_with_config, nshortest = 10, unique = false):
         # forward distances + reversed machine on the device, heap search over rows fetched from HBM, device trim
         cfg10 = R.ShortestPathConfig(nshortest=10)

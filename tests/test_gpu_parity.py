@@ -442,3 +442,41 @@ def test_sigma_compose_fuzz(seed):
                         continue
                     got = R.compose_with_config(pa, pb, cfg)
                     assert_same(got, expected, f"sigma fuzz seed={seed} mode={mode} allowed={allowed} filt={filt} c={connect}")
+
+
+def test_connect_with_hub_states_in_both_directions():
+    """fst_connect on a star: the start state has 10 000 out-arcs and the final state 10 000 in-arcs (both above the
+    4096-neighbour threshold that routes a vertex to the 64-CTA hub kernel of the BFS levels), plus dead branches
+    that must be trimmed; compared with the oracle's DFS-based connect (connect.rs:51-66)."""
+    from rustfst_b200.fst import TR_DTYPE
+    m = 10_000
+    n = m + 2 + 500  # start, m middle states, final, 500 dead states
+    rows, offsets = [], [0]
+    for k in range(m):
+        rows.append((1 + k % 13, 1 + k % 7, (k % 64) / 8.0, 1 + k))
+    for k in range(250):  # dead ends reachable from the start (not coaccessible)
+        rows.append((99, 99, 1.0, m + 2 + k))
+    offsets.append(len(rows))
+    for k in range(m):
+        if k % 10 != 9:  # every tenth middle state is a dead end
+            rows.append((2, 3, (k % 32) / 4.0, m + 1))
+        offsets.append(len(rows))
+    offsets.append(len(rows))  # final state: no arcs
+    for k in range(500):  # dead states; the last 250 are unreachable but point at the final state
+        if k >= 250:
+            rows.append((5, 5, 0.5, m + 1))
+        offsets.append(len(rows))
+    arr = np.zeros(len(rows), dtype=TR_DTYPE)
+    for i, r in enumerate(rows):
+        arr[i] = r
+    finals = np.full(n, np.inf, dtype=np.float32)
+    finals[m + 1] = 0.25
+    d = {"offsets": np.array(offsets, dtype=np.uint32), "arcs": arr, "finals": finals, "start": 0, "props": 0}
+    o = O.OFst.from_csr(d["offsets"].astype(np.uint64), arr, finals, 0, 0)
+    o.compute_props()
+    d["props"] = o.props
+    p, o = both_from_dict(d)
+    p.connect()
+    o.connect()
+    assert p.num_states() == 2 + m - m // 10
+    assert_same(p, o, "hub connect")

@@ -127,7 +127,7 @@ DevFst reverse_device(const DevFst& fst, cudaStream_t s, uint64_t* launches = nu
 // the result tree is trimmed on the device.  (Machines with `Some(+inf)` final weights are refused by upload().)
 struct NShortestStats {
   SsspStats distance;
-  uint64_t heap_pops = 0, rows_fetched = 0, arcs_fetched = 0, states_before_trim = 0;
+  uint64_t heap_pops = 0, rows_fetched = 0, rows_cached = 0, arcs_fetched = 0, states_before_trim = 0;
   float ms_distance = 0, ms_reverse = 0, ms_search_host = 0, ms_total = 0;
 };
 CsrFst n_shortest_paths_device(const DevFst& fst, const QueuePlan& plan,

@@ -80,14 +80,37 @@ __global__ void k_rev_finals(float* __restrict__ fin, uint32_t n1, uint32_t fina
 // One row of the reversed machine, packed for the host search: out[0] = {#arcs, 0, 0, 0}; when the row fits `cap`,
 // out[1 + k] = arc k and dists[k] = forward distance of its source state (distance_2[nextstate], i.e. dist[nextstate
 // - 1]).  The host never holds the distance array or the row offsets of a multi-million-state machine.
+// One hop ahead: a best-first search pops, more often than not, a state it has just pushed, i.e. the target of one of
+// these arcs.  Blocks 1.. therefore also pack the rows of the first kPrefetchKids targets (those with at most
+// kKidCap arcs) behind the main row: kid slot k = kid_out + k * (1 + kKidCap) entries, header {#arcs or ~0 = not
+// packed, state, 0, 0}, distances likewise in kid_dists.  The host keeps them in a cache keyed by state.
+constexpr uint32_t kPrefetchKids = 64, kKidCap = 32;
 __global__ void __launch_bounds__(kThreads)
 k_fetch_row(const uint32_t* __restrict__ roff, const Tr* __restrict__ rarcs, const float* __restrict__ dist,
-            uint32_t n, uint32_t q, uint32_t cap, int4* __restrict__ out, float* __restrict__ dists) {
+            uint32_t n, uint32_t q, uint32_t cap, int4* __restrict__ out, float* __restrict__ dists,
+            int4* __restrict__ kid_out, float* __restrict__ kid_dists, uint32_t main_blocks) {
   const uint32_t b = roff[q], deg = roff[q + 1] - b;
+  if (blockIdx.x >= main_blocks) {  // ---- kid rows: one warp per kid
+    const uint32_t kid = (blockIdx.x - main_blocks) * (kThreads / 32) + threadIdx.x / 32, lane = threadIdx.x & 31;
+    if (kid >= kPrefetchKids) return;
+    int4* const slot = kid_out + (size_t)kid * (1 + kKidCap);
+    if (deg > kPrefetchKids || kid >= deg) { if (lane == 0) slot[0] = make_int4(-1, 0, 0, 0); return; }
+    const uint32_t cs = __ldg(&rarcs[b + kid].nextstate);
+    const uint32_t cb = roff[cs], cdeg = roff[cs + 1] - cb;
+    if (cdeg > kKidCap) { if (lane == 0) slot[0] = make_int4(-1, (int)cs, 0, 0); return; }
+    if (lane == 0) slot[0] = make_int4((int)cdeg, (int)cs, 0, 0);
+    if (lane < cdeg) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(&rarcs[cb + lane]));
+      slot[1 + lane] = v;
+      const uint32_t src = (uint32_t)v.w - 1u;
+      kid_dists[(size_t)kid * kKidCap + lane] = (dist && src < n) ? dist[src] : w_zero();
+    }
+    return;
+  }
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0) out[0] = make_int4((int)deg, 0, 0, 0);
   if (deg > cap) return;
-  for (uint32_t k = tid; k < deg; k += gridDim.x * blockDim.x) {
+  for (uint32_t k = tid; k < deg; k += main_blocks * blockDim.x) {
     const int4 v = __ldg(reinterpret_cast<const int4*>(&rarcs[b + k]));
     out[1 + k] = v;
     const uint32_t src = (uint32_t)v.w - 1u;  // rows never point at the superinitial state
@@ -101,13 +124,16 @@ struct Staging {
   size_t cap = 0;
   int4* arcs() const { return static_cast<int4*>(base); }
   float* dists() const { return reinterpret_cast<float*>(static_cast<char*>(base) + (cap + 1) * 16); }
+  int4* kid_arcs() const { return reinterpret_cast<int4*>(static_cast<char*>(base) + (cap + 1) * 16 + cap * 4); }
+  float* kid_dists() const { return reinterpret_cast<float*>(kid_arcs() + (size_t)kPrefetchKids * (1 + kKidCap)); }
   void ensure(size_t want) {
     if (want <= cap) return;
     if (base) cudaFreeHost(base);
     base = nullptr; cap = 0;
     size_t c = 4096;
     while (c < want) c <<= 1;
-    B200_CUDA(cudaHostAlloc(&base, (c + 1) * 16 + c * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+    const size_t bytes = (c + 1) * 16 + c * 4 + (size_t)kPrefetchKids * (1 + kKidCap) * 16 + (size_t)kPrefetchKids * kKidCap * 4;
+    B200_CUDA(cudaHostAlloc(&base, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
     cap = c;
   }
   ~Staging() { if (base) cudaFreeHost(base); }
@@ -197,12 +223,23 @@ CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
   stage.ensure(std::max<size_t>(r_row0_len, 4096));
   std::vector<Tr> row;
   std::vector<float> row_dist;
+  struct CachedRow { std::vector<Tr> arcs; std::vector<float> dists; };
+  std::unordered_map<uint32_t, CachedRow> row_cache;  // rows that arrived one hop ahead of their pop
   auto fetch_row = [&](uint32_t q) {
+    auto hit = row_cache.find(q);
+    if (hit != row_cache.end()) {  // rows are immutable; a state can be expanded up to nshortest times
+      row = hit->second.arcs; row_dist = hit->second.dists;
+      st.rows_cached++;
+      return;
+    }
     while (true) {
       const uint32_t cap = (uint32_t)stage.cap;
-      const size_t hint = q == 0 ? std::max<size_t>(r_row0_len, 1) : 1024;  // rows are short; the kernel strides
-      k_fetch_row<<<blocks_for(std::min<size_t>(cap, hint)), kThreads, 0, s>>>(r.offsets.p, r.arcs.p, d_dist_p, n, q, cap, stage.arcs(),
-                                                       stage.dists());
+      const size_t hint = q == 0 ? std::max<size_t>(r_row0_len, 1) : 256;  // rows are short; the kernel strides
+      const uint32_t main_blocks = blocks_for(std::min<size_t>(cap, hint));
+      const uint32_t kid_blocks = q == 0 ? 0u : kPrefetchKids / (kThreads / 32);
+      k_fetch_row<<<main_blocks + kid_blocks, kThreads, 0, s>>>(r.offsets.p, r.arcs.p, d_dist_p, n, q, cap, stage.arcs(),
+                                                                stage.dists(), stage.kid_arcs(), stage.kid_dists(),
+                                                                main_blocks);
       st.distance.kernel_launches++;
       B200_CUDA(cudaStreamSynchronize(s));
       const uint32_t deg = (uint32_t)stage.arcs()[0].x;
@@ -211,6 +248,20 @@ CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
         if (deg) {
           std::memcpy(row.data(), stage.arcs() + 1, (size_t)deg * 16);
           std::memcpy(row_dist.data(), stage.dists(), (size_t)deg * 4);
+        }
+        if (q != 0 && deg <= 4096) { CachedRow& cr = row_cache[q]; cr.arcs = row; cr.dists = row_dist; }
+        if (kid_blocks) {
+          for (uint32_t k = 0; k < kPrefetchKids && k < deg; k++) {
+            const int4* slot = stage.kid_arcs() + (size_t)k * (1 + kKidCap);
+            if (slot[0].x < 0) continue;
+            const uint32_t cdeg = (uint32_t)slot[0].x, cs = (uint32_t)slot[0].y;
+            CachedRow& cr = row_cache[cs];
+            cr.arcs.resize(cdeg); cr.dists.resize(cdeg);
+            if (cdeg) {
+              std::memcpy(cr.arcs.data(), slot + 1, (size_t)cdeg * 16);
+              std::memcpy(cr.dists.data(), stage.kid_dists() + (size_t)k * kKidCap, (size_t)cdeg * 4);
+            }
+          }
         }
         break;
       }
@@ -353,10 +404,10 @@ CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
   const float ms_trim = (float)(now_ms() - t0);
   st.ms_total = (float)(now_ms() - t_begin);
   if (std::getenv("B200_NSHORTEST_TRACE"))
-    std::fprintf(stderr, "[nshortest] n=%zu distance %.2f ms (path %d) reverse %.2f ms search %.2f ms (%llu pops, %llu rows, "
+    std::fprintf(stderr, "[nshortest] n=%zu distance %.2f ms (path %d) reverse %.2f ms search %.2f ms (%llu pops, %llu rows fetched + %llu from the one-hop cache, "
                  "%llu arcs fetched, %llu tree states) trim %.2f ms total %.2f ms\n", nshortest, st.ms_distance,
                  st.distance.path, st.ms_reverse, st.ms_search_host, (unsigned long long)st.heap_pops,
-                 (unsigned long long)st.rows_fetched, (unsigned long long)st.arcs_fetched,
+                 (unsigned long long)st.rows_fetched, (unsigned long long)st.rows_cached, (unsigned long long)st.arcs_fetched,
                  (unsigned long long)st.states_before_trim, ms_trim, st.ms_total);
   return out;
 }

@@ -253,11 +253,19 @@ __global__ void k_decode_dist(const uint32_t* __restrict__ enc, uint32_t n, floa
 __global__ void k_final_min(const float* __restrict__ fin, uint32_t n, const uint32_t* __restrict__ dist,
                             const uint32_t* __restrict__ order, unsigned long long* __restrict__ fkey) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  float rho = fin[s];
-  if (rho == w_zero() || dist[s] == kEncInf) return;
-  float v = w_times(dec_f32(dist[s]), rho);
-  atomicMin(fkey, ((unsigned long long)enc_f32(v) << 32) | (order ? order[s] : s));
+  unsigned long long key = kNoParent;
+  if (s < n) {
+    float rho = fin[s];
+    if (rho != w_zero() && dist[s] != kEncInf)
+      key = ((unsigned long long)enc_f32(w_times(dec_f32(dist[s]), rho)) << 32) | (order ? order[s] : s);
+  }
+  // one atomic per warp: a lattice has ~1e5 final states and they all hit the same 8 bytes
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+    key = other < key ? other : key;
+  }
+  if ((threadIdx.x & 31) == 0 && key != kNoParent) atomicMin(fkey, key);
 }
 __global__ void k_final_check(const float* __restrict__ fin, uint32_t n, const uint32_t* __restrict__ dist,
                               const unsigned long long* __restrict__ fkey, uint32_t* __restrict__ flags) {

@@ -563,7 +563,8 @@ __global__ void k_of_roots(const uint32_t* __restrict__ indeg, uint32_t n, uint3
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   warp_push(s < n && indeg[s] == 0, s, topo, cursor);
 }
-// ctl: [0] append cursor into topo (starts at #roots), [1] levels, [2] states processed
+// ctl: [0] append cursor into topo (starts at #roots), [1] levels, [2] states processed, [3] grid barrier,
+// [4..6] rotating per-level append counters
 template <bool kAbs>
 __global__ void __launch_bounds__(kThreads)
 k_of_fold(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t source,
@@ -577,6 +578,10 @@ k_of_fold(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_
   const uint32_t gsize = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t lo = 0, hi = n_roots, levels = 0;
   while (lo < hi) {
+    // ctl[4 + (levels + 1) % 3] counts the states appended during this level (= the next level), ctl[4 + (levels + 2) % 3]
+    // is cleared for the level after it (nobody reads or writes it now), ctl[4 + levels % 3] is this level's own size
+    uint32_t* const next_level = &ctl[4 + (levels + 1) % 3];
+    if (gtid == 0) ctl[4 + (levels + 2) % 3] = 0;
     if (threadIdx.x == 0) s_qn = 0;
     __syncthreads();
     for (uint32_t i = lo + gtid; i < hi; i += gsize) {
@@ -599,19 +604,22 @@ k_of_fold(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_
         if (atomicSub(&indeg[u], 1u) == 1u) {
           const uint32_t pos = atomicAdd(&s_qn, 1u);
           if (pos < kQueueCap) s_q[pos] = u;
-          else topo[atomicAdd(&ctl[0], 1u)] = u;
+          else { topo[atomicAdd(&ctl[0], 1u)] = u; atomicAdd(next_level, 1u); }
         }
       }
     }
     __syncthreads();
     const uint32_t qn = min(s_qn, kQueueCap);
-    if (threadIdx.x == 0 && qn) s_gbase = atomicAdd(&ctl[0], qn);
+    if (threadIdx.x == 0 && qn) { s_gbase = atomicAdd(&ctl[0], qn); atomicAdd(next_level, qn); }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < qn; i += kThreads) topo[s_gbase + i] = s_q[i];
     levels++;
     coop::grid_barrier(&ctl[3], bar_epoch);
+    // The size of the next level comes from a counter nobody touches during that level (a CTA that races ahead appends
+    // to the cursor ctl[0] — and to the NEXT rotating counter — while slower CTAs are still reading): every CTA sees
+    // the same [lo, hi) and leaves the loop in the same iteration.
     lo = hi;
-    hi = __ldcg(&ctl[0]);
+    hi = lo + __ldcg(next_level);
   }
   if (gtid == 0) { ctl[1] = levels; ctl[2] = hi; }
 }
@@ -764,11 +772,11 @@ bool run_order_faithful_fold(const DevFst& f, const uint32_t* order_p, bool abs_
   const uint32_t n = f.num_states, A = f.num_arcs;
   DevBuf<unsigned long long> k_in(s, A ? A : 1), k_out(s, A ? A : 1);
   DevBuf<uint32_t> v_in(s, A ? A : 1), in_arc(s, A ? A : 1), src_of(s, A ? A : 1), indeg(s, n), roff(s, (size_t)n + 1),
-      topo(s, n), ctl(s, 4);
+      topo(s, n), ctl(s, 8);
   DevBuf<uint8_t> tmp(s);
   out.dist.reserve_discard(n); out.pstate.reserve_discard(n); out.ppos.reserve_discard(n);
   B200_CUDA(cudaMemsetAsync(indeg.p, 0, (size_t)n * 4, s));
-  B200_CUDA(cudaMemsetAsync(ctl.p, 0, 16, s));
+  B200_CUDA(cudaMemsetAsync(ctl.p, 0, 32, s));
   k_of_keys<<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, order_p, k_in.p, v_in.p, src_of.p, indeg.p);
   B200_CUDA(cudaMemcpyAsync(roff.p, indeg.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
   B200_CUDA(cudaMemsetAsync(roff.p + n, 0, 4, s));

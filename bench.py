@@ -343,7 +343,7 @@ def main():
     scan_gbs = 48.0 * tot["arcs_emitted"] / (tot["ms_phase_emit"] * 1e-3) / 1e9 if tot["ms_phase_emit"] > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "compose_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.workload == "C3" and args.scale == 1.0:  # the capture is of the full-size C3 kernel
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:

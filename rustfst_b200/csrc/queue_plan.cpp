@@ -86,6 +86,62 @@ DfsResult dfs(const CsrFst& f, bool want_scc, bool stop_on_back_arc) {
   return r;
 }
 
+// The same traversal specialised for the TopOrderVisitor (no SCC bookkeeping) and tuned for multi-million-state
+// lattices, where it is the one sequential host step of a shortest-path call: the walk is a chain of dependent cache
+// misses (offsets of the state -> its arcs -> colour of every target), so the colours of all targets of a state are
+// prefetched when the state is first visited and the frame keeps the end of the arc range (C4 lattice, 5M states /
+// 50M arcs: 2.05 s -> 1.15 s on the development container).  Tried and dropped: prefetching the targets' offsets as
+// well (no gain), colour and offset fused in one 64-bit word + look-ahead prefetch of the next target's arcs (slower:
+// the byte-sized colour array stays cache resident, the 8-byte words do not).  Identical visiting order, hence
+// identical finish order.
+DfsResult dfs_top_order(const CsrFst& f) {
+  const size_t n = f.num_states();
+  DfsResult r;
+  r.finish.reserve(n);
+  if (!f.has_start) return r;
+  enum : uint8_t { kWhite = 0, kGrey = 1, kBlack = 2 };
+  std::vector<uint8_t> color(n, kWhite);
+  struct Frame { uint32_t s, pos, end; };
+  std::vector<Frame> stack;
+  stack.reserve(1024);
+  const uint32_t* off = f.offsets.data();
+  const Tr* arcs = f.arcs.data();
+  uint8_t* col = color.data();
+  auto push = [&](uint32_t t) {
+    col[t] = kGrey;
+    const uint32_t lo = off[t], hi = off[t + 1];
+    for (uint32_t e = lo; e < hi; e++) __builtin_prefetch(&col[arcs[e].nextstate], 0, 1);
+    stack.push_back({t, lo, hi});
+  };
+  size_t root = f.start;
+  while (root < n) {
+    push((uint32_t)root);
+    while (!stack.empty()) {
+      Frame& fr = stack.back();
+      if (fr.pos >= fr.end) {
+        col[fr.s] = kBlack;
+        r.finish.push_back(fr.s);
+        stack.pop_back();
+        if (!stack.empty()) stack.back().pos++;
+        continue;
+      }
+      const uint32_t t = arcs[fr.pos].nextstate;
+      const uint8_t c = col[t];
+      if (c == kWhite) {
+        push(t);
+      } else if (c == kGrey) {  // back arc: TopOrderVisitor::back_tr stops the visit (top_sort.rs:40-43)
+        r.acyclic = false;
+        return r;
+      } else {
+        fr.pos++;
+      }
+    }
+    root = (root == f.start) ? 0 : root + 1;
+    while (root < n && col[root] != kWhite) root++;
+  }
+  return r;
+}
+
 }  // namespace
 
 QueuePlan build_queue_plan(const CsrFst& f) {
@@ -99,7 +155,7 @@ QueuePlan build_queue_plan(const CsrFst& f) {
   };
   if ((p & props::kTopSorted) || !f.has_start) { plan.kind = kStateOrderQueue; return done(); }
   if (p & props::kAcyclic) {
-    DfsResult r = dfs(f, false, true);
+    DfsResult r = dfs_top_order(f);
     if (!r.acyclic) throw FstError("Unexpectted Acyclic FST for TopOprerQueue");  // top_order_queue.rs:25-27 (panic)
     plan.kind = kTopOrderQueue;
     plan.order.assign(n, 0);  // top_sort.rs:52-59: order[finish[len-1-s]] = s

@@ -100,6 +100,8 @@ def test_nshortest_on_composed_lattices_all_distance_paths():
     got, exp, st = _both(pc, oc, 10)
     assert st["queue_kind"] == 1 and st["path"] == 0, st
     assert_same(got, exp, "10 best of the C2 lattice")
+    got, exp, st = _both(pc, oc, 64)  # many pops per state: rows served again and again from the one-hop cache
+    assert_same(got, exp, "64 best of the C2 lattice")
     got, exp, st = _both(pa, oa, 10)  # TOP_SORTED acceptor: StateOrderQueue
     assert st["queue_kind"] == 0 and st["path"] == 0, st
     assert_same(got, exp, "10 best of the acceptor")

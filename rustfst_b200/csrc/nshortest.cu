@@ -14,7 +14,8 @@
 // The n-best search itself is a best-first search driven by a binary heap whose pop order (ties included) decides
 // the numbering of the result states: inherently sequential, O(n * path length * degree) steps that touch a few
 // thousand arcs.  It runs on the host (as SURVEY.md §8f ranks it) over rows of the reversed machine fetched on
-// demand from HBM — the reversed machine never leaves the device.  The search tree is trimmed by connect_device.
+// demand from HBM — the reversed machine never leaves the device.  The search tree is a host structure (one arc per
+// state, all chains ending in the final state), so its `connect` is a walk along the n result chains.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -380,27 +381,40 @@ CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
   }
   st.ms_search_host = (float)(now_ms() - t0);
   t0 = now_ms();
-  CsrFst ho;
+  // ---- connect (:511) + shortest_path_properties(.., false) (:512-515).  The search tree never leaves the host: every
+  // state >= 2 has exactly one arc, towards the state it was expanded from, and those chains all end in the final
+  // state 1, so every state is coaccessible as soon as the start state has an arc, and the accessible states are
+  // exactly the chains hanging off the start state's arcs.  del_states (mutable_fst.rs:132-189) keeps them in id order.
   const size_t ns = single_arc.size() + 2;
   st.states_before_trim = ns;
-  ho.offsets.resize(ns + 1);
-  ho.arcs.resize(start_arcs.size() + single_arc.size());
-  ho.finals.assign(ns, w_zero());
-  ho.finals[final_state] = 0.0f;
-  std::copy(start_arcs.begin(), start_arcs.end(), ho.arcs.begin());
-  std::copy(single_arc.begin(), single_arc.end(), ho.arcs.begin() + start_arcs.size());
-  ho.offsets[0] = 0; ho.offsets[1] = (uint32_t)start_arcs.size(); ho.offsets[2] = (uint32_t)start_arcs.size();
-  for (size_t i = 2; i < ns; i++) ho.offsets[i + 1] = ho.offsets[i] + 1;
-  ho.has_start = true; ho.start = ostart;
-  ho.props = pw & props::kTrinary;
-
-  // ---- device: connect (:511) + shortest_path_properties(.., false) (:512-515)
-  DevFst dofst = upload(ho, s);
-  uint64_t trim_launches = 0;
-  DevFst trimmed = connect_device(dofst, false, &trim_launches, s);
-  st.distance.kernel_launches += trim_launches;
-  CsrFst out = download(trimmed, s);
-  out.props = props::of_shortest_path(out.props, false) & props::kTrinary;
+  CsrFst out;
+  out.props = props::of_shortest_path(props::after_connect(pw & props::kTrinary), false) & props::kTrinary;
+  if (!start_arcs.empty()) {
+    std::vector<uint8_t> keep(ns, 0);
+    keep[ostart] = 1; keep[final_state] = 1;
+    for (const Tr& a : start_arcs)
+      for (StateId x = a.nextstate; x >= 2 && !keep[x]; x = single_arc[x - 2].nextstate) keep[x] = 1;
+    std::vector<uint32_t> new_id(ns, 0);
+    uint32_t nk = 0;
+    for (size_t x = 0; x < ns; x++) if (keep[x]) new_id[x] = nk++;
+    out.offsets.resize((size_t)nk + 1);
+    out.finals.assign(nk, w_zero());
+    out.arcs.resize(start_arcs.size() + (nk - 2));
+    size_t o = 0;
+    out.offsets[0] = 0;
+    for (const Tr& a : start_arcs) { Tr t = a; t.nextstate = new_id[a.nextstate]; out.arcs[o++] = t; }
+    out.offsets[1] = (uint32_t)o;          // new id of the start state is 0
+    out.offsets[2] = (uint32_t)o;          // the final state (new id 1) has no arcs
+    out.finals[1] = 0.0f;
+    for (size_t x = 2; x < ns; x++) {
+      if (!keep[x]) continue;
+      Tr t = single_arc[x - 2];
+      t.nextstate = new_id[t.nextstate];
+      out.arcs[o++] = t;
+      out.offsets[(size_t)new_id[x] + 1] = (uint32_t)o;
+    }
+    out.has_start = true; out.start = 0;
+  }
   const float ms_trim = (float)(now_ms() - t0);
   st.ms_total = (float)(now_ms() - t_begin);
   if (std::getenv("B200_NSHORTEST_TRACE"))

@@ -14,6 +14,11 @@
 // known-answer tests (rustfst-python/tests/algorithms/test_compose.py:13-154,
 // test_shortest_path.py:5-51, doc-test compose_static.rs:313-321) — see tests/test_oracle_kat.py —
 // and is otherwise a line-by-line restatement.  Every function cites the reference file:line.
+// The nshortest > 1 route (shortest_distance, reverse, n_shortest_path) has no in-tree known answer; it is pinned
+// by the criterion of the reference's own test (tests_openfst/algorithms/shortest_path.rs:62-92: number of paths,
+// weights position by position, paths exist in the input) against a brute-force enumeration of all paths of small
+// machines — tests/test_oracle_nshortest.py.  unique = true is not restated: the reference's own output is
+// process-dependent there (HashMap iteration order in determinize_fsa_op.rs:154-165).
 //
 // All paths below are relative to /root/reference/.
 #pragma once

@@ -480,3 +480,40 @@ def test_connect_with_hub_states_in_both_directions():
     o.connect()
     assert p.num_states() == 2 + m - m // 10
     assert_same(p, o, "hub connect")
+
+
+def test_concurrent_calls_on_shared_handles_from_several_host_threads():
+    """SURVEY.md §8b threading contract: calls are synchronous and re-entrant, concurrent calls on shared-const handles
+    are safe (every call has its own CUDA stream, the error slot and the n-best staging buffer are per thread).
+    Eight host threads run compose / shortest_path / 5-best on the same operands at once; every result must equal the
+    sequential one bit for bit."""
+    import threading
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    a, b = synth.workload("C2", scale=0.05)
+    pa, _ = both_from_dict(a)
+    pb, _ = both_from_dict(b)
+    ref_c = pa.compose(pb)
+    ref_sp = ref_c.shortest_path()
+    ref_nb = ref_c.shortest_path(R.ShortestPathConfig(nshortest=5))
+    want = (ref_c.to_bytes(), ref_sp.to_bytes(), ref_nb.to_bytes())
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(3):
+                c = pa.compose(pb)
+                sp = c.shortest_path()
+                nb = ref_c.shortest_path(R.ShortestPathConfig(nshortest=5))  # shared input handle
+                got = (c.to_bytes(), sp.to_bytes(), nb.to_bytes())
+                if got != want:
+                    errors.append(f"thread {k}: result differs")
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {k}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

@@ -176,9 +176,17 @@ def device_shortest_path(d: DeviceFst, plan_from: Optional[VectorFst] = None, fo
 
 def compose_batch(acceptors: List[VectorFst], transducer: VectorFst, config: Optional[ComposeConfig] = None):
     n = len(acceptors)
-    ins = (C.c_void_p * n)(*[a.ptr.value if isinstance(a.ptr, C.c_void_p) else a.ptr for a in acceptors])
+    ins = (C.c_void_p * n)(*[getattr(a.ptr, "value", a.ptr) for a in acceptors])
     outs = (C.c_void_p * n)()
     st = ComposeStats()
     check_ffi_error(lib.b200_compose_batch(ins, n, transducer.ptr, config.ptr if config else None, outs, C.byref(st)),
                     "Error in batched compose")
-    return [VectorFst(C.c_void_p(outs[i])) for i in range(n)], st.as_dict()
+    # thousands of results: build the wrappers without going through __init__ (raw handle values are fine as `ptr`,
+    # every entry point declares its argument types)
+    results = []
+    new = VectorFst.__new__
+    for p in outs:
+        v = new(VectorFst)
+        v.ptr = p
+        results.append(v)
+    return results, st.as_dict()

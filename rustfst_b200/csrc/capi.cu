@@ -2,6 +2,8 @@
 // Error convention and handle ownership follow rustfst-ffi/src/lib.rs:29-85 and rustfst-ffi/src/fst/mod.rs.
 #include <algorithm>
 #include <chrono>
+#include <thread>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -99,6 +101,28 @@ void fill(B200SsspStats* out, const SsspStats& st, int kind, float h2d) {
   out->kernel_launches = st.kernel_launches; out->relax_launches = st.relax_launches; out->path = st.path;
   out->queue_kind = kind; out->ms_device = st.ms_device; out->ms_relax_kernel = st.ms_relax_kernel;
   out->ms_h2d = h2d; out->ms_queue_plan_host = st.plan_host_ms;
+}
+
+// Runs fn(begin, end) over [0, n) on a few host threads (the batched mode repacks thousands of small machines; the
+// copies are independent once the prefix offsets are known).
+template <class F>
+void parallel_ranges(size_t n, F fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = std::min<size_t>(hw ? hw : 1, 8);
+  if (n < 4096 || nt <= 1) { fn((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  std::exception_ptr err;
+  std::mutex mu;
+  const size_t chunk = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; t++) {
+    const size_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([&, b, e] {
+      try { fn(b, e); } catch (...) { std::lock_guard<std::mutex> g(mu); err = std::current_exception(); }
+    });
+  }
+  for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
 }
 
 CFst* compose_host(const CFst* a, const CFst* b, const CComposeConfig* cfg, B200ComposeStats* stats) {
@@ -579,27 +603,36 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
     if (sum_states >= 0x7FFFFFF0ull || sum_arcs >= 0xFFFFFFF0ull) uniform = false;
 
     bool done = false;
+    double t_union = 0, t_split = 0, t_handles = 0;
     if (uniform) {
+      const double tu0 = now_ms();
       CsrFst u;
       u.offsets.resize(sum_states + 1);
       u.arcs.resize(sum_arcs);
       u.finals.resize(sum_states);
-      std::vector<uint32_t> starts(n), base_state(n + 1), acc_of(sum_states);
-      size_t so = 0, ao = 0;
-      for (size_t i = 0; i < n; i++) {
-        const CsrFst& h = *hs[i];
-        base_state[i] = (uint32_t)so;
-        starts[i] = (uint32_t)(so + h.start);
-        const size_t ns = h.num_states(), na = h.arcs.size();
-        for (size_t s = 0; s < ns; s++) { u.offsets[so + s] = (uint32_t)(ao + h.offsets[s]); acc_of[so + s] = (uint32_t)i; }
-        std::memcpy(u.finals.data() + so, h.finals.data(), ns * 4);
-        for (size_t k = 0; k < na; k++) { Tr t = h.arcs[k]; t.nextstate += (uint32_t)so; u.arcs[ao + k] = t; }
-        so += ns; ao += na;
+      std::vector<uint32_t> starts(n), base_state(n + 1), base_arc(n + 1), acc_of(sum_states);
+      {
+        size_t so = 0, ao = 0;
+        for (size_t i = 0; i < n; i++) {
+          base_state[i] = (uint32_t)so; base_arc[i] = (uint32_t)ao;
+          starts[i] = (uint32_t)(so + hs[i]->start);
+          so += hs[i]->num_states(); ao += hs[i]->arcs.size();
+        }
+        base_state[n] = (uint32_t)so; base_arc[n] = (uint32_t)ao;
       }
-      base_state[n] = (uint32_t)so;
-      u.offsets[sum_states] = (uint32_t)ao;
+      parallel_ranges(n, [&](size_t lo_i, size_t hi_i) {
+        for (size_t i = lo_i; i < hi_i; i++) {
+          const CsrFst& h = *hs[i];
+          const size_t so = base_state[i], ao = base_arc[i], ns = h.num_states(), na = h.arcs.size();
+          for (size_t s = 0; s < ns; s++) { u.offsets[so + s] = (uint32_t)(ao + h.offsets[s]); acc_of[so + s] = (uint32_t)i; }
+          std::memcpy(u.finals.data() + so, h.finals.data(), ns * 4);
+          for (size_t k = 0; k < na; k++) { Tr t = h.arcs[k]; t.nextstate += (uint32_t)so; u.arcs[ao + k] = t; }
+        }
+      });
+      u.offsets[sum_states] = base_arc[n];
       u.has_start = true; u.start = starts[0];
       u.props = and_props & props::kTrinary;
+      t_union = now_ms() - tu0;
       t0 = now_ms();
       DevFst du = upload(u, st.s);
       DevBuf<uint32_t> d_starts(st.s, n), d_s1(st.s), d_map(st.s);
@@ -619,16 +652,17 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
         B200_CUDA(cudaMemcpyAsync(smap.data(), d_map.p, n * 4, cudaMemcpyDeviceToHost, st.s));
         B200_CUDA(cudaStreamSynchronize(st.s));
         acc.ms_d2h += (float)(now_ms() - t0);
+        const double ts0 = now_ms();
         // ---- split the union result per acceptor; ids inside a component keep their relative order, which is
         // exactly the numbering of the stand-alone composition (same BFS restricted to that component)
-        std::vector<uint32_t> comp(rn), local(rn), n_st(n, 0), n_ar(n, 0);
+        std::vector<uint32_t> comp(rn), local(rn), arc_at(rn), n_st(n, 0), n_ar(n, 0);
         for (size_t s = 0; s < rn; s++) {
           uint32_t c = acc_of[tag[s]];
           comp[s] = c; local[s] = n_st[c]++;
+          arc_at[s] = n_ar[c];  // first arc of the state inside its own result
           n_ar[c] += r.offsets[s + 1] - r.offsets[s];
         }
         std::vector<CsrFst> parts(n);
-        std::vector<uint32_t> arc_fill(n, 0);
         for (size_t i = 0; i < n; i++) {
           parts[i].offsets.resize((size_t)n_st[i] + 1);
           parts[i].arcs.resize(n_ar[i]);
@@ -640,21 +674,28 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
           parts[i].has_start = smap[i] != 0xFFFFFFFFu;
           parts[i].start = parts[i].has_start ? local[smap[i]] : 0;
         }
-        for (size_t s = 0; s < rn; s++) {
-          CsrFst& p = parts[comp[s]];
-          const uint32_t ls = local[s];
-          p.finals[ls] = r.finals[s];
-          uint32_t o = arc_fill[comp[s]];
-          p.offsets[ls] = o;
-          for (uint32_t k = r.offsets[s]; k < r.offsets[s + 1]; k++) {
-            Tr t = r.arcs[k];
-            t.nextstate = local[t.nextstate];
-            p.arcs[o++] = t;
+        parallel_ranges(rn, [&](size_t lo_s, size_t hi_s) {  // every state writes its own slots of its own result
+          for (size_t s = lo_s; s < hi_s; s++) {
+            CsrFst& p = parts[comp[s]];
+            const uint32_t ls = local[s];
+            p.finals[ls] = r.finals[s];
+            uint32_t o = arc_at[s];
+            p.offsets[ls] = o;
+            for (uint32_t k = r.offsets[s]; k < r.offsets[s + 1]; k++) {
+              Tr t = r.arcs[k];
+              t.nextstate = local[t.nextstate];
+              p.arcs[o++] = t;
+            }
           }
-          arc_fill[comp[s]] = o;
-        }
+        });
+        t_split = now_ms() - ts0;
+        const double th0 = now_ms();
         for (size_t i = 0; i < n; i++) results[i] = new CFst{HostFst(std::move(parts[i]))};
+        t_handles = now_ms() - th0;
         fill(&acc, cs, acc.ms_h2d, acc.ms_d2h);
+        if (std::getenv("B200_BATCH_TRACE"))
+          std::fprintf(stderr, "[batch] n=%zu union build %.2f ms, h2d %.2f, expand %.2f, connect %.2f, d2h %.2f, split %.2f, "
+                       "handles %.2f ms\n", n, t_union, acc.ms_h2d, cs.ms_expand, cs.ms_connect, acc.ms_d2h, t_split, t_handles);
         done = true;
       }
     }

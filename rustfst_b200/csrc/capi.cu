@@ -656,9 +656,12 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
         // ---- split the union result per acceptor; ids inside a component keep their relative order, which is
         // exactly the numbering of the stand-alone composition (same BFS restricted to that component)
         std::vector<uint32_t> comp(rn), local(rn), arc_at(rn), n_st(n, 0), n_ar(n, 0);
+        parallel_ranges(rn, [&](size_t lo_s, size_t hi_s) {  // random look-ups into a 1.6M-entry table: spread them
+          for (size_t s = lo_s; s < hi_s; s++) comp[s] = acc_of[tag[s]];
+        });
         for (size_t s = 0; s < rn; s++) {
-          uint32_t c = acc_of[tag[s]];
-          comp[s] = c; local[s] = n_st[c]++;
+          const uint32_t c = comp[s];
+          local[s] = n_st[c]++;
           arc_at[s] = n_ar[c];  // first arc of the state inside its own result
           n_ar[c] += r.offsets[s + 1] - r.offsets[s];
         }

@@ -1,24 +1,32 @@
-// sssp.cu — single shortest path over the tropical semiring on B200.
+// sssp.cu — single shortest path and forward shortest distances over the tropical semiring on B200.
 //
 // Replaces (paths relative to /root/reference):
 //   rustfst/src/algorithms/shortest_path.rs:173-239  single_shortest_path (queue-ordered label-correcting relaxation)
 //   rustfst/src/algorithms/shortest_path.rs:241-282  single_shortest_path_backtrace
-//   rustfst/src/algorithms/queues/{state_order,top_order,lifo,fifo,trivial,scc}_queue.rs  (serial kernel only)
+//   rustfst/src/algorithms/shortest_distance.rs:153-237  shortest_distance (forward; feeds the n-best search, nshortest.cu)
+//   rustfst/src/algorithms/queues/{state_order,top_order,lifo,fifo,trivial,scc}_queue.rs  (serial kernels only)
 //
-// Two device paths, selected per call:
+// Three device paths, selected per call (SsspStats::path):
 //
-//  (1) PARALLEL path — taken when the reference would process states in a topological order (StateOrderQueue on a
+//  (0) PARALLEL path — taken when the reference would process states in a topological order (StateOrderQueue on a
 //      TOP_SORTED input, or TopOrderQueue).  Distances are exact minima computed by frontier relaxation waves with
 //      atomicMin on order-preserving integer images of the f32 distances and warp-aggregated frontier
-//      compaction.  One more edge scan then (a) selects for every state the parent the reference would end up
-//      with: the first candidate, in its processing order (order[src], arc position), that attains the minimum,
-//      and (b) CERTIFIES that the reference's approximate relaxation test (`d != min(d, c)` with KDELTA = 1/1024
-//      tolerance, shortest_path.rs:225) cannot have kept a non-minimal candidate: no candidate value c of any
-//      state lies in (m, fl(m + KDELTA)] where m is that state's minimum.  When the certificate holds the
-//      reference's sequential fold provably ends with the same (distance, parent) at every state.
+//      compaction (k_relax_coop: every wave inside one cooperative launch).  One more edge scan (k_parents) then
+//      (a) selects for every state the parent the reference would end up with: the first candidate, in its
+//      processing order (order[src], arc position), that attains the minimum, and (b) CERTIFIES that the
+//      reference's approximate relaxation test (`d != min(d, c)` with KDELTA = 1/1024 tolerance,
+//      shortest_path.rs:225; `|d - min(d, c)| <= delta` for shortest_distance.rs:217) cannot have kept a non-minimal
+//      candidate: no candidate value c of any state lies in (m, m + tolerance] where m is that state's minimum.
+//      When the certificate holds the reference's sequential fold provably ends with the same (distance, parent)
+//      at every state.
 //
-//  (2) ORDER-FAITHFUL SERIAL kernel — one device thread replays the reference's loop verbatim (queue discipline
-//      included) for everything else: cyclic inputs (SccQueue / LIFO) and inputs whose certificate fails.
+//  (2) ORDER-FAITHFUL PARALLEL FOLD — same queue kinds, taken when the certificate fails (near-ties): a reverse CSR
+//      with in-arcs sorted by the reference's processing order, states scheduled level by level (Kahn), one thread
+//      per state replays the reference's fold verbatim (k_of_fold).
+//
+//  (1) ORDER-FAITHFUL SERIAL kernels — one device thread replays the reference's loop verbatim (queue discipline
+//      included) for everything else: cyclic inputs (SccQueue / LIFO) and graphs the fold finds cyclic
+//      (k_serial_sssp, k_serial_sdist).
 //
 // The backtrace runs on the device as well; only the shortest path itself (a few hundred bytes) returns to the host.
 #include <cooperative_groups.h>
@@ -70,40 +78,8 @@ __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, uint32_t
   if (i < n) p[i] = v;
 }
 
-// One relaxation wave: every frontier state pushes d[s] (x) w over its arcs with atomicMin.
-// counters[0] = next frontier size, counters[1] (64-bit at +2) = arcs relaxed.
-__global__ void __launch_bounds__(kThreads)
-k_relax(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, const uint32_t* __restrict__ frontier,
-        uint32_t nf, uint32_t* __restrict__ dist, uint32_t* __restrict__ stamp, uint32_t wave,
-        uint32_t* __restrict__ next, uint32_t* __restrict__ counters) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t relaxed = 0;
-  if (i < nf) {
-    uint32_t s = frontier[i];
-    float ds = dec_f32(dist[s]);
-    uint32_t b = off[s], e = off[s + 1];
-    relaxed = e - b;
-    for (uint32_t k = b; k < e; k++) {
-      int4 v = __ldg(reinterpret_cast<const int4*>(&arcs[k]));
-      float c = w_times(ds, __int_as_float(v.z));
-      uint32_t t = (uint32_t)v.w;
-      bool push = false;
-      if (c != w_zero()) {
-        uint32_t ec = enc_f32(c);
-        if (ec < dist[t]) {  // cheap pre-test; the atomic decides
-          uint32_t old = atomicMin(&dist[t], ec);
-          if (ec < old) push = atomicExch(&stamp[t], wave) != wave;
-        }
-      }
-      warp_push(push, t, next, &counters[0]);
-    }
-  }
-  // arcs-relaxed statistic: one atomic per warp
-  for (int o = 16; o > 0; o >>= 1) relaxed += __shfl_down_sync(0xFFFFFFFFu, relaxed, o);
-  if ((threadIdx.x & 31) == 0 && relaxed) atomicAdd(reinterpret_cast<unsigned long long*>(&counters[2]), relaxed);
-}
-
-// Persistent variant: the whole relaxation (all waves) in one cooperative launch.  kG lanes share a frontier state
+// The whole relaxation (all waves) in one cooperative launch: every frontier state pushes d[s] (x) w over its arcs
+// with atomicMin.  kG lanes share a frontier state
 // and stride over its arcs (128-bit loads).  Newly improved states are first collected in a per-CTA shared-memory
 // queue and flushed to the next frontier with ONE global atomic per CTA and wave (a single global counter hit by
 // every warp serialises in the L2 atomic unit: ~30k same-address atomics per wave on C4).  Three frontier counters

@@ -104,6 +104,9 @@ RUSTFST_FFI_RESULT b200_shortest_path_config_destroy(CShortestPathConfig* ptr); 
 
 /* rustfst-ffi/src/algorithms/connect.rs:13-23 (in place) */
 RUSTFST_FFI_RESULT fst_connect(CFst* ptr);
+/* rustfst-ffi/src/algorithms/reverse.rs:14-29 (rustfst/src/algorithms/reverse.rs:33-87): new FST with a superinitial
+ * state 0; built on the device (one stable radix sort + gather), the same kernel that feeds the n-best search. */
+RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr);
 /* rustfst-ffi/src/algorithms/tr_sort.rs:14-30 (in place; host, stable) */
 RUSTFST_FFI_RESULT fst_tr_sort(CFst* ptr, bool ilabel_comp);
 

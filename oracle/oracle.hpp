@@ -1112,9 +1112,16 @@ inline std::vector<float> shortest_distance(const Fst& fst, float delta) {
   return distance;
 }
 
-// algorithms/reverse.rs:33-87 (TropicalWeight: reverse() is the identity).  The property word written at :78-83
-// (reverse_properties) is never read on the shortest-path route and is not restated: props are what the mutations
-// leave.
+// fst_properties/mutate_properties.rs:622-638
+inline uint64_t reverse_properties(uint64_t inprops, bool has_superinitial) {
+  uint64_t out = (P::ACCEPTOR | P::NOT_ACCEPTOR | P::EPSILONS | P::I_EPSILONS | P::O_EPSILONS | P::UNWEIGHTED |
+                  P::CYCLIC | P::ACYCLIC | P::WEIGHTED_CYCLES | P::UNWEIGHTED_CYCLES) & inprops;
+  if (has_superinitial) out |= P::WEIGHTED & inprops;
+  return out;
+}
+
+// algorithms/reverse.rs:33-87 (TropicalWeight: reverse() is the identity), incl. the property word of :78-83.
+// Pinned by rustfst-python/tests/algorithms/test_reverse.py (tests/test_oracle_kat.py).
 inline Fst reverse(const Fst& ifst) {
   Fst ofst;
   StateId ostart = ofst.add_state();
@@ -1129,6 +1136,7 @@ inline Fst reverse(const Fst& ifst) {
   }
   for (size_t s = 0; s < states_trs.size(); s++) ofst.set_trs_unchecked((StateId)s, std::move(states_trs[s]));
   ofst.set_start(ostart);
+  ofst.set_properties_with_mask(reverse_properties(ifst.props, true) | ofst.props, P::ALL);
   return ofst;
 }
 

@@ -121,6 +121,8 @@ void shortest_distance_device(const DevFst& fst, const QueuePlan& plan, float de
 // per final state (in state order, weight = final weight), state t + 1 = in-arcs of t in (source state, arc
 // position) order with nextstate = source + 1; final: start + 1 with weight one().
 DevFst reverse_device(const DevFst& fst, cudaStream_t s, uint64_t* launches = nullptr);
+// The same as a host FST with the reference's property word (fst_reverse).
+CsrFst reverse_fst_device(const DevFst& fst, cudaStream_t s);
 
 // n > 1 shortest paths (shortest_path.rs:135-170 with unique = false, n_shortest_path :409-518): distances and the
 // reversed machine are built on the device, the n-best heap search runs on the host over rows fetched on demand,

@@ -257,6 +257,14 @@ RUSTFST_FFI_RESULT fst_connect(CFst* ptr) {
     ptr->fst.replace(download(r, st.s));
   });
 }
+RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr) {
+  return wrap([&] {
+    const CsrFst& h = nn(ptr, "fst")->fst.freeze();
+    Stream st;
+    DevFst d = upload(h, st.s);
+    *res_ptr = new CFst{HostFst(reverse_fst_device(d, st.s))};
+  });
+}
 RUSTFST_FFI_RESULT fst_tr_sort(CFst* ptr, bool ilabel_comp) {
   return wrap([&] {
     nn(ptr, "fst");

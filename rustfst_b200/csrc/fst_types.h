@@ -172,6 +172,46 @@ inline uint64_t of_shortest_path(uint64_t p, bool tree) {
   if (!tree) out |= kCoAccessible;
   return out;
 }
+// fst_properties/mutate_properties.rs:622-638
+inline uint64_t of_reverse(uint64_t p, bool has_superinitial) {
+  uint64_t out = (kAcceptorPair | kEpsilons | kIEpsilons | kOEpsilons | kUnweighted | kCyclePair | kWCyclesPair) & p;
+  if (has_superinitial) out |= kWeighted & p;
+  return out;
+}
+// The effect of on_add_tr over a whole set of arcs, from the OR of their "events".  The sequential rule only ever
+// moves a pair from its positive to its negative bit, masks with the same constant after every arc and re-derives
+// ACYCLIC / INITIAL_ACYCLIC from TOP_SORTED, so the result depends on the set of events, not on their order
+// (checked against the sequential replay by tests/test_host_api.py and the reverse parity tests).
+enum ArcEvent : uint32_t {
+  kEvNotAcceptor = 1, kEvIEps = 2, kEvEps = 4, kEvOEps = 8, kEvIUnsorted = 16, kEvOUnsorted = 32, kEvWeighted = 64,
+  kEvNotTopSorted = 128
+};
+B200_HD uint32_t arc_events(StateId state, const Tr& tr, const Tr* prev) {
+  uint32_t e = 0;
+  if (tr.ilabel != tr.olabel) e |= kEvNotAcceptor;
+  if (tr.ilabel == kEps) { e |= kEvIEps; if (tr.olabel == kEps) e |= kEvEps; }
+  if (tr.olabel == kEps) e |= kEvOEps;
+  if (prev) { if (prev->ilabel > tr.ilabel) e |= kEvIUnsorted; if (prev->olabel > tr.olabel) e |= kEvOUnsorted; }
+  if (!w_is_zero(tr.weight) && !w_is_one(tr.weight)) e |= kEvWeighted;
+  if (tr.nextstate <= state) e |= kEvNotTopSorted;
+  return e;
+}
+inline uint64_t apply_arc_events(uint64_t p, uint32_t ev, bool any_arc) {
+  if (!any_arc) return p;
+  uint64_t out = p;
+  if (ev & kEvNotAcceptor) { out |= kNotAcceptor; out &= ~kAcceptor; }
+  if (ev & kEvIEps) { out |= kIEpsilons; out &= ~kNoIEpsilons; }
+  if (ev & kEvEps) { out |= kEpsilons; out &= ~kNoEpsilons; }
+  if (ev & kEvOEps) { out |= kOEpsilons; out &= ~kNoOEpsilons; }
+  if (ev & kEvIUnsorted) { out |= kNotILabelSorted; out &= ~kILabelSorted; }
+  if (ev & kEvOUnsorted) { out |= kNotOLabelSorted; out &= ~kOLabelSorted; }
+  if (ev & kEvWeighted) { out |= kWeighted; out &= ~kUnweighted; }
+  if (ev & kEvNotTopSorted) { out |= kNotTopSorted; out &= ~kTopSorted; }
+  out &= kKeepOnAddArc | kAcceptor | kNoEpsilons | kNoIEpsilons | kNoOEpsilons | kILabelSorted | kOLabelSorted |
+         kUnweighted | kTopSorted;
+  if (out & kTopSorted) out |= kAcyclic | kInitialAcyclic;
+  return out;
+}
 // algorithms/tr_sort.rs:21-28,39-46
 inline uint64_t after_tr_sort(uint64_t p, bool ilabel) {
   uint64_t out = (p & kKeepOnArcSort) | (ilabel ? kILabelSorted : kOLabelSorted);

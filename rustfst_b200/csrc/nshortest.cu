@@ -73,6 +73,25 @@ k_rev_gather(const Tr* __restrict__ arcs, const float* __restrict__ fin, uint32_
   *reinterpret_cast<int4*>(&out[k]) = *reinterpret_cast<const int4*>(&tr);
 }
 
+// OR of the add_tr_properties events (fst_types.h: arc_events) of every arc of a CSR machine.
+__global__ void __launch_bounds__(kThreads)
+k_arc_events(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t* __restrict__ out) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t ev = 0;
+  if (s < n) {
+    Tr prev;
+    bool has_prev = false;
+    for (uint32_t e = off[s]; e < off[s + 1]; e++) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(&arcs[e]));
+      Tr tr; tr.ilabel = (uint32_t)v.x; tr.olabel = (uint32_t)v.y; tr.weight = __int_as_float(v.z); tr.nextstate = (uint32_t)v.w;
+      ev |= props::arc_events(s, tr, has_prev ? &prev : nullptr);
+      prev = tr; has_prev = true;
+    }
+  }
+  ev = __reduce_or_sync(0xFFFFFFFFu, ev);
+  if ((threadIdx.x & 31) == 0 && ev) atomicOr(out, ev);
+}
+
 __global__ void k_rev_finals(float* __restrict__ fin, uint32_t n1, uint32_t final_state, bool has_final) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < n1) fin[s] = (has_final && s == final_state) ? 0.0f : w_zero();
@@ -187,9 +206,29 @@ DevFst reverse_device(const DevFst& f, cudaStream_t s, uint64_t* launches) {
   r.finals.reserve_discard((size_t)n + 1);
   k_rev_finals<<<blocks_for((size_t)n + 1), kThreads, 0, s>>>(r.finals.p, n + 1, f.start + 1, f.has_start);
   nl++;
-  r.props = 0;  // reverse_properties (reverse.rs:78-83) is never read on this route
+  r.props = 0;  // the n-best route never reads it; reverse_fst_device() below computes it (reverse.rs:78-83)
   if (launches) *launches += nl + 2;  // + scan + sort (library passes counted once each)
   return r;
+}
+
+CsrFst reverse_fst_device(const DevFst& f, cudaStream_t s) {
+  DevFst r = reverse_device(f, s, nullptr);
+  // Property word: replay reverse.rs' mutation sequence on VectorFst::new() — add_state, add_states(n), set_final of
+  // the old start, every set_trs_unchecked (an order-independent function of the arcs' events, one reduction on
+  // the device), set_start — then OR in reverse_properties(input, true)  (reverse.rs:40-83).
+  DevBuf<uint32_t> ev(s, 1);
+  B200_CUDA(cudaMemsetAsync(ev.p, 0, 4, s));
+  k_arc_events<<<blocks_for(r.num_states), kThreads, 0, s>>>(r.offsets.p, r.arcs.p, r.num_states, ev.p);
+  const uint32_t events = read_u32(ev.p, s);
+  uint64_t p = props::kNull;
+  p = props::on_add_state(p);
+  p &= props::kKeepOnAddState;
+  const float one = 0.0f;
+  if (f.has_start) p = props::on_set_final(p, nullptr, &one);
+  p = props::apply_arc_events(p, events, r.num_arcs > 0);
+  p = props::on_set_start(p);
+  r.props = (props::of_reverse(f.props, true) | p) & props::kTrinary;
+  return download(r, s);
 }
 
 CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,

@@ -211,6 +211,11 @@ class VectorFst:
     def tr_sort(self, ilabel_cmp: bool = True):
         check_ffi_error(lib.fst_tr_sort(self.ptr, bool(ilabel_cmp)), "Error during tr_sort")
 
+    def reverse(self) -> "VectorFst":  # vector_fst.py:599 / algorithms/reverse.py:11-31
+        out = C.c_void_p()
+        check_ffi_error(lib.fst_reverse(self.ptr, C.byref(out)), "Error during reverse")
+        return VectorFst(ptr=out)
+
     def connect(self) -> "VectorFst":
         check_ffi_error(lib.fst_connect(self.ptr), "Error during connect")
         return self

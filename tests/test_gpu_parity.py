@@ -517,3 +517,41 @@ def test_concurrent_calls_on_shared_handles_from_several_host_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_fst_reverse_matches_the_reference_kat_and_the_oracle():
+    """fst_reverse (rustfst-ffi/src/algorithms/reverse.rs:14-29) on the device: the reference's Python KAT
+    (test_reverse.py:4-54), every fixture machine and random machines, bit-exact incl. the property word."""
+    import rustfst_b200 as R
+    f = R.VectorFst()
+    s1, s2, s3 = f.add_state(), f.add_state(), f.add_state()
+    f.set_start(s1)
+    f.set_final(s3, 1.0)
+    f.add_tr(s1, R.Tr(1, 2, 1.0, s2))
+    f.add_tr(s1, R.Tr(3, 4, 2.0, s2))
+    f.add_tr(s2, R.Tr(5, 6, 1.5, s2))
+    f.add_tr(s2, R.Tr(3, 5, 1.0, s3))
+    e = R.VectorFst()
+    t1, t2, t3, t4 = e.add_state(), e.add_state(), e.add_state(), e.add_state()
+    e.set_start(t1)
+    e.set_final(t2)
+    e.add_tr(t1, R.Tr(0, 0, 1.0, t4))
+    e.add_tr(t4, R.Tr(3, 5, 1.0, t3))
+    e.add_tr(t3, R.Tr(1, 2, 1.0, t2))
+    e.add_tr(t3, R.Tr(3, 4, 2.0, t2))
+    e.add_tr(t3, R.Tr(5, 6, 1.5, t3))
+    assert f.reverse() == e
+    for name in FIXTURES:
+        for which in ("raw", "compose"):
+            p, o = both_from_path(golden_path(name, which))
+            assert_same(p.reverse(), o.reverse(), f"{name}/{which} reverse")
+    rng = np.random.default_rng(4242)
+    for k in range(8):
+        d = random_fst(rng, int(rng.integers(1, 60)), 5, 6, eps_prob=0.2, cyclic=(k % 2 == 0), acceptor=(k % 3 == 0))
+        p, o = both_from_dict(d)
+        assert_same(p.reverse(), o.reverse(), f"random reverse {k}")
+    # no start state, no states
+    g = R.VectorFst(); og = O.OFst()
+    assert_same(g.reverse(), og.reverse(), "empty reverse")
+    g.add_state(); og.add_state()
+    assert_same(g.reverse(), og.reverse(), "startless reverse")

@@ -173,3 +173,26 @@ def test_sigma_errors():
         O.compose_sigma(query, sigma, filter=3, connect=True, sigma2=(0, 0, None))
     with pytest.raises(O.OracleError, match="bad label"):
         O.compose_sigma(acceptor_fst([1, 5, 4]), sigma, filter=3, connect=True, sigma2=(5, 0, None))
+
+
+def test_reverse_kat_from_the_reference_python_tests():
+    """rustfst-python/tests/algorithms/test_reverse.py:4-54 — pins reverse(), which the n-best route is built on:
+    superinitial state 0, old state s becomes s + 1, in-arcs of a state in (source state, arc position) order."""
+    f = O.OFst()
+    s1, s2, s3 = f.add_state(), f.add_state(), f.add_state()
+    f.set_start(s1)
+    f.set_final(s3, 1.0)
+    f.add_tr(s1, 1, 2, 1.0, s2)
+    f.add_tr(s1, 3, 4, 2.0, s2)
+    f.add_tr(s2, 5, 6, 1.5, s2)
+    f.add_tr(s2, 3, 5, 1.0, s3)
+    e = O.OFst()
+    t1, t2, t3, t4 = e.add_state(), e.add_state(), e.add_state(), e.add_state()
+    e.set_start(t1)
+    e.set_final(t2, 0.0)
+    e.add_tr(t1, 0, 0, 1.0, t4)
+    e.add_tr(t4, 3, 5, 1.0, t3)
+    e.add_tr(t3, 1, 2, 1.0, t2)
+    e.add_tr(t3, 3, 4, 2.0, t2)
+    e.add_tr(t3, 5, 6, 1.5, t3)
+    assert f.reverse() == e

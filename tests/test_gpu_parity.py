@@ -555,3 +555,24 @@ def test_fst_reverse_matches_the_reference_kat_and_the_oracle():
     assert_same(g.reverse(), og.reverse(), "empty reverse")
     g.add_state(); og.add_state()
     assert_same(g.reverse(), og.reverse(), "startless reverse")
+
+
+def test_connect_kat_through_cabi():
+    """rustfst-python/tests/algorithms/test_connect.py:4-52 through fst_connect on the device."""
+    import rustfst_b200 as R
+    f = R.VectorFst()
+    for _ in range(5):
+        f.add_state()
+    f.set_start(0)
+    f.set_final(1, 0.0)
+    for (src, il, ol, w, dst) in [(4, 1, 2, 1.0, 0), (0, 3, 4, 2.0, 1), (1, 4, 5, 3.0, 2), (2, 4, 6, 4.0, 3), (2, 7, 8, 5.0, 0)]:
+        f.add_tr(src, R.Tr(il, ol, w, dst))
+    e = R.VectorFst()
+    for _ in range(3):
+        e.add_state()
+    e.set_start(0)
+    e.set_final(1, 0.0)
+    for (src, il, ol, w, dst) in [(0, 3, 4, 2.0, 1), (1, 4, 5, 3.0, 2), (2, 7, 8, 5.0, 0)]:
+        e.add_tr(src, R.Tr(il, ol, w, dst))
+    res = f.connect()
+    assert f == e and res == e

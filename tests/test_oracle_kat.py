@@ -196,3 +196,51 @@ def test_reverse_kat_from_the_reference_python_tests():
     e.add_tr(t3, 3, 4, 2.0, t2)
     e.add_tr(t3, 5, 6, 1.5, t3)
     assert f.reverse() == e
+
+
+def _build(cls_new, add_tr, arcs, n_states, start, finals):
+    f = cls_new()
+    for _ in range(n_states):
+        f.add_state()
+    f.set_start(start)
+    for st, w in finals:
+        f.set_final(st, w)
+    for (src, il, ol, w, dst) in arcs:
+        add_tr(f, src, il, ol, w, dst)
+    return f
+
+
+def test_connect_kat_from_the_reference_python_tests():
+    """rustfst-python/tests/algorithms/test_connect.py:4-52 — pins connect (trim + order-preserving renumbering)."""
+    add = lambda f, s, il, ol, w, d: f.add_tr(s, il, ol, w, d)  # noqa: E731
+    f = _build(O.OFst, add, [(4, 1, 2, 1.0, 0), (0, 3, 4, 2.0, 1), (1, 4, 5, 3.0, 2), (2, 4, 6, 4.0, 3), (2, 7, 8, 5.0, 0)],
+               5, 0, [(1, 0.0)])
+    e = _build(O.OFst, add, [(0, 3, 4, 2.0, 1), (1, 4, 5, 3.0, 2), (2, 7, 8, 5.0, 0)], 3, 0, [(1, 0.0)])
+    f.connect()
+    assert f == e
+
+
+def test_tr_sort_kats_from_the_reference_python_tests():
+    """rustfst-python/tests/algorithms/test_tr_sort.py:4-95 — stable sort by ilabel / olabel."""
+    add = lambda f, s, il, ol, w, d: f.add_tr(s, il, ol, w, d)  # noqa: E731
+    arcs = [(0, 1, 2, 1.0, 1), (0, 3, 3, 2.0, 1), (0, 1, 5, 3.0, 1), (0, 2, 6, 4.0, 1)]
+    f = _build(O.OFst, add, arcs, 2, 0, [(1, 0.0)])
+    f.tr_sort(True)
+    assert f == _build(O.OFst, add, [(0, 1, 2, 1.0, 1), (0, 1, 5, 3.0, 1), (0, 2, 6, 4.0, 1), (0, 3, 3, 2.0, 1)], 2, 0, [(1, 0.0)])
+    g = _build(O.OFst, add, arcs, 2, 0, [(1, 0.0)])
+    g.tr_sort(False)
+    assert g == _build(O.OFst, add, [(0, 1, 2, 1.0, 1), (0, 3, 3, 2.0, 1), (0, 1, 5, 3.0, 1), (0, 2, 6, 4.0, 1)], 2, 0, [(1, 0.0)])
+
+
+def test_tr_sort_kats_through_the_cabi_host_container():
+    """The same KATs through fst_tr_sort of the product library: machines this small are sorted by the host container
+    (the device path needs >= 64K arcs), so the check runs without a GPU."""
+    import rustfst_b200 as R
+    add = lambda f, s, il, ol, w, d: f.add_tr(s, R.Tr(il, ol, w, d))  # noqa: E731
+    arcs = [(0, 1, 2, 1.0, 1), (0, 3, 3, 2.0, 1), (0, 1, 5, 3.0, 1), (0, 2, 6, 4.0, 1)]
+    f = _build(R.VectorFst, add, arcs, 2, 0, [(1, 0.0)])
+    f.tr_sort()
+    assert f == _build(R.VectorFst, add, [(0, 1, 2, 1.0, 1), (0, 1, 5, 3.0, 1), (0, 2, 6, 4.0, 1), (0, 3, 3, 2.0, 1)], 2, 0, [(1, 0.0)])
+    g = _build(R.VectorFst, add, arcs, 2, 0, [(1, 0.0)])
+    g.tr_sort(ilabel_cmp=False)
+    assert g == _build(R.VectorFst, add, [(0, 1, 2, 1.0, 1), (0, 3, 3, 2.0, 1), (0, 1, 5, 3.0, 1), (0, 2, 6, 4.0, 1)], 2, 0, [(1, 0.0)])

@@ -16,7 +16,10 @@
 using namespace b200;
 
 // ---- opaque handle types
-struct CFst { HostFst fst; };
+struct CFst {
+  HostFst fst;
+  bool is_const = false;  // handle made by const_fst_* (ConstFst<TropicalWeight>); everything else is a VectorFst
+};
 struct CTrs { std::shared_ptr<std::vector<Tr>> v; };
 struct CTrsIterator { std::vector<Tr> trs; size_t index = 0; };
 struct CMutTrsIterator { CFst* fst; StateId state; size_t index = 0; };
@@ -66,6 +69,22 @@ T* nn(T* p, const char* what) {  // ffi_convert raw_borrow on a null pointer is 
 }
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+// Downcasts of the opaque handle (rustfst-ffi/src/fst/mod.rs:99-111 as_fst!, algorithms/compose.rs:315-321)
+template <class T>
+T* vec_alg(T* p, const char* what) {  // algorithms: "Could not downcast to vector FST"
+  if (nn(p, what)->is_const) throw FstError("Could not downcast to vector FST");
+  return p;
+}
+template <class T>
+T* vec_h(T* p, const char* what) {  // vec_fst_* accessors
+  if (nn(p, what)->is_const) throw FstError("Could not downcast to VectorFst<TropicalWeight> FST");
+  return p;
+}
+template <class T>
+T* const_h(T* p, const char* what) {  // const_fst_* accessors
+  if (!nn(p, what)->is_const) throw FstError("Could not downcast to ConstFst<TropicalWeight> FST");
+  return p;
 }
 
 ComposeOptions to_options(const CComposeConfig* c) {
@@ -127,8 +146,8 @@ void parallel_ranges(size_t n, F fn) {
 
 CFst* compose_host(const CFst* a, const CFst* b, const CComposeConfig* cfg, B200ComposeStats* stats) {
   ComposeOptions opt = to_options(cfg);
-  const CsrFst& ha = nn(a, "fst_1")->fst.freeze();
-  const CsrFst& hb = nn(b, "fst_2")->fst.freeze();
+  const CsrFst& ha = vec_alg(a, "fst_1")->fst.freeze();
+  const CsrFst& hb = vec_alg(b, "fst_2")->fst.freeze();
   Stream st;
   double t0 = now_ms();
   DevFst da = upload(ha, st.s);
@@ -175,7 +194,7 @@ CFst* shortest_path_host(const CFst* in, const CShortestPathConfig* cfg, B200Sss
     return new CFst{};
   }
   check_sp_config(cfg);
-  const CsrFst& h = nn(in, "fst")->fst.freeze();
+  const CsrFst& h = vec_alg(in, "fst")->fst.freeze();
   QueuePlan plan = build_queue_plan(h);
   Stream st;
   double t0 = now_ms();
@@ -250,7 +269,7 @@ RUSTFST_FFI_RESULT b200_shortest_path_config_destroy(CShortestPathConfig* p) { r
 
 RUSTFST_FFI_RESULT fst_connect(CFst* ptr) {
   return wrap([&] {
-    const CsrFst& h = nn(ptr, "fst")->fst.freeze();
+    const CsrFst& h = vec_alg(ptr, "fst")->fst.freeze();
     Stream st;
     DevFst d = upload(h, st.s);
     DevFst r = connect_device(d, false, nullptr, st.s);
@@ -259,7 +278,7 @@ RUSTFST_FFI_RESULT fst_connect(CFst* ptr) {
 }
 RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr) {
   return wrap([&] {
-    const CsrFst& h = nn(ptr, "fst")->fst.freeze();
+    const CsrFst& h = vec_alg(ptr, "fst")->fst.freeze();
     Stream st;
     DevFst d = upload(h, st.s);
     *res_ptr = new CFst{HostFst(reverse_fst_device(d, st.s))};
@@ -267,7 +286,7 @@ RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr) {
 }
 RUSTFST_FFI_RESULT fst_tr_sort(CFst* ptr, bool ilabel_comp) {
   return wrap([&] {
-    nn(ptr, "fst");
+    vec_alg(ptr, "fst");
     // Large machines are sorted on the device (one radix sort + gather); small ones, and any machine on a box
     // without a GPU, by the host container (same stable order either way; tr_sort is not part of the hot path).
     int ndev = 0;
@@ -312,17 +331,17 @@ RUSTFST_FFI_RESULT fst_destroy(CFst* p) { return wrap([&] { delete p; }); }
 
 // ---------------------------------------------------------------- VectorFst
 RUSTFST_FFI_RESULT vec_fst_new(const CFst** ptr) { return wrap([&] { *ptr = new CFst{}; }); }
-RUSTFST_FFI_RESULT vec_fst_set_start(CFst* f, CStateId s) { return wrap([&] { nn(f, "fst")->fst.set_start(s); }); }
+RUSTFST_FFI_RESULT vec_fst_set_start(CFst* f, CStateId s) { return wrap([&] { vec_h(f, "fst")->fst.set_start(s); }); }
 RUSTFST_FFI_RESULT vec_fst_set_final(CFst* f, CStateId s, float w) {
-  return wrap([&] { nn(f, "fst")->fst.set_final(s, w); });
+  return wrap([&] { vec_h(f, "fst")->fst.set_final(s, w); });
 }
-RUSTFST_FFI_RESULT vec_fst_add_state(CFst* f, CStateId* s) { return wrap([&] { *s = nn(f, "fst")->fst.add_state(); }); }
-RUSTFST_FFI_RESULT vec_fst_delete_states(CFst* f) { return wrap([&] { nn(f, "fst")->fst.del_all_states(); }); }
+RUSTFST_FFI_RESULT vec_fst_add_state(CFst* f, CStateId* s) { return wrap([&] { *s = vec_h(f, "fst")->fst.add_state(); }); }
+RUSTFST_FFI_RESULT vec_fst_delete_states(CFst* f) { return wrap([&] { vec_h(f, "fst")->fst.del_all_states(); }); }
 RUSTFST_FFI_RESULT vec_fst_add_tr(CFst* f, CStateId s, const CTr* tr) {
-  return wrap([&] { nn(f, "fst")->fst.add_tr(s, as_tr(nn(tr, "tr"))); });
+  return wrap([&] { vec_h(f, "fst")->fst.add_tr(s, as_tr(nn(tr, "tr"))); });
 }
 RUSTFST_FFI_RESULT vec_fst_del_final_weight(CFst* f, CStateId s) {
-  return wrap([&] { nn(f, "fst")->fst.delete_final_weight(s); });
+  return wrap([&] { vec_h(f, "fst")->fst.delete_final_weight(s); });
 }
 RUSTFST_FFI_RESULT vec_fst_from_path(const CFst** ptr, const char* path) {
   return wrap([&] {
@@ -331,23 +350,23 @@ RUSTFST_FFI_RESULT vec_fst_from_path(const CFst** ptr, const char* path) {
   });
 }
 RUSTFST_FFI_RESULT vec_fst_write_file(const CFst* f, const char* path) {
-  return wrap([&] { io::write_file(nn(path, "path"), io::store_vector_fst(nn(f, "fst")->fst.freeze())); });
+  return wrap([&] { io::write_file(nn(path, "path"), io::store_vector_fst(vec_h(f, "fst")->fst.freeze())); });
 }
 RUSTFST_FFI_RESULT vec_fst_num_states(const CFst* f, size_t* n) {
-  return wrap([&] { *n = nn(f, "fst")->fst.num_states(); });
+  return wrap([&] { *n = vec_h(f, "fst")->fst.num_states(); });
 }
 RUSTFST_FFI_RESULT vec_fst_equals(const CFst* a, const CFst* b, size_t* eq) {
-  return wrap([&] { *eq = nn(a, "fst")->fst.equals(nn(b, "other_fst")->fst) ? 1 : 0; });
+  return wrap([&] { *eq = vec_h(a, "fst")->fst.equals(vec_h(b, "other_fst")->fst) ? 1 : 0; });
 }
 RUSTFST_FFI_RESULT vec_fst_copy(const CFst* f, const CFst** clone) {
-  return wrap([&] { *clone = new CFst{HostFst(nn(f, "fst")->fst)}; });
+  return wrap([&] { *clone = new CFst{HostFst(vec_h(f, "fst")->fst)}; });
 }
 RUSTFST_FFI_RESULT vec_fst_display(const CFst* f, const char** s) {
-  return wrap([&] { *s = dup_cstr(nn(f, "fst")->fst.display()); });
+  return wrap([&] { *s = dup_cstr(vec_h(f, "fst")->fst.display()); });
 }
 RUSTFST_FFI_RESULT vec_fst_to_bytes(const CFst* f, const CArrayU8** out) {
   return wrap([&] {
-    auto bytes = io::store_vector_fst(nn(f, "fst")->fst.freeze());
+    auto bytes = io::store_vector_fst(vec_h(f, "fst")->fst.freeze());
     uint8_t* p = (uint8_t*)std::malloc(bytes.size() ? bytes.size() : 1);
     std::memcpy(p, bytes.data(), bytes.size());
     *out = new CArrayU8{p, bytes.size()};
@@ -361,6 +380,26 @@ RUSTFST_FFI_RESULT vec_fst_from_bytes(const CArrayU8* bytes, const CFst** ptr) {
     nn(bytes, "bytes");
     *ptr = new CFst{HostFst(io::parse_vector_fst(bytes->data_ptr, bytes->size))};
   });
+}
+
+// ---------------------------------------------------------------- ConstFst (rustfst-ffi/src/fst/const_fst.rs)
+RUSTFST_FFI_RESULT const_fst_from_path(const CFst** ptr, const char* path) {
+  return wrap([&] {
+    auto bytes = io::read_file(nn(path, "path"));
+    *ptr = new CFst{HostFst(io::parse_const_fst(bytes.data(), bytes.size())), true};
+  });
+}
+RUSTFST_FFI_RESULT const_fst_write_file(const CFst* f, const char* path) {
+  return wrap([&] { io::write_file(nn(path, "path"), io::store_const_fst(const_h(f, "fst")->fst.freeze())); });
+}
+RUSTFST_FFI_RESULT const_fst_equals(const CFst* a, const CFst* b, size_t* eq) {
+  return wrap([&] { *eq = const_h(a, "fst")->fst.equals(const_h(b, "other_fst")->fst) ? 1 : 0; });
+}
+RUSTFST_FFI_RESULT const_fst_copy(const CFst* f, const CFst** clone) {
+  return wrap([&] { *clone = new CFst{HostFst(const_h(f, "fst")->fst), true}; });
+}
+RUSTFST_FFI_RESULT const_fst_display(const CFst* f, const char** s) {
+  return wrap([&] { *s = dup_cstr(const_h(f, "fst")->fst.display()); });
 }
 
 // ---------------------------------------------------------------- Tr
@@ -503,6 +542,9 @@ RUSTFST_FFI_RESULT b200_fst_from_csr(uint64_t n, const uint32_t* offsets, const 
     c.props = props_word & props::kTrinary;
     *out = new CFst{HostFst(std::move(c))};
   });
+}
+RUSTFST_FFI_RESULT b200_fst_num_states(const CFst* f, uint64_t* n) {
+  return wrap([&] { *n = nn(f, "fst")->fst.num_states(); });
 }
 RUSTFST_FFI_RESULT b200_fst_num_trs_total(const CFst* f, uint64_t* n) {
   return wrap([&] { *n = nn(f, "fst")->fst.freeze().arcs.size(); });

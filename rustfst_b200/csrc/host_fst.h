@@ -415,6 +415,98 @@ inline std::vector<uint8_t> store_vector_fst(const CsrFst& c) {
   return buf;
 }
 
+// OpenFst binary "const" format — rustfst/src/fst_impls/const_fst/serializable_fst.rs:30-79 (store), :180-236 (load),
+// const_fst/mod.rs:11-14 (versions: 1 = aligned to 16 bytes, 2 = packed).  A const FST *is* a CSR block (one state array
+// {final weight, first arc, #arcs, #input eps, #output eps}, one arc array), so both directions are straight copies.
+inline CsrFst parse_const_fst(const uint8_t* data, size_t len) {
+  const char* kErr = "Error while parsing binary ConstFst";
+  Reader r{data, len};
+  try {
+    if (r.get<int32_t>() != kMagic) throw FstError(kErr);
+    if (r.str() != "const") throw FstError(kErr);
+    if (r.str() != "standard") throw FstError(kErr);
+    const int32_t version = r.get<int32_t>();
+    if (version < 1) throw FstError(kErr);
+    const uint32_t flags = r.get<uint32_t>();
+    if (flags & ~7u) throw FstError(kErr);
+    const uint64_t props_word = r.get<uint64_t>();
+    const int64_t start = r.get<int64_t>();
+    const int64_t num_states = r.get<int64_t>();
+    const int64_t num_trs = r.get<int64_t>();
+    if (flags & 1) skip_symbol_table(r);
+    if (flags & 2) skip_symbol_table(r);
+    if (num_states < 0 || num_trs < 0 || (uint64_t)num_trs > 0xFFFFFFF0ull) throw FstError(kErr);
+    const bool aligned = version == 1;
+    auto align = [&](int64_t count) {
+      if (aligned && count > 0 && r.off % 16 != 0) {
+        r.off += 16 - r.off % 16;
+        if (r.off > r.n) throw FstError(kErr);
+      }
+    };
+    align(num_states);
+    struct St { float fw; int32_t pos, ntrs, nie, noe; };
+    std::vector<St> sts((size_t)num_states);
+    for (int64_t s = 0; s < num_states; s++) {
+      sts[s].fw = r.get<float>(); sts[s].pos = r.get<int32_t>(); sts[s].ntrs = r.get<int32_t>();
+      sts[s].nie = r.get<int32_t>(); sts[s].noe = r.get<int32_t>();
+    }
+    align(num_trs);
+    if (r.off + (size_t)num_trs * 16 > r.n) throw FstError(kErr);
+    const uint8_t* arcs = r.p + r.off;
+    CsrFst c;
+    c.props = props_word & props::kTrinary;  // FstProperties::from_bits_truncate
+    c.has_start = start != -1;
+    c.start = (StateId)start;
+    c.offsets.resize((size_t)num_states + 1);
+    c.finals.resize((size_t)num_states);
+    size_t total = 0;
+    for (int64_t s = 0; s < num_states; s++) {
+      if (sts[s].pos < 0 || sts[s].ntrs < 0 || (int64_t)sts[s].pos + sts[s].ntrs > num_trs) throw FstError(kErr);
+      total += (size_t)sts[s].ntrs;
+    }
+    c.arcs.resize(total);
+    size_t o = 0;
+    for (int64_t s = 0; s < num_states; s++) {
+      c.finals[s] = w_approx_eq(sts[s].fw, w_zero()) ? w_zero() : sts[s].fw;  // utils_parsing.rs:17-26
+      c.offsets[s] = (uint32_t)o;
+      if (sts[s].ntrs) std::memcpy(c.arcs.data() + o, arcs + (size_t)sts[s].pos * 16, (size_t)sts[s].ntrs * 16);
+      o += (size_t)sts[s].ntrs;
+    }
+    c.offsets[num_states] = (uint32_t)o;
+    return c;
+  } catch (const FstError&) {
+    throw FstError(kErr);  // load() maps every parse failure to this message (serializable_fst.rs:36-40)
+  }
+}
+
+inline std::vector<uint8_t> store_const_fst(const CsrFst& c) {
+  const size_t n = c.num_states();
+  std::vector<uint8_t> buf;
+  buf.reserve(64 + n * 20 + c.arcs.size() * 16);
+  auto put = [&](const void* p, size_t k) { const uint8_t* b = (const uint8_t*)p; buf.insert(buf.end(), b, b + k); };
+  auto put_i32 = [&](int32_t v) { put(&v, 4); };
+  auto put_i64 = [&](int64_t v) { put(&v, 8); };
+  auto put_str = [&](const char* s) { int32_t l = (int32_t)std::strlen(s); put_i32(l); put(s, (size_t)l); };
+  put_i32(kMagic);
+  put_str("const");
+  put_str("standard");
+  put_i32(2);  // CONST_FILE_VERSION: packed
+  uint32_t flags = 0; put(&flags, 4);
+  uint64_t p = c.props | props::kExpanded; put(&p, 8);  // static_properties() = EXPANDED (data_structure.rs:32-36)
+  put_i64(c.has_start ? (int64_t)c.start : -1);
+  put_i64((int64_t)n);
+  put_i64((int64_t)c.arcs.size());
+  for (size_t s = 0; s < n; s++) {
+    put(&c.finals[s], 4);
+    const uint32_t lo = c.offsets[s], hi = c.offsets[s + 1];
+    int32_t nie = 0, noe = 0;
+    for (uint32_t e = lo; e < hi; e++) { nie += c.arcs[e].ilabel == kEps; noe += c.arcs[e].olabel == kEps; }
+    put_i32((int32_t)lo); put_i32((int32_t)(hi - lo)); put_i32(nie); put_i32(noe);
+  }
+  if (!c.arcs.empty()) put(c.arcs.data(), c.arcs.size() * 16);
+  return buf;
+}
+
 inline std::vector<uint8_t> read_file(const std::string& path) {
   std::ifstream in(path, std::ios::binary);
   if (!in) throw FstError("Error while opening file \"" + path + "\"");

@@ -139,6 +139,12 @@ _sig("state_iterator_destroy", _P)
 _sig("b200_fst_properties", _P, C.POINTER(C.c_uint64))
 _sig("b200_fst_set_properties", _P, C.c_uint64)
 _sig("b200_fst_from_csr", C.c_uint64, _P, _P, _P, C.c_int64, C.c_uint64, _PP)
+_sig("b200_fst_num_states", _P, C.POINTER(C.c_uint64))
+_sig("const_fst_from_path", _PP, C.c_char_p)
+_sig("const_fst_write_file", _P, C.c_char_p)
+_sig("const_fst_equals", _P, _P, C.POINTER(C.c_size_t))
+_sig("const_fst_copy", _P, _PP)
+_sig("const_fst_display", _P, C.POINTER(C.c_char_p))
 _sig("b200_fst_num_trs_total", _P, C.POINTER(C.c_uint64))
 _sig("b200_fst_to_csr", _P, _P, _P, _P, C.POINTER(C.c_int64))
 _sig("b200_compose_with_stats", _P, _P, _P, _PP, C.POINTER(ComposeStats))

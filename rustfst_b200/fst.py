@@ -288,3 +288,64 @@ class VectorFst:
         check_ffi_error(lib.b200_fst_to_csr(self.ptr, offsets.ctypes.data, arcs.ctypes.data, finals.ctypes.data,
                                             C.byref(start)), "`to_csr` failed")
         return offsets, arcs, finals, (None if start.value < 0 else start.value)
+
+
+class ConstFst:
+    """rustfst-python/rustfst/fst/const_fst.py:16-175 — immutable FST in the OpenFst "const" layout (read / write /
+    compare / copy / print; the generic read accessors of `Fst`).  Algorithms take VectorFst handles, as in the
+    reference; `from_vector_fst` and `draw` are not part of this build."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            lib.fst_destroy(self.ptr)
+        except Exception:
+            pass
+
+    @classmethod
+    def read(cls, path) -> "ConstFst":  # const_fst.py:90-107
+        p = C.c_void_p()
+        check_ffi_error(lib.const_fst_from_path(C.byref(p), str(path).encode("utf-8")), f"Read failed. file: {path}")
+        return cls(p)
+
+    def write(self, path):  # const_fst.py:127-139
+        check_ffi_error(lib.const_fst_write_file(self.ptr, str(path).encode("utf-8")), f"Write failed. file: {path}")
+
+    def equals(self, other: "ConstFst") -> bool:  # const_fst.py:141-154
+        r = C.c_size_t()
+        check_ffi_error(lib.const_fst_equals(self.ptr, other.ptr, C.byref(r)), "Error checking equality")
+        return bool(r.value)
+
+    def __eq__(self, other):
+        return isinstance(other, ConstFst) and self.equals(other)
+
+    def copy(self) -> "ConstFst":  # const_fst.py:156-166
+        p = C.c_void_p()
+        check_ffi_error(lib.const_fst_copy(self.ptr, C.byref(p)), "Error copying fst")
+        return ConstFst(p)
+
+    def __str__(self):  # const_fst.py:168-175
+        s = C.c_char_p()
+        check_ffi_error(lib.const_fst_display(self.ptr, C.byref(s)), "Error displaying ConstFst")
+        out = C.string_at(s).decode("utf8")
+        lib.rustfst_destroy_string(s)
+        return out
+
+    # generic accessors of the reference's `Fst` base class (fst.py): they work on any handle kind
+    start = VectorFst.start
+    final = VectorFst.final
+    is_final = VectorFst.is_final
+    is_start = VectorFst.is_start
+    num_trs = VectorFst.num_trs
+    trs = VectorFst.trs
+    num_trs_total = VectorFst.num_trs_total
+    properties = VectorFst.properties
+
+    def num_states(self) -> int:
+        n = C.c_uint64()
+        check_ffi_error(lib.b200_fst_num_states(self.ptr, C.byref(n)), "Error getting number of states")
+        return n.value
+
+    to_csr = VectorFst.to_csr

@@ -142,13 +142,14 @@ RUSTFST_FFI_RESULT vec_fst_from_bytes(const CArrayU8* bytes, const CFst** ptr);
 
 /* ConstFst handles (rustfst-ffi/src/fst/const_fst.rs:10-155; OpenFst binary "const" format, packed and 16-byte aligned
  * versions: rustfst/src/fst_impls/const_fst/serializable_fst.rs).  A const handle answers the generic fst_* accessors;
- * algorithms and vec_fst_* refuse it with the reference's downcast errors.  const_fst_from_vec_fst (needs the full
- * property computation) and const_fst_draw are not part of this build. */
+ * algorithms and vec_fst_* refuse it with the reference's downcast errors.  const_fst_draw is not part of this build. */
 RUSTFST_FFI_RESULT const_fst_from_path(const CFst** ptr, const char* path);
 RUSTFST_FFI_RESULT const_fst_write_file(const CFst* fst, const char* path);
 RUSTFST_FFI_RESULT const_fst_equals(const CFst* fst, const CFst* other_fst, size_t* is_equal);
 RUSTFST_FFI_RESULT const_fst_copy(const CFst* fst_ptr, const CFst** clone_ptr);
 RUSTFST_FFI_RESULT const_fst_display(const CFst* fst_ptr, const char** s);
+/* rustfst-ffi/src/fst/const_fst.rs:157-170: copy of a VectorFst with ALL properties computed (converters.rs:7-37). */
+RUSTFST_FFI_RESULT const_fst_from_vec_fst(const CFst* vec_fst_ptr, const CFst** const_fst_ptr);
 RUSTFST_FFI_RESULT b200_bytes_destroy(CArrayU8* bytes); /* the reference leaks the array of vec_fst_to_bytes */
 
 /* ---- Tr: rustfst-ffi/src/tr.rs:47-191 (setters take the VALUE in the pointer-typed parameter, as upstream) */
@@ -205,6 +206,9 @@ RUSTFST_FFI_RESULT b200_fst_set_properties(CFst* fst, uint64_t props);
 RUSTFST_FFI_RESULT b200_fst_from_csr(uint64_t num_states, const uint32_t* offsets, const CTr* arcs, const float* finals,
                                      int64_t start, uint64_t props, const CFst** out);
 RUSTFST_FFI_RESULT b200_fst_num_states(const CFst* fst, uint64_t* num_states); /* any handle kind (vector or const) */
+/* compute_and_update_properties_all (rustfst/src/fst_traits/mutable_fst.rs:435-446): fills in every unknown property
+ * bit from the machine's content (host; e.g. the sortedness bits compose needs on a machine built from raw arrays). */
+RUSTFST_FFI_RESULT b200_fst_compute_properties(CFst* fst, uint64_t* props /* may be NULL */);
 RUSTFST_FFI_RESULT b200_fst_num_trs_total(const CFst* fst, uint64_t* num_trs);
 /* Copies into caller buffers sized with vec_fst_num_states / b200_fst_num_trs_total (any pointer may be NULL). */
 RUSTFST_FFI_RESULT b200_fst_to_csr(const CFst* fst, uint32_t* offsets, CTr* arcs, float* finals, int64_t* start);

@@ -398,6 +398,13 @@ RUSTFST_FFI_RESULT const_fst_equals(const CFst* a, const CFst* b, size_t* eq) {
 RUSTFST_FFI_RESULT const_fst_copy(const CFst* f, const CFst** clone) {
   return wrap([&] { *clone = new CFst{HostFst(const_h(f, "fst")->fst), true}; });
 }
+RUSTFST_FFI_RESULT const_fst_from_vec_fst(const CFst* vec_fst, const CFst** const_fst) {
+  return wrap([&] {  // ConstFst::from(vec_fst.clone()): all properties are computed once and frozen (converters.rs:7-37)
+    auto c = std::make_unique<CFst>(CFst{HostFst(vec_h(vec_fst, "vec_fst")->fst), true});
+    c->fst.compute_and_update_properties_all();
+    *const_fst = c.release();
+  });
+}
 RUSTFST_FFI_RESULT const_fst_display(const CFst* f, const char** s) {
   return wrap([&] { *s = dup_cstr(const_h(f, "fst")->fst.display()); });
 }
@@ -541,6 +548,12 @@ RUSTFST_FFI_RESULT b200_fst_from_csr(uint64_t n, const uint32_t* offsets, const 
     if (c.has_start && (uint64_t)start >= n) throw FstError("The state " + std::to_string(start) + " doesn't exist");
     c.props = props_word & props::kTrinary;
     *out = new CFst{HostFst(std::move(c))};
+  });
+}
+RUSTFST_FFI_RESULT b200_fst_compute_properties(CFst* f, uint64_t* p) {
+  return wrap([&] {
+    const uint64_t v = nn(f, "fst")->fst.compute_and_update_properties_all();
+    if (p) *p = v;
   });
 }
 RUSTFST_FFI_RESULT b200_fst_num_states(const CFst* f, uint64_t* n) {

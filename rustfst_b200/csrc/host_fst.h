@@ -66,6 +66,147 @@ struct CsrFst {
   size_t num_states() const { return finals.size(); }
 };
 
+// All trinary properties of a machine, recomputed from its content — the result of compute_fst_properties(fst,
+// all_properties(), .., use_stored = false) (rustfst/src/fst_properties/compute_fst_properties.rs:14-208).  The
+// reference derives the DFS group (cyclic, initial-cyclic, accessible, coaccessible, SCC membership for the
+// weighted-cycles test) from one Tarjan visit with roots start, 0, 1, 2, …; all of these are facts about the graph,
+// not about the visiting order, so they are computed here by an iterative Tarjan over the CSR plus one forward
+// reachability pass.  The label / weight / shape group is the reference's single pass over the arcs.
+inline uint64_t compute_properties_all(const CsrFst& c) {
+  using namespace props;
+  const size_t n = c.num_states();
+  const uint32_t* off = c.offsets.data();
+  const Tr* arcs = c.arcs.data();
+  uint64_t out = 0;
+  std::vector<int32_t> scc(n, -1);
+  if (!c.has_start) {
+    // dfs_visit returns before visiting anything (dfs_visit.rs:103-109): the visitor's initial word stands and every
+    // state keeps the same (unset) component
+    out |= kAcyclic | kInitialAcyclic | kAccessible | kCoAccessible;
+  } else {
+    // ---- Tarjan SCC over all states (iterative), cycle detection
+    std::vector<int32_t> index(n, -1), low(n, 0);
+    std::vector<uint8_t> onstack(n, 0);
+    std::vector<uint32_t> tstack, cursor(n, 0);
+    struct Frame { uint32_t s; };
+    std::vector<uint32_t> call;
+    int32_t next_index = 0, nscc = 0;
+    bool cyclic = false;
+    for (size_t root = 0; root < n; root++) {
+      if (index[root] >= 0) continue;
+      call.push_back((uint32_t)root);
+      index[root] = low[root] = next_index++;
+      tstack.push_back((uint32_t)root); onstack[root] = 1; cursor[root] = off[root];
+      while (!call.empty()) {
+        const uint32_t s = call.back();
+        if (cursor[s] < off[s + 1]) {
+          const uint32_t t = arcs[cursor[s]++].nextstate;
+          if (index[t] < 0) {
+            index[t] = low[t] = next_index++;
+            tstack.push_back(t); onstack[t] = 1; cursor[t] = off[t];
+            call.push_back(t);
+          } else if (onstack[t]) {
+            if (index[t] < low[s]) low[s] = index[t];
+          }
+        } else {
+          call.pop_back();
+          if (!call.empty() && low[s] < low[call.back()]) low[call.back()] = low[s];
+          if (low[s] == index[s]) {
+            size_t members = 0;
+            uint32_t t;
+            do { t = tstack.back(); tstack.pop_back(); onstack[t] = 0; scc[t] = nscc; members++; } while (t != s);
+            if (members > 1) cyclic = true;
+            nscc++;
+          }
+        }
+      }
+    }
+    for (size_t s = 0; s < n && !cyclic; s++)
+      for (uint32_t e = off[s]; e < off[s + 1]; e++) if (arcs[e].nextstate == s) { cyclic = true; break; }
+    out |= cyclic ? kCyclic : kAcyclic;
+    // the start state lies on a cycle iff it has a self loop or shares its component with another state
+    bool initial_cyclic = false;
+    for (uint32_t e = off[c.start]; e < off[c.start + 1]; e++) if (arcs[e].nextstate == c.start) initial_cyclic = true;
+    if (!initial_cyclic)
+      for (size_t s = 0; s < n; s++) if (s != c.start && scc[s] == scc[c.start]) { initial_cyclic = true; break; }
+    out |= initial_cyclic ? kInitialCyclic : kInitialAcyclic;
+    // ---- accessible: forward reachability from the start state
+    std::vector<uint8_t> acc(n, 0);
+    std::vector<uint32_t> work{c.start};
+    acc[c.start] = 1;
+    size_t n_acc = 1;
+    while (!work.empty()) {
+      const uint32_t s = work.back(); work.pop_back();
+      for (uint32_t e = off[s]; e < off[s + 1]; e++) {
+        const uint32_t t = arcs[e].nextstate;
+        if (!acc[t]) { acc[t] = 1; n_acc++; work.push_back(t); }
+      }
+    }
+    out |= (n_acc == n) ? kAccessible : kNotAccessible;
+    // ---- coaccessible: Tarjan numbers components in reverse topological order (successors first), so one sweep over
+    // the components in creation order propagates "reaches a final state" from successors to predecessors
+    std::vector<uint8_t> comp_co((size_t)nscc, 0);
+    std::vector<std::vector<uint32_t>> by_comp((size_t)nscc);
+    for (size_t s = 0; s < n; s++) by_comp[scc[s]].push_back((uint32_t)s);
+    bool all_co = true;
+    for (int32_t k = 0; k < nscc; k++) {
+      bool co = false;
+      for (uint32_t s : by_comp[k]) {
+        if (c.finals[s] != w_zero() || std::binary_search(c.inf_finals.begin(), c.inf_finals.end(), s)) co = true;
+        for (uint32_t e = off[s]; e < off[s + 1] && !co; e++) {
+          const int32_t kt = scc[arcs[e].nextstate];
+          if (kt != k && comp_co[kt]) co = true;
+        }
+        if (co) break;
+      }
+      comp_co[k] = co;
+      if (!co) all_co = false;
+    }
+    out |= all_co ? kCoAccessible : kNotCoAccessible;
+  }
+  // ---- label / weight / shape group (compute_fst_properties.rs:56-196)
+  out |= kAcceptor | kNoEpsilons | kNoIEpsilons | kNoOEpsilons | kILabelSorted | kOLabelSorted | kUnweighted |
+         kTopSorted | kString | kIDeterministic | kODeterministic | kUnweightedCycles;
+  auto flip = [&](uint64_t neg, uint64_t pos) { out |= neg; out &= ~pos; };
+  size_t nfinal = 0;
+  std::vector<Label> il, ol;
+  for (size_t s = 0; s < n; s++) {
+    const uint32_t lo = off[s], hi = off[s + 1];
+    il.clear(); ol.clear();
+    for (uint32_t e = lo; e < hi; e++) {
+      const Tr& tr = arcs[e];
+      il.push_back(tr.ilabel); ol.push_back(tr.olabel);
+      if (tr.ilabel != tr.olabel) flip(kNotAcceptor, kAcceptor);
+      if (tr.ilabel == kEps && tr.olabel == kEps) flip(kEpsilons, kNoEpsilons);
+      if (tr.ilabel == kEps) flip(kIEpsilons, kNoIEpsilons);
+      if (tr.olabel == kEps) flip(kOEpsilons, kNoOEpsilons);
+      if (e > lo) {
+        if (tr.ilabel < arcs[e - 1].ilabel) flip(kNotILabelSorted, kILabelSorted);
+        if (tr.olabel < arcs[e - 1].olabel) flip(kNotOLabelSorted, kOLabelSorted);
+      }
+      if (!w_is_one(tr.weight) && !w_is_zero(tr.weight)) {
+        flip(kWeighted, kUnweighted);
+        if ((out & kUnweightedCycles) && scc[s] == scc[tr.nextstate]) flip(kWeightedCycles, kUnweightedCycles);
+      }
+      if (tr.nextstate <= s) flip(kNotTopSorted, kTopSorted);
+      if (tr.nextstate != s + 1) flip(kNotString, kString);
+    }
+    std::sort(il.begin(), il.end()); std::sort(ol.begin(), ol.end());
+    if (std::adjacent_find(il.begin(), il.end()) != il.end()) flip(kNotIDeterministic, kIDeterministic);
+    if (std::adjacent_find(ol.begin(), ol.end()) != ol.end()) flip(kNotODeterministic, kODeterministic);
+    if (nfinal > 0) flip(kNotString, kString);
+    const bool inf_final = std::binary_search(c.inf_finals.begin(), c.inf_finals.end(), (StateId)s);
+    if (c.finals[s] != w_zero() || inf_final) {
+      if (!w_is_one(c.finals[s])) flip(kWeighted, kUnweighted);
+      nfinal++;
+    } else if (hi - lo != 1) {
+      flip(kNotString, kString);
+    }
+  }
+  if (c.has_start && c.start != 0) flip(kNotString, kString);
+  return out;
+}
+
 class HostFst {
  public:
   HostFst() = default;
@@ -173,6 +314,15 @@ class HostFst {
       if (ilabel) std::stable_sort(b, e, by_i); else std::stable_sort(b, e, by_o);
     }
     props_ = props::after_tr_sort(props_, ilabel) & props::kTrinary;
+  }
+
+  // compute_and_update_properties_all (fst_traits/mutable_fst.rs:435-446): the stored word is returned untouched when
+  // every property is already known (use_stored = true), otherwise everything is recomputed.
+  uint64_t compute_and_update_properties_all() {
+    const CsrFst& c = freeze();
+    std::lock_guard<std::mutex> g(mu_);
+    if ((props::known(props_) & props::kAll) != props::kAll) props_ = compute_properties_all(c) & props::kTrinary;
+    return props_;
   }
 
   // ---- CSR access for the device path. freeze() makes CSR the live representation.

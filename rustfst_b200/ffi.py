@@ -145,6 +145,8 @@ _sig("const_fst_write_file", _P, C.c_char_p)
 _sig("const_fst_equals", _P, _P, C.POINTER(C.c_size_t))
 _sig("const_fst_copy", _P, _PP)
 _sig("const_fst_display", _P, C.POINTER(C.c_char_p))
+_sig("const_fst_from_vec_fst", _P, _PP)
+_sig("b200_fst_compute_properties", _P, C.POINTER(C.c_uint64))
 _sig("b200_fst_num_trs_total", _P, C.POINTER(C.c_uint64))
 _sig("b200_fst_to_csr", _P, _P, _P, _P, C.POINTER(C.c_int64))
 _sig("b200_compose_with_stats", _P, _P, _P, _PP, C.POINTER(ComposeStats))

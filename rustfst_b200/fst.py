@@ -199,6 +199,12 @@ class VectorFst:
     def properties(self, p: int):
         check_ffi_error(lib.b200_fst_set_properties(self.ptr, p), "Error setting properties")
 
+    def compute_properties(self) -> int:
+        """compute_and_update_properties_all: fills in every unknown property bit from the content (b200 addition)."""
+        p = C.c_uint64()
+        check_ffi_error(lib.b200_fst_compute_properties(self.ptr, C.byref(p)), "Error computing properties")
+        return p.value
+
     # ---- algorithms (rustfst-python/rustfst/fst/vector_fst.py:419-436, 621-638, tr_sort, connect)
     def compose(self, other: "VectorFst", config=None) -> "VectorFst":
         from .algorithms import compose, compose_with_config
@@ -292,8 +298,8 @@ class VectorFst:
 
 class ConstFst:
     """rustfst-python/rustfst/fst/const_fst.py:16-175 — immutable FST in the OpenFst "const" layout (read / write /
-    compare / copy / print; the generic read accessors of `Fst`).  Algorithms take VectorFst handles, as in the
-    reference; `from_vector_fst` and `draw` are not part of this build."""
+    compare / copy / print / from_vector_fst; the generic read accessors of `Fst`).  Algorithms take VectorFst handles,
+    as in the reference; `draw` is not part of this build."""
 
     def __init__(self, ptr):
         self.ptr = ptr
@@ -320,6 +326,12 @@ class ConstFst:
 
     def __eq__(self, other):
         return isinstance(other, ConstFst) and self.equals(other)
+
+    @classmethod
+    def from_vector_fst(cls, fst: "VectorFst") -> "ConstFst":  # const_fst.py:109-125
+        p = C.c_void_p()
+        check_ffi_error(lib.const_fst_from_vec_fst(fst.ptr, C.byref(p)), "Error converting VectorFst to ConstFst")
+        return cls(p)
 
     def copy(self) -> "ConstFst":  # const_fst.py:156-166
         p = C.c_void_p()

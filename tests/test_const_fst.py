@@ -99,3 +99,72 @@ def test_handle_kinds_are_not_interchangeable():
                  lambda: lib.fst_tr_sort(c.ptr, True)):
         with pytest.raises(ValueError, match="Could not downcast to vector FST"):
             R.check_ffi_error(call(), "algorithm on a const handle")
+
+
+def _props_both(d):
+    """Property word computed by the product from the content (all bits unknown beforehand) and by the oracle."""
+    p = R.VectorFst.from_csr(d["offsets"], d["arcs"], d["finals"], d["start"], 0)
+    o = O.OFst.from_csr(d["offsets"].astype(np.uint64), d["arcs"], d["finals"], d["start"], 0)
+    o.compute_props()
+    return p.compute_properties(), o.props
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_compute_properties_matches_the_oracle_on_random_machines(seed):
+    """b200_fst_compute_properties = compute_and_update_properties_all (compute_fst_properties.rs:14-208): cyclic /
+    acyclic machines, epsilons, acceptors, unreachable and dead states, weighted cycles."""
+    from tests.parity_utils import random_fst
+    rng = np.random.default_rng(9000 + seed)
+    d = random_fst(rng, int(rng.integers(1, 30)), int(rng.integers(1, 5)), int(rng.integers(1, 6)), eps_prob=0.2,
+                   acceptor=(seed % 3 == 0), sort=[None, "ilabel", "olabel"][seed % 3], cyclic=(seed % 2 == 0),
+                   weight_grid=True, final_prob=0.3)
+    got, want = _props_both(d)
+    assert got == want, f"{got:#x} != {want:#x}"
+
+
+def test_compute_properties_on_fixtures_and_degenerate_machines():
+    from tests.parity_utils import FIXTURES
+    for name in FIXTURES:
+        for which in ("raw", "compose"):
+            v = R.VectorFst.read(golden_path(name, which))
+            off, arcs, fin, start = v.to_csr()
+            got, want = _props_both({"offsets": off, "arcs": arcs, "finals": fin, "start": start})
+            assert got == want, f"{name}/{which}: {got:#x} != {want:#x}"
+            assert got == v.properties, "the fixture files carry fully computed words"
+    # no start state (the DFS group keeps the visitor's initial word), empty machine, a string, a self loop on the start
+    from rustfst_b200.fst import TR_DTYPE
+    one = np.zeros(1, dtype=TR_DTYPE); one[0] = (1, 1, 2.5, 0)
+    cases = [
+        {"offsets": np.array([0, 1], np.uint32), "arcs": one, "finals": np.array([np.inf], np.float32), "start": None},
+        {"offsets": np.array([0], np.uint32), "arcs": np.zeros(0, TR_DTYPE), "finals": np.zeros(0, np.float32), "start": None},
+        {"offsets": np.array([0, 1], np.uint32), "arcs": one, "finals": np.array([0.0], np.float32), "start": 0},
+    ]
+    chain = np.zeros(2, dtype=TR_DTYPE); chain[0] = (1, 1, 0.0, 1); chain[1] = (2, 2, 0.0, 2)
+    cases.append({"offsets": np.array([0, 1, 2, 2], np.uint32), "arcs": chain,
+                  "finals": np.array([np.inf, np.inf, 0.0], np.float32), "start": 0})
+    for d in cases:
+        got, want = _props_both(d)
+        assert got == want, f"{got:#x} != {want:#x}"
+
+
+def test_const_from_vector_fst_freezes_all_properties(tmp_path):
+    """const_fst_from_vec_fst (const_fst.rs:157-170, converters.rs:7-37): a copy with every property computed; the
+    source handle keeps its own word."""
+    v = R.VectorFst()
+    s0, s1 = v.add_state(), v.add_state()
+    v.set_start(s0)
+    v.set_final(s1, 1.5)
+    v.add_tr(s0, R.Tr(2, 2, 0.5, s1))
+    v.add_tr(s0, R.Tr(1, 1, 0.25, s1))
+    before = v.properties
+    c = R.ConstFst.from_vector_fst(v)
+    assert v.properties == before
+    o = O.OFst()
+    o.add_state(); o.add_state(); o.set_start(0); o.set_final(1, 1.5)
+    o.add_tr(0, 2, 2, 0.5, 1); o.add_tr(0, 1, 1, 0.25, 1)
+    o.compute_props()
+    assert c.properties == o.props
+    assert str(c) == str(v) and c.num_states() == 2
+    out = tmp_path / "c.fst"
+    c.write(out)
+    assert R.ConstFst.read(out) == c

@@ -107,6 +107,10 @@ RUSTFST_FFI_RESULT fst_connect(CFst* ptr);
 /* rustfst-ffi/src/algorithms/reverse.rs:14-29 (rustfst/src/algorithms/reverse.rs:33-87): new FST with a superinitial
  * state 0; built on the device (one stable radix sort + gather), the same kernel that feeds the n-best search. */
 RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr);
+/* rustfst-ffi/src/algorithms/top_sort.rs:13-21 (rustfst/src/algorithms/top_sort.rs:75-95): in place; host side (the
+ * numbering is the finish order of the reference's sequential DFS).  A composed lattice that is top-sorted once takes
+ * the StateOrderQueue route of fst_shortest_path afterwards (no DFS per call). */
+RUSTFST_FFI_RESULT fst_top_sort(CFst* ptr);
 /* rustfst-ffi/src/algorithms/tr_sort.rs:14-30 (in place; host, stable) */
 RUSTFST_FFI_RESULT fst_tr_sort(CFst* ptr, bool ilabel_comp);
 

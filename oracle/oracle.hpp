@@ -993,6 +993,41 @@ struct TopOrderVisitor : Visitor {
   }
 };
 
+// algorithms/state_sort.rs:16-78.  The reference permutes in place along the cycles of `order` (old state s becomes
+// state order[s], arcs keep their order, nextstates are mapped) and finally overwrites the property word with the
+// stored word restricted to statesort_properties() (properties.rs:319-349), so the mutations in between leave no trace.
+inline void state_sort(Fst& fst, const std::vector<StateId>& order) {
+  if (order.size() != fst.num_states())
+    throw std::runtime_error("StateSort : Bad order vector size : " + std::to_string(order.size()) + ". Expected " +
+                             std::to_string(fst.num_states()));
+  if (!fst.has_start) return;
+  const uint64_t statesort_mask = P::ALL & ~(P::TOP_SORTED | P::NOT_TOP_SORTED | P::STRING | P::NOT_STRING);
+  const uint64_t props = fst.props & statesort_mask;
+  std::vector<State> ns(fst.states.size());
+  for (size_t s = 0; s < fst.states.size(); s++) {
+    State st = fst.states[s];
+    for (Tr& tr : st.trs) tr.nextstate = order[tr.nextstate];
+    ns[order[s]] = std::move(st);
+  }
+  fst.states.swap(ns);
+  fst.start = order[fst.start];
+  fst.set_properties_with_mask(props, P::ALL);
+}
+
+// algorithms/top_sort.rs:75-95
+inline void top_sort(Fst& fst) {
+  TopOrderVisitor v;
+  dfs_visit(fst, v, false);
+  if (v.acyclic) {
+    state_sort(fst, v.order);
+    const uint64_t p = P::ACYCLIC | P::INITIAL_ACYCLIC | P::TOP_SORTED;
+    fst.set_properties_with_mask(p, p);
+  } else {
+    const uint64_t p = P::CYCLIC | P::NOT_TOP_SORTED;
+    fst.set_properties_with_mask(p, p);
+  }
+}
+
 enum QueueKind { QK_STATE_ORDER, QK_TOP_ORDER, QK_LIFO, QK_SCC };
 
 // queues/auto_queue.rs:23-99 (distance = None => less = None) and :101-157 scc_queue_type

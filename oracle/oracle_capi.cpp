@@ -26,6 +26,7 @@ int oracle_fst_add_tr(void* f, uint32_t s, uint32_t il, uint32_t ol, float w, ui
 }
 int oracle_fst_tr_sort(void* f, int ilabel) { GUARD(tr_sort(*(Fst*)f, ilabel != 0)); }
 int oracle_fst_connect(void* f) { GUARD(connect(*(Fst*)f)); }
+int oracle_fst_top_sort(void* f) { GUARD(top_sort(*(Fst*)f)); }
 int oracle_fst_reverse(void* f, void** out) { GUARD(*out = new Fst(reverse(*(Fst*)f))); }
 int oracle_fst_compute_props(void* f) { GUARD(((Fst*)f)->props = compute_fst_properties_all(*(Fst*)f)); }
 uint64_t oracle_fst_props(void* f) { return ((Fst*)f)->props; }

@@ -93,6 +93,8 @@ struct QueuePlan {
   double host_ms = 0;               // time spent on the host DFS
 };
 QueuePlan build_queue_plan(const CsrFst& fst);
+// Topological order of an acyclic machine as the reference's TopOrderVisitor numbers it (false = cyclic).
+bool top_order(const CsrFst& fst, std::vector<uint32_t>& order);
 
 struct SsspStats {
   uint64_t arcs_relaxed = 0;   // E

@@ -284,6 +284,18 @@ RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr) {
     *res_ptr = new CFst{HostFst(reverse_fst_device(d, st.s))};
   });
 }
+RUSTFST_FFI_RESULT fst_top_sort(CFst* ptr) {
+  return wrap([&] {  // top_sort.rs:75-95: the DFS is the reference's sequential one, the renumbering one pass over the CSR
+    HostFst& f = vec_alg(ptr, "fst")->fst;
+    std::vector<uint32_t> order;
+    if (top_order(f.freeze(), order)) {
+      f.state_sort(order);
+      f.or_properties(props::kAcyclic | props::kInitialAcyclic | props::kTopSorted);
+    } else {
+      f.or_properties(props::kCyclic | props::kNotTopSorted);
+    }
+  });
+}
 RUSTFST_FFI_RESULT fst_tr_sort(CFst* ptr, bool ilabel_comp) {
   return wrap([&] {
     vec_alg(ptr, "fst");

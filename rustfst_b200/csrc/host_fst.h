@@ -316,6 +316,43 @@ class HostFst {
     props_ = props::after_tr_sort(props_, ilabel) & props::kTrinary;
   }
 
+  // state_sort (algorithms/state_sort.rs:16-78): old state s becomes state order[s]; arcs keep their order, next states
+  // are mapped; the property word keeps only statesort_properties() (properties.rs:319-349).
+  void state_sort(const std::vector<uint32_t>& order) {
+    const CsrFst& c = freeze();
+    std::lock_guard<std::mutex> g(mu_);
+    const size_t n = c.num_states();
+    if (order.size() != n)
+      throw FstError("StateSort : Bad order vector size : " + std::to_string(order.size()) + ". Expected " +
+                     std::to_string(n));
+    if (!has_start_) return;
+    CsrFst o;
+    o.offsets.resize(n + 1);
+    o.finals.resize(n);
+    o.arcs.resize(c.arcs.size());
+    std::vector<uint32_t> inv(n);
+    for (size_t s = 0; s < n; s++) inv[order[s]] = (uint32_t)s;
+    size_t w = 0;
+    for (size_t t = 0; t < n; t++) {
+      const uint32_t s = inv[t];
+      o.offsets[t] = (uint32_t)w;
+      o.finals[t] = c.finals[s];
+      for (uint32_t e = c.offsets[s]; e < c.offsets[s + 1]; e++) {
+        Tr tr = c.arcs[e];
+        tr.nextstate = order[tr.nextstate];
+        o.arcs[w++] = tr;
+      }
+    }
+    o.offsets[n] = (uint32_t)w;
+    for (StateId s : c.inf_finals) o.inf_finals.push_back(order[s]);
+    std::sort(o.inf_finals.begin(), o.inf_finals.end());
+    start_ = order[start_];
+    props_ &= props::kTrinary & ~(props::kTopPair | props::kStringPair);
+    o.has_start = true; o.start = start_; o.props = props_;
+    csr_ = std::move(o);
+  }
+  void or_properties(uint64_t bits) { std::lock_guard<std::mutex> g(mu_); props_ |= bits & props::kTrinary; }
+
   // compute_and_update_properties_all (fst_traits/mutable_fst.rs:435-446): the stored word is returned untouched when
   // every property is already known (use_stored = true), otherwise everything is recomputed.
   uint64_t compute_and_update_properties_all() {

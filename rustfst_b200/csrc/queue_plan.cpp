@@ -144,6 +144,16 @@ DfsResult dfs_top_order(const CsrFst& f) {
 
 }  // namespace
 
+// TopOrderVisitor of top_sort.rs:12-61 for fst_top_sort: false when a back arc is met, otherwise order[state] = position
+// of the state in reverse DFS finish order.
+bool top_order(const CsrFst& f, std::vector<uint32_t>& order) {
+  DfsResult r = dfs_top_order(f);
+  if (!r.acyclic) return false;
+  order.assign(r.finish.size(), 0);
+  for (size_t i = 0; i < r.finish.size(); i++) order[r.finish[r.finish.size() - 1 - i]] = (uint32_t)i;
+  return true;
+}
+
 QueuePlan build_queue_plan(const CsrFst& f) {
   auto t0 = std::chrono::steady_clock::now();
   QueuePlan plan;

@@ -217,6 +217,10 @@ class VectorFst:
     def tr_sort(self, ilabel_cmp: bool = True):
         check_ffi_error(lib.fst_tr_sort(self.ptr, bool(ilabel_cmp)), "Error during tr_sort")
 
+    def top_sort(self) -> "VectorFst":  # vector_fst.py (top_sort) / algorithms/top_sort.py
+        check_ffi_error(lib.fst_top_sort(self.ptr), "Error during top_sort")
+        return self
+
     def reverse(self) -> "VectorFst":  # vector_fst.py:599 / algorithms/reverse.py:11-31
         out = C.c_void_p()
         check_ffi_error(lib.fst_reverse(self.ptr, C.byref(out)), "Error during reverse")

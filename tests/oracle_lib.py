@@ -33,6 +33,7 @@ def lib():
         L.oracle_fst_add_tr.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32]
         L.oracle_fst_tr_sort.argtypes = [C.c_void_p, C.c_int]
         L.oracle_fst_connect.argtypes = [C.c_void_p]
+        L.oracle_fst_top_sort.argtypes = [C.c_void_p]
         L.oracle_fst_reverse.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.oracle_fst_compute_props.argtypes = [C.c_void_p]
         L.oracle_fst_props.argtypes = [C.c_void_p]
@@ -102,6 +103,9 @@ class OFst:
 
     def connect(self):
         _check(lib().oracle_fst_connect(self.ptr))
+
+    def top_sort(self):
+        _check(lib().oracle_fst_top_sort(self.ptr))
 
     def reverse(self):
         out = C.c_void_p()

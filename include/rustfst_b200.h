@@ -111,6 +111,9 @@ RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr);
  * numbering is the finish order of the reference's sequential DFS).  A composed lattice that is top-sorted once takes
  * the StateOrderQueue route of fst_shortest_path afterwards (no DFS per call). */
 RUSTFST_FFI_RESULT fst_top_sort(CFst* ptr);
+/* rustfst-ffi/src/algorithms/isomorphic.rs:11-30 (rustfst/src/algorithms/isomorphic.rs:49-160): same machines up to
+ * state numbering and arc order (weights within KDELTA); host side. */
+RUSTFST_FFI_RESULT fst_isomorphic(const CFst* fst, const CFst* other_fst, size_t* is_isomorphic);
 /* rustfst-ffi/src/algorithms/tr_sort.rs:14-30 (in place; host, stable) */
 RUSTFST_FFI_RESULT fst_tr_sort(CFst* ptr, bool ilabel_comp);
 

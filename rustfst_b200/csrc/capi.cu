@@ -284,6 +284,11 @@ RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr) {
     *res_ptr = new CFst{HostFst(reverse_fst_device(d, st.s))};
   });
 }
+RUSTFST_FFI_RESULT fst_isomorphic(const CFst* fst, const CFst* other_fst, size_t* is_isomorphic) {
+  return wrap([&] {
+    *is_isomorphic = isomorphic(vec_alg(fst, "fst")->fst.freeze(), vec_alg(other_fst, "other_fst")->fst.freeze()) ? 1 : 0;
+  });
+}
 RUSTFST_FFI_RESULT fst_top_sort(CFst* ptr) {
   return wrap([&] {  // top_sort.rs:75-95: the DFS is the reference's sequential one, the renumbering one pass over the CSR
     HostFst& f = vec_alg(ptr, "fst")->fst;

@@ -12,6 +12,7 @@
 #pragma once
 #include <algorithm>
 #include <charconv>
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <mutex>
@@ -205,6 +206,72 @@ inline uint64_t compute_properties_all(const CsrFst& c) {
   }
   if (c.has_start && c.start != 0) flip(kNotString, kString);
   return out;
+}
+
+// isomorphic (rustfst/src/algorithms/isomorphic.rs:49-160, delta = KDELTA): breadth-first pairing of states from the
+// two start states; the arcs of a pair are compared after sorting by (ilabel, olabel, weight, nextstate).  Kept verbatim,
+// including the one-permutation limitation (an error, not `false`, when a mismatch follows arcs that are equal as an
+// unweighted automaton).  Used as the result verifier SURVEY.md §8f names.
+inline bool isomorphic(const CsrFst& a, const CsrFst& b, float delta = kDelta) {
+  if (!a.has_start && !b.has_start) return true;
+  if (!a.has_start || !b.has_start) return false;
+  auto approx = [delta](float x, float y) { return std::fabs(x - y) <= delta; };  // TropicalWeight::approx_equal
+  auto final_of = [](const CsrFst& f, StateId s, float* w) {
+    if (f.finals[s] != w_zero()) { *w = f.finals[s]; return true; }
+    if (std::binary_search(f.inf_finals.begin(), f.inf_finals.end(), s)) { *w = w_zero(); return true; }
+    return false;
+  };
+  auto less = [](const Tr& x, const Tr& y) {
+    if (x.ilabel != y.ilabel) return x.ilabel < y.ilabel;
+    if (x.olabel != y.olabel) return x.olabel < y.olabel;
+    if (x.weight < y.weight) return true;
+    if (x.weight > y.weight) return false;
+    return x.nextstate < y.nextstate;
+  };
+  std::vector<int64_t> pair(a.num_states(), -1);
+  std::vector<std::pair<StateId, StateId>> queue;
+  size_t head = 0;
+  bool non_det = false;
+  auto pair_state = [&](StateId s1, StateId s2) {
+    if (pair[s1] == (int64_t)s2) return true;
+    if (pair[s1] >= 0) return false;
+    pair[s1] = s2;
+    queue.emplace_back(s1, s2);
+    return true;
+  };
+  pair_state(a.start, b.start);
+  std::vector<Tr> t1, t2;
+  while (head < queue.size()) {
+    const auto [s1, s2] = queue[head++];
+    bool ok = true;
+    float w1 = 0, w2 = 0;
+    const bool f1 = final_of(a, s1, &w1), f2 = final_of(b, s2, &w2);
+    if (f1 != f2 || (f1 && !approx(w1, w2))) ok = false;
+    if (ok && a.offsets[s1 + 1] - a.offsets[s1] != b.offsets[s2 + 1] - b.offsets[s2]) ok = false;
+    if (ok) {
+      t1.assign(a.arcs.begin() + a.offsets[s1], a.arcs.begin() + a.offsets[s1 + 1]);
+      t2.assign(b.arcs.begin() + b.offsets[s2], b.arcs.begin() + b.offsets[s2 + 1]);
+      std::stable_sort(t1.begin(), t1.end(), less);
+      std::stable_sort(t2.begin(), t2.end(), less);
+      for (size_t i = 0; i < t1.size() && ok; i++) {
+        if (t1[i].ilabel != t2[i].ilabel || t1[i].olabel != t2[i].olabel || !approx(t1[i].weight, t2[i].weight) ||
+            !pair_state(t1[i].nextstate, t2[i].nextstate)) {
+          ok = false;
+          break;
+        }
+        if (i > 0 && t1[i].ilabel == t1[i - 1].ilabel && t1[i].olabel == t1[i - 1].olabel &&
+            approx(t1[i].weight, t1[i - 1].weight))
+          non_det = true;
+      }
+    }
+    if (!ok) {
+      if (non_det)
+        throw FstError("Isomorphic: Non-determinism as an unweighted automaton. state1 = " + std::to_string(s1) +
+                       " state2 = " + std::to_string(s2));
+      return false;
+    }
+  }
+  return true;
 }
 
 class HostFst {

@@ -76,6 +76,7 @@ _sig("b200_shortest_path_config_destroy", _P)
 _sig("fst_connect", _P)
 _sig("fst_reverse", _P, _PP)
 _sig("fst_top_sort", _P)
+_sig("fst_isomorphic", _P, _P, C.POINTER(C.c_size_t))
 _sig("fst_tr_sort", _P, C.c_bool)
 _sig("fst_start", _P, C.POINTER(C.c_uint32))
 _sig("fst_final_weight", _P, C.c_uint32, C.POINTER(C.c_float))

@@ -217,6 +217,11 @@ class VectorFst:
     def tr_sort(self, ilabel_cmp: bool = True):
         check_ffi_error(lib.fst_tr_sort(self.ptr, bool(ilabel_cmp)), "Error during tr_sort")
 
+    def isomorphic(self, other: "VectorFst") -> bool:  # vector_fst.py:718-728
+        r = C.c_size_t()
+        check_ffi_error(lib.fst_isomorphic(self.ptr, other.ptr, C.byref(r)), "Error during isomorphic")
+        return bool(r.value)
+
     def top_sort(self) -> "VectorFst":  # vector_fst.py (top_sort) / algorithms/top_sort.py
         check_ffi_error(lib.fst_top_sort(self.ptr), "Error during top_sort")
         return self

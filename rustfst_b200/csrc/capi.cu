@@ -122,28 +122,6 @@ void fill(B200SsspStats* out, const SsspStats& st, int kind, float h2d) {
   out->ms_h2d = h2d; out->ms_queue_plan_host = st.plan_host_ms;
 }
 
-// Runs fn(begin, end) over [0, n) on a few host threads (the batched mode repacks thousands of small machines; the
-// copies are independent once the prefix offsets are known).
-template <class F>
-void parallel_ranges(size_t n, F fn) {
-  unsigned hw = std::thread::hardware_concurrency();
-  size_t nt = std::min<size_t>(hw ? hw : 1, 8);
-  if (n < 4096 || nt <= 1) { fn((size_t)0, n); return; }
-  std::vector<std::thread> th;
-  std::exception_ptr err;
-  std::mutex mu;
-  const size_t chunk = (n + nt - 1) / nt;
-  for (size_t t = 0; t < nt; t++) {
-    const size_t b = t * chunk, e = std::min(n, b + chunk);
-    if (b >= e) break;
-    th.emplace_back([&, b, e] {
-      try { fn(b, e); } catch (...) { std::lock_guard<std::mutex> g(mu); err = std::current_exception(); }
-    });
-  }
-  for (auto& t : th) t.join();
-  if (err) std::rethrow_exception(err);
-}
-
 CFst* compose_host(const CFst* a, const CFst* b, const CComposeConfig* cfg, B200ComposeStats* stats) {
   ComposeOptions opt = to_options(cfg);
   const CsrFst& ha = vec_alg(a, "fst_1")->fst.freeze();
@@ -367,7 +345,14 @@ RUSTFST_FFI_RESULT vec_fst_from_path(const CFst** ptr, const char* path) {
   });
 }
 RUSTFST_FFI_RESULT vec_fst_write_file(const CFst* f, const char* path) {
-  return wrap([&] { io::write_file(nn(path, "path"), io::store_vector_fst(vec_h(f, "fst")->fst.freeze())); });
+  return wrap([&] {
+    const CsrFst& c = vec_h(f, "fst")->fst.freeze();
+    const size_t size = io::vector_fst_bytes(c);
+    std::unique_ptr<uint8_t, decltype(&std::free)> buf((uint8_t*)std::malloc(size ? size : 1), &std::free);
+    if (!buf) throw std::bad_alloc();
+    io::store_vector_fst_into(c, buf.get());
+    io::write_file(nn(path, "path"), buf.get(), size);
+  });
 }
 RUSTFST_FFI_RESULT vec_fst_num_states(const CFst* f, size_t* n) {
   return wrap([&] { *n = vec_h(f, "fst")->fst.num_states(); });
@@ -383,10 +368,12 @@ RUSTFST_FFI_RESULT vec_fst_display(const CFst* f, const char** s) {
 }
 RUSTFST_FFI_RESULT vec_fst_to_bytes(const CFst* f, const CArrayU8** out) {
   return wrap([&] {
-    auto bytes = io::store_vector_fst(vec_h(f, "fst")->fst.freeze());
-    uint8_t* p = (uint8_t*)std::malloc(bytes.size() ? bytes.size() : 1);
-    std::memcpy(p, bytes.data(), bytes.size());
-    *out = new CArrayU8{p, bytes.size()};
+    const CsrFst& c = vec_h(f, "fst")->fst.freeze();
+    const size_t size = io::vector_fst_bytes(c);
+    uint8_t* p = (uint8_t*)std::malloc(size ? size : 1);
+    if (!p) throw std::bad_alloc();
+    io::store_vector_fst_into(c, p);
+    *out = new CArrayU8{p, size};
   });
 }
 RUSTFST_FFI_RESULT b200_bytes_destroy(CArrayU8* b) {

@@ -21,6 +21,7 @@
 #include <utility>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fst_types.h"
@@ -30,6 +31,28 @@ namespace b200 {
 struct FstError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
+
+// Runs fn(begin, end) over [0, n) on a few host threads (bulk copies of multi-hundred-megabyte machines: file parsing,
+// serialisation, the repacking of batched compositions).
+template <class F>
+void parallel_ranges(size_t n, F fn, size_t min_parallel = 4096) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = std::min<size_t>(hw ? hw : 1, 8);
+  if (n < min_parallel || nt <= 1) { fn((size_t)0, n); return; }
+  std::vector<std::thread> th;
+  std::exception_ptr err;
+  std::mutex mu;
+  const size_t chunk = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; t++) {
+    const size_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([&, b, e] {
+      try { fn(b, e); } catch (...) { std::lock_guard<std::mutex> g(mu); err = std::current_exception(); }
+    });
+  }
+  for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
+}
 
 // Large host arrays live in page-locked memory taken from a process-wide pool (device_common.cu) so that the three
 // CSR arrays move to and from HBM at PCIe/C2C line rate with plain cudaMemcpyAsync; on a box without a CUDA device the
@@ -614,40 +637,47 @@ inline CsrFst parse_vector_fst(const uint8_t* data, size_t len) {
   c.start = (StateId)start;
   c.offsets.resize((size_t)num_states + 1);
   c.finals.resize((size_t)num_states);
-  // One pass to size, one pass to copy: the arc records are already in the 16-byte device layout.
+  // One pass to size (sequential: every state record tells where the next one starts), one pass to copy (host
+  // threads): the arc records are already in the 16-byte device layout.
+  std::vector<uint64_t> rec_at((size_t)num_states);  // byte offset of every state record
   size_t total = 0;
   {
     Reader q = r;
     for (int64_t s = 0; s < num_states; s++) {
+      rec_at[s] = q.off;
       q.get<float>();
       int64_t na = q.get<int64_t>();
       if (na < 0 || q.off + (size_t)na * 16 > q.n) throw FstError("Error while parsing binary VectorFst. Error kind Eof");
+      c.offsets[s] = (uint32_t)total;
       q.off += (size_t)na * 16;
       total += (size_t)na;
+      if (total > 0xFFFFFFF0ull) throw FstError("FST has more than 2^32 transitions");
     }
   }
-  if (total > 0xFFFFFFF0ull) throw FstError("FST has more than 2^32 transitions");
+  c.offsets[num_states] = (uint32_t)total;
   c.arcs.resize(total);
-  size_t o = 0;
-  for (int64_t s = 0; s < num_states; s++) {
-    float fw = r.get<float>();
-    // parsers/bin_fst/utils_parsing.rs:17-26: None iff approx-equal to zero() (i.e. +inf)
-    c.finals[s] = w_approx_eq(fw, w_zero()) ? w_zero() : fw;
-    int64_t na = r.get<int64_t>();
-    c.offsets[s] = (uint32_t)o;
-    if (na) std::memcpy(c.arcs.data() + o, r.p + r.off, (size_t)na * 16);
-    r.off += (size_t)na * 16;
-    o += (size_t)na;
-  }
-  c.offsets[num_states] = (uint32_t)o;
+  const uint8_t* base = r.p;
+  parallel_ranges((size_t)num_states, [&](size_t lo, size_t hi) {
+    for (size_t s = lo; s < hi; s++) {
+      float fw;
+      std::memcpy(&fw, base + rec_at[s], 4);
+      // parsers/bin_fst/utils_parsing.rs:17-26: None iff approx-equal to zero() (i.e. +inf)
+      c.finals[s] = w_approx_eq(fw, w_zero()) ? w_zero() : fw;
+      const size_t na = c.offsets[s + 1] - c.offsets[s];
+      if (na) std::memcpy(c.arcs.data() + c.offsets[s], base + rec_at[s] + 12, na * 16);
+    }
+  }, 1 << 16);
   return c;
 }
 
-inline std::vector<uint8_t> store_vector_fst(const CsrFst& c) {
-  size_t n = c.num_states();
-  std::vector<uint8_t> buf;
-  buf.reserve(64 + n * 12 + c.arcs.size() * 16);
-  auto put = [&](const void* p, size_t k) { const uint8_t* b = (const uint8_t*)p; buf.insert(buf.end(), b, b + k); };
+constexpr size_t kVectorHeaderBytes = 4 + (4 + 6) + (4 + 8) + 4 + 4 + 8 + 8 + 8 + 8;
+inline size_t vector_fst_bytes(const CsrFst& c) { return kVectorHeaderBytes + c.num_states() * 12 + c.arcs.size() * 16; }
+// Serialises into caller-provided memory of vector_fst_bytes(c) bytes (no intermediate buffer, no zero fill).
+inline void store_vector_fst_into(const CsrFst& c, uint8_t* out) {
+  const size_t n = c.num_states();
+  // header: magic, "vector", "standard", version, flags, properties, start, #states, #arcs
+  uint8_t* w = out;
+  auto put = [&](const void* p, size_t k) { std::memcpy(w, p, k); w += k; };
   auto put_i32 = [&](int32_t v) { put(&v, 4); };
   auto put_i64 = [&](int64_t v) { put(&v, 8); };
   auto put_str = [&](const char* s) { int32_t l = (int32_t)std::strlen(s); put_i32(l); put(s, (size_t)l); };
@@ -660,12 +690,20 @@ inline std::vector<uint8_t> store_vector_fst(const CsrFst& c) {
   put_i64(c.has_start ? (int64_t)c.start : -1);
   put_i64((int64_t)n);
   put_i64((int64_t)c.arcs.size());
-  for (size_t s = 0; s < n; s++) {
-    put(&c.finals[s], 4);
-    uint32_t na = c.offsets[s + 1] - c.offsets[s];
-    put_i64((int64_t)na);
-    if (na) put(c.arcs.data() + c.offsets[s], (size_t)na * 16);
-  }
+  uint8_t* body = w;  // state s starts at body + 12 * s + 16 * offsets[s]
+  parallel_ranges(n, [&](size_t lo, size_t hi) {
+    for (size_t s = lo; s < hi; s++) {
+      uint8_t* q = body + 12 * s + 16 * (size_t)c.offsets[s];
+      const int64_t na = c.offsets[s + 1] - c.offsets[s];
+      std::memcpy(q, &c.finals[s], 4);
+      std::memcpy(q + 4, &na, 8);
+      if (na) std::memcpy(q + 12, c.arcs.data() + c.offsets[s], (size_t)na * 16);
+    }
+  }, 1 << 16);
+}
+inline std::vector<uint8_t> store_vector_fst(const CsrFst& c) {
+  std::vector<uint8_t> buf(vector_fst_bytes(c));
+  store_vector_fst_into(c, buf.data());
   return buf;
 }
 
@@ -762,9 +800,19 @@ inline std::vector<uint8_t> store_const_fst(const CsrFst& c) {
 }
 
 inline std::vector<uint8_t> read_file(const std::string& path) {
-  std::ifstream in(path, std::ios::binary);
+  std::ifstream in(path, std::ios::binary | std::ios::ate);
   if (!in) throw FstError("Error while opening file \"" + path + "\"");
-  return std::vector<uint8_t>((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  const std::streamsize size = in.tellg();
+  in.seekg(0, std::ios::beg);
+  std::vector<uint8_t> buf((size_t)(size > 0 ? size : 0));
+  if (size > 0 && !in.read(reinterpret_cast<char*>(buf.data()), size))
+    throw FstError("Error while reading file \"" + path + "\"");
+  return buf;
+}
+inline void write_file(const std::string& path, const uint8_t* data, size_t size) {
+  std::ofstream out(path, std::ios::binary);
+  if (!out) throw FstError("Error while creating file \"" + path + "\"");
+  out.write((const char*)data, (std::streamsize)size);
 }
 inline void write_file(const std::string& path, const std::vector<uint8_t>& b) {
   std::ofstream out(path, std::ios::binary);

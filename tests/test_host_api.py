@@ -198,3 +198,26 @@ def test_queue_plan_fuzz(seed):
         assert np.array_equal(po, oo)
     if ok == 3:
         assert np.array_equal(pf, of)
+
+
+def test_large_machine_io_round_trip_uses_the_threaded_copy_path(tmp_path):
+    """Above 65 536 states parse / store copy on several host threads; bytes must equal the oracle's serialisation and
+    the machine must survive file and in-memory round trips."""
+    import numpy as np
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    from tests import oracle_lib as O
+    g = synth.layered_acceptor(150_000, 900_000, 50, 11, 30)
+    v = synth.to_vector_fst(g)
+    o = O.OFst.from_csr(g["offsets"].astype(np.uint64), g["arcs"], g["finals"], g["start"], g["props"])
+    b = v.to_bytes()
+    assert b == o.to_bytes()
+    w = R.VectorFst.from_bytes(b)
+    assert w == v and w.properties == v.properties
+    path = tmp_path / "big.fst"
+    v.write(path)
+    assert path.read_bytes() == b
+    r = R.VectorFst.read(path)
+    ro, ra, rf, rs = r.to_csr()
+    assert np.array_equal(ro, g["offsets"]) and ra.tobytes() == g["arcs"].tobytes() and rf.tobytes() == g["finals"].tobytes()
+    assert rs == g["start"]

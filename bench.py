@@ -110,20 +110,49 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "source": self.source, "window": "compose warm-up + timed region"}
 
 
-def gen_compose_workload(name, scale, rank):
-    from rustfst_b200 import synth
+def load_synth():
+    """rustfst_b200/synth.py loaded by file path: the generators are numpy-only, and the reference arm must not map the
+    product library into its process (importing the package would dlopen it)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("b200_synth", os.path.join(ROOT, "rustfst_b200", "synth.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def gen_compose_workload(name, scale, rank, synth=None):
+    """Operands of the compose leg.  Every replica composes machines of the SAME shape (generator seeds 3 / 4: the same
+    states, labels and targets, hence the same product size on every rank, so per-GPU work is fixed as N grows); the
+    arc and final weights are re-drawn per rank, so the data differ.  (Round 1 seeded the whole generator per rank; the
+    start states of ranks 1, 3 and 6 then shared no label and those replicas composed an empty product.)"""
+    synth = synth or load_synth()
     if name == "C2":
         n, a, lv, v, ov = int(100_000 * scale), int(1_000_000 * scale), 25, 32, 2000
     else:
         n, a, lv, v, ov = int(1_000_000 * scale), int(10_000_000 * scale), 50, 32, 20000
-    a1 = synth.layered_acceptor(n, a, v, 3 + 100 * rank, lv)
-    a2 = synth.bigram_transducer(n, a, v, 4 + 100 * rank, lv, out_vocab=ov)
+    a1 = synth.layered_acceptor(n, a, v, 3, lv)
+    a2 = synth.bigram_transducer(n, a, v, 4, lv, out_vocab=ov)
+    if rank:
+        rng = np.random.default_rng(1000 + rank)
+        for d in (a1, a2):
+            d["arcs"]["weight"] = rng.integers(0, 640, size=len(d["arcs"])).astype(np.float32) / np.float32(64.0)
+            fin = np.isfinite(d["finals"])
+            d["finals"][fin] = rng.integers(0, 640, size=int(fin.sum())).astype(np.float32) / np.float32(64.0)
     return a1, a2
 
 
-def gen_sssp_workload(scale, rank):
-    from rustfst_b200 import synth
+def gen_sssp_workload(scale, rank, synth=None):
+    synth = synth or load_synth()
     return synth.layered_acceptor(int(5_000_000 * scale), int(50_000_000 * scale), 1000, 6 + 100 * rank, 50)
+
+
+def compose_config(workload, scale, world, a1, a2):
+    """`config` of the JSON line — identical for the b200 arm and the reference arm (the driver compares them)."""
+    return {"workload": f"{workload}: layered acyclic acceptor ({a1['num_states']} states, {len(a1['arcs'])} arcs, "
+                        f"olabel-sorted) o bigram-structured transducer ({a2['num_states']} states, "
+                        f"{len(a2['arcs'])} arcs, ilabel-sorted), TropicalWeight, AutoFilter, connect=true",
+            "scale": scale, "replicas": world, "parallelism": f"replicas x{world} (no data-path collective)",
+            "l2": "operands + table + output (>= 0.8 GB) exceed the 126 MB L2; no flush needed"}
 
 
 def csr_bytes(d):
@@ -131,21 +160,19 @@ def csr_bytes(d):
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle port of rustfst's compose on the host cores (1 thread: the reference is single-threaded)."""
+    """CPU arm: the oracle port of rustfst's compose on the host cores (1 thread: the reference is single-threaded),
+    on the SAME full-size operands as the b200 arm (rank 0's), every warm-up and every step a full compose + connect
+    (about 10 s each).  Nothing of the product is imported: the generators are loaded by path, the oracle through
+    tests/oracle_lib.py."""
     if rank != 0:
         return
     from tests import oracle_lib as O
-    # One full C3 compose costs ~9 s on one core.  Time the FULL workload whenever steps + warm-up fit in a few
-    # minutes (CPU throughput drops with size, so a smaller sample would flatter the CPU); otherwise a 1/4-scale
-    # instance of the same generator.  The CPU needs no clock/cache warm-up beyond one pass.
-    warm = min(args.warmup, 1)
-    sample_scale = args.scale if (args.steps + warm) <= 12 else 0.25 * args.scale
     workload = "C3" if args.workload == "C5" else args.workload
-    a1, a2 = gen_compose_workload(workload, sample_scale, 0)
+    a1, a2 = gen_compose_workload(workload, args.scale, 0)
     oa = O.OFst.from_csr(a1["offsets"].astype(np.uint64), a1["arcs"], a1["finals"], a1["start"], a1["props"])
     ob = O.OFst.from_csr(a2["offsets"].astype(np.uint64), a2["arcs"], a2["finals"], a2["start"], a2["props"])
     arcs = 0
-    for _ in range(warm):
+    for _ in range(args.warmup):
         O.compose(oa, ob)
     t = 0.0
     for _ in range(args.steps):
@@ -153,14 +180,15 @@ def run_reference(args, rank, world):
         t += st["seconds"]
         arcs += st["arcs_emitted"]
     value = arcs / t
-    sample = (f"{workload} generator at scale {sample_scale} ({a1['num_states']} x {a2['num_states']} states, "
-              f"{len(a1['arcs'])} + {len(a2['arcs'])} arcs), full compose+connect per step, {warm} warm-up pass(es), "
-              "oracle port of rustfst's algorithm (C++ -O3), 1 thread: the reference is single-threaded")
+    sample = (f"the full {workload} workload ({a1['num_states']} x {a2['num_states']} states, {len(a1['arcs'])} + "
+              f"{len(a2['arcs'])} arcs), one complete compose+connect per step ({arcs // max(1, args.steps)} arcs emitted), "
+              f"{args.warmup} warm-up passes, oracle port of rustfst's algorithm (C++ -O3), 1 thread: the reference is "
+              "single-threaded")
     line = {
         "impl": "reference", "metric": "composed_arcs_per_sec", "value": value, "unit": "arcs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * t / max(1, args.steps),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{workload} compose on the host CPU", "sample": sample},
+        "config": compose_config(workload, args.scale, args.gpus, a1, a2),
         "cpu_baseline": {"value": value, "unit": "arcs/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "arcs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -305,7 +333,7 @@ def main():
         return
 
     # ------------------------------------------------------------------ compose leg
-    a1, a2 = gen_compose_workload(args.workload, args.scale, rank)
+    a1, a2 = gen_compose_workload(args.workload, args.scale, rank, synth)
     h1, h2 = synth.to_vector_fst(a1), synth.to_vector_fst(a2)
     d1, d2 = R.DeviceFst.upload(h1), R.DeviceFst.upload(h2)  # inputs resident in HBM before the timed region
     sampler = ClockSampler(local_rank)  # samples every 200 ms from the warm-up on: the timed region is ~50 ms
@@ -414,7 +442,7 @@ def main():
     # ------------------------------------------------------------------ SSSP leg (C4)
     sssp = None
     if not args.no_sssp:
-        g = gen_sssp_workload(args.scale, rank)
+        g = gen_sssp_workload(args.scale, rank, synth)
         hg = synth.to_vector_fst(g)
         dg = R.DeviceFst.upload(hg)
         for _ in range(args.warmup):
@@ -516,14 +544,10 @@ def main():
             "metric": "composed_arcs_per_sec", "value": value, "unit": "arcs/s", "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms_region / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: layered acyclic acceptor ({a1['num_states']} states, "
-                                   f"{len(a1['arcs'])} arcs, olabel-sorted) o bigram-structured transducer "
-                                   f"({a2['num_states']} states, {len(a2['arcs'])} arcs, ilabel-sorted), "
-                                   "TropicalWeight, AutoFilter, connect=true",
-                       "scale": args.scale, "replicas": world, "parallelism": f"replicas x{world} (no data-path collective)",
-                       "l2": "operands + table + output (>= 0.8 GB) exceed the 126 MB L2; no flush needed",
-                       "states_expanded_per_step": tot["states_expanded"] // steps,
-                       "arcs_emitted_per_step": tot["arcs_emitted"] // steps, "waves_per_step": tot["waves"] // steps},
+            "config": compose_config(args.workload, args.scale, world, a1, a2),
+            "workload_stats": {"states_expanded_per_step": tot["states_expanded"] // steps,
+                               "arcs_emitted_per_step": tot["arcs_emitted"] // steps,
+                               "waves_per_step": tot["waves"] // steps},
             "wall_ms_per_step": wall_ms / steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sssp": sssp,
             "gpu_launches": int(tot["kernel_launches"]), "clocks": clocks,

@@ -61,6 +61,16 @@ struct BatchStarts {
 bool compose_device_coop(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
                          cudaStream_t s, DevFst* out, const BatchStarts* batch = nullptr);
 
+// Back end 3 (default): the persistent warp-stream kernel of compose_ws.cu — one exchange and one grid barrier per BFS
+// wave.  Returns 0 on success, otherwise the overflow flags (compose_match.cuh) of the capacity that was too small;
+// `caps` carries the capacities of the attempt in and out (0 = derive from the operands).
+struct WsCaps { size_t states = 0, arcs = 0, items = 0, runs = 0, waves = 0; };
+int compose_device_ws(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats, cudaStream_t s,
+                      DevFst* out, const BatchStarts* batch = nullptr, WsCaps* caps = nullptr);
+// The persistent back ends with growth on overflow (false = not representable, use back end 1).
+bool compose_device_persistent(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
+                               cudaStream_t s, DevFst* out, const BatchStarts* batch = nullptr);
+
 // Trim: keep states that are accessible and coaccessible, order-preserving renumbering
 // (rustfst/src/algorithms/connect.rs:51-66, rustfst/src/fst_impls/vector_fst/mutable_fst.rs:132-189).
 // assume_accessible skips the forward pass (true for a freshly composed FST: every state was reached by the BFS).

@@ -1,7 +1,9 @@
 // capi.cu — the extern "C" surface declared in include/rustfst_b200.h.
 // Error convention and handle ownership follow rustfst-ffi/src/lib.rs:29-85 and rustfst-ffi/src/fst/mod.rs.
 #include <algorithm>
+#include <charconv>
 #include <chrono>
+#include <cmath>
 #include <thread>
 #include <mutex>
 #include <cstdio>
@@ -124,8 +126,8 @@ void fill(B200SsspStats* out, const SsspStats& st, int kind, float h2d) {
 
 CFst* compose_host(const CFst* a, const CFst* b, const CComposeConfig* cfg, B200ComposeStats* stats) {
   ComposeOptions opt = to_options(cfg);
-  const CsrFst& ha = vec_alg(a, "fst_1")->fst.freeze();
-  const CsrFst& hb = vec_alg(b, "fst_2")->fst.freeze();
+  const CsrFst& ha = vec_alg(a, "fst_1")->fst.checked();
+  const CsrFst& hb = vec_alg(b, "fst_2")->fst.checked();
   Stream st;
   double t0 = now_ms();
   DevFst da = upload(ha, st.s);
@@ -172,7 +174,7 @@ CFst* shortest_path_host(const CFst* in, const CShortestPathConfig* cfg, B200Sss
     return new CFst{};
   }
   check_sp_config(cfg);
-  const CsrFst& h = vec_alg(in, "fst")->fst.freeze();
+  const CsrFst& h = vec_alg(in, "fst")->fst.checked();
   QueuePlan plan = build_queue_plan(h);
   Stream st;
   double t0 = now_ms();
@@ -247,7 +249,7 @@ RUSTFST_FFI_RESULT b200_shortest_path_config_destroy(CShortestPathConfig* p) { r
 
 RUSTFST_FFI_RESULT fst_connect(CFst* ptr) {
   return wrap([&] {
-    const CsrFst& h = vec_alg(ptr, "fst")->fst.freeze();
+    const CsrFst& h = vec_alg(ptr, "fst")->fst.checked();
     Stream st;
     DevFst d = upload(h, st.s);
     DevFst r = connect_device(d, false, nullptr, st.s);
@@ -256,7 +258,7 @@ RUSTFST_FFI_RESULT fst_connect(CFst* ptr) {
 }
 RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr) {
   return wrap([&] {
-    const CsrFst& h = vec_alg(ptr, "fst")->fst.freeze();
+    const CsrFst& h = vec_alg(ptr, "fst")->fst.checked();
     Stream st;
     DevFst d = upload(h, st.s);
     *res_ptr = new CFst{HostFst(reverse_fst_device(d, st.s))};
@@ -264,14 +266,14 @@ RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr) {
 }
 RUSTFST_FFI_RESULT fst_isomorphic(const CFst* fst, const CFst* other_fst, size_t* is_isomorphic) {
   return wrap([&] {
-    *is_isomorphic = isomorphic(vec_alg(fst, "fst")->fst.freeze(), vec_alg(other_fst, "other_fst")->fst.freeze()) ? 1 : 0;
+    *is_isomorphic = isomorphic(vec_alg(fst, "fst")->fst.checked(), vec_alg(other_fst, "other_fst")->fst.checked()) ? 1 : 0;
   });
 }
 RUSTFST_FFI_RESULT fst_top_sort(CFst* ptr) {
   return wrap([&] {  // top_sort.rs:75-95: the DFS is the reference's sequential one, the renumbering one pass over the CSR
     HostFst& f = vec_alg(ptr, "fst")->fst;
     std::vector<uint32_t> order;
-    if (top_order(f.freeze(), order)) {
+    if (top_order(f.checked(), order)) {
       f.state_sort(order);
       f.or_properties(props::kAcyclic | props::kInitialAcyclic | props::kTopSorted);
     } else {
@@ -285,7 +287,7 @@ RUSTFST_FFI_RESULT fst_tr_sort(CFst* ptr, bool ilabel_comp) {
     // Large machines are sorted on the device (one radix sort + gather); small ones, and any machine on a box
     // without a GPU, by the host container (same stable order either way; tr_sort is not part of the hot path).
     int ndev = 0;
-    const CsrFst& h = ptr->fst.freeze();
+    const CsrFst& h = ptr->fst.checked();
     if (h.arcs.size() >= (1u << 16) && h.inf_finals.empty() && cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
       Stream st;
       DevFst d = upload(h, st.s);
@@ -456,13 +458,28 @@ RUSTFST_FFI_RESULT trs_vec_shallow_clone(const CTrs* trs, const CTrs** out) {
 RUSTFST_FFI_RESULT trs_vec_len(const CTrs* trs, size_t* n) { return wrap([&] { *n = nn(trs, "trs")->v->size(); }); }
 RUSTFST_FFI_RESULT trs_vec_display(const CTrs* trs, const char** out) {
   return wrap([&] {
+    // format!("{:?}", TrsVec<TropicalWeight>) (rustfst-ffi/src/trs.rs:100): the derived Debug of TrsVec(Arc<Vec<Tr>>),
+    // Tr, TropicalWeight { value: OrderedFloat<f32> } — floats in Rust's shortest round-trip form
+    auto fmt_f32 = [](float w) {
+      if (std::isinf(w)) return std::string(w > 0 ? "inf" : "-inf");
+      if (std::isnan(w)) return std::string("NaN");
+      char buf[64];
+      auto r = std::to_chars(buf, buf + sizeof(buf), w);  // shortest representation that round-trips
+      std::string t(buf, r.ptr);
+      if (t.find('e') != std::string::npos) {  // Rust's {:?} switches to exponent form at other thresholds; fixed is exact here
+        r = std::to_chars(buf, buf + sizeof(buf), w, std::chars_format::fixed);
+        t.assign(buf, r.ptr);
+      }
+      if (t.find('.') == std::string::npos) t += ".0";
+      return t;
+    };
     std::string s = "TrsVec([";
     bool first = true;
     for (const Tr& t : *nn(trs, "trs")->v) {
       if (!first) s += ", ";
       first = false;
       s += "Tr { ilabel: " + std::to_string(t.ilabel) + ", olabel: " + std::to_string(t.olabel) +
-           ", weight: TropicalWeight { value: " + std::to_string(t.weight) + " }, nextstate: " +
+           ", weight: TropicalWeight { value: OrderedFloat(" + fmt_f32(t.weight) + ") }, nextstate: " +
            std::to_string(t.nextstate) + " }";
     }
     s += "])";
@@ -541,6 +558,8 @@ RUSTFST_FFI_RESULT b200_fst_from_csr(uint64_t n, const uint32_t* offsets, const 
                                      int64_t start, uint64_t props_word, const CFst** out) {
   return wrap([&] {
     if (n >= 0x7FFFFFFFull) throw FstError("too many states");
+    for (uint64_t s = 0; s < n; s++)
+      if (offsets[s + 1] < offsets[s]) throw FstError("b200_fst_from_csr: offsets must be non-decreasing");
     CsrFst c;
     c.offsets.assign(offsets, offsets + n + 1);
     size_t a = c.offsets[n];
@@ -551,6 +570,7 @@ RUSTFST_FFI_RESULT b200_fst_from_csr(uint64_t n, const uint32_t* offsets, const 
     c.start = (StateId)start;
     if (c.has_start && (uint64_t)start >= n) throw FstError("The state " + std::to_string(start) + " doesn't exist");
     c.props = props_word & props::kTrinary;
+    validate_state_ids(c, "b200_fst_from_csr: a transition points to a state that does not exist");
     *out = new CFst{HostFst(std::move(c))};
   });
 }
@@ -578,7 +598,7 @@ RUSTFST_FFI_RESULT b200_fst_to_csr(const CFst* f, uint32_t* offsets, CTr* arcs, 
 
 RUSTFST_FFI_RESULT b200_device_fst_upload(const CFst* f, const B200DeviceFst** out) {
   return wrap([&] {
-    const CsrFst& h = nn(f, "fst")->fst.freeze();
+    const CsrFst& h = nn(f, "fst")->fst.checked();
     auto d = std::make_unique<B200DeviceFst>();
     d->d = upload(h, d->stream.s);
     *out = d.release();
@@ -616,7 +636,7 @@ RUSTFST_FFI_RESULT b200_device_compose(const B200DeviceFst* a, const B200DeviceF
 RUSTFST_FFI_RESULT b200_device_shortest_path(const B200DeviceFst* d, const CFst* plan_from, const CFst** out,
                                              B200SsspStats* stats, bool force_serial) {
   return wrap([&] {
-    QueuePlan plan = build_queue_plan(nn(plan_from, "plan_from")->fst.freeze());
+    QueuePlan plan = build_queue_plan(nn(plan_from, "plan_from")->fst.checked());
     SsspStats ss;
     CsrFst r = shortest_path_device(nn(d, "dfst")->d, plan, &ss, d->stream.s, force_serial);
     fill(stats, ss, (int)plan.kind, 0.0f);
@@ -633,7 +653,7 @@ RUSTFST_FFI_RESULT b200_device_shortest_path_with_config(const B200DeviceFst* d,
       return;
     }
     check_sp_config(cfg);
-    QueuePlan plan = build_queue_plan(nn(plan_from, "plan_from")->fst.freeze());
+    QueuePlan plan = build_queue_plan(nn(plan_from, "plan_from")->fst.checked());
     *out = new CFst{HostFst(shortest_path_dispatch(nn(d, "dfst")->d, plan, cfg, stats, 0.0f, d->stream.s, force_serial))};
   });
 }
@@ -641,7 +661,7 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
                                       const CComposeConfig* cfg, const CFst** results, B200ComposeStats* total) {
   return wrap([&] {
     ComposeOptions opt = to_options(cfg);
-    const CsrFst& ht = nn(transducer, "transducer")->fst.freeze();
+    const CsrFst& ht = nn(transducer, "transducer")->fst.checked();
     for (size_t i = 0; i < n; i++) results[i] = nullptr;
     B200ComposeStats acc;
     std::memset(&acc, 0, sizeof(acc));
@@ -657,7 +677,7 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
     uint64_t and_props = ~0ull, or_props = 0;
     size_t sum_states = 0, sum_arcs = 0;
     for (size_t i = 0; i < n; i++) {
-      hs[i] = &nn(acceptors[i], "acceptor")->fst.freeze();
+      hs[i] = &nn(acceptors[i], "acceptor")->fst.checked();
       if (!hs[i]->inf_finals.empty()) uniform = false;
       if (!hs[i]->has_start) uniform = false;
       and_props &= hs[i]->props; or_props |= hs[i]->props;
@@ -710,7 +730,7 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
       bs.d_starts1 = d_starts.p; bs.n = (uint32_t)n; bs.out_s1 = &d_s1; bs.out_start_map = &d_map;
       ComposeStats cs;
       DevFst dr(st.s);
-      if (compose_device_coop(du, dt, opt, &cs, st.s, &dr, &bs)) {
+      if (compose_device_persistent(du, dt, opt, &cs, st.s, &dr, &bs)) {
         t0 = now_ms();
         CsrFst r = download(dr, st.s);
         const size_t rn = r.num_states();
@@ -771,7 +791,7 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
     }
     if (!done) {  // heterogeneous batch or pre-sized buffers too small: one composition at a time
       for (size_t i = 0; i < n; i++) {
-        DevFst da = upload(nn(acceptors[i], "acceptor")->fst.freeze(), st.s);
+        DevFst da = upload(nn(acceptors[i], "acceptor")->fst.checked(), st.s);
         ComposeStats cs;
         DevFst dr = compose_device(da, dt, opt, &cs, st.s);
         results[i] = new CFst{HostFst(download(dr, st.s))};
@@ -787,7 +807,7 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
 RUSTFST_FFI_RESULT b200_shortest_path_queue_plan(const CFst* fst, int32_t* kind, uint32_t* order_or_scc,
                                                  uint8_t* scc_is_fifo, uint32_t* n_scc) {
   return wrap([&] {
-    QueuePlan plan = build_queue_plan(nn(fst, "fst")->fst.freeze());
+    QueuePlan plan = build_queue_plan(nn(fst, "fst")->fst.checked());
     if (kind) *kind = (int32_t)plan.kind;
     if (n_scc) *n_scc = (uint32_t)plan.scc_is_fifo.size();
     if (order_or_scc) {

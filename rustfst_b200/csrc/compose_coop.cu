@@ -28,7 +28,7 @@
 #include <utility>
 #include <vector>
 
-#include "compose_common.cuh"
+#include "compose_match.cuh"
 #include "coop_utils.cuh"
 
 namespace cg = cooperative_groups;
@@ -40,15 +40,6 @@ using namespace coop;
 
 constexpr uint32_t kTempFlag = 0x80000000u;   // slot.id holds (cta << 20 | local rank) between phases C and D
 constexpr uint32_t kLocalRankBits = 20;
-
-enum Overflow : uint32_t { kOvArcs = 1, kOvStates = 2, kOvTable = 4, kOvScratch = 8, kOvChunk = 16, kOvWaves = 32,
-                           kErrBothRequire = 0x100, kErrBadSigmaLabel = 0x200 };
-
-// Device view of one SigmaMatcher (sigma_matcher.rs): arcs labelled sigma_label on the matched side match any
-// (allowed) label that has no ordinary match at the state; the matched arc is relabelled.
-struct SigmaDev {
-  uint32_t enabled; uint32_t label; uint32_t rewrite_both; const uint32_t* allowed; uint32_t n_allowed;
-};
 
 struct CoopParams {
   FstView a, b;
@@ -83,22 +74,6 @@ struct CoopParams {
 };
 
 
-// does state [lo, hi) of the matched side carry an arc labelled sigma? (has_sigma, sigma_matcher.rs:33-45)
-template <bool kByOlabel>
-__device__ __forceinline__ bool dev_has_sigma(const SigmaDev& sg, const Tr* arcs, uint32_t lo, uint32_t hi) {
-  if (!sg.enabled || sg.label == kNoLabel) return false;
-  const uint32_t p = lower_bound_label<kByOlabel>(arcs, lo, hi, sg.label);
-  if (p >= hi) return false;
-  return (kByOlabel ? __ldg(&arcs[p].olabel) : __ldg(&arcs[p].ilabel)) == sg.label;
-}
-__device__ __forceinline__ bool dev_sigma_allowed(const SigmaDev& sg, Label l) {
-  if (!sg.n_allowed) return true;
-  uint32_t lo = 0, hi = sg.n_allowed;
-  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (__ldg(&sg.allowed[mid]) < l) lo = mid + 1; else hi = mid; }
-  return lo < sg.n_allowed && __ldg(&sg.allowed[lo]) == l;
-}
-
-constexpr uint32_t kSideBit = 0x80000000u;
 constexpr uint32_t kTile = kCoopThreads;
 constexpr uint32_t kWarps = kCoopThreads / 32;
 constexpr int kArcsPerThread = 4;  // rank / resolve phases: consecutive arcs per thread and round
@@ -121,78 +96,12 @@ constexpr int kEmitArcs = B200_EMIT_ARCS_PER_LANE;  // emit phase: arcs per lane
 #define PROF_USE(x) do { } while (0)
 #endif
 
-// Lower bound + equal run of `key` in the label-sorted slice [lo, hi) with as few DEPENDENT loads as possible: the
-// kernel is latency-bound, so a 4-ary narrowing (3 independent probes per round) is followed by one round that loads
-// a 16-arc window at once and counts "< key" and "== key" (sorted_matcher.rs:141-142,166-184: lower_bound_by, then
-// iterate while the label matches).  from_lo = the epsilon-loop search, which starts at lo instead of bisecting.
-// The matcher compares fst1 output labels with fst2 input labels only, so both are kept once more as dense 4-byte
-// arrays (lab1[i] = fst1 arc i .olabel, lab2[i] = fst2 arc i .ilabel; padded by kLabelPad entries): the label of an
-// iterated arc is a coalesced 4-byte load, and the 16-label window of a search is five aligned 128-bit loads instead
-// of sixteen strided ones.  Lanes matching on different sides run the same instruction stream (pointer select).
-constexpr uint32_t kLabelPad = 32;
 __global__ void k_extract_labels(const Tr* __restrict__ arcs, uint32_t n, uint32_t n_padded, int olabel,
                                  uint32_t* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = olabel ? __ldg(&arcs[i].olabel) : __ldg(&arcs[i].ilabel);
   else if (i < n_padded) out[i] = kNoLabel;
 }
-__device__ __forceinline__ uint32_t lower_bound_lab(const uint32_t* __restrict__ lab, uint32_t lo, uint32_t hi, Label key) {
-  while (lo < hi) {
-    const uint32_t mid = lo + ((hi - lo) >> 1);
-    if (__ldg(&lab[mid]) < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-__device__ __forceinline__ uint32_t run_end_lab(const uint32_t* __restrict__ lab, uint32_t pos, uint32_t hi, Label key) {
-  uint32_t p = pos;
-  const uint32_t lim = pos + 8 < hi ? pos + 8 : hi;
-  while (p < lim) { if (__ldg(&lab[p]) != key) return p; p++; }
-  if (p == hi) return p;
-  return lower_bound_lab(lab, p, hi, key + 1);  // key + 1 cannot overflow: kNoLabel is never searched for
-}
-// Lower bound + equal run of `key` in the sorted label slice [lo, hi) with as few DEPENDENT loads as possible
-// (sorted_matcher.rs:141-142,166-184: lower_bound_by, then iterate while the label matches): 4-ary narrowing (three
-// independent probes per round) down to 16 labels, then one round that fetches the window and counts "< key" and
-// "== key".  from_lo = the epsilon-loop search, which starts at lo instead of bisecting.
-__device__ __forceinline__ void match_range(const uint32_t* __restrict__ lab, uint32_t lo, uint32_t hi, Label key,
-                                            bool from_lo, uint32_t& pos, uint32_t& end) {
-  uint32_t l = lo, h = hi;
-  if (!from_lo) {
-    while (h - l > 16) {  // invariant: labels below l are < key, labels from h on are >= key
-      const uint32_t q = (h - l) >> 2, m1 = l + q, m2 = m1 + q, m3 = m2 + q;
-      const Label x1 = __ldg(&lab[m1]), x2 = __ldg(&lab[m2]), x3 = __ldg(&lab[m3]);
-      if (x1 >= key) h = m1;
-      else if (x2 >= key) { l = m1 + 1; h = m2; }
-      else if (x3 >= key) { l = m2 + 1; h = m3; }
-      else l = m3 + 1;
-    }
-  }
-  // window [l, l + 16) lies inside the five aligned quads starting at l & ~3 (reads past hi hit the padding)
-  const uint32_t l4 = l & ~3u;
-  const uint4* __restrict__ q4 = reinterpret_cast<const uint4*>(lab + l4);
-  const uint32_t w_end = min(hi, l + 16);
-  uint4 v[5];
-#pragma unroll
-  for (int k = 0; k < 5; k++) v[k] = __ldg(q4 + k);
-  // "< key" / "== key" collected as 20-bit masks (one compare + one predicated OR per label), cut to the valid window
-  // [l, w_end) once
-  uint32_t lt_m = 0, eq_m = 0;
-#pragma unroll
-  for (int k = 0; k < 5; k++) {
-    const uint32_t xs[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (xs[u] < key) lt_m |= 1u << (4 * k + u);
-      if (xs[u] == key) eq_m |= 1u << (4 * k + u);
-    }
-  }
-  const uint32_t vm = ((1u << (w_end - l4)) - 1u) & ~((1u << (l - l4)) - 1u);
-  const uint32_t n_lt = __popc(lt_m & vm), n_eq = __popc(eq_m & vm);
-  pos = l + n_lt;
-  end = pos + n_eq;
-  if (end == l + 16 && end < hi) end = run_end_lab(lab, end, hi, key);  // run leaves the window (rare)
-}
-
 // State table lookup-or-insert: linear probing, kW consecutive slots fetched per round.  Loaded non-empty keys are permanent (no deletions); loaded empties are confirmed by the CAS.  Returns the
 // id stored in the slot (kUnassigned for a tuple discovered in this wave) and the slot index in h.
 template <int kW>
@@ -748,12 +657,6 @@ __global__ void k_unpack_s1(const unsigned long long* __restrict__ tuples, uint3
   if (i < n) { uint32_t fs, s1, s2; unpack_key(tuples[i], fs, s1, s2); s1_out[i] = s1; }
   if (i < n_starts) start_map[i] = i;
 }
-void launch_unpack_s1(const unsigned long long* tuples, uint32_t n, uint32_t* s1_out, uint32_t n_starts,
-                      uint32_t* start_map, cudaStream_t s) {
-  uint32_t m = n > n_starts ? n : n_starts;
-  if (m) k_unpack_s1<<<blocks_for(m), kThreads, 0, s>>>(tuples, n, s1_out, n_starts, start_map);
-}
-
 static int grid_used = 1;
 float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
   CoopParams P = P0;
@@ -801,6 +704,18 @@ float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
 }
 
 }  // namespace
+
+namespace composeimpl {
+void launch_unpack_s1(const unsigned long long* tuples, uint32_t n, uint32_t* s1_out, uint32_t n_starts,
+                      uint32_t* start_map, cudaStream_t s) {
+  uint32_t m = n > n_starts ? n : n_starts;
+  if (m) k_unpack_s1<<<blocks_for(m), kThreads, 0, s>>>(tuples, n, s1_out, n_starts, start_map);
+}
+
+void launch_extract_labels(const Tr* arcs, uint32_t n, uint32_t n_padded, int olabel, uint32_t* out, cudaStream_t s) {
+  k_extract_labels<<<blocks_for(n_padded), kThreads, 0, s>>>(arcs, n, n_padded, olabel, out);
+}
+}  // namespace composeimpl
 
 bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOptions& opt, ComposeStats* stats,
                          cudaStream_t s, DevFst* result, const BatchStarts* batch) {
@@ -860,8 +775,8 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   }
   P.kind = kind; P.side = side;
   DevBuf<uint32_t> lab1(s, (size_t)fa.num_arcs + kLabelPad), lab2(s, (size_t)fb.num_arcs + kLabelPad);
-  k_extract_labels<<<blocks_for((size_t)fa.num_arcs + kLabelPad), kThreads, 0, s>>>(fa.arcs.p, fa.num_arcs, fa.num_arcs + kLabelPad, 1, lab1.p);
-  k_extract_labels<<<blocks_for((size_t)fb.num_arcs + kLabelPad), kThreads, 0, s>>>(fb.arcs.p, fb.num_arcs, fb.num_arcs + kLabelPad, 0, lab2.p);
+  launch_extract_labels(fa.arcs.p, fa.num_arcs, fa.num_arcs + kLabelPad, 1, lab1.p, s);
+  launch_extract_labels(fb.arcs.p, fb.num_arcs, fb.num_arcs + kLabelPad, 0, lab2.p, s);
   P.lab1 = lab1.p; P.lab2 = lab2.p; st.kernel_launches += 2;
   DevBuf<uint32_t> allowed1(s), allowed2(s);
   auto mk_sigma = [&](const SigmaSpec& sp, uint64_t fprops, DevBuf<uint32_t>& buf) {
@@ -1002,13 +917,38 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
   return true;
 }
 
+// Persistent back ends with growth: the warp-stream kernel (compose_ws.cu) is run with capacities derived from the
+// operands; whatever overflowed is doubled and the call repeated, so results larger than the first guess (including
+// sigma-matcher compositions, which only the persistent kernels implement) are still computed.  Returns false only
+// when the result cannot be represented by the kernel at all (the caller then uses the multi-kernel back end).
+bool compose_device_persistent(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
+                               cudaStream_t s, DevFst* out, const BatchStarts* batch) {
+  const char* impl = std::getenv("B200_COMPOSE_IMPL");
+  if (impl && std::string(impl) == "coop") return compose_device_coop(a, b, opt, stats, s, out, batch);
+  WsCaps caps;
+  for (int attempt = 0; attempt < 40; attempt++) {
+    const int rc = compose_device_ws(a, b, opt, stats, s, out, batch, &caps);
+    if (rc == 0) return true;
+    if (rc & kOvChunk) return false;  // one warp would emit >= 2^20 arcs in one wave
+    bool grown = false;
+    auto grow = [&](size_t& v, size_t limit) { if (v < limit) { v = std::min(limit, v * 2); grown = true; } };
+    if (rc & kOvArcs) grow(caps.arcs, 0xFFFFFFF0ull);
+    if (rc & (kOvStates | kOvTable)) grow(caps.states, 0x7FFFFFF0ull);
+    if (rc & kOvScratch) grow(caps.items, 0xFFFFFF00ull);
+    if (rc & kOvRuns) grow(caps.runs, 0xFFFFFFF0ull);
+    if (rc & kOvWaves) grow(caps.waves, 0x7FFFFFF0ull);
+    if (!grown) return false;
+  }
+  return false;
+}
+
 DevFst compose_device(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
                       cudaStream_t s) {
   const char* impl = std::getenv("B200_COMPOSE_IMPL");
   bool want_waves = impl && std::string(impl) == "waves";
   if (!want_waves) {
     DevFst out(s);
-    if (compose_device_coop(a, b, opt, stats, s, &out, nullptr)) return out;
+    if (compose_device_persistent(a, b, opt, stats, s, &out, nullptr)) return out;
   }
   return compose_device_waves(a, b, opt, stats, s);
 }

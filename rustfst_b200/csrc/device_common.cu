@@ -3,6 +3,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -84,11 +85,17 @@ CsrFst download(const DevFst& d, cudaStream_t s) {
 // ---- page-locked host pool ------------------------------------------------------------------------------------
 namespace {
 constexpr size_t kPinThreshold = 256 * 1024;          // smaller blocks: plain malloc
-constexpr size_t kPoolKeepBytes = 24ull << 30;        // cached free blocks above this are returned to the driver
+size_t pool_keep_bytes() {                             // cached free blocks above this are returned to the driver
+  static const size_t v = [] {
+    const char* e = std::getenv("B200_PINNED_POOL_MB");  // default 8 GiB; the C3 end-to-end path cycles ~1.4 GB
+    return e ? (size_t)std::strtoull(e, nullptr, 10) << 20 : (size_t)8 << 30;
+  }();
+  return v;
+}
 std::mutex g_pool_mu;
 std::map<size_t, std::vector<void*>> g_pool_free;     // size class -> cached blocks
 size_t g_pool_cached = 0;
-int g_pin_state = 0;                                  // 0 unknown, 1 pinned allocations work, -1 no device
+std::atomic<int> g_pin_state{0};                      // 0 unknown, 1 pinned allocations work, -1 no device
 size_t size_class(size_t b) { size_t c = kPinThreshold; while (c < b) c <<= 1; return c; }
 }  // namespace
 
@@ -133,7 +140,7 @@ void host_pool_free(void* p, size_t bytes) noexcept {
   auto& reg = g_pool_free[0];
   for (size_t i = 0; i < reg.size(); i++)
     if (reg[i] == p) { reg[i] = reg.back(); reg.pop_back(); std::free(p); return; }
-  if (g_pool_cached + cls > kPoolKeepBytes) { cudaFreeHost(p); return; }
+  if (g_pool_cached + cls > pool_keep_bytes()) { cudaFreeHost(p); return; }
   g_pool_free[cls].push_back(p);
   g_pool_cached += cls;
 }

@@ -11,6 +11,7 @@
 // representation that is frozen to CSR on first algorithmic use.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cmath>
 #include <cstring>
@@ -89,6 +90,22 @@ struct CsrFst {
   uint64_t props = props::kNull;
   size_t num_states() const { return finals.size(); }
 };
+
+// Every algorithm (host or device) indexes per-state arrays with `start` and with every arc's `nextstate`; a machine
+// that arrives from outside (file image, CSR ingest) is checked once, here, before anything walks it.
+inline void validate_state_ids(const CsrFst& c, const std::string& err) {
+  const size_t n = c.num_states();
+  if (c.has_start && (size_t)c.start >= n) throw FstError(err);
+  if (c.offsets.size() != n + 1 || c.offsets[n] != c.arcs.size()) throw FstError(err);
+  std::atomic<bool> bad{false};
+  const Tr* arcs = c.arcs.data();
+  parallel_ranges(c.arcs.size(), [&](size_t lo, size_t hi) {
+    uint32_t mx = 0;
+    for (size_t e = lo; e < hi; e++) mx = arcs[e].nextstate > mx ? arcs[e].nextstate : mx;
+    if (hi > lo && (size_t)mx >= n) bad = true;
+  }, 1 << 18);
+  if (bad) throw FstError(err);
+}
 
 // All trinary properties of a machine, recomputed from its content — the result of compute_fst_properties(fst,
 // all_properties(), .., use_stored = false) (rustfst/src/fst_properties/compute_fst_properties.rs:14-208).  The
@@ -306,7 +323,7 @@ class HostFst {
   HostFst(const HostFst& o) {
     std::lock_guard<std::mutex> g(o.mu_);
     b_ = o.b_; csr_ = o.csr_; is_builder_ = o.is_builder_;
-    has_start_ = o.has_start_; start_ = o.start_; props_ = o.props_;
+    has_start_ = o.has_start_; start_ = o.start_; props_ = o.props_; max_next_ = o.max_next_;
   }
 
   // ---- inspection (fst_impls/vector_fst/fst.rs:40-106)
@@ -377,6 +394,7 @@ class HostFst {
       if (!b_[s].trs.empty()) { prev_copy = b_[s].trs.back(); prev = &prev_copy; }
       b_[s].trs.push_back(tr);
     }
+    if (tr.nextstate > max_next_) max_next_ = tr.nextstate;
     props_ = props::on_add_tr(props_, s, tr, prev);
   }
   void set_tr(StateId s, size_t idx, const Tr& tr) {  // trs_iter_mut: properties of a set arc are unknown
@@ -385,6 +403,7 @@ class HostFst {
     to_builder_unlocked();
     if (idx >= b_[s].trs.size()) throw FstError("transition index out of range");
     b_[s].trs[idx] = tr;
+    if (tr.nextstate > max_next_) max_next_ = tr.nextstate;
     props_ &= props::kBinary;  // properties.rs set_arc_properties() == empty
   }
   void del_all_states() {  // :191-199
@@ -409,7 +428,7 @@ class HostFst {
   // state_sort (algorithms/state_sort.rs:16-78): old state s becomes state order[s]; arcs keep their order, next states
   // are mapped; the property word keeps only statesort_properties() (properties.rs:319-349).
   void state_sort(const std::vector<uint32_t>& order) {
-    const CsrFst& c = freeze();
+    const CsrFst& c = checked();
     std::lock_guard<std::mutex> g(mu_);
     const size_t n = c.num_states();
     if (order.size() != n)
@@ -446,7 +465,7 @@ class HostFst {
   // compute_and_update_properties_all (fst_traits/mutable_fst.rs:435-446): the stored word is returned untouched when
   // every property is already known (use_stored = true), otherwise everything is recomputed.
   uint64_t compute_and_update_properties_all() {
-    const CsrFst& c = freeze();
+    const CsrFst& c = checked();
     std::lock_guard<std::mutex> g(mu_);
     if ((props::known(props_) & props::kAll) != props::kAll) props_ = compute_properties_all(c) & props::kTrinary;
     return props_;
@@ -458,6 +477,22 @@ class HostFst {
     to_csr_unlocked();
     csr_.has_start = has_start_; csr_.start = start_; csr_.props = props_;
     return csr_;
+  }
+  // freeze() for an algorithm: add_tr / set_tr accept any `nextstate` (as the reference does), so before anything
+  // indexes by it the machine is checked for arcs into states that do not exist.  max_next_ is an upper bound of every
+  // nextstate added since the last full check, so the scan only runs when it can fail.
+  const CsrFst& checked() const {
+    const CsrFst& c = freeze();
+    std::lock_guard<std::mutex> g(mu_);
+    const size_t n = c.num_states();
+    if (!c.arcs.empty() && (size_t)max_next_ >= n) {
+      StateId mx = 0;
+      for (const Tr& t : c.arcs) mx = t.nextstate > mx ? t.nextstate : mx;
+      if ((size_t)mx >= n)
+        throw FstError("transition to state " + std::to_string(mx) + " but the FST has only " + std::to_string(n) + " states");
+      max_next_ = mx;
+    }
+    return c;
   }
   void replace(CsrFst&& csr) {  // in-place algorithms (fst_connect) install their result
     std::lock_guard<std::mutex> g(mu_);
@@ -582,6 +617,7 @@ class HostFst {
   mutable std::vector<BState> b_;
   mutable CsrFst csr_;
   mutable bool is_builder_ = true;
+  mutable StateId max_next_ = 0;  // upper bound of the nextstate of every arc added through add_tr / set_tr
   bool has_start_ = false;
   StateId start_ = 0;
   uint64_t props_ = props::kNull;
@@ -631,6 +667,9 @@ inline CsrFst parse_vector_fst(const uint8_t* data, size_t len) {
   if (flags & 1) skip_symbol_table(r);
   if (flags & 2) skip_symbol_table(r);
   if (num_states < 0) throw FstError("Error while parsing binary VectorFst. Error kind Count");
+  // every state record takes at least 12 bytes: a header that claims more states than the file can hold is rejected
+  // before anything is allocated from it
+  if ((uint64_t)num_states > (uint64_t)(r.n - r.off) / 12) throw FstError("Error while parsing binary VectorFst. Error kind Eof");
   CsrFst c;
   c.props = props_word & props::kTrinary;  // FstProperties::from_bits_truncate
   c.has_start = start != -1;
@@ -667,6 +706,9 @@ inline CsrFst parse_vector_fst(const uint8_t* data, size_t len) {
       if (na) std::memcpy(c.arcs.data() + c.offsets[s], base + rec_at[s] + 12, na * 16);
     }
   }, 1 << 16);
+  // the reference is memory-safe on files whose start / nextstate fields point outside the machine (its algorithms
+  // panic); here such a file is refused at the door
+  validate_state_ids(c, "Error while parsing binary VectorFst. Error kind Verify");
   return c;
 }
 
@@ -728,6 +770,8 @@ inline CsrFst parse_const_fst(const uint8_t* data, size_t len) {
     if (flags & 1) skip_symbol_table(r);
     if (flags & 2) skip_symbol_table(r);
     if (num_states < 0 || num_trs < 0 || (uint64_t)num_trs > 0xFFFFFFF0ull) throw FstError(kErr);
+    // 20 bytes per state record, 16 per arc: reject impossible counts before allocating from them
+    if ((uint64_t)num_states > (uint64_t)(r.n - r.off) / 20 || (uint64_t)num_trs > (uint64_t)(r.n - r.off) / 16) throw FstError(kErr);
     const bool aligned = version == 1;
     auto align = [&](int64_t count) {
       if (aligned && count > 0 && r.off % 16 != 0) {
@@ -765,6 +809,7 @@ inline CsrFst parse_const_fst(const uint8_t* data, size_t len) {
       o += (size_t)sts[s].ntrs;
     }
     c.offsets[num_states] = (uint32_t)o;
+    validate_state_ids(c, kErr);
     return c;
   } catch (const FstError&) {
     throw FstError(kErr);  // load() maps every parse failure to this message (serializable_fst.rs:36-40)

@@ -15,10 +15,19 @@ composition proceeds level by level (BFS depth = L) and the size of the product 
 Weights are dyadic (k/64) so every path sum is exact in f32 (ties are exact, never "near").
 Arcs are label-sorted per state (fst1 by olabel, fst2 by ilabel) and the property word says so.
 """
+import os
+
 import numpy as np
 
-from . import props as P
-from .fst import TR_DTYPE
+try:
+    from . import props as P
+except ImportError:  # loaded by file path (bench.py --impl reference must not map the product library)
+    import importlib.util as _ilu
+    _spec = _ilu.spec_from_file_location("_b200_props", os.path.join(os.path.dirname(os.path.abspath(__file__)), "props.py"))
+    P = _ilu.module_from_spec(_spec)
+    _spec.loader.exec_module(P)
+
+TR_DTYPE = np.dtype([("ilabel", "<u4"), ("olabel", "<u4"), ("weight", "<f4"), ("nextstate", "<u4")])
 
 
 def _level_layout(n_states, levels):

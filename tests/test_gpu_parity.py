@@ -1,6 +1,8 @@
 """GPU parity tests proper: every result of the CUDA path (called through the C-ABI) is compared bit-for-bit
 with the CPU oracle on the same inputs: state ids, arc order, labels, next states, weight bit patterns,
 final weights and property words."""
+import os
+
 import numpy as np
 import pytest
 
@@ -284,10 +286,11 @@ def test_shortest_path_with_near_ties_uses_the_order_faithful_parallel_path():
     assert_same(got2, O.shortest_path(oc), "continuous weights, serial replay")
 
 
-def test_dense_product_overflows_presized_buffers_and_falls_back():
+def test_dense_product_overflows_presized_buffers_and_grows():
     """Single-label complete machines: the product has (n1*n2) states and (n1*n2)^2-ish arcs, far beyond the
-    persistent kernel's pre-sized buffers (4 x input arcs) -> it must stop cleanly and the growing multi-kernel back
-    end must produce the same FST as the oracle (also exercises table rehash and buffer growth)."""
+    persistent kernel's first capacity guess (4 x input arcs) -> it must stop cleanly, the call must double what
+    overflowed and run again until the result fits, and the growing multi-kernel back end must agree (also exercises
+    table rehash and buffer growth)."""
     import rustfst_b200 as R
     from rustfst_b200.fst import TR_DTYPE
     from rustfst_b200 import props as P
@@ -309,9 +312,17 @@ def test_dense_product_overflows_presized_buffers_and_falls_back():
     pa, oa = both_from_dict(complete(40, 1))
     pb, ob = both_from_dict(complete(45, 2))
     got, st = R.compose_with_stats(pa, pb)
-    assert st["emit_launches"] > 1, "expected the fallback (multi-kernel) back end"
+    assert st["emit_launches"] == 1, "expected the persistent kernel (after capacity growth)"
     assert st["arcs_emitted"] == (40 * 45) * (40 * 45)
-    assert_same(got, O.compose(oa, ob), "dense product")
+    expected = O.compose(oa, ob)
+    assert_same(got, expected, "dense product")
+    os.environ["B200_COMPOSE_IMPL"] = "waves"
+    try:
+        got2, st2 = R.compose_with_stats(pa, pb)
+    finally:
+        del os.environ["B200_COMPOSE_IMPL"]
+    assert st2["emit_launches"] > 1
+    assert_same(got2, expected, "dense product, multi-kernel back end")
 
 
 def test_hub_state_with_long_label_runs():

@@ -196,77 +196,86 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks):
+def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks, synth, standalone=True):
     """BASELINE.json configs[4]: `--batch` linear acceptors (200 arcs each, label strings sampled as walks of T)
-    against one shared 500K-state/5M-arc transducer.  Acceptors are block-sharded over the ranks, T is replicated,
-    every rank runs ONE device BFS for its whole shard (b200_compose_batch), and the result FSTs are gathered on
-    rank 0 over NCCL (strong scaling: the batch is fixed)."""
+    against one shared 500K-state/5M-arc transducer.  STRONG scaling: the batch is fixed, the acceptors are block-
+    sharded over the ranks, the transducer is replicated and stays resident in HBM (uploaded once, outside the timed
+    region, like any shared model), every rank runs ONE device BFS for its whole shard (b200_compose_batch_packed:
+    union of the shard's acceptors uploaded inside the timed region, results split per acceptor on the device and
+    brought back as one block) and sends its block to rank 0 over NCCL (point-to-point; rank 0 ends up holding every
+    result).  Returns the c5 object of the JSON line (rank 0) or None."""
     import torch
     import rustfst_b200 as R
-    from rustfst_b200 import synth
-    from rustfst_b200.parallel import gather_blobs, shard_range
+    from rustfst_b200.parallel import gather_buffers, shard_range
     n_t, a_t = int(500_000 * args.scale), int(5_000_000 * args.scale)
     t = synth.random_graph_transducer(n_t, a_t, 5000, seed=5)
     rng = np.random.default_rng(77)
     t["finals"] = np.where(rng.random(n_t) < 0.5, rng.integers(0, 640, size=n_t) / 64.0, np.inf).astype(np.float32)
     ht = synth.to_vector_fst(t)
+    dt = R.DeviceFst.upload(ht)
     lo, hi = shard_range(args.batch, rank, world)
-    accs = [synth.to_vector_fst(synth.linear_acceptor(synth.sample_path_labels(t, 200, seed=100 + i), seed=100 + i))
-            for i in range(lo, hi)]
+    labels = synth.sample_path_labels_batch(t, 200, args.batch, seed=100)  # the same strings on every rank
+    acc_dicts = [synth.linear_acceptor(labels[i], seed=100 + i) for i in range(lo, hi)]
+    accs = [synth.to_vector_fst(d) for d in acc_dicts]
+    dev = torch.device("cuda", local_rank)
 
-    def step(gather):
-        results, st = R.compose_batch(accs, ht)
-        blobs = None
-        if gather and dist is not None:
-            packed = []
-            for r in results:
-                o, a, f, _ = r.to_csr()
-                packed.append(o.tobytes() + a.tobytes() + f.tobytes())
-            blobs = gather_blobs(packed, dist, device=torch.device("cuda", local_rank))
-        return results, st, blobs
+    def step():
+        pb, st = R.compose_batch_packed(accs, device_transducer=dt)
+        blocks = None
+        if dist is not None:
+            blocks = gather_buffers(torch.from_numpy(pb.to_numpy()), dist, device=dev)
+        return pb, st, blocks
 
     for _ in range(args.warmup):
-        step(True)
+        step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    arcs, launches, waves = 0, 0, 0
+    t0 = time.perf_counter()
+    arcs, launches, waves, got = 0, 0, 0, 0
     for _ in range(args.steps):
-        results, st, blobs = step(True)
+        pb, st, blocks = step()
         arcs += st["arcs_out"]; launches += st["kernel_launches"]; waves += st["waves"]
+        if blocks is not None:
+            torch.cuda.synchronize()
+            got = sum(int(b.numel()) for b in blocks)
     e1.record()
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))  # the step is host-driven: take the larger clock
     total_arcs = sum_over_ranks(float(arcs))
+    info = pb.info()
+    check = None
+    if rank == 0 and blocks is not None:  # rank 0 really holds everything: rebuild the blocks and count
+        n_res = sum(len(R.PackedBatch.from_buffer(b.cpu().numpy())) for b in blocks)
+        check = {"results_on_rank0": n_res, "bytes_on_rank0": got}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from tests import oracle_lib as O
         ot = O.OFst.from_csr(t["offsets"].astype(np.uint64), t["arcs"], t["finals"], t["start"], t["props"])
-        n_sample = min(args.batch, 2048)
-        oaccs = []
-        for i in range(n_sample):
-            d = synth.linear_acceptor(synth.sample_path_labels(t, 200, seed=100 + i), seed=100 + i)
-            oaccs.append(O.OFst.from_csr(d["offsets"].astype(np.uint64), d["arcs"], d["finals"], d["start"], d["props"]))
+        n_sample = min(args.batch, 1024)
         secs, oarcs = 0.0, 0
-        for oa in oaccs:
+        for d in acc_dicts[:n_sample]:
+            oa = O.OFst.from_csr(d["offsets"].astype(np.uint64), d["arcs"], d["finals"], d["start"], d["props"])
             r, ost = O.compose(oa, ot, want_stats=True)
             secs += ost["seconds"]; oarcs += r.num_trs
         cpu = {"value": oarcs / secs, "unit": "arcs/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
                "sample": f"the first {n_sample} acceptors of the batch composed one by one with the same transducer "
                          f"({oarcs} result arcs in {secs:.2f} s), oracle port, 1 thread"}
-    if rank == 0:
-        line = {"metric": "composed_arcs_per_sec", "value": total_arcs / (ms * 1e-3), "unit": "arcs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"C5: {args.batch} linear acceptors (200 arcs) o {n_t}-state/{len(t['arcs'])}-arc "
-                                       "transducer, sharded by acceptor, results gathered on rank 0 over NCCL",
-                           "parallelism": f"acceptor shards x{world}, transducer replicated",
-                           "waves_per_step": waves // max(1, args.steps)},
-                "e2e": {"value": total_arcs / (ms * 1e-3), "unit": "arcs/s", "api": "b200_compose_batch on host handles",
-                        "h2d_bytes_per_step": int(csr_bytes(t) + (hi - lo) * (201 * 8 + 200 * 16 + 4)),
-                        "d2h_bytes_per_step": int(arcs // max(1, args.steps) * 16)},
-                "cpu_baseline": cpu, "gpu_launches": int(launches)}
-        print(json.dumps(line), flush=True)
+    del dt
+    if rank != 0:
+        return None
+    return {"metric": "composed_arcs_per_sec (result arcs of the whole batch / step time)",
+            "value": total_arcs / (ms * 1e-3), "unit": "arcs/s", "n_gpus": world, "ms_per_batch": ms / args.steps,
+            "scaling": "strong", "steps": args.steps, "warmup": args.warmup,
+            "workload": f"C5: {args.batch} linear acceptors (200 arcs) o {n_t}-state/{len(t['arcs'])}-arc transducer, "
+                        f"sharded by acceptor x{world}, transducer resident in HBM on every rank, result blocks sent "
+                        "to rank 0 over NCCL",
+            "per_step": {"h2d_bytes_per_rank": int((hi - lo) * (201 * 8 + 200 * 16 + 4)),
+                         "d2h_bytes_per_rank": int(info["bytes"]), "waves": waves // max(1, args.steps),
+                         "result_states_rank0_shard": info["num_states"], "result_arcs_rank0_shard": info["num_trs"]},
+            "gather": check, "cpu_baseline": cpu, "gpu_launches": int(launches),
+            "timer": "max(CUDA events, host wall clock) around K host-driven steps, max over ranks"}
 
 
 def main():
@@ -280,6 +289,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; full size = 1.0)")
     ap.add_argument("--callers", type=int, default=3, help="host threads of the supplementary concurrent e2e figure (1 = skip)")
     ap.add_argument("--no-sssp", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -327,7 +337,9 @@ def main():
     peak_gbs, peak_src = measured_peak_gbs()
 
     if args.workload == "C5":
-        run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks)
+        c5 = run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks, synth)
+        if rank == 0:
+            print(json.dumps(c5), flush=True)
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -440,41 +452,58 @@ def main():
     del d1, d2
 
     # ------------------------------------------------------------------ SSSP leg (C4)
+    # Headline = the lattice with the property word compose leaves behind (ACYCLIC known, TOP_SORTED unknown): AutoQueue
+    # picks the TopOrderQueue, whose order is the reference's DFS order — computed on the device (dag_order.cu) inside
+    # every timed call.  The same lattice with TOP_SORTED known (StateOrderQueue, no order needed) is reported next to it.
     sssp = None
     if not args.no_sssp:
-        g = gen_sssp_workload(args.scale, rank, synth)
+        from rustfst_b200 import props as PR
+        g_sorted = gen_sssp_workload(args.scale, rank, synth)
+        g = dict(g_sorted, props=g_sorted["props"] & ~(PR.TOP_SORTED | PR.NOT_TOP_SORTED))
         hg = synth.to_vector_fst(g)
         dg = R.DeviceFst.upload(hg)
-        for _ in range(args.warmup):
-            R.device_shortest_path(dg)
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        stot = {"arcs_relaxed": 0, "states_settled": 0, "ms_relax_kernel": 0.0, "ms_device": 0.0, "relax_launches": 0,
-                "kernel_launches": 0}
-        path_kind = None
-        for _ in range(steps):
-            sp, sst = R.device_shortest_path(dg)
-            for k in stot:
-                stot[k] += sst[k]
-            path_kind = sst["path"]
-        s1.record()
-        barrier()
-        sssp_ms = max_over_ranks(s0.elapsed_time(s1))
+
+        def sssp_run(dev, n_steps):
+            for _ in range(args.warmup):
+                R.device_shortest_path(dev)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            tw = time.perf_counter()
+            tot_ = {"arcs_relaxed": 0, "states_settled": 0, "ms_relax_kernel": 0.0, "ms_device": 0.0, "relax_launches": 0,
+                    "kernel_launches": 0, "ms_order_device": 0.0, "ms_queue_plan_host": 0.0}
+            last = None
+            for _ in range(n_steps):
+                _, last = R.device_shortest_path(dev)
+                for k in tot_:
+                    tot_[k] += last[k]
+            s1.record()
+            barrier()
+            wall = 1e3 * (time.perf_counter() - tw)
+            return max_over_ranks(max(s0.elapsed_time(s1), wall)), tot_, last
+
+        sssp_ms, stot, last = sssp_run(dg, steps)
         edges = sum_over_ranks(float(stot["arcs_relaxed"]))
         n_states = g["num_states"]
         sssp_bytes = 16.0 * stot["arcs_relaxed"] + 20.0 * n_states * steps
         relax_gbs = (16.0 * stot["arcs_relaxed"] + 12.0 * stot["states_settled"]) / (stot["ms_relax_kernel"] * 1e-3) / 1e9
         sssp = {
             "metric": "sssp_edges_per_sec", "value": edges / (sssp_ms * 1e-3), "unit": "edges/s",
-            "ms_per_step": sssp_ms / steps, "workload": f"C4: shortest_path(n=1), {n_states}-state/{len(g['arcs'])}-arc "
-            "layered acyclic lattice, TOP_SORTED known (StateOrderQueue), dyadic weights",
-            "device_path": "parallel relaxation + certificate" if path_kind == 0 else "serial replay",
+            "ms_per_step": sssp_ms / steps,
+            "workload": f"C4 as a composed lattice: shortest_path(n=1), {n_states}-state/{len(g['arcs'])}-arc layered acyclic "
+                        "lattice, property word as compose leaves it (ACYCLIC known, TOP_SORTED unknown -> TopOrderQueue), "
+                        "dyadic weights; lattice resident in HBM",
+            "queue_kind": last["queue_kind"], "order_on_device": last["order_on_device"],
+            "ms_order_device_per_step": stot["ms_order_device"] / steps,
+            "ms_queue_plan_host_per_step": stot["ms_queue_plan_host"] / steps,
+            "ms_relax_and_backtrace_per_step": stot["ms_device"] / steps,
+            "device_path": {0: "parallel relaxation + certificate", 1: "serial replay", 2: "order-faithful parallel fold"}.get(last["path"]),
             "roofline": {"bound": "hbm", "kernel": "k_relax", "achieved": relax_gbs, "peak": peak_gbs, "unit": "GB/s",
                          "frac": relax_gbs / peak_gbs, "traffic": None,
-                         "whole_call": {"bytes_model": "16*E + 20*N", "achieved_GBps": sssp_bytes / (stot["ms_device"] * 1e-3) / 1e9,
-                                        "frac": sssp_bytes / (stot["ms_device"] * 1e-3) / 1e9 / peak_gbs}},
+                         "whole_call": {"bytes_model": "16*E + 20*N", "achieved_GBps": sssp_bytes / (sssp_ms * 1e-3) / 1e9,
+                                        "frac": sssp_bytes / (sssp_ms * 1e-3) / 1e9 / peak_gbs}},
             "gpu_launches": stot["kernel_launches"],
+            "timer": "max(CUDA events, host wall clock) around K blocking calls, max over ranks",
         }
         # end to end through fst_shortest_path on the host handle (H2D of the lattice inside)
         barrier()
@@ -486,24 +515,24 @@ def main():
         barrier()
         sssp["e2e"] = {"value": e2e_edges / (time.perf_counter() - t0), "unit": "edges/s",
                        "h2d_bytes_per_step": csr_bytes(g), "d2h_bytes_per_step": 16 * 64}
-        # SURVEY.md §8d asks for the lattice "with props as compose would leave them" as well: ACYCLIC known, TOP_SORTED
-        # unknown -> AutoQueue picks TopOrderQueue, whose order comes from the reference's sequential DFS (run on the
-        # host, exactly as the reference does; its time is reported next to the device time)
-        from rustfst_b200 import props as PR
-        hg_top = synth.to_vector_fst(dict(g, props=g["props"] & ~(PR.TOP_SORTED | PR.NOT_TOP_SORTED)))
-        dg_top = R.DeviceFst.upload(hg_top)
-        R.device_shortest_path(dg_top)
-        barrier()
-        t0 = time.perf_counter()
-        top_steps = min(steps, 2)
-        for _ in range(top_steps):
-            _, tst = R.device_shortest_path(dg_top)
-        barrier()
-        sssp["top_order_variant"] = {
-            "workload": "same lattice, ACYCLIC known / TOP_SORTED unknown (TopOrderQueue)", "queue_kind": tst["queue_kind"],
-            "ms_per_call_wall": (time.perf_counter() - t0) * 1e3 / top_steps, "ms_device": tst["ms_device"],
-            "ms_queue_plan_host_dfs": tst["ms_queue_plan_host"], "device_path": tst["path"]}
-        del dg_top, hg_top
+        # the same lattice with TOP_SORTED known: StateOrderQueue, no order to compute
+        hg_s = synth.to_vector_fst(g_sorted)
+        dg_s = R.DeviceFst.upload(hg_s)
+        ms_s, st_s, last_s = sssp_run(dg_s, steps)
+        sssp["top_sorted_variant"] = {
+            "workload": "same lattice, TOP_SORTED known (StateOrderQueue)", "queue_kind": last_s["queue_kind"],
+            "value": sum_over_ranks(float(st_s["arcs_relaxed"])) / (ms_s * 1e-3), "unit": "edges/s",
+            "ms_per_step": ms_s / steps, "device_path": last_s["path"]}
+        del dg_s, hg_s
+        # the host DFS the device order replaces (B200_HOST_DFS=1 forces it), one call
+        os.environ["B200_HOST_DFS"] = "1"
+        try:
+            t0 = time.perf_counter()
+            _, hst = R.device_shortest_path(dg)
+            sssp["host_dfs_variant"] = {"ms_per_call_wall": (time.perf_counter() - t0) * 1e3,
+                                        "ms_queue_plan_host_dfs": hst["ms_queue_plan_host"], "ms_device": hst["ms_device"]}
+        finally:
+            del os.environ["B200_HOST_DFS"]
         # n-best on the same device-resident lattice (fst_shortest_path_with_config, nshortest = 10, unique = false):
         # forward distances + reversed machine on the device, heap search over rows fetched from HBM, device trim
         cfg10 = R.ShortestPathConfig(nshortest=10)
@@ -533,11 +562,17 @@ def main():
             og = O.OFst.from_csr(g["offsets"].astype(np.uint64), g["arcs"], g["finals"], g["start"], g["props"])
             _, sst = O.shortest_path(og, want_stats=True)
             cpu["sssp"] = {"value": sst["arcs_relaxed"] / sst["seconds"], "unit": "edges/s",
-                           "sample": f"one full C4 shortest_path ({sst['arcs_relaxed']} edges in {sst['seconds']:.2f} s)"}
+                           "sample": f"one full C4 shortest_path on the same lattice and property word, DFS order included "
+                                     f"({sst['arcs_relaxed']} edges in {sst['seconds']:.2f} s)"}
             t0 = time.perf_counter()
             O.shortest_path(og, nshortest=10)
             cpu["sssp"]["nbest_ms"] = (time.perf_counter() - t0) * 1e3
             cpu["sssp"]["nbest_sample"] = "one full C4 shortest_path(nshortest=10), oracle port, 1 thread"
+
+    # ------------------------------------------------------------------ batched compose leg (C5), sharded over the ranks
+    c5 = None
+    if not args.no_c5:
+        c5 = run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks, synth)
 
     if rank == 0:
         line = {
@@ -549,7 +584,7 @@ def main():
                                "arcs_emitted_per_step": tot["arcs_emitted"] // steps,
                                "waves_per_step": tot["waves"] // steps},
             "wall_ms_per_step": wall_ms / steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sssp": sssp,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sssp": sssp, "c5": c5,
             "gpu_launches": int(tot["kernel_launches"]), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

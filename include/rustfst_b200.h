@@ -235,7 +235,9 @@ typedef struct B200SsspStats {
   int32_t queue_kind; /* 0 StateOrder, 1 TopOrder, 2 Lifo, 3 Scc */
   float ms_device, ms_relax_kernel;
   float ms_h2d;
-  double ms_queue_plan_host;
+  double ms_queue_plan_host; /* host time spent building the queue plan (0 when the order was computed on the device) */
+  float ms_order_device;     /* device time of the TopOrderQueue order of an acyclic machine (dag_order.cu), else 0 */
+  int32_t order_on_device;   /* 1: that order was computed on the device, 0: host DFS or no DFS order needed */
 } B200SsspStats;
 /* Same as fst_compose_with_config (config may be NULL = default) but also reports stats. */
 RUSTFST_FFI_RESULT b200_compose_with_stats(const CFst* fst_1, const CFst* fst_2, const CComposeConfig* config,
@@ -253,8 +255,10 @@ RUSTFST_FFI_RESULT b200_device_fst_destroy(B200DeviceFst* dfst);
 RUSTFST_FFI_RESULT b200_device_compose(const B200DeviceFst* fst_1, const B200DeviceFst* fst_2,
                                        const CComposeConfig* config, const B200DeviceFst** out,
                                        B200ComposeStats* stats);
-/* plan_from supplies the host copy used to build the queue plan (DFS orders); it must be the FST dfst was uploaded
- * from. */
+/* plan_from (may be NULL) is the host copy dfst was uploaded from.  The queue discipline is decided from the property
+ * word stored with dfst; the DFS order of an acyclic machine is computed on the device.  The host copy is only needed
+ * for machines that are not known to be acyclic (Tarjan SCC order) or too deep for the device path (more than 65 536
+ * topological levels). */
 RUSTFST_FFI_RESULT b200_device_shortest_path(const B200DeviceFst* dfst, const CFst* plan_from, const CFst** res_fst,
                                              B200SsspStats* stats, bool force_serial);
 
@@ -268,11 +272,33 @@ RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, co
                                       const CComposeConfig* config, const CFst** results /* n slots */,
                                       B200ComposeStats* total_stats);
 
+/* The same as one block: the n results stay packed (no per-result handle is created), can be fetched one by one,
+ * and serialise to / from one contiguous byte string — what a rank sends to rank 0 over NCCL in the sharded mode.
+ * The transducer is given either as a host handle (uploaded by the call) or as a device-resident handle (stays in
+ * HBM across calls); exactly one of the two may be NULL. */
+typedef struct B200PackedBatch B200PackedBatch;
+RUSTFST_FFI_RESULT b200_compose_batch_packed(const CFst* const* acceptors, size_t n, const CFst* transducer,
+                                             const B200DeviceFst* dev_transducer, const CComposeConfig* config,
+                                             const B200PackedBatch** out, B200ComposeStats* total_stats);
+RUSTFST_FFI_RESULT b200_packed_batch_info(const B200PackedBatch* batch, uint64_t* n, uint64_t* num_states,
+                                          uint64_t* num_trs, uint64_t* serialized_bytes);
+RUSTFST_FFI_RESULT b200_packed_batch_get(const B200PackedBatch* batch, size_t i, const CFst** out);
+RUSTFST_FFI_RESULT b200_packed_batch_serialize(const B200PackedBatch* batch, uint8_t* dst, size_t capacity);
+RUSTFST_FFI_RESULT b200_packed_batch_deserialize(const uint8_t* src, size_t len, const B200PackedBatch** out);
+RUSTFST_FFI_RESULT b200_packed_batch_destroy(B200PackedBatch* batch);
+
 /* The queue discipline rustfst's AutoQueue would pick for `fst` from its stored property bits (host logic, no GPU):
  * kind 0 StateOrder, 1 TopOrder, 2 Lifo, 3 Scc.  order_or_scc (num_states entries, may be NULL) receives order[state]
  * for TopOrder and scc[state] for Scc; scc_is_fifo (num_states entries, may be NULL) the per-component queue type. */
 RUSTFST_FFI_RESULT b200_shortest_path_queue_plan(const CFst* fst, int32_t* kind, uint32_t* order_or_scc,
                                                  uint8_t* scc_is_fifo, uint32_t* n_scc);
+
+/* The TopOrderQueue order of an acyclic machine computed ON THE DEVICE (csrc/dag_order.cu; replaces the sequential DFS
+ * of rustfst/src/algorithms/top_sort.rs:12-61 + dfs_visit.rs:97-187 for acyclic inputs): order[state] = position in
+ * reverse DFS finish order.  *ok = 0 when the machine is cyclic or deeper than the device path handles (then `order`
+ * is untouched and b200_shortest_path_queue_plan gives the host answer).  Tests compare the two. */
+RUSTFST_FFI_RESULT b200_dag_top_order_device(const CFst* fst, uint32_t* order /* num_states */, int32_t* ok,
+                                             float* ms_device);
 
 /* Device management for one-process-per-GPU launches. */
 RUSTFST_FFI_RESULT b200_set_device(int device);

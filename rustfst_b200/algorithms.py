@@ -163,15 +163,75 @@ def device_compose(a: DeviceFst, b: DeviceFst, config: Optional[ComposeConfig] =
 def device_shortest_path(d: DeviceFst, plan_from: Optional[VectorFst] = None, force_serial=False,
                          config: Optional[ShortestPathConfig] = None):
     host = plan_from or d.host
+    hp = host.ptr if host is not None else None
     out = C.c_void_p()
     st = SsspStats()
     if config is None:
-        rc = lib.b200_device_shortest_path(d.ptr, host.ptr, C.byref(out), C.byref(st), bool(force_serial))
+        rc = lib.b200_device_shortest_path(d.ptr, hp, C.byref(out), C.byref(st), bool(force_serial))
     else:
-        rc = lib.b200_device_shortest_path_with_config(d.ptr, host.ptr, config.ptr, C.byref(out), C.byref(st),
+        rc = lib.b200_device_shortest_path_with_config(d.ptr, hp, config.ptr, C.byref(out), C.byref(st),
                                                        bool(force_serial))
     check_ffi_error(rc, "Error computing shortest path")
     return VectorFst(out), st.as_dict()
+
+
+class PackedBatch:
+    """The results of a batched composition as ONE block (b200_compose_batch_packed): fetch results one by one with
+    result(i), or move the whole block as bytes (what a rank sends to rank 0 in the sharded mode)."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            lib.b200_packed_batch_destroy(self.ptr)
+            self.ptr = None
+
+    def info(self):
+        n, st, tr, by = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check_ffi_error(lib.b200_packed_batch_info(self.ptr, C.byref(n), C.byref(st), C.byref(tr), C.byref(by)), "info")
+        return {"n": n.value, "num_states": st.value, "num_trs": tr.value, "bytes": by.value}
+
+    def __len__(self):
+        return self.info()["n"]
+
+    def result(self, i: int) -> VectorFst:
+        out = C.c_void_p()
+        check_ffi_error(lib.b200_packed_batch_get(self.ptr, i, C.byref(out)), "Error fetching a batch result")
+        return VectorFst(out)
+
+    def to_numpy(self):
+        """The block as a uint8 array (one copy)."""
+        import numpy as np
+        buf = np.empty(self.info()["bytes"], dtype=np.uint8)
+        check_ffi_error(lib.b200_packed_batch_serialize(self.ptr, buf.ctypes.data, buf.nbytes), "Error serialising")
+        return buf
+
+    def to_bytes(self) -> bytes:
+        return self.to_numpy().tobytes()
+
+    @classmethod
+    def from_buffer(cls, buf) -> "PackedBatch":
+        import numpy as np
+        a = np.frombuffer(buf, dtype=np.uint8)
+        out = C.c_void_p()
+        check_ffi_error(lib.b200_packed_batch_deserialize(a.ctypes.data, a.nbytes, C.byref(out)), "Error deserialising")
+        return cls(out)
+
+
+def compose_batch_packed(acceptors: List[VectorFst], transducer: Optional[VectorFst] = None,
+                         config: Optional[ComposeConfig] = None, device_transducer: Optional["DeviceFst"] = None):
+    """acceptors[i] o transducer for all i in one device BFS; the transducer is a host FST (uploaded by the call) or a
+    DeviceFst that stays resident in HBM across calls."""
+    n = len(acceptors)
+    ins = (C.c_void_p * n)(*[getattr(a.ptr, "value", a.ptr) for a in acceptors])
+    out = C.c_void_p()
+    st = ComposeStats()
+    check_ffi_error(lib.b200_compose_batch_packed(ins, n, transducer.ptr if transducer is not None else None,
+                                                  device_transducer.ptr if device_transducer is not None else None,
+                                                  config.ptr if config else None, C.byref(out), C.byref(st)),
+                    "Error in batched compose")
+    return PackedBatch(out), st.as_dict()
 
 
 def compose_batch(acceptors: List[VectorFst], transducer: VectorFst, config: Optional[ComposeConfig] = None):

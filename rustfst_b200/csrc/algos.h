@@ -71,6 +71,27 @@ int compose_device_ws(const DevFst& a, const DevFst& b, const ComposeOptions& op
 bool compose_device_persistent(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
                                cudaStream_t s, DevFst* out, const BatchStarts* batch = nullptr);
 
+// The n results of a batched composition in one block (no per-result allocation): result i owns the states
+// [state_off[i], state_off[i+1]) and the arcs [arc_off[i], arc_off[i+1]); `offsets` are per-state arc offsets into the
+// block's arc array, arc next states and `starts` are local to their result (-1 = no start state).
+struct PackedBatch {
+  uint64_t n = 0;
+  std::vector<uint32_t> state_off, arc_off;
+  std::vector<int32_t> starts;
+  std::vector<uint64_t> props;
+  PoolVec<uint32_t> offsets;
+  PoolVec<float> finals;
+  PoolVec<Tr> arcs;
+  size_t byte_size() const;
+  void serialize(uint8_t* dst) const;                              // byte_size() bytes
+  static PackedBatch deserialize(const uint8_t* src, size_t len);  // validates every index
+  CsrFst result(size_t i) const;
+  void append(const CsrFst& c);
+};
+// Stable partition of a batched composition result by component, on the device (batch.cu).
+void split_batch_device(const DevFst& r, const uint32_t* d_tag, const uint32_t* d_start_map,
+                        const std::vector<uint32_t>& base_state, PackedBatch& out, uint64_t* launches, cudaStream_t s);
+
 // Trim: keep states that are accessible and coaccessible, order-preserving renumbering
 // (rustfst/src/algorithms/connect.rs:51-66, rustfst/src/fst_impls/vector_fst/mutable_fst.rs:132-189).
 // assume_accessible skips the forward pass (true for a freshly composed FST: every state was reached by the BFS).
@@ -84,8 +105,17 @@ struct TrimExtras {  // optional per-state payload carried through the compactio
   DevBuf<uint32_t>* out_tag = nullptr;         // s1 of every KEPT state, in new-id order
   DevBuf<uint32_t>* out_start_map = nullptr;   // new id of input states 0..n_starts-1 (0xFFFFFFFF = deleted)
 };
+// `pa` (optional): the arcs of `in` are not in in.arcs but still in the provisional runs of compose_ws.cu; in.offsets,
+// in.finals and in.num_arcs describe the canonical machine, pa->next its resolved next states in canonical order.
+struct ProvArcs {
+  const Tr* prov = nullptr;
+  const uint2* st_first = nullptr;   // per state: (run, index in the run) of its first arc
+  const uint32_t* run_src = nullptr; // first provisional arc of every run
+  const uint32_t* run_cnt = nullptr; // arcs of every run
+  const uint32_t* next = nullptr;    // num_arcs resolved next states, canonical order
+};
 DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_t n_waves, uint64_t* launches,
-                            cudaStream_t s, const TrimExtras* extras = nullptr);
+                            cudaStream_t s, const TrimExtras* extras = nullptr, const ProvArcs* pa = nullptr);
 
 // Stable per-state arc sort by input or output label, in place on the device (algorithms/tr_sort.rs:51-62).
 void tr_sort_device(DevFst& f, bool ilabel, cudaStream_t s);
@@ -101,8 +131,18 @@ struct QueuePlan {
   std::vector<uint32_t> scc;        // kSccQueue: scc[state]
   std::vector<uint8_t> scc_is_fifo; // kSccQueue: per component, 1 = FifoQueue, 0 = TrivialQueue
   double host_ms = 0;               // time spent on the host DFS
+  bool deferred = false;            // kTopOrderQueue of an ACYCLIC machine whose order has not been computed yet
+  const uint32_t* d_order = nullptr; // kTopOrderQueue: the order, already on the device (dag_order.cu); else `order`
+  float device_ms = 0;              // device time spent computing d_order
 };
-QueuePlan build_queue_plan(const CsrFst& fst);
+// defer_acyclic_order: for a machine whose properties say ACYCLIC, only record the decision (the caller computes the
+// order on the device with dag_top_order_device and falls back to the full host plan if that declines).
+QueuePlan build_queue_plan(const CsrFst& fst, bool defer_acyclic_order = false);
+// The decision alone, from a property word (auto_queue.rs:28-45,68-76); kSccQueue = "needs the host DFS".
+QueueKind queue_kind_from_props(uint64_t props, bool has_start);
+// order[s] = position of s in the reverse finish order of the reference's DFS (top_sort.rs:12-61) for an acyclic
+// machine, computed on the device.  false = cyclic, or deeper than the device path handles: use the host DFS.
+bool dag_top_order_device(const DevFst& f, DevBuf<uint32_t>& order, float* ms, uint64_t* launches, cudaStream_t s);
 // Topological order of an acyclic machine as the reference's TopOrderVisitor numbers it (false = cyclic).
 bool top_order(const CsrFst& fst, std::vector<uint32_t>& order);
 
@@ -116,6 +156,8 @@ struct SsspStats {
   uint64_t relax_launches = 0;
   uint64_t kernel_launches = 0;
   double plan_host_ms = 0;
+  float order_device_ms = 0;   // device time of the TopOrderQueue order (dag_order.cu)
+  bool order_on_device = false;
 };
 
 // Returns the single-shortest-path FST exactly as rustfst's single_shortest_path + backtrace would

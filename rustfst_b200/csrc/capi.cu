@@ -122,6 +122,32 @@ void fill(B200SsspStats* out, const SsspStats& st, int kind, float h2d) {
   out->kernel_launches = st.kernel_launches; out->relax_launches = st.relax_launches; out->path = st.path;
   out->queue_kind = kind; out->ms_device = st.ms_device; out->ms_relax_kernel = st.ms_relax_kernel;
   out->ms_h2d = h2d; out->ms_queue_plan_host = st.plan_host_ms;
+  out->ms_order_device = st.order_device_ms; out->order_on_device = st.order_on_device ? 1 : 0;
+}
+
+// Queue plan (AutoQueue::new, auto_queue.rs:23-99) of a machine that is resident on the device.  The discipline follows
+// from the property word; the DFS order of a machine known to be ACYCLIC is computed on the device (dag_order.cu).
+// `host` (may be null for device-only callers) is the same machine on the host: it is needed for machines that are not
+// known to be acyclic (Tarjan SCC numbering) and as the fallback when the device path declines (too deep).
+struct DevicePlan {
+  QueuePlan plan;
+  DevBuf<uint32_t> order;
+};
+void resolve_plan(DevicePlan& dp, const CsrFst* host, const DevFst& d, cudaStream_t s) {
+  const QueueKind kind = queue_kind_from_props(d.props, d.has_start);
+  const bool try_device = kind == kTopOrderQueue && !std::getenv("B200_HOST_DFS");
+  if (kind == kStateOrderQueue || kind == kLifoQueue) { dp.plan.kind = kind; return; }
+  if (try_device) {
+    dp.order = DevBuf<uint32_t>(s);
+    float ms = 0;
+    if (dag_top_order_device(d, dp.order, &ms, nullptr, s)) {
+      dp.plan.kind = kTopOrderQueue; dp.plan.d_order = dp.order.p; dp.plan.device_ms = ms;
+      return;
+    }
+  }
+  if (!host) throw FstError("shortest path on a device-resident FST that is not known to be top-sorted, acyclic or "
+                            "unweighted needs the host copy (plan_from) for the DFS order");
+  dp.plan = build_queue_plan(*host);
 }
 
 CFst* compose_host(const CFst* a, const CFst* b, const CComposeConfig* cfg, B200ComposeStats* stats) {
@@ -175,12 +201,13 @@ CFst* shortest_path_host(const CFst* in, const CShortestPathConfig* cfg, B200Sss
   }
   check_sp_config(cfg);
   const CsrFst& h = vec_alg(in, "fst")->fst.checked();
-  QueuePlan plan = build_queue_plan(h);
   Stream st;
   double t0 = now_ms();
   DevFst d = upload(h, st.s);
   double t1 = now_ms();
-  return new CFst{HostFst(shortest_path_dispatch(d, plan, cfg, stats, (float)(t1 - t0), st.s, force_serial))};
+  DevicePlan dp;
+  resolve_plan(dp, &h, d, st.s);
+  return new CFst{HostFst(shortest_path_dispatch(d, dp.plan, cfg, stats, (float)(t1 - t0), st.s, force_serial))};
 }
 }  // namespace
 
@@ -636,10 +663,11 @@ RUSTFST_FFI_RESULT b200_device_compose(const B200DeviceFst* a, const B200DeviceF
 RUSTFST_FFI_RESULT b200_device_shortest_path(const B200DeviceFst* d, const CFst* plan_from, const CFst** out,
                                              B200SsspStats* stats, bool force_serial) {
   return wrap([&] {
-    QueuePlan plan = build_queue_plan(nn(plan_from, "plan_from")->fst.checked());
+    DevicePlan dp;
+    resolve_plan(dp, plan_from ? &plan_from->fst.checked() : nullptr, nn(d, "dfst")->d, d->stream.s);
     SsspStats ss;
-    CsrFst r = shortest_path_device(nn(d, "dfst")->d, plan, &ss, d->stream.s, force_serial);
-    fill(stats, ss, (int)plan.kind, 0.0f);
+    CsrFst r = shortest_path_device(d->d, dp.plan, &ss, d->stream.s, force_serial);
+    fill(stats, ss, (int)dp.plan.kind, 0.0f);
     *out = new CFst{HostFst(std::move(r))};
   });
 }
@@ -653,156 +681,180 @@ RUSTFST_FFI_RESULT b200_device_shortest_path_with_config(const B200DeviceFst* d,
       return;
     }
     check_sp_config(cfg);
-    QueuePlan plan = build_queue_plan(nn(plan_from, "plan_from")->fst.checked());
-    *out = new CFst{HostFst(shortest_path_dispatch(nn(d, "dfst")->d, plan, cfg, stats, 0.0f, d->stream.s, force_serial))};
+    DevicePlan dp;
+    resolve_plan(dp, plan_from ? &plan_from->fst.checked() : nullptr, nn(d, "dfst")->d, d->stream.s);
+    *out = new CFst{HostFst(shortest_path_dispatch(d->d, dp.plan, cfg, stats, 0.0f, d->stream.s, force_serial))};
   });
 }
+// Core of the batched mode: acceptors[i] o T for i in [0, n) -> one PackedBatch.  T comes either as a host handle
+// (uploaded here) or as a device-resident handle (the shared transducer of a long-running service stays in HBM).
+static void compose_batch_core(const CFst* const* acceptors, size_t n, const CFst* transducer,
+                               const B200DeviceFst* dev_transducer, const CComposeConfig* cfg, PackedBatch& out,
+                               B200ComposeStats* total) {
+  ComposeOptions opt = to_options(cfg);
+  B200ComposeStats acc;
+  std::memset(&acc, 0, sizeof(acc));
+  Stream st;
+  double t0 = now_ms();
+  DevFst dt_local(st.s);
+  const DevFst* dtp = nullptr;
+  if (dev_transducer) dtp = &dev_transducer->d;
+  else {
+    const CsrFst& ht = vec_alg(transducer, "transducer")->fst.checked();
+    dt_local = upload(ht, st.s);
+    dtp = &dt_local;
+  }
+  const DevFst& dt = *dtp;
+  acc.ms_h2d += (float)(now_ms() - t0);
+
+  // ---- one BFS for the whole batch: the acceptors become one FST with disjoint state ranges and n start tuples.
+  // Every acceptor must lead to the same match side (same sortedness bits); otherwise fall back to a loop.
+  std::vector<const CsrFst*> hs(n);
+  bool uniform = n > 0 && dt.has_start;
+  uint64_t and_props = ~0ull, or_props = 0;
+  size_t sum_states = 0, sum_arcs = 0;
+  for (size_t i = 0; i < n; i++) {
+    hs[i] = &vec_alg(acceptors[i], "acceptor")->fst.checked();
+    if (!hs[i]->inf_finals.empty()) uniform = false;
+    if (!hs[i]->has_start) uniform = false;
+    and_props &= hs[i]->props; or_props |= hs[i]->props;
+    sum_states += hs[i]->num_states(); sum_arcs += hs[i]->arcs.size();
+  }
+  const uint64_t steer = props::kOLabelSorted | props::kNotOLabelSorted | props::kAcceptor | props::kNotAcceptor |
+                         props::kNoEpsilons | props::kNoIEpsilons | props::kNoOEpsilons | props::kAcyclic |
+                         props::kInitialAcyclic | props::kIDeterministic | props::kODeterministic;
+  if ((and_props & steer) != (or_props & steer)) uniform = false;  // property bits that steer compose must agree
+  if (sum_states >= 0x7FFFFFF0ull || sum_arcs >= 0xFFFFFFF0ull) uniform = false;
+
+  bool done = false;
+  if (uniform) {
+    const double tu0 = now_ms();
+    CsrFst u;
+    u.offsets.resize(sum_states + 1);
+    u.arcs.resize(sum_arcs);
+    u.finals.resize(sum_states);
+    std::vector<uint32_t> starts(n), base_state(n + 1), base_arc(n + 1);
+    {
+      size_t so = 0, ao = 0;
+      for (size_t i = 0; i < n; i++) {
+        base_state[i] = (uint32_t)so; base_arc[i] = (uint32_t)ao;
+        starts[i] = (uint32_t)(so + hs[i]->start);
+        so += hs[i]->num_states(); ao += hs[i]->arcs.size();
+      }
+      base_state[n] = (uint32_t)so; base_arc[n] = (uint32_t)ao;
+    }
+    parallel_ranges(n, [&](size_t lo_i, size_t hi_i) {
+      for (size_t i = lo_i; i < hi_i; i++) {
+        const CsrFst& h = *hs[i];
+        const size_t so = base_state[i], ao = base_arc[i], ns = h.num_states(), na = h.arcs.size();
+        for (size_t s = 0; s < ns; s++) u.offsets[so + s] = (uint32_t)(ao + h.offsets[s]);
+        std::memcpy(u.finals.data() + so, h.finals.data(), ns * 4);
+        for (size_t k = 0; k < na; k++) { Tr t = h.arcs[k]; t.nextstate += (uint32_t)so; u.arcs[ao + k] = t; }
+      }
+    }, 64);
+    u.offsets[sum_states] = base_arc[n];
+    u.has_start = true; u.start = starts[0];
+    u.props = and_props & props::kTrinary;
+    const double t_union = now_ms() - tu0;
+    t0 = now_ms();
+    DevFst du = upload(u, st.s);
+    DevBuf<uint32_t> d_starts(st.s, n), d_s1(st.s), d_map(st.s);
+    B200_CUDA(cudaMemcpyAsync(d_starts.p, starts.data(), n * 4, cudaMemcpyHostToDevice, st.s));
+    B200_CUDA(cudaStreamSynchronize(st.s));
+    acc.ms_h2d += (float)(now_ms() - t0);
+    BatchStarts bs;
+    bs.d_starts1 = d_starts.p; bs.n = (uint32_t)n; bs.out_s1 = &d_s1; bs.out_start_map = &d_map;
+    ComposeStats cs;
+    DevFst dr(st.s);
+    if (compose_device_persistent(du, dt, opt, &cs, st.s, &dr, &bs)) {
+      // ---- split the union result per acceptor on the device and bring it back as one block
+      t0 = now_ms();
+      uint64_t launches = 0;
+      split_batch_device(dr, d_s1.p, d_map.p, base_state, out, &launches, st.s);
+      cs.kernel_launches += launches;
+      out.props.resize(n);
+      for (size_t i = 0; i < n; i++) {
+        uint64_t p = props::of_compose(hs[i]->props, dt.props);
+        if (opt.connect) p = props::after_connect(p);
+        out.props[i] = p & props::kTrinary;
+      }
+      acc.ms_d2h += (float)(now_ms() - t0);
+      fill(&acc, cs, acc.ms_h2d, acc.ms_d2h);
+      if (std::getenv("B200_BATCH_TRACE"))
+        std::fprintf(stderr, "[batch] n=%zu union build %.2f ms, h2d %.2f, expand %.2f, connect %.2f, split + d2h %.2f ms\n",
+                     n, t_union, acc.ms_h2d, cs.ms_expand, cs.ms_connect, acc.ms_d2h);
+      done = true;
+    }
+  }
+  if (!done) {  // heterogeneous batch: one composition at a time, packed on the host
+    out = PackedBatch();
+    for (size_t i = 0; i < n; i++) {
+      DevFst da = upload(vec_alg(acceptors[i], "acceptor")->fst.checked(), st.s);
+      ComposeStats cs;
+      DevFst dr = compose_device(da, dt, opt, &cs, st.s);
+      out.append(download(dr, st.s));
+      acc.states_expanded += cs.states_expanded; acc.arcs_iterated += cs.arcs_iterated;
+      acc.arcs_emitted += cs.arcs_emitted; acc.waves += cs.waves; acc.states_out += cs.states_out;
+      acc.arcs_out += cs.arcs_out; acc.kernel_launches += cs.kernel_launches; acc.emit_launches += cs.emit_launches;
+      acc.ms_expand += cs.ms_expand; acc.ms_connect += cs.ms_connect; acc.ms_emit_kernel += cs.ms_emit_kernel;
+    }
+    if (n == 0) { out.state_off.assign(1, 0); out.arc_off.assign(1, 0); out.offsets.assign(1, 0); }
+  }
+  if (total) *total = acc;
+}
+
+struct B200PackedBatch { PackedBatch b; };
+
 RUSTFST_FFI_RESULT b200_compose_batch(const CFst* const* acceptors, size_t n, const CFst* transducer,
                                       const CComposeConfig* cfg, const CFst** results, B200ComposeStats* total) {
   return wrap([&] {
-    ComposeOptions opt = to_options(cfg);
-    const CsrFst& ht = nn(transducer, "transducer")->fst.checked();
     for (size_t i = 0; i < n; i++) results[i] = nullptr;
-    B200ComposeStats acc;
-    std::memset(&acc, 0, sizeof(acc));
-    Stream st;
-    double t0 = now_ms();
-    DevFst dt = upload(ht, st.s);
-    acc.ms_h2d += (float)(now_ms() - t0);
-
-    // ---- one BFS for the whole batch: the acceptors become one FST with disjoint state ranges and n start tuples.
-    // Every acceptor must lead to the same match side (same sortedness bits); otherwise fall back to a loop.
-    std::vector<const CsrFst*> hs(n);
-    bool uniform = n > 0 && ht.has_start;
-    uint64_t and_props = ~0ull, or_props = 0;
-    size_t sum_states = 0, sum_arcs = 0;
-    for (size_t i = 0; i < n; i++) {
-      hs[i] = &nn(acceptors[i], "acceptor")->fst.checked();
-      if (!hs[i]->inf_finals.empty()) uniform = false;
-      if (!hs[i]->has_start) uniform = false;
-      and_props &= hs[i]->props; or_props |= hs[i]->props;
-      sum_states += hs[i]->num_states(); sum_arcs += hs[i]->arcs.size();
-    }
-    const uint64_t steer = props::kOLabelSorted | props::kNotOLabelSorted | props::kAcceptor | props::kNotAcceptor |
-                           props::kNoEpsilons | props::kNoIEpsilons | props::kNoOEpsilons | props::kAcyclic |
-                           props::kInitialAcyclic | props::kIDeterministic | props::kODeterministic;
-    if ((and_props & steer) != (or_props & steer)) uniform = false;  // property bits that steer compose must agree
-    if (sum_states >= 0x7FFFFFF0ull || sum_arcs >= 0xFFFFFFF0ull) uniform = false;
-
-    bool done = false;
-    double t_union = 0, t_split = 0, t_handles = 0;
-    if (uniform) {
-      const double tu0 = now_ms();
-      CsrFst u;
-      u.offsets.resize(sum_states + 1);
-      u.arcs.resize(sum_arcs);
-      u.finals.resize(sum_states);
-      std::vector<uint32_t> starts(n), base_state(n + 1), base_arc(n + 1), acc_of(sum_states);
-      {
-        size_t so = 0, ao = 0;
-        for (size_t i = 0; i < n; i++) {
-          base_state[i] = (uint32_t)so; base_arc[i] = (uint32_t)ao;
-          starts[i] = (uint32_t)(so + hs[i]->start);
-          so += hs[i]->num_states(); ao += hs[i]->arcs.size();
-        }
-        base_state[n] = (uint32_t)so; base_arc[n] = (uint32_t)ao;
-      }
-      parallel_ranges(n, [&](size_t lo_i, size_t hi_i) {
-        for (size_t i = lo_i; i < hi_i; i++) {
-          const CsrFst& h = *hs[i];
-          const size_t so = base_state[i], ao = base_arc[i], ns = h.num_states(), na = h.arcs.size();
-          for (size_t s = 0; s < ns; s++) { u.offsets[so + s] = (uint32_t)(ao + h.offsets[s]); acc_of[so + s] = (uint32_t)i; }
-          std::memcpy(u.finals.data() + so, h.finals.data(), ns * 4);
-          for (size_t k = 0; k < na; k++) { Tr t = h.arcs[k]; t.nextstate += (uint32_t)so; u.arcs[ao + k] = t; }
-        }
-      });
-      u.offsets[sum_states] = base_arc[n];
-      u.has_start = true; u.start = starts[0];
-      u.props = and_props & props::kTrinary;
-      t_union = now_ms() - tu0;
-      t0 = now_ms();
-      DevFst du = upload(u, st.s);
-      DevBuf<uint32_t> d_starts(st.s, n), d_s1(st.s), d_map(st.s);
-      B200_CUDA(cudaMemcpyAsync(d_starts.p, starts.data(), n * 4, cudaMemcpyHostToDevice, st.s));
-      B200_CUDA(cudaStreamSynchronize(st.s));
-      acc.ms_h2d += (float)(now_ms() - t0);
-      BatchStarts bs;
-      bs.d_starts1 = d_starts.p; bs.n = (uint32_t)n; bs.out_s1 = &d_s1; bs.out_start_map = &d_map;
-      ComposeStats cs;
-      DevFst dr(st.s);
-      if (compose_device_persistent(du, dt, opt, &cs, st.s, &dr, &bs)) {
-        t0 = now_ms();
-        CsrFst r = download(dr, st.s);
-        const size_t rn = r.num_states();
-        std::vector<uint32_t> tag(rn ? rn : 1), smap(n);
-        if (rn) B200_CUDA(cudaMemcpyAsync(tag.data(), d_s1.p, rn * 4, cudaMemcpyDeviceToHost, st.s));
-        B200_CUDA(cudaMemcpyAsync(smap.data(), d_map.p, n * 4, cudaMemcpyDeviceToHost, st.s));
-        B200_CUDA(cudaStreamSynchronize(st.s));
-        acc.ms_d2h += (float)(now_ms() - t0);
-        const double ts0 = now_ms();
-        // ---- split the union result per acceptor; ids inside a component keep their relative order, which is
-        // exactly the numbering of the stand-alone composition (same BFS restricted to that component)
-        std::vector<uint32_t> comp(rn), local(rn), arc_at(rn), n_st(n, 0), n_ar(n, 0);
-        parallel_ranges(rn, [&](size_t lo_s, size_t hi_s) {  // random look-ups into a 1.6M-entry table: spread them
-          for (size_t s = lo_s; s < hi_s; s++) comp[s] = acc_of[tag[s]];
-        });
-        for (size_t s = 0; s < rn; s++) {
-          const uint32_t c = comp[s];
-          local[s] = n_st[c]++;
-          arc_at[s] = n_ar[c];  // first arc of the state inside its own result
-          n_ar[c] += r.offsets[s + 1] - r.offsets[s];
-        }
-        std::vector<CsrFst> parts(n);
-        for (size_t i = 0; i < n; i++) {
-          parts[i].offsets.resize((size_t)n_st[i] + 1);
-          parts[i].arcs.resize(n_ar[i]);
-          parts[i].finals.resize(n_st[i]);
-          parts[i].offsets[n_st[i]] = n_ar[i];
-          uint64_t p = props::of_compose(hs[i]->props, ht.props);
-          if (opt.connect) p = props::after_connect(p);
-          parts[i].props = p & props::kTrinary;
-          parts[i].has_start = smap[i] != 0xFFFFFFFFu;
-          parts[i].start = parts[i].has_start ? local[smap[i]] : 0;
-        }
-        parallel_ranges(rn, [&](size_t lo_s, size_t hi_s) {  // every state writes its own slots of its own result
-          for (size_t s = lo_s; s < hi_s; s++) {
-            CsrFst& p = parts[comp[s]];
-            const uint32_t ls = local[s];
-            p.finals[ls] = r.finals[s];
-            uint32_t o = arc_at[s];
-            p.offsets[ls] = o;
-            for (uint32_t k = r.offsets[s]; k < r.offsets[s + 1]; k++) {
-              Tr t = r.arcs[k];
-              t.nextstate = local[t.nextstate];
-              p.arcs[o++] = t;
-            }
-          }
-        });
-        t_split = now_ms() - ts0;
-        const double th0 = now_ms();
-        for (size_t i = 0; i < n; i++) results[i] = new CFst{HostFst(std::move(parts[i]))};
-        t_handles = now_ms() - th0;
-        fill(&acc, cs, acc.ms_h2d, acc.ms_d2h);
-        if (std::getenv("B200_BATCH_TRACE"))
-          std::fprintf(stderr, "[batch] n=%zu union build %.2f ms, h2d %.2f, expand %.2f, connect %.2f, d2h %.2f, split %.2f, "
-                       "handles %.2f ms\n", n, t_union, acc.ms_h2d, cs.ms_expand, cs.ms_connect, acc.ms_d2h, t_split, t_handles);
-        done = true;
-      }
-    }
-    if (!done) {  // heterogeneous batch or pre-sized buffers too small: one composition at a time
-      for (size_t i = 0; i < n; i++) {
-        DevFst da = upload(nn(acceptors[i], "acceptor")->fst.checked(), st.s);
-        ComposeStats cs;
-        DevFst dr = compose_device(da, dt, opt, &cs, st.s);
-        results[i] = new CFst{HostFst(download(dr, st.s))};
-        acc.states_expanded += cs.states_expanded; acc.arcs_iterated += cs.arcs_iterated;
-        acc.arcs_emitted += cs.arcs_emitted; acc.waves += cs.waves; acc.states_out += cs.states_out;
-        acc.arcs_out += cs.arcs_out; acc.kernel_launches += cs.kernel_launches; acc.emit_launches += cs.emit_launches;
-        acc.ms_expand += cs.ms_expand; acc.ms_connect += cs.ms_connect; acc.ms_emit_kernel += cs.ms_emit_kernel;
-      }
-    }
-    if (total) *total = acc;
+    PackedBatch pb;
+    compose_batch_core(acceptors, n, nn(transducer, "transducer"), nullptr, cfg, pb, total);
+    // the handles are only released to the caller once every one of them exists
+    std::vector<std::unique_ptr<CFst>> made(n);
+    for (size_t i = 0; i < n; i++) made[i].reset(new CFst{HostFst(pb.result(i))});
+    for (size_t i = 0; i < n; i++) results[i] = made[i].release();
   });
+}
+RUSTFST_FFI_RESULT b200_compose_batch_packed(const CFst* const* acceptors, size_t n, const CFst* transducer,
+                                             const B200DeviceFst* dev_transducer, const CComposeConfig* cfg,
+                                             const B200PackedBatch** out, B200ComposeStats* total) {
+  return wrap([&] {
+    if (!transducer && !dev_transducer) throw FstError("unexpected null pointer: transducer");
+    auto r = std::make_unique<B200PackedBatch>();
+    compose_batch_core(acceptors, n, transducer, dev_transducer, cfg, r->b, total);
+    *out = r.release();
+  });
+}
+RUSTFST_FFI_RESULT b200_packed_batch_info(const B200PackedBatch* b, uint64_t* n, uint64_t* states, uint64_t* trs,
+                                          uint64_t* bytes) {
+  return wrap([&] {
+    nn(b, "batch");
+    if (n) *n = b->b.n;
+    if (states) *states = b->b.finals.size();
+    if (trs) *trs = b->b.arcs.size();
+    if (bytes) *bytes = b->b.byte_size();
+  });
+}
+RUSTFST_FFI_RESULT b200_packed_batch_get(const B200PackedBatch* b, size_t i, const CFst** out) {
+  return wrap([&] { *out = new CFst{HostFst(nn(b, "batch")->b.result(i))}; });
+}
+RUSTFST_FFI_RESULT b200_packed_batch_serialize(const B200PackedBatch* b, uint8_t* dst, size_t capacity) {
+  return wrap([&] {
+    if (capacity < nn(b, "batch")->b.byte_size()) throw FstError("packed batch: destination too small");
+    b->b.serialize(nn(dst, "dst"));
+  });
+}
+RUSTFST_FFI_RESULT b200_packed_batch_deserialize(const uint8_t* src, size_t len, const B200PackedBatch** out) {
+  return wrap([&] {
+    auto r = std::make_unique<B200PackedBatch>();
+    r->b = PackedBatch::deserialize(nn(src, "src"), len);
+    *out = r.release();
+  });
+}
+RUSTFST_FFI_RESULT b200_packed_batch_destroy(B200PackedBatch* b) {
+  return wrap([&] { delete b; });
 }
 RUSTFST_FFI_RESULT b200_shortest_path_queue_plan(const CFst* fst, int32_t* kind, uint32_t* order_or_scc,
                                                  uint8_t* scc_is_fifo, uint32_t* n_scc) {
@@ -815,6 +867,22 @@ RUSTFST_FFI_RESULT b200_shortest_path_queue_plan(const CFst* fst, int32_t* kind,
       if (!v.empty()) std::memcpy(order_or_scc, v.data(), v.size() * 4);
     }
     if (scc_is_fifo && !plan.scc_is_fifo.empty()) std::memcpy(scc_is_fifo, plan.scc_is_fifo.data(), plan.scc_is_fifo.size());
+  });
+}
+RUSTFST_FFI_RESULT b200_dag_top_order_device(const CFst* fst, uint32_t* order, int32_t* ok, float* ms_device) {
+  return wrap([&] {
+    const CsrFst& h = nn(fst, "fst")->fst.checked();
+    Stream st;
+    DevFst d = upload(h, st.s);
+    DevBuf<uint32_t> d_order(st.s);
+    float ms = 0;
+    const bool done = dag_top_order_device(d, d_order, &ms, nullptr, st.s);
+    if (ok) *ok = done ? 1 : 0;
+    if (ms_device) *ms_device = ms;
+    if (done && order && h.num_states()) {
+      B200_CUDA(cudaMemcpyAsync(order, d_order.p, h.num_states() * 4, cudaMemcpyDeviceToHost, st.s));
+      st.sync();
+    }
   });
 }
 RUSTFST_FFI_RESULT b200_set_device(int device) {

@@ -783,57 +783,45 @@ __global__ void k_ws_offsets(const uint2* __restrict__ st_first, const uint32_t*
   else if (s == n) off[n] = __ldg(&run_dst[n_runs]);
 }
 
-// Moves every provisional arc run to its canonical place and resolves the pending targets (slot index -> published id).
-// One warp per run, 128 arcs (2 KB) per step: bulk copy in, patch in shared memory, bulk copy out; two buffers, so the
-// load of step k+1 and the store of step k-1 overlap the patching of step k.
-constexpr uint32_t kMoveArcs = 128;
+// Canonical order of the arcs = runs in (wave, warp) order; run_dst = exclusive prefix of the run lengths.  One warp per
+// run, four arcs per lane in flight.  Pending targets (slot index) are resolved to the published state id on the way.
+// k_ws_move_next only produces the dense array of (resolved) next states — all the trim needs before its final gather,
+// which then reads the arcs straight from their provisional runs; k_ws_move_arcs moves whole arcs (connect = false).
 constexpr uint32_t kMoveWarps = 8;
+template <bool kWholeArcs>
 __global__ void __launch_bounds__(kMoveWarps * 32)
-k_ws_move_runs(const Tr* __restrict__ prov, const uint32_t* __restrict__ run_src, const uint32_t* __restrict__ run_cnt,
-               const uint32_t* __restrict__ run_dst, uint32_t n_runs, const Slot* __restrict__ slots,
-               Tr* __restrict__ out) {
-  __shared__ __align__(128) Tr s_buf[kMoveWarps][2][kMoveArcs];
-  __shared__ unsigned long long s_bar[kMoveWarps][2];
+k_ws_move(const Tr* __restrict__ prov, const uint32_t* __restrict__ run_src, const uint32_t* __restrict__ run_cnt,
+          const uint32_t* __restrict__ run_dst, uint32_t n_runs, const Slot* __restrict__ slots,
+          Tr* __restrict__ out_arcs, uint32_t* __restrict__ out_next) {
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  if (lane == 0) { bulk::mbar_init(&s_bar[wid][0], 1); bulk::mbar_init(&s_bar[wid][1], 1); bulk::fence_mbar_init(); }
-  __syncwarp();
-  uint32_t par = 0;
   const uint32_t warps = gridDim.x * kMoveWarps;
   for (uint32_t r = blockIdx.x * kMoveWarps + wid; r < n_runs; r += warps) {
     const uint32_t cnt = __ldg(&run_cnt[r]);
     if (!cnt) continue;
-    const Tr* src = prov + __ldg(&run_src[r]);
-    Tr* dst = out + __ldg(&run_dst[r]);
-    const uint32_t steps = (cnt + kMoveArcs - 1) / kMoveArcs;
-    if (lane == 0) {
-      const uint32_t n = min(kMoveArcs, cnt);
-      bulk::mbar_expect_tx(&s_bar[wid][0], n * 16u);
-      bulk::g2s(s_buf[wid][0], src, n * 16u, &s_bar[wid][0]);
-    }
-    for (uint32_t k = 0; k < steps; k++) {
-      const uint32_t b = k & 1u, n = min(kMoveArcs, cnt - k * kMoveArcs);
-      if (k + 1 < steps) {
-        if (lane == 0) {
-          bulk::wait_group_read<0>();  // the store that last used the other buffer has read it
-          const uint32_t n2 = min(kMoveArcs, cnt - (k + 1) * kMoveArcs);
-          bulk::mbar_expect_tx(&s_bar[wid][b ^ 1u], n2 * 16u);
-          bulk::g2s(s_buf[wid][b ^ 1u], src + (size_t)(k + 1) * kMoveArcs, n2 * 16u, &s_bar[wid][b ^ 1u]);
+    const Tr* __restrict__ src = prov + __ldg(&run_src[r]);
+    const uint32_t dst = __ldg(&run_dst[r]);
+    for (uint32_t e0 = 0; e0 < cnt; e0 += 128) {
+      int4 v[4];
+      uint32_t ns[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint32_t e = e0 + 32u * q + lane;
+        if (kWholeArcs) { v[q] = e < cnt ? __ldg(reinterpret_cast<const int4*>(&src[e])) : make_int4(0, 0, 0, 0); ns[q] = (uint32_t)v[q].w; }
+        else ns[q] = e < cnt ? __ldg(&src[e].nextstate) : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (ns[q] & kPendingBit) ns[q] = __ldg(&slots[ns[q] & ~kPendingBit].id);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint32_t e = e0 + 32u * q + lane;
+        if (e < cnt) {
+          if (kWholeArcs) { v[q].w = (int)ns[q]; *reinterpret_cast<int4*>(&out_arcs[dst + e]) = v[q]; }
+          else out_next[dst + e] = ns[q];
         }
       }
-      bulk::mbar_wait(&s_bar[wid][b], (par >> b) & 1u);
-      par ^= 1u << b;
-      for (uint32_t q = lane; q < n; q += 32) {
-        const uint32_t ns = s_buf[wid][b][q].nextstate;
-        if (ns & kPendingBit) s_buf[wid][b][q].nextstate = __ldg(&slots[ns & ~kPendingBit].id);
-      }
-      bulk::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) { bulk::s2g(dst + (size_t)k * kMoveArcs, s_buf[wid][b], n * 16u); bulk::commit_group(); }
     }
-    if (lane == 0) bulk::wait_group_read<0>();
-    __syncwarp();
   }
-  if (lane == 0) bulk::wait_group<0>();
 }
 
 static int ws_grid_used = 1;
@@ -1033,11 +1021,15 @@ int compose_device_ws(const DevFst& fa, const DevFst& fb, const ComposeOptions& 
   B200_CUDA(cudaMemsetAsync(run_cnt.p + n_runs, 0, 4, s));
   exclusive_sum_u32(run_cnt.p, run_dst.p, (size_t)n_runs + 1, scan_tmp, s);
   out.offsets.reserve_discard((size_t)n_states + 1);
-  out.arcs.reserve_discard(n_arcs ? n_arcs : 1);
   k_ws_offsets<<<blocks_for((size_t)n_states + 1), kThreads, 0, s>>>(st_first.p, run_dst.p, n_states, n_runs, out.offsets.p);
-  if (n_runs) {
-    const unsigned move_grid = std::min<unsigned>((n_runs + kMoveWarps - 1) / kMoveWarps, (unsigned)sm_count() * 8u);
-    k_ws_move_runs<<<move_grid, kMoveWarps * 32, 0, s>>>(prov_arcs.p, run_src.p, run_cnt.p, run_dst.p, n_runs, slots.p, out.arcs.p);
+  const unsigned move_grid = std::min<unsigned>((n_runs + kMoveWarps - 1) / kMoveWarps, (unsigned)sm_count() * 8u);
+  DevBuf<uint32_t> next(s);
+  if (opt.connect) {  // the trim only needs the resolved next states; it gathers the arcs from their runs itself
+    next.reserve_discard(n_arcs ? n_arcs : 1);
+    if (n_runs) k_ws_move<false><<<move_grid, kMoveWarps * 32, 0, s>>>(prov_arcs.p, run_src.p, run_cnt.p, run_dst.p, n_runs, slots.p, nullptr, next.p);
+  } else {
+    out.arcs.reserve_discard(n_arcs ? n_arcs : 1);
+    if (n_runs) k_ws_move<true><<<move_grid, kMoveWarps * 32, 0, s>>>(prov_arcs.p, run_src.p, run_cnt.p, run_dst.p, n_runs, slots.p, out.arcs.p, nullptr);
   }
   st.kernel_launches += 3;
   out.num_states = n_states; out.num_arcs = n_arcs;
@@ -1051,7 +1043,9 @@ int compose_device_ws(const DevFst& fa, const DevFst& fb, const ComposeOptions& 
     extras.n_starts = n_starts;
     extras.out_tag = batch ? batch->out_s1 : nullptr;
     extras.out_start_map = batch ? batch->out_start_map : nullptr;
-    DevFst trimmed = connect_waves_device(out, wave_lo.p, (uint32_t)st.waves, &launches, s, &extras);
+    ProvArcs pa;
+    pa.prov = prov_arcs.p; pa.st_first = st_first.p; pa.run_src = run_src.p; pa.run_cnt = run_cnt.p; pa.next = next.p;
+    DevFst trimmed = connect_waves_device(out, wave_lo.p, (uint32_t)st.waves, &launches, s, &extras, &pa);
     st.kernel_launches += launches;
     out = std::move(trimmed);
   } else if (batch) {

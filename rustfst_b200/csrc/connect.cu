@@ -141,6 +141,9 @@ struct TrimParams {
   const unsigned long long* tuples; uint32_t* ntag;   // optional: s1 component of the packed tuple, gathered
   uint32_t n_starts; uint32_t* start_map;             // optional: new ids of input states 0..n_starts-1
   uint32_t light_barrier;  // 1: arrival-counter barrier of coop_utils.cuh on ctl[5] instead of cg::grid_group::sync()
+  // optional (compose_ws.cu): the arcs still sit in provisional (wave, warp) runs; `next` is the dense array of their
+  // resolved next states in canonical order (all the sweeps need), st_first[s] = (run, index) of the first arc of state s
+  const uint32_t* next; const Tr* prov; const uint2* st_first; const uint32_t* run_src; const uint32_t* run_cnt;
 };
 
 #define TRIM_SYNC() do { if (P.light_barrier) grid_barrier(P.ctl + 5, bar_epoch); else grid.sync(); } while (0)
@@ -167,7 +170,7 @@ k_trim_coop(TrimParams P) {
           bool back = false;
           co = (sweeps == 0 && P.fin[s] != w_zero()) ? 1 : 0;
           for (uint32_t i = P.off[s]; i < P.off[s + 1] && !co; i++) {
-            const uint32_t t = __ldg(&P.arcs[i].nextstate);
+            const uint32_t t = P.next ? __ldg(&P.next[i]) : __ldg(&P.arcs[i].nextstate);
             if (t < whi) back = true;  // same or earlier wave: value may still change in this sweep
             co = __ldcg(&P.coacc[t]);
           }
@@ -218,7 +221,10 @@ k_trim_coop(TrimParams P) {
         for (uint32_t i = a_lo; i < a_hi; i += 4) {  // four arcs per round: the target look-ups fly together
           uint32_t t[4], x[4];
 #pragma unroll
-          for (int q = 0; q < 4; q++) t[q] = __ldg(&P.arcs[min(i + q, a_hi - 1)].nextstate);
+          for (int q = 0; q < 4; q++) {
+            const uint32_t k = min(i + q, a_hi - 1);
+            t[q] = P.next ? __ldg(&P.next[k]) : __ldg(&P.arcs[k].nextstate);
+          }
 #pragma unroll
           for (int q = 0; q < 4; q++) x[q] = __ldcg(&P.id_loc[t[q]]);
 #pragma unroll
@@ -246,6 +252,39 @@ k_trim_coop(TrimParams P) {
     P.noff[ns] = o;
     if (P.ntag) P.ntag[ns] = (uint32_t)(P.tuples[s] & 0x7FFFFFFFull);
     const uint32_t a_lo = P.off[s], a_hi = P.off[s + 1];
+    if (P.prov) {
+      // the arcs of the state start at st_first[s] in a provisional run and continue at the start of the following
+      // run(s); their resolved next states are next[a_lo .. a_hi) in canonical order
+      const uint2 f = __ldg(&P.st_first[s]);
+      uint32_t r = f.x, el = f.y, i = a_lo;
+      while (i < a_hi) {
+        const uint32_t rc = __ldg(&P.run_cnt[r]);
+        if (el >= rc) { r++; el = 0; continue; }
+        const uint32_t take = min(a_hi - i, rc - el);
+        const Tr* __restrict__ src = P.prov + __ldg(&P.run_src[r]) + el;
+        for (uint32_t k = 0; k < take; k += 4) {
+          int4 v[4];
+          uint32_t t[4], x[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const uint32_t kk = min(k + q, take - 1);
+            v[q] = __ldg(reinterpret_cast<const int4*>(&src[kk]));
+            t[q] = __ldg(&P.next[i + kk]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) x[q] = __ldcg(&P.id_loc[t[q]]);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (k + q < take && x[q] != 0xFFFFFFFFu) {
+              v[q].w = (int)(s_pref_id[t[q] / sc] + x[q]);
+              *reinterpret_cast<int4*>(&P.narcs[o++]) = v[q];
+            }
+          }
+        }
+        i += take; el += take;
+      }
+      continue;
+    }
     for (uint32_t i = a_lo; i < a_hi; i += 4) {
       int4 v[4];
       uint32_t x[4];
@@ -376,7 +415,7 @@ DevFst connect_device(const DevFst& in, bool assume_accessible, uint64_t* launch
 }
 
 DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_t n_waves, uint64_t* launches,
-                            cudaStream_t s, const TrimExtras* extras) {
+                            cudaStream_t s, const TrimExtras* extras, const ProvArcs* pa) {
   DevFst out(s);
   out.props = props::after_connect(in.props);
   const uint32_t n = in.num_states;
@@ -406,6 +445,7 @@ DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_
   P.part_keep = parts.p; P.part_deg = parts.p + 2049;
   P.noff = out.offsets.p; P.narcs = out.arcs.p; P.nfin = out.finals.p; P.ctl = ctl.p;
   P.light_barrier = std::getenv("B200_TRIM_CG") ? 0u : 1u;
+  if (pa) { P.next = pa->next; P.prov = pa->prov; P.st_first = pa->st_first; P.run_src = pa->run_src; P.run_cnt = pa->run_cnt; }
   if (extras && extras->out_tag) {
     extras->out_tag->reserve_discard(n);
     extras->out_start_map->reserve_discard(extras->n_starts);

@@ -154,7 +154,14 @@ bool top_order(const CsrFst& f, std::vector<uint32_t>& order) {
   return true;
 }
 
-QueuePlan build_queue_plan(const CsrFst& f) {
+QueueKind queue_kind_from_props(uint64_t p, bool has_start) {
+  if ((p & props::kTopSorted) || !has_start) return kStateOrderQueue;
+  if (p & props::kAcyclic) return kTopOrderQueue;
+  if (p & props::kUnweighted) return kLifoQueue;
+  return kSccQueue;
+}
+
+QueuePlan build_queue_plan(const CsrFst& f, bool defer_acyclic_order) {
   auto t0 = std::chrono::steady_clock::now();
   QueuePlan plan;
   const size_t n = f.num_states();
@@ -165,6 +172,7 @@ QueuePlan build_queue_plan(const CsrFst& f) {
   };
   if ((p & props::kTopSorted) || !f.has_start) { plan.kind = kStateOrderQueue; return done(); }
   if (p & props::kAcyclic) {
+    if (defer_acyclic_order) { plan.kind = kTopOrderQueue; plan.deferred = true; return done(); }
     DfsResult r = dfs_top_order(f);
     if (!r.acyclic) throw FstError("Unexpectted Acyclic FST for TopOprerQueue");  // top_order_queue.rs:25-27 (panic)
     plan.kind = kTopOrderQueue;

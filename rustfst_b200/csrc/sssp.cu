@@ -829,7 +829,11 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
   DevBuf<uint32_t> meta(s, 4);
   DevBuf<uint32_t> d_order(s);
   const uint32_t* order_p = nullptr;
-  if (plan.kind == kTopOrderQueue) {
+  if (plan.kind == kTopOrderQueue && plan.d_order) {
+    order_p = plan.d_order;  // computed on the device (dag_order.cu)
+    st.order_device_ms = plan.device_ms; st.order_on_device = true;
+  } else if (plan.kind == kTopOrderQueue) {
+    if (plan.order.size() != n) throw FstError("shortest path: the TopOrderQueue order has not been computed");
     d_order.reserve_discard(n);
     B200_CUDA(cudaMemcpyAsync(d_order.p, plan.order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
     order_p = d_order.p;
@@ -947,7 +951,11 @@ void shortest_distance_device(const DevFst& f, const QueuePlan& plan, float delt
   EventPairs relax_events;
   DevBuf<uint32_t> d_order(s);
   const uint32_t* order_p = nullptr;
-  if (plan.kind == kTopOrderQueue) {
+  if (plan.kind == kTopOrderQueue && plan.d_order) {
+    order_p = plan.d_order;  // computed on the device (dag_order.cu)
+    st.order_device_ms = plan.device_ms; st.order_on_device = true;
+  } else if (plan.kind == kTopOrderQueue) {
+    if (plan.order.size() != n) throw FstError("shortest path: the TopOrderQueue order has not been computed");
     d_order.reserve_discard(n);
     B200_CUDA(cudaMemcpyAsync(d_order.p, plan.order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
     order_p = d_order.p;

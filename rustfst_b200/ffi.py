@@ -46,7 +46,7 @@ class SsspStats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("relax_launches", C.c_uint64),
                 ("path", C.c_int32), ("queue_kind", C.c_int32),
                 ("ms_device", C.c_float), ("ms_relax_kernel", C.c_float), ("ms_h2d", C.c_float),
-                ("ms_queue_plan_host", C.c_double)]
+                ("ms_queue_plan_host", C.c_double), ("ms_order_device", C.c_float), ("order_on_device", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -162,6 +162,13 @@ _sig("b200_device_shortest_path", _P, _P, _PP, C.POINTER(SsspStats), C.c_bool)
 _sig("b200_device_shortest_path_with_config", _P, _P, _P, _PP, C.POINTER(SsspStats), C.c_bool)
 _sig("b200_compose_batch", C.POINTER(C.c_void_p), C.c_size_t, _P, _P, C.POINTER(C.c_void_p), C.POINTER(ComposeStats))
 _sig("b200_shortest_path_queue_plan", _P, C.POINTER(C.c_int32), _P, _P, C.POINTER(C.c_uint32))
+_sig("b200_compose_batch_packed", _P, C.c_size_t, _P, _P, _P, _PP, C.POINTER(ComposeStats))
+_sig("b200_packed_batch_info", _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+_sig("b200_packed_batch_get", _P, C.c_size_t, _PP)
+_sig("b200_packed_batch_serialize", _P, _P, C.c_size_t)
+_sig("b200_packed_batch_deserialize", _P, C.c_size_t, _PP)
+_sig("b200_packed_batch_destroy", _P)
+_sig("b200_dag_top_order_device", _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_float))
 _sig("b200_set_device", C.c_int)
 _sig("b200_device_count", C.POINTER(C.c_int))
 _sig("b200_device_synchronize")

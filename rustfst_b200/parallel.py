@@ -54,6 +54,35 @@ def gather_blobs(blobs: Sequence[bytes], dist, device=None, dst: int = 0) -> Opt
     return out
 
 
+def gather_buffers(local, dist, device=None, dst: int = 0):
+    """One variable-length uint8 buffer per rank -> list of buffers on `dst` (rank order), None elsewhere.  Only the
+    destination receives payload: an all_gather of the byte counts (8 bytes per rank), then point-to-point send/recv
+    of exactly those bytes (NCCL send/recv over NVLink on GPUs, gloo in the CPU tests)."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    t = torch.as_tensor(local, dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device, non_blocking=True)
+    size = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    if rank != dst:
+        if t.numel():
+            dist.send(t, dst)
+        return None
+    out = []
+    for r in range(world):
+        n = int(sizes[r].item())
+        if r == dst:
+            out.append(t)
+        else:
+            buf = torch.empty(n, dtype=torch.uint8, device=t.device)
+            if n:
+                dist.recv(buf, r)
+            out.append(buf)
+    return out
+
+
 def batched_compose_sharded(acceptor_blobs: Sequence[bytes], transducer_blob: bytes,
                             compose_fn: Callable[[List[bytes], bytes], List[bytes]], dist=None, device=None):
     """Shard `acceptor_blobs` over the ranks of `dist`, run `compose_fn(local_acceptors, transducer)` locally and

@@ -92,9 +92,11 @@ def layered_acceptor(n_states, n_arcs, vocab, seed, levels=32, start_fanout=Fals
 
 
 def bigram_transducer(n_states, n_arcs, vocab, seed, levels=32, out_vocab=None, start_fanout=False,
-                      continuous=False):
+                      continuous=False, spread=False):
     """Layered transducer whose arc target is a function of the input label (LM-like); ilabel-sorted.
-    With start_fanout the start state carries every input label once."""
+    With start_fanout the start state carries every input label once.  With spread the target also depends on the
+    source state (slot = mix(ilabel, source) % w), so ALL w states of a level are reached and the arc lists a
+    composition searches are spread over the whole machine (HBM-resident) instead of `vocab` slots per level."""
     rng = np.random.default_rng(seed)
     out_vocab = out_vocab or vocab
     n, w, base = _level_layout(n_states, levels)
@@ -113,7 +115,12 @@ def bigram_transducer(n_states, n_arcs, vocab, seed, levels=32, out_vocab=None, 
     if start_fanout:
         ilabel[:vocab] = np.arange(1, vocab + 1)
     # a per-level rotation keeps consecutive levels from using the same slots for the same label
-    target = base[level + 1] + (ilabel - 1 + 7919 * level) % w
+    if spread:
+        mix = (ilabel * 0x9E3779B1 + src * 0x85EBCA77) & 0xFFFFFFFF
+        mix ^= mix >> 15
+        target = base[level + 1] + (mix * 0x2C1B3C6D & 0xFFFFFFFF) % w
+    else:
+        target = base[level + 1] + (ilabel - 1 + 7919 * level) % w
     weight = _weights(rng, total, continuous)
     order = np.lexsort((olabel, ilabel, src))
     arcs = np.zeros(total, dtype=TR_DTYPE)
@@ -122,6 +129,34 @@ def bigram_transducer(n_states, n_arcs, vocab, seed, levels=32, out_vocab=None, 
     finals = np.full(n, np.inf, dtype=np.float32)
     finals[n - w:] = _weights(rng, w, continuous)
     return _finish(n, offsets, arcs, finals, False, True, False)
+
+
+def window_dag(n_states, n_arcs, vocab, seed, window=1000, continuous=False):
+    """SURVEY.md 8d's acyclic acceptor: state s has ~A/N arcs to targets uniform in (s, min(N-1, s+window)], so arcs
+    skip levels (a label-correcting relaxation revisits states) and the machine is topologically sorted by state id.
+    The last 1 % of the states are final."""
+    rng = np.random.default_rng(seed)
+    n = int(n_states)
+    n_src = n - 1
+    deg = _degrees(rng, n_src, n_arcs)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    offsets[1:n_src + 1] = np.cumsum(deg)
+    offsets[n_src + 1:] = offsets[n_src]
+    total = int(offsets[n_src])
+    src = np.repeat(np.arange(n_src, dtype=np.int64), deg)
+    span = np.minimum(window, n - 1 - src)
+    target = src + 1 + (rng.random(total) * span).astype(np.int64)
+    target = np.minimum(target, n - 1)
+    label = rng.integers(1, vocab + 1, size=total, dtype=np.int64)
+    weight = _weights(rng, total, continuous)
+    order = np.lexsort((label, src))
+    arcs = np.zeros(total, dtype=TR_DTYPE)
+    arcs["ilabel"] = label[order]; arcs["olabel"] = label[order]
+    arcs["weight"] = weight[order]; arcs["nextstate"] = target[order]
+    finals = np.full(n, np.inf, dtype=np.float32)
+    nf = max(1, n // 100)
+    finals[n - nf:] = _weights(rng, nf, continuous)
+    return _finish(n, offsets, arcs, finals, True, True, True)
 
 
 def linear_acceptor(labels, seed):
@@ -175,6 +210,26 @@ def sample_path_labels(t, length, seed):
         a = arcs[rng.integers(lo, hi)]
         labels[i] = a["ilabel"]
         s = int(a["nextstate"])
+    return labels
+
+
+def sample_path_labels_batch(t, length, count, seed):
+    """`count` label strings at once (vectorised random walks in `t`; the rest of a walk that hits a dead end is filled
+    with random labels).  Returns an int64 array (count, length)."""
+    rng = np.random.default_rng(seed)
+    off, arcs = t["offsets"].astype(np.int64), t["arcs"]
+    vmax = int(arcs["ilabel"].max()) if len(arcs) else 1
+    s = np.full(count, t["start"], dtype=np.int64)
+    alive = np.ones(count, dtype=bool)
+    labels = rng.integers(1, 1 + vmax, size=(count, length), dtype=np.int64)
+    for i in range(length):
+        lo, hi = off[s], off[s + 1]
+        alive &= hi > lo
+        pick = lo + (rng.random(count) * np.maximum(hi - lo, 1)).astype(np.int64)
+        pick = np.minimum(pick, np.maximum(hi - 1, 0))
+        a = arcs[np.where(alive, pick, 0)]
+        labels[alive, i] = a["ilabel"][alive]
+        s = np.where(alive, a["nextstate"].astype(np.int64), s)
     return labels
 
 

@@ -244,6 +244,14 @@ def test_batched_compose_equals_individual_composes(connect):
         assert_same(r, expected, f"batch item {i} connect={connect}")
         nonempty += expected.num_states > 0
     assert nonempty > 10
+    # the same batch as ONE packed block, transducer resident in HBM; the block survives a trip through bytes
+    dt = R.DeviceFst.upload(pt)
+    pb, st2 = R.compose_batch_packed([p for p, _ in pairs], config=cfg, device_transducer=dt)
+    assert len(pb) == 64 and st2["arcs_out"] == st["arcs_out"]
+    back = R.PackedBatch.from_buffer(pb.to_bytes())
+    assert back.info() == pb.info()
+    for i, r in enumerate(results):
+        assert pb.result(i).to_bytes() == r.to_bytes() == back.result(i).to_bytes(), f"packed batch item {i}"
 
 
 def test_batched_compose_heterogeneous_falls_back():
@@ -256,6 +264,9 @@ def test_batched_compose_heterogeneous_falls_back():
     results, _ = R.compose_batch([p for p, _ in pairs], pb)
     for (p, o), r in zip(pairs, results):
         assert_same(r, O.compose(o, ob), "heterogeneous batch")
+    packed, _ = R.compose_batch_packed([p for p, _ in pairs], pb)
+    for i, r in enumerate(results):
+        assert packed.result(i).to_bytes() == r.to_bytes()
 
 
 def test_shortest_path_with_near_ties_uses_the_order_faithful_parallel_path():

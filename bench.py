@@ -278,6 +278,86 @@ def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_ove
             "timer": "max(CUDA events, host wall clock) around K host-driven steps, max over ranks"}
 
 
+def run_extras(args, R, synth, torch, peak_gbs, barrier):
+    """Two workloads next to the headline ones (N = 1 only), chosen to be UNfavourable where the headline ones are kind:
+      * compose_spread — the same operand sizes as C3, but the transducer's arc target depends on (label, source), so
+        every state of a level is reached and the arc lists the matcher searches are spread over the whole 160 MB
+        machine (HBM-resident) instead of 32 slots per level; both start states fan out (a 20 000-arc hub), labels
+        are drawn from 93 symbols so that the product neither dies nor explodes (~1 successor per product state).
+      * sssp_window — SURVEY.md 8d's acyclic acceptor with arcs to targets up to 1000 ids ahead: arcs skip levels, the
+        longest path has tens of thousands of hops, and a label-correcting relaxation re-relaxes states many times."""
+    from tests import oracle_lib as O
+    out = {}
+    steps = max(1, min(args.steps, 5))
+    n, a = int(1_000_000 * args.scale), int(10_000_000 * args.scale)
+    a1 = synth.layered_acceptor(n, a, 93, 3, 50, start_fanout=True)
+    a2 = synth.bigram_transducer(n, a, 93, 4, 50, out_vocab=20000, start_fanout=True, spread=True)
+    d1, d2 = R.DeviceFst.upload(synth.to_vector_fst(a1)), R.DeviceFst.upload(synth.to_vector_fst(a2))
+    for _ in range(3):
+        r, st = R.device_compose(d1, d2)
+        del r
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tot = {"arcs_emitted": 0, "arcs_iterated": 0, "states_expanded": 0, "ms_emit_kernel": 0.0, "ms_expand": 0.0, "ms_connect": 0.0}
+    for _ in range(steps):
+        r, st = R.device_compose(d1, d2)
+        for k in tot:
+            tot[k] += st[k]
+        del r
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    bytes_c = 16.0 * tot["arcs_iterated"] + 48.0 * tot["arcs_emitted"] + 32.0 * tot["states_expanded"]
+    out["compose_spread"] = {
+        "workload": f"layered acceptor ({a1['num_states']} states, {len(a1['arcs'])} arcs) o spread transducer "
+                    f"({a2['num_states']} states, {len(a2['arcs'])} arcs), 93 labels, start states fan out",
+        "value": tot["arcs_emitted"] / (ms * 1e-3), "unit": "arcs/s", "ms_per_step": ms / steps,
+        "states_expanded_per_step": tot["states_expanded"] // steps, "arcs_emitted_per_step": tot["arcs_emitted"] // steps,
+        "arcs_iterated_per_step": tot["arcs_iterated"] // steps,
+        "expand_ms_per_step": tot["ms_expand"] / steps, "connect_ms_per_step": tot["ms_connect"] / steps,
+        "roofline": {"bound": "hbm", "kernel": "k_compose_ws", "bytes_model": "16*A_it + 48*A_out + 32*S",
+                     "achieved": bytes_c / (tot["ms_emit_kernel"] * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": bytes_c / (tot["ms_emit_kernel"] * 1e-3) / 1e9 / peak_gbs,
+                     "avg_launch_ms": tot["ms_emit_kernel"] / steps}}
+    if not args.no_cpu_baseline:
+        oa = O.OFst.from_csr(a1["offsets"].astype(np.uint64), a1["arcs"], a1["finals"], a1["start"], a1["props"])
+        ob = O.OFst.from_csr(a2["offsets"].astype(np.uint64), a2["arcs"], a2["finals"], a2["start"], a2["props"])
+        _, ost = O.compose(oa, ob, want_stats=True)
+        out["compose_spread"]["cpu_baseline"] = {"value": ost["arcs_emitted"] / ost["seconds"], "unit": "arcs/s", "cores": 1,
+                                                 "kind": "port", "sample": f"one full compose+connect ({ost['seconds']:.2f} s)"}
+        del oa, ob
+    del d1, d2
+    g = synth.window_dag(int(5_000_000 * args.scale), int(50_000_000 * args.scale), 1000, 6, window=1000)
+    dg = R.DeviceFst.upload(synth.to_vector_fst(g))
+    for _ in range(2):
+        R.device_shortest_path(dg)
+    barrier()
+    t0 = time.perf_counter()
+    edges, relaxed, waves = 0, 0, 0
+    wsteps = max(1, min(steps, 3))
+    for _ in range(wsteps):
+        _, sst = R.device_shortest_path(dg)
+        relaxed += sst["arcs_relaxed"]; waves = sst["waves"]
+    barrier()
+    ms = 1e3 * (time.perf_counter() - t0)
+    n_edges = len(g["arcs"])
+    out["sssp_window"] = {
+        "workload": f"window DAG: {g['num_states']} states, {n_edges} arcs, targets up to 1000 ids ahead (TOP_SORTED known)",
+        "value": n_edges * wsteps / (ms * 1e-3), "unit": "edges/s (distinct edges of the machine / call time)",
+        "ms_per_step": ms / wsteps, "relaxation_waves": waves, "arcs_relaxed_per_call": relaxed // wsteps,
+        "re_relaxation_factor": relaxed / wsteps / max(1, n_edges), "device_path": sst["path"],
+        "note": "label-correcting waves revisit a state whenever a shorter route arrives; a topological pass touches every "
+                "arc once, which is what the CPU does"}
+    if not args.no_cpu_baseline:
+        og = O.OFst.from_csr(g["offsets"].astype(np.uint64), g["arcs"], g["finals"], g["start"], g["props"])
+        _, cst = O.shortest_path(og, want_stats=True)
+        out["sssp_window"]["cpu_baseline"] = {"value": cst["arcs_relaxed"] / cst["seconds"], "unit": "edges/s", "cores": 1,
+                                              "kind": "port", "sample": f"one full shortest_path ({cst['seconds']:.2f} s)"}
+    del dg
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -290,6 +370,7 @@ def main():
     ap.add_argument("--callers", type=int, default=3, help="host threads of the supplementary concurrent e2e figure (1 = skip)")
     ap.add_argument("--no-sssp", action="store_true")
     ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the two extra workloads (spread compose, window-DAG SSSP)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -574,6 +655,10 @@ def main():
     if not args.no_c5:
         c5 = run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks, synth)
 
+    extras = None
+    if world == 1 and not args.no_extras and args.workload == "C3":
+        extras = run_extras(args, R, synth, torch, peak_gbs, barrier)
+
     if rank == 0:
         line = {
             "metric": "composed_arcs_per_sec", "value": value, "unit": "arcs/s", "n_gpus": world, "steps": steps,
@@ -584,7 +669,7 @@ def main():
                                "arcs_emitted_per_step": tot["arcs_emitted"] // steps,
                                "waves_per_step": tot["waves"] // steps},
             "wall_ms_per_step": wall_ms / steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sssp": sssp, "c5": c5,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "sssp": sssp, "c5": c5, "extra_workloads": extras,
             "gpu_launches": int(tot["kernel_launches"]), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

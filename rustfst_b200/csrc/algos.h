@@ -112,6 +112,8 @@ struct ProvArcs {
   const uint2* st_first = nullptr;   // per state: (run, index in the run) of its first arc
   const uint32_t* run_src = nullptr; // first provisional arc of every run
   const uint32_t* run_cnt = nullptr; // arcs of every run
+  const uint32_t* run_dst = nullptr; // canonical index of every run's first arc (n_runs + 1 entries)
+  uint32_t n_runs = 0;
   const uint32_t* next = nullptr;    // num_arcs resolved next states, canonical order
 };
 DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_t n_waves, uint64_t* launches,

@@ -90,6 +90,7 @@ struct WsParams {
 #define B200_WS_RA 4
 #endif
 constexpr uint32_t kEA = B200_WS_EA, kRA = B200_WS_RA;
+static_assert(kEA == 1, "the emit phase locates records with a 32-bit start mask: one arc per lane and round");
 constexpr uint32_t kMT = 32;        // items per match tile (one per lane)
 constexpr uint32_t kET = 32 * kEA;  // arcs per emit round
 constexpr uint32_t kSegN = (kMT > kET ? kMT : kET) + 1;
@@ -98,7 +99,6 @@ struct __align__(128) WarpSmem {
   StRec win[2][kMT + 2];      // match: state records of the current / next tile (kMT + 1 used)
   uint4 brec[2][kET];         // emit: match records of the current / next round
   uint32_t bloc[2][kET + 8];  // emit: their warp-local arc offsets (a 16-byte aligned window)
-  uint32_t seg[kSegN + 3];    // item offsets (match) / arc offsets (emit) of the current window
   unsigned long long mbar[4]; // [0,1] match windows, [2,3] emit windows
 };
 // the rank phase keeps the slots of the first emissions it found in the (then idle) match windows
@@ -383,26 +383,29 @@ k_compose_ws(WsParams P) {
         par ^= 1u << buf;
         const StRec* __restrict__ win = W.win[buf];
         const uint32_t n_win = min(kMT + 1u, F - i_base);
-        W.seg[lane] = lane < n_win ? s_wpref[win[lane].meta >> 8] + (win[lane].item_loc & ~kSideBit) : T;
-        if (lane == 0) W.seg[32] = 32u < n_win ? s_wpref[win[32].meta >> 8] + (win[32].item_loc & ~kSideBit) : T;
-        __syncwarp();
+        // lane x holds the first item of state i_base + x (and every lane that of state i_base + 32).  A state starts at a
+        // lane of the tile iff its first item falls inside the tile: one warp-wide OR of those bits, and the state of a
+        // lane's item is the number of starts at or before the lane (no per-lane binary search).
+        const uint32_t sv = lane < n_win ? s_wpref[win[lane].meta >> 8] + (win[lane].item_loc & ~kSideBit) : T;
+        const uint32_t sv32 = 32u < n_win ? s_wpref[win[32].meta >> 8] + (win[32].item_loc & ~kSideBit) : T;
+        const uint32_t starts = __reduce_or_sync(0xFFFFFFFFu, (lane >= 1 && sv > t0 && sv - t0 < 32u) ? 1u << (sv - t0) : 0u);
         Item it;
         it.se_lo = 0; it.se_hi = 0; it.it_idx = 0xFFFFFFFFu; it.flags = 0; it.sidx = 0; it.label = kNoLabel;
         it.id = 0; it.slot = kNoSlot; it.fin_bits = 0; it.key_lo = 0; it.key_hi = 0;
         const uint32_t t = t0 + lane;
         it.valid = t < we;
-        uint32_t k = 0, next_note = 0;
-        if (it.valid) {
-          k = smem_segment(W.seg, kMT + 1u, t);
-          // the lane on the tile's last item knows which state holds the first item of the next tile
-          next_note = i_base + k + (W.seg[k + 1] <= t + 1 ? 1u : 0u);
-        }
+        const uint32_t k = __popc(starts & (lt_mask | (1u << lane)));
+        const uint32_t seg_k = __shfl_sync(0xFFFFFFFFu, sv, k & 31u);
+        const uint32_t seg_k1s = __shfl_sync(0xFFFFFFFFu, sv, (k + 1u) & 31u);
+        const uint32_t seg_k1 = k + 1u < 32u ? seg_k1s : sv32;
+        // the lane on the tile's last item knows which state holds the first item of the next tile
+        const uint32_t next_note = it.valid ? i_base + k + (seg_k1 <= t + 1 ? 1u : 0u) : 0u;
         i_next = __shfl_sync(0xFFFFFFFFu, next_note, 31);
         if (t0 + kMT < we) issue_awin(buf ^ 1u, i_next, (win[min(i_next - i_base, n_win - 1u)].meta >> 8) / kWarps);
         if (it.valid) {
           const uint4 so = *reinterpret_cast<const uint4*>(&win[k]);
           const uint4 sm = *(reinterpret_cast<const uint4*>(&win[k]) + 1);  // item_loc, meta, key
-          const uint32_t i = i_base + k, j = t - W.seg[k];
+          const uint32_t i = i_base + k, j = t - seg_k;
           const bool match_input = (sm.x & kSideBit) != 0;
           const uint32_t owner = (sm.y >> 8) / kWarps;
           it.sidx = s_sbase[owner] + (i - s_pref_new[owner]);
@@ -416,7 +419,7 @@ k_compose_ws(WsParams P) {
             it.id = lo + i; it.slot = cold.x; it.fin_bits = cold.y; it.key_lo = sm.z; it.key_hi = sm.w;
           }
         }
-        __syncwarp();  // W.seg and the other window buffer are rewritten by the next stage A
+        __syncwarp();  // the other window buffer is rewritten by the next stage A
         return it;
       };
       issue_awin(0, i_cur, p_cur);
@@ -441,7 +444,7 @@ k_compose_ws(WsParams P) {
           const bool has_loop = (lab == kEps);
           const Label key = (lab == kNoLabel) ? kEps : lab;
           uint32_t pos, end;
-          match_range(se_lab, cur.se_lo, cur.se_hi, key, has_loop, pos, end);
+          match_range_eq(se_lab, cur.se_lo, cur.se_hi, key, has_loop, pos, end);
           uint32_t cnt = end - pos;
           // filter_tr sees (arc1.olabel, arc2.ilabel): the iterated arc's label on its own side, the match on the other
           const uint32_t fs_loop = !has_loop ? kNoFs
@@ -496,6 +499,20 @@ k_compose_ws(WsParams P) {
     const unsigned long long tm1 = globaltimer_ns();
 
     // ------------------------------------------------------------------ reserve the run, emit
+    // the first emit window is requested before the run is reserved: the bulk copy flies during the atomic's round trip
+    auto issue_bwin = [&](uint32_t buf, uint32_t cur) {
+      if (lane == 0) {
+        const uint32_t n = min(kET, w_active - cur);
+        bulk::mbar_expect_tx(&W.mbar[2 + buf], n * 16u + (kET + 8u) * 4u);
+        bulk::g2s(W.brec[buf], P.recs + wb + cur, n * 16u, &W.mbar[2 + buf]);
+        bulk::g2s(W.bloc[buf], P.arc_loc + ((wb + cur) & ~3u), (kET + 8u) * 4u, &W.mbar[2 + buf]);
+      }
+    };
+    if (w_arcs) {
+      bulk::fence_async_global();  // the records written above come back through bulk copies
+      __syncwarp();
+      issue_bwin(0, 0);
+    }
     uint32_t prov = 0;
     bool emit_ok = w_arcs != 0;
     if (gw < w_act) {
@@ -516,35 +533,31 @@ k_compose_ws(WsParams P) {
     const uint32_t ekey = gw << kKeyBits;
     Tr* __restrict__ run_arcs = P.prov_arcs + prov;
     if (emit_ok) {
-      bulk::fence_async_global();  // the records written above come back through bulk copies
-      __syncwarp();
-      auto issue_bwin = [&](uint32_t buf, uint32_t cur) {
-        if (lane == 0) {
-          const uint32_t n = min(kET, w_active - cur);
-          bulk::mbar_expect_tx(&W.mbar[2 + buf], n * 16u + (kET + 8u) * 4u);
-          bulk::g2s(W.brec[buf], P.recs + wb + cur, n * 16u, &W.mbar[2 + buf]);
-          bulk::g2s(W.bloc[buf], P.arc_loc + ((wb + cur) & ~3u), (kET + 8u) * 4u, &W.mbar[2 + buf]);
-        }
-      };
-      issue_bwin(0, 0);
+      // Tried and dropped: keeping the warp's records (and the next-state words for the rank phase) in shared memory so
+      // that the emit phase needs no fence / copy / wait.  With 160 records + 256 words per warp (201 KB per CTA) the
+      // kernel went from 4.01 to 4.68 ms — the L1 cache shrinks to what the carve-out leaves and the label windows of
+      // the match phase stop hitting it; with 64 + 128 (144 KB) it was a wash (3.89 vs 3.86 ms).
       uint32_t buf = 0, cursor = 0;  // first record (warp-local) that can contain the round's first arc
       for (uint32_t e0 = 0; e0 < w_arcs; e0 += kET) {
+        // lane x holds the first arc of record cursor + x; which record an arc belongs to follows from one warp-wide OR
+        // of the record starts inside the round (as in the match phase)
         bulk::mbar_wait(&W.mbar[2 + buf], (par >> (2 + buf)) & 1u);
         par ^= 4u << buf;
         const uint32_t off4 = (wb + cursor) & 3u;
-        for (uint32_t x = lane; x < kET + 1u; x += 32)
-          W.seg[x] = (cursor + x < w_active) ? W.bloc[buf][off4 + x] : w_arcs;
-        __syncwarp();
-        uint32_t el[kEA], k[kEA];
+        const uint32_t lv = cursor + lane < w_active ? W.bloc[buf][off4 + lane] : w_arcs;
+        const uint32_t lv32 = cursor + 32u < w_active ? W.bloc[buf][off4 + 32u] : w_arcs;
+        const uint4* __restrict__ rec_win = W.brec[buf];
+        const uint32_t starts = __reduce_or_sync(0xFFFFFFFFu, (lane >= 1 && lv > e0 && lv - e0 < 32u) ? 1u << (lv - e0) : 0u);
+        uint32_t el[kEA], k[kEA], seg_k[kEA];
         bool valid[kEA];
-#pragma unroll
-        for (uint32_t q = 0; q < kEA; q++) {
-          el[q] = e0 + 32u * q + lane;
-          valid[q] = el[q] < w_arcs;
-          k[q] = valid[q] ? smem_segment(W.seg, kET + 1u, el[q]) : 0u;
-        }
+        el[0] = e0 + lane;
+        valid[0] = el[0] < w_arcs;
+        k[0] = __popc(starts & (lt_mask | (1u << lane)));
+        seg_k[0] = __shfl_sync(0xFFFFFFFFu, lv, k[0] & 31u);
+        const uint32_t seg_k1s = __shfl_sync(0xFFFFFFFFu, lv, (k[0] + 1u) & 31u);
+        const uint32_t seg_k1 = k[0] + 1u < 32u ? seg_k1s : lv32;
         // the lane on the round's last arc knows which record holds the first arc of the next round
-        const uint32_t next_note = valid[kEA - 1] ? cursor + k[kEA - 1] + (W.seg[k[kEA - 1] + 1] <= el[kEA - 1] + 1 ? 1u : 0u) : 0u;
+        const uint32_t next_note = valid[0] ? cursor + k[0] + (seg_k1 <= el[0] + 1 ? 1u : 0u) : 0u;
         const uint32_t cursor_next = __shfl_sync(0xFFFFFFFFu, next_note, 31);
         if (e0 + kET < w_arcs) issue_bwin(buf ^ 1u, cursor_next);
         // step 1: gather the two component arcs of every arc of the lane
@@ -555,8 +568,8 @@ k_compose_ws(WsParams P) {
         for (uint32_t q = 0; q < kEA; q++) {
           mi[q] = false; fsn[q] = 0;
           if (valid[q]) {
-            const uint4 rec = W.brec[buf][k[q]];
-            const uint32_t kk = el[q] - W.seg[k[q]];
+            const uint4 rec = rec_win[k[q]];
+            const uint32_t kk = el[q] - seg_k[q];
             const bool loop_ok = (rec.y >> 26) & 1u;
             const bool match_input = rec.y >> 31;
             const bool it_is_loop = rec.w == 0xFFFFFFFFu, cand_is_loop = loop_ok && kk == 0;
@@ -668,6 +681,9 @@ k_compose_ws(WsParams P) {
       }
       return n;
     };
+    // Tried and dropped: resolving the pending targets of the warp's PREVIOUS run here (their ids were published while
+    // this wave was matched, the slots are still in L2) instead of in the final pass.  The final pass got 0.22 ms
+    // shorter, this phase 0.24 ms longer (C3): a wash, and one more pass over the arcs inside the wave loop.
     const bool listed = emit_ok && w_arcs <= kFirstCap;  // otherwise (rare) count now, list chunk by chunk later
     uint32_t n_w = 0;
     if (emit_ok) n_w = list_firsts(0, w_arcs, listed);
@@ -1045,6 +1061,7 @@ int compose_device_ws(const DevFst& fa, const DevFst& fb, const ComposeOptions& 
     extras.out_start_map = batch ? batch->out_start_map : nullptr;
     ProvArcs pa;
     pa.prov = prov_arcs.p; pa.st_first = st_first.p; pa.run_src = run_src.p; pa.run_cnt = run_cnt.p; pa.next = next.p;
+    pa.run_dst = run_dst.p; pa.n_runs = n_runs;
     DevFst trimmed = connect_waves_device(out, wave_lo.p, (uint32_t)st.waves, &launches, s, &extras, &pa);
     st.kernel_launches += launches;
     out = std::move(trimmed);

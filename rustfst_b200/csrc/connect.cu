@@ -137,21 +137,28 @@ struct TrimParams {
   uint32_t* deg_loc;     // slice-local new arc offset of every KEPT state (indexed by old id)
   uint32_t* part_keep; uint32_t* part_deg;
   uint32_t* noff; Tr* narcs; float* nfin;
-  uint32_t* ctl;         // [0] changed flag per sweep, [1] back-arc seen, [2] n_keep, [3] a_keep, [4] sweeps
+  uint32_t* ctl;         // [0] changed flag per sweep, [1] back-arc seen at an undecided state, [2] n_keep, [3] a_keep, [4] sweeps,
+                         // [5] barrier, [6] some arc stays inside its wave or goes back (first-sweep counts not final)
   const unsigned long long* tuples; uint32_t* ntag;   // optional: s1 component of the packed tuple, gathered
   uint32_t n_starts; uint32_t* start_map;             // optional: new ids of input states 0..n_starts-1
   uint32_t light_barrier;  // 1: arrival-counter barrier of coop_utils.cuh on ctl[5] instead of cg::grid_group::sync()
   // optional (compose_ws.cu): the arcs still sit in provisional (wave, warp) runs; `next` is the dense array of their
   // resolved next states in canonical order (all the sweeps need), st_first[s] = (run, index) of the first arc of state s
   const uint32_t* next; const Tr* prov; const uint2* st_first; const uint32_t* run_src; const uint32_t* run_cnt;
+  const uint32_t* run_dst; uint32_t n_runs;  // canonical index of every run's first arc (n_runs + 1 entries)
 };
 
+// A state with thousands of arcs (a start state that fans out, a hub) would keep ONE thread busy for milliseconds in the
+// sweep and in the gather; such states are set aside and walked by the whole CTA.
+constexpr uint32_t kBigDegree = 512, kBigMax = 64;
 #define TRIM_SYNC() do { if (P.light_barrier) grid_barrier(P.ctl + 5, bar_epoch); else grid.sync(); } while (0)
 __global__ void __launch_bounds__(kCoopThreads, 2)
 k_trim_coop(TrimParams P) {
   cg::grid_group grid = cg::this_grid();
   unsigned int bar_epoch = 0;
   __shared__ uint32_t s_warp[kCoopThreads / 32];
+  __shared__ uint32_t s_big[kBigMax];  // states with more than kBigDegree arcs met by this CTA: handled by the whole CTA
+  __shared__ uint32_t s_nbig, s_acc[2];
   extern __shared__ uint32_t s_dyn[];
   uint32_t* s_pref_id = s_dyn;
   uint32_t* s_pref_deg = s_dyn + gridDim.x + 1;
@@ -164,19 +171,73 @@ k_trim_coop(TrimParams P) {
   while (true) {
     for (uint32_t k = P.n_waves; k-- > 0;) {
       const uint32_t wlo = P.wave_lo[k], whi = P.wave_lo[k + 1];
+      if (tid == 0) s_nbig = 0;
+      __syncthreads();
       for (uint32_t s = wlo + gtid; s < whi; s += gsize) {
         uint8_t co = __ldcg(&P.coacc[s]);
         if (!co) {
           bool back = false;
-          co = (sweeps == 0 && P.fin[s] != w_zero()) ? 1 : 0;
-          for (uint32_t i = P.off[s]; i < P.off[s + 1] && !co; i++) {
-            const uint32_t t = P.next ? __ldg(&P.next[i]) : __ldg(&P.arcs[i].nextstate);
-            if (t < whi) back = true;  // same or earlier wave: value may still change in this sweep
-            co = __ldcg(&P.coacc[t]);
+          const uint32_t a_lo = P.off[s], a_hi = P.off[s + 1];
+          if (sweeps == 0 && a_hi - a_lo > kBigDegree) {
+            const uint32_t q = atomicAdd(&s_nbig, 1u);
+            if (q < kBigMax) { s_big[q] = s; continue; }  // the CTA walks it below; beyond kBigMax: this thread does
+          }
+          if (sweeps == 0) {
+            // first sweep: look at every arc (four at a time, look-ups in flight together) and count the coaccessible
+            // targets — when no arc stays inside its wave or goes back (ctl[6]), that count is final and the degree
+            // pass below does not have to read the arcs again
+            uint32_t cnt = 0;
+            for (uint32_t i = a_lo; i < a_hi; i += 4) {
+              uint32_t t[4];
+              uint8_t x[4];
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const uint32_t k = min(i + q, a_hi - 1);
+                t[q] = P.next ? __ldg(&P.next[k]) : __ldg(&P.arcs[k].nextstate);
+              }
+#pragma unroll
+              for (int q = 0; q < 4; q++) x[q] = __ldcg(&P.coacc[t[q]]);
+#pragma unroll
+              for (int q = 0; q < 4; q++)
+                if (i + q < a_hi) { if (t[q] < whi) back = true; cnt += x[q]; }
+            }
+            P.deg_loc[s] = cnt;
+            co = (P.fin[s] != w_zero() || cnt) ? 1 : 0;
+            if (back) P.ctl[6] = 1;
+          } else {
+            for (uint32_t i = a_lo; i < a_hi && !co; i++) {
+              const uint32_t t = P.next ? __ldg(&P.next[i]) : __ldg(&P.arcs[i].nextstate);
+              if (t < whi) back = true;  // same or earlier wave: value may still change in this sweep
+              co = __ldcg(&P.coacc[t]);
+            }
           }
           if (co) { P.coacc[s] = 1; if (sweeps > 0) P.ctl[0] = 1; }
           else if (back) P.ctl[1] = 1;
         }
+      }
+      __syncthreads();
+      for (uint32_t q = 0; q < min(s_nbig, kBigMax); q++) {  // big states of this CTA and wave (first sweep only)
+        const uint32_t s = s_big[q];
+        const uint32_t a_lo = P.off[s], a_hi = P.off[s + 1];
+        if (tid == 0) { s_acc[0] = 0; s_acc[1] = 0; }
+        __syncthreads();
+        uint32_t cnt = 0, back = 0;
+        for (uint32_t i = a_lo + tid; i < a_hi; i += kCoopThreads) {
+          const uint32_t t = P.next ? __ldg(&P.next[i]) : __ldg(&P.arcs[i].nextstate);
+          if (t < whi) back = 1;
+          cnt += __ldcg(&P.coacc[t]);
+        }
+        if (cnt) atomicAdd(&s_acc[0], cnt);
+        if (back) s_acc[1] = 1;
+        __syncthreads();
+        if (tid == 0) {
+          P.deg_loc[s] = s_acc[0];
+          const bool co = P.fin[s] != w_zero() || s_acc[0];
+          if (s_acc[1]) P.ctl[6] = 1;
+          if (co) P.coacc[s] = 1;
+          else if (s_acc[1]) P.ctl[1] = 1;
+        }
+        __syncthreads();
       }
       TRIM_SYNC();
     }
@@ -212,11 +273,13 @@ k_trim_coop(TrimParams P) {
   const unsigned long long t_ids = globaltimer_ns();
   // ---- surviving out-degrees: slice-local scan, indexed by old state id
   {
+    const bool counted = __ldcg(&P.ctl[6]) == 0u;  // the first sweep's counts are final (no arc inside a wave or back)
     uint32_t run = 0;
     for (uint32_t s0 = s_begin; s0 < s_end; s0 += kCoopThreads) {
       const uint32_t s = s0 + tid;
       uint32_t d = 0;
-      if (s < s_end && __ldcg(&P.coacc[s])) {
+      if (s < s_end && __ldcg(&P.coacc[s]) && counted) d = __ldcg(&P.deg_loc[s]);
+      else if (s < s_end && __ldcg(&P.coacc[s])) {
         const uint32_t a_lo = P.off[s], a_hi = P.off[s + 1];
         for (uint32_t i = a_lo; i < a_hi; i += 4) {  // four arcs per round: the target look-ups fly together
           uint32_t t[4], x[4];
@@ -244,6 +307,8 @@ k_trim_coop(TrimParams P) {
 
   const unsigned long long t_deg = globaltimer_ns();
   // ---- gather (mutable_fst.rs:132-189: survivors keep their relative order, arcs into deleted states are dropped)
+  if (tid == 0) s_nbig = 0;
+  __syncthreads();
   for (uint32_t s = s_begin + tid; s < s_end; s += kCoopThreads) {
     if (!__ldcg(&P.coacc[s])) continue;
     const uint32_t ns = s_pref_id[c] + P.id_loc[s];
@@ -252,6 +317,10 @@ k_trim_coop(TrimParams P) {
     P.noff[ns] = o;
     if (P.ntag) P.ntag[ns] = (uint32_t)(P.tuples[s] & 0x7FFFFFFFull);
     const uint32_t a_lo = P.off[s], a_hi = P.off[s + 1];
+    if (a_hi - a_lo > kBigDegree) {
+      const uint32_t q = atomicAdd(&s_nbig, 1u);
+      if (q < kBigMax) { s_big[q] = s; continue; }  // the CTA gathers it below
+    }
     if (P.prov) {
       // the arcs of the state start at st_first[s] in a provisional run and continue at the start of the following
       // run(s); their resolved next states are next[a_lo .. a_hi) in canonical order
@@ -299,6 +368,40 @@ k_trim_coop(TrimParams P) {
           *reinterpret_cast<int4*>(&P.narcs[o++]) = v[q];
         }
       }
+    }
+  }
+  __syncthreads();
+  for (uint32_t q = 0; q < min(s_nbig, kBigMax); q++) {  // big states of this slice: order-preserving compaction by the CTA
+    const uint32_t s = s_big[q];
+    const uint32_t a_lo = P.off[s], a_hi = P.off[s + 1];
+    uint32_t o = s_pref_deg[c] + P.deg_loc[s];
+    uint32_t r_lo = 0, r_hi = 0;
+    if (P.prov) { r_lo = __ldg(&P.st_first[s]).x; r_hi = P.n_runs; }
+    for (uint32_t i0 = a_lo; i0 < a_hi; i0 += kCoopThreads) {
+      const uint32_t i = i0 + tid;
+      int4 v = make_int4(0, 0, 0, 0);
+      uint32_t t = 0, x = 0xFFFFFFFFu;
+      if (i < a_hi) {
+        if (P.prov) {
+          // canonical arc i lives in the run r with run_dst[r] <= i < run_dst[r + 1]
+          uint32_t lo = r_lo, hi = r_hi;
+          while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&P.run_dst[mid]) <= i) lo = mid; else hi = mid; }
+          v = __ldg(reinterpret_cast<const int4*>(&P.prov[__ldg(&P.run_src[lo]) + (i - __ldg(&P.run_dst[lo]))]));
+          t = __ldg(&P.next[i]);
+        } else {
+          v = __ldg(reinterpret_cast<const int4*>(&P.arcs[i]));
+          t = (uint32_t)v.w;
+        }
+        x = __ldcg(&P.id_loc[t]);
+      }
+      const bool keep = x != 0xFFFFFFFFu;
+      uint32_t tot;
+      const uint32_t ex = cta_exclusive_scan(keep ? 1u : 0u, s_warp, tot);
+      if (keep) {
+        v.w = (int)(s_pref_id[t / sc] + x);
+        *reinterpret_cast<int4*>(&P.narcs[o + ex]) = v;
+      }
+      o += tot;
     }
   }
   if (P.start_map)
@@ -445,7 +548,10 @@ DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_
   P.part_keep = parts.p; P.part_deg = parts.p + 2049;
   P.noff = out.offsets.p; P.narcs = out.arcs.p; P.nfin = out.finals.p; P.ctl = ctl.p;
   P.light_barrier = std::getenv("B200_TRIM_CG") ? 0u : 1u;
-  if (pa) { P.next = pa->next; P.prov = pa->prov; P.st_first = pa->st_first; P.run_src = pa->run_src; P.run_cnt = pa->run_cnt; }
+  if (pa) {
+    P.next = pa->next; P.prov = pa->prov; P.st_first = pa->st_first; P.run_src = pa->run_src; P.run_cnt = pa->run_cnt;
+    P.run_dst = pa->run_dst; P.n_runs = pa->n_runs;
+  }
   if (extras && extras->out_tag) {
     extras->out_tag->reserve_discard(n);
     extras->out_start_map->reserve_discard(extras->n_starts);

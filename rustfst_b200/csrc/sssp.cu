@@ -810,6 +810,17 @@ void upload_scc_plan(const QueuePlan& plan, uint32_t n, SerialPlanBufs& b, Seria
 
 }  // namespace
 
+// The serial replay walks the machine with one device thread (dependent accesses, ~10 M arcs per second); beyond this
+// size a call would look like a hang, so it is refused with an explanation instead.  B200_SERIAL_SSSP_MAX_ARCS overrides.
+void check_serial_size(const DevFst& f, const char* what) {
+  size_t limit = (size_t)1 << 26;
+  if (const char* e = std::getenv("B200_SERIAL_SSSP_MAX_ARCS")) limit = (size_t)std::strtoull(e, nullptr, 10);
+  if (f.num_arcs > limit)
+    throw FstError(std::string(what) + ": this machine is cyclic (or forces the order-faithful serial replay) and has " +
+                   std::to_string(f.num_arcs) + " transitions; the serial replay is limited to " + std::to_string(limit) +
+                   " (set B200_SERIAL_SSSP_MAX_ARCS to override)");
+}
+
 CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* stats, cudaStream_t s,
                             bool force_serial) {
   SsspStats local;
@@ -895,6 +906,7 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
   }
 
   if (!done) {  // order-faithful serial replay
+    check_serial_size(f, "shortest_path");
     st.path = 1;
     DevBuf<float> dist(s, n);
     DevBuf<uint32_t> pstate(s, n), ppos(s, n), stack(s, (size_t)n + 1);
@@ -989,6 +1001,7 @@ void shortest_distance_device(const DevFst& f, const QueuePlan& plan, float delt
     }
   }
   if (!done) {  // order-faithful serial replay with the queue discipline AutoQueue picks
+    check_serial_size(f, "shortest_distance");
     st.path = 1;
     // Unlike single_shortest_path, shortest_distance re-enqueues a state that is already queued
     // (shortest_distance.rs:224 tests enqueued[state], not enqueued[nextstate]), so LIFO / FIFO queues hold

@@ -598,3 +598,24 @@ def test_connect_kat_through_cabi():
         e.add_tr(src, R.Tr(il, ol, w, dst))
     res = f.connect()
     assert f == e and res == e
+
+
+def test_spread_transducer_and_window_dag_workloads_at_reduced_scale():
+    """The two extra bench workloads (bench.py run_extras) at a size the oracle finishes in seconds: a composition whose
+    searched side is spread over the whole transducer with fan-out start states (a hub in the first wave), and the
+    shortest path of a DAG with skip-level arcs."""
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    a1 = synth.layered_acceptor(40_000, 400_000, 93, 3, 50, start_fanout=True)
+    a2 = synth.bigram_transducer(40_000, 400_000, 93, 4, 50, out_vocab=20000, start_fanout=True, spread=True)
+    pa, oa = both_from_dict(a1)
+    pb, ob = both_from_dict(a2)
+    got, st = R.compose_with_stats(pa, pb)
+    exp, ost = O.compose(oa, ob, want_stats=True)
+    assert st["arcs_emitted"] == ost["arcs_emitted"] and st["arcs_emitted"] > 10_000
+    assert_same(got, exp, "spread compose")
+    g = synth.window_dag(100_000, 1_000_000, 1000, 6, window=1000)
+    pg, og = both_from_dict(g)
+    sp, sst = R.shortestpath_with_stats(pg)
+    assert sst["queue_kind"] == 0
+    assert_same(sp, O.shortest_path(og), "window dag shortest path")

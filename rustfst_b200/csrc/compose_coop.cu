@@ -705,6 +705,38 @@ float run_coop(const CoopParams& P0, int sms, cudaStream_t s) {
 
 }  // namespace
 
+const uint32_t* label_column(const DevFst& f, bool olabel, uint32_t pad, cudaStream_t s, bool* built) {
+  DevFst& m = const_cast<DevFst&>(f);  // the columns are a cache of derived data
+  if (built) *built = false;
+  {
+    static std::mutex g_create;
+    std::lock_guard<std::mutex> g(g_create);
+    if (!m.columns) m.columns = std::make_shared<DevLabelColumns>();
+  }
+  DevLabelColumns& c = *m.columns;
+  std::lock_guard<std::mutex> g(c.mu);
+  DevBuf<uint32_t>& buf = olabel ? c.olab : c.ilab;
+  bool& has = olabel ? c.has_olab : c.has_ilab;
+  const cudaStream_t own = f.arcs.s;  // the machine's own stream: the column lives and dies with the machine
+  if (!has) {
+    if (!c.ready) B200_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+    if (own != s) {  // the arcs may still be in flight on the caller's stream (upload on s, column on own)
+      cudaEvent_t e;
+      B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      B200_CUDA(cudaEventRecord(e, s));
+      B200_CUDA(cudaStreamWaitEvent(own, e, 0));
+      cudaEventDestroy(e);
+    }
+    buf = DevBuf<uint32_t>(own, (size_t)f.num_arcs + pad);
+    composeimpl::launch_extract_labels(f.arcs.p, f.num_arcs, f.num_arcs + pad, olabel ? 1 : 0, buf.p, own);
+    B200_CUDA(cudaEventRecord(c.ready, own));
+    has = true;
+    if (built) *built = true;
+  }
+  if (own != s) B200_CUDA(cudaStreamWaitEvent(s, c.ready, 0));
+  return buf.p;
+}
+
 namespace composeimpl {
 void launch_unpack_s1(const unsigned long long* tuples, uint32_t n, uint32_t* s1_out, uint32_t n_starts,
                       uint32_t* start_map, cudaStream_t s) {

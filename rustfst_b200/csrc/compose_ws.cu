@@ -933,10 +933,10 @@ int compose_device_ws(const DevFst& fa, const DevFst& fb, const ComposeOptions& 
     P.b.neps = neps2.p; st.kernel_launches++;
   }
   P.kind = kind; P.side = side;
-  DevBuf<uint32_t> lab1(s, (size_t)fa.num_arcs + kLabelPad), lab2(s, (size_t)fb.num_arcs + kLabelPad);
-  launch_extract_labels(fa.arcs.p, fa.num_arcs, fa.num_arcs + kLabelPad, 1, lab1.p, s);
-  launch_extract_labels(fb.arcs.p, fb.num_arcs, fb.num_arcs + kLabelPad, 0, lab2.p, s);
-  P.lab1 = lab1.p; P.lab2 = lab2.p; st.kernel_launches += 2;
+  bool built1 = false, built2 = false;
+  P.lab1 = label_column(fa, true, kLabelPad, s, &built1);   // cached with the machine: resident operands pay once
+  P.lab2 = label_column(fb, false, kLabelPad, s, &built2);
+  st.kernel_launches += (built1 ? 1 : 0) + (built2 ? 1 : 0);
   DevBuf<uint32_t> allowed1(s), allowed2(s);
   bool host_temporaries = false;
   auto mk_sigma = [&](const SigmaSpec& sp, uint64_t fprops, DevBuf<uint32_t>& buf) {

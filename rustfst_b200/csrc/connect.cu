@@ -617,6 +617,7 @@ void tr_sort_device(DevFst& f, bool ilabel, cudaStream_t s) {
   sort_pairs_u64_u32(k_in.p, k_out.p, v_in.p, perm.p, a, 64, tmp, s);
   k_gather_arcs<<<blocks_for(a), kThreads, 0, s>>>(f.arcs.p, perm.p, a, sorted.p);
   f.arcs = std::move(sorted);
+  f.columns.reset();  // derived label columns (compose matcher) describe the old arc order
   f.props = props::after_tr_sort(f.props, ilabel) & props::kTrinary;
   B200_CUDA(cudaStreamSynchronize(s));
 }

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <utility>
 
@@ -88,6 +90,17 @@ struct DevBuf {
   }
 };
 
+// Derived columns of a device-resident machine that the composition matcher reads (dense label arrays: fst1 output
+// labels / fst2 input labels, padded).  Built on first use on the machine's own stream and kept with it, so a machine
+// that stays in HBM across calls pays for them once; consumers on other streams wait for `ready`.
+struct DevLabelColumns {
+  std::mutex mu;
+  DevBuf<uint32_t> olab, ilab;
+  bool has_olab = false, has_ilab = false;
+  cudaEvent_t ready = nullptr;
+  ~DevLabelColumns() { if (ready) cudaEventDestroy(ready); }
+};
+
 // Device-resident CSR FST (what the kernels read and produce).
 struct DevFst {
   DevBuf<uint32_t> offsets;  // num_states + 1
@@ -98,10 +111,15 @@ struct DevFst {
   bool has_start = false;
   StateId start = 0;
   uint64_t props = props::kNull;
+  std::shared_ptr<DevLabelColumns> columns;  // lazily built by label_column(); never copied with the arrays
   DevFst() = default;
   explicit DevFst(cudaStream_t s) : offsets(s), arcs(s), finals(s) {}
   size_t bytes() const { return (size_t)(num_states + 1) * 4 + (size_t)num_arcs * 16 + (size_t)num_states * 4; }
 };
+
+// Dense label column of `f` (olabel = true: output labels, else input labels), padded with kNoLabel by `pad` entries;
+// built once per machine, valid on stream `s` when the call returns.  *built = a kernel was launched for it.
+const uint32_t* label_column(const DevFst& f, bool olabel, uint32_t pad, cudaStream_t s, bool* built);
 
 DevFst upload(const CsrFst& h, cudaStream_t s);
 CsrFst download(const DevFst& d, cudaStream_t s);

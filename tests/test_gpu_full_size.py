@@ -73,3 +73,32 @@ def test_c3_full_size_properties_and_oracle():
     assert again.to_bytes() == r1.to_bytes()
     # and the oracle agrees (about 10 s of CPU)
     assert_same(r1, O.compose(oa, ob), "C3 full size")
+
+
+def test_c5_full_shape_batch_matches_oracle_on_a_256_acceptor_sample():
+    """BASELINE.json configs[4] at its full shape: 8192 linear acceptors (200 arcs) against one 500K-state / 5M-arc
+    transducer in ONE batched call (packed result, transducer resident in HBM); 256 of the results, spread over the
+    batch, are compared bit-for-bit with the oracle composing that acceptor alone."""
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    n_t = 500_000
+    t = synth.random_graph_transducer(n_t, 5_000_000, 5000, seed=5)
+    rng = np.random.default_rng(77)
+    t["finals"] = np.where(rng.random(n_t) < 0.5, rng.integers(0, 640, size=n_t) / 64.0, np.inf).astype(np.float32)
+    pt, ot = both_from_dict(t)
+    dt = R.DeviceFst.upload(pt)
+    labels = synth.sample_path_labels_batch(t, 200, 8192, seed=100)
+    dicts = [synth.linear_acceptor(labels[i], seed=100 + i) for i in range(8192)]
+    accs = [synth.to_vector_fst(d) for d in dicts]
+    pb, st = R.compose_batch_packed(accs, device_transducer=dt)
+    assert len(pb) == 8192 and st["waves"] == 201 and st["emit_launches"] == 1
+    back = R.PackedBatch.from_buffer(pb.to_numpy())
+    assert back.info() == pb.info()
+    nonempty = 0
+    for i in range(0, 8192, 32):
+        d = dicts[i]
+        oa = O.OFst.from_csr(d["offsets"].astype(np.uint64), d["arcs"], d["finals"], d["start"], d["props"])
+        expected = O.compose(oa, ot)
+        assert_same(pb.result(i), expected, f"C5 batch item {i}")
+        nonempty += expected.num_states > 0
+    assert nonempty >= 128

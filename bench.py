@@ -233,9 +233,12 @@ def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_ove
     e0.record()
     t0 = time.perf_counter()
     arcs, launches, waves, got = 0, 0, 0, 0
+    inside = {"ms_h2d": 0.0, "ms_expand": 0.0, "ms_connect": 0.0, "ms_d2h": 0.0}
     for _ in range(args.steps):
         pb, st, blocks = step()
         arcs += st["arcs_out"]; launches += st["kernel_launches"]; waves += st["waves"]
+        for k in inside:
+            inside[k] += st[k]
         if blocks is not None:
             torch.cuda.synchronize()
             got = sum(int(b.numel()) for b in blocks)
@@ -274,6 +277,9 @@ def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_ove
             "per_step": {"h2d_bytes_per_rank": int((hi - lo) * (201 * 8 + 200 * 16 + 4)),
                          "d2h_bytes_per_rank": int(info["bytes"]), "waves": waves // max(1, args.steps),
                          "result_states_rank0_shard": info["num_states"], "result_arcs_rank0_shard": info["num_trs"]},
+            "inside_the_call_ms_per_step": {"union_upload": inside["ms_h2d"] / args.steps, "expand": inside["ms_expand"] / args.steps,
+                                            "connect": inside["ms_connect"] / args.steps,
+                                            "split_and_download": inside["ms_d2h"] / args.steps},
             "gather": check, "cpu_baseline": cpu, "gpu_launches": int(launches),
             "timer": "max(CUDA events, host wall clock) around K host-driven steps, max over ranks"}
 
@@ -367,7 +373,9 @@ def main():
     ap.add_argument("--workload", default="C3", choices=["C3", "C2", "C5"])
     ap.add_argument("--batch", type=int, default=8192, help="C5: number of linear acceptors")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; full size = 1.0)")
-    ap.add_argument("--callers", type=int, default=3, help="host threads of the supplementary concurrent e2e figure (1 = skip)")
+    ap.add_argument("--callers", type=int, default=2, help="host threads of the supplementary concurrent e2e figure (1 = skip); "
+                    "the persistent kernels own the whole GPU, so beyond two callers calls only queue (measured: 2 callers "
+                    "15.0 ms per compose, 3 callers 27.5 ms)")
     ap.add_argument("--no-sssp", action="store_true")
     ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the two extra workloads (spread compose, window-DAG SSSP)")

@@ -255,6 +255,12 @@ RUSTFST_FFI_RESULT b200_device_fst_destroy(B200DeviceFst* dfst);
 RUSTFST_FFI_RESULT b200_device_compose(const B200DeviceFst* fst_1, const B200DeviceFst* fst_2,
                                        const CComposeConfig* config, const B200DeviceFst** out,
                                        B200ComposeStats* stats);
+/* isomorphic (rustfst/src/algorithms/isomorphic.rs:49-160) of two device-resident machines, as a verifier that needs
+ * no download: *result = 1 isomorphic, 0 not isomorphic, -1 undecided on the device (a check failed after rows with
+ * equal neighbouring arcs were visited, where the reference either returns false or raises its non-determinism error
+ * depending on the visiting order; fst_isomorphic on the host copies gives the reference's answer). */
+RUSTFST_FFI_RESULT b200_device_isomorphic(const B200DeviceFst* fst_1, const B200DeviceFst* fst_2, int32_t* result);
+
 /* plan_from (may be NULL) is the host copy dfst was uploaded from.  The queue discipline is decided from the property
  * word stored with dfst; the DFS order of an acyclic machine is computed on the device.  The host copy is only needed
  * for machines that are not known to be acyclic (Tarjan SCC order) or too deep for the device path (more than 65 536

@@ -145,6 +145,13 @@ class DeviceFst:
         check_ffi_error(lib.b200_device_fst_info(self.ptr, C.byref(n), C.byref(a), C.byref(pr)), "info failed")
         return n.value, a.value, pr.value
 
+    def isomorphic(self, other: "DeviceFst") -> Optional[bool]:
+        """isomorphic() of two machines in HBM (no download).  None = undecided on the device (the reference's answer
+        depends on its visiting order there): use VectorFst.isomorphic on the host copies."""
+        r = C.c_int32()
+        check_ffi_error(lib.b200_device_isomorphic(self.ptr, other.ptr, C.byref(r)), "Error during isomorphic")
+        return None if r.value < 0 else bool(r.value)
+
     def __del__(self):
         try:
             lib.b200_device_fst_destroy(self.ptr)

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 _SUFFIX = os.environ.get("B200_LIB_SUFFIX", "")
 OBJ = os.path.join(HERE, "build" + ("_" + _SUFFIX if _SUFFIX else ""))
 LIB = os.path.join(HERE, "librustfst_b200" + ("_" + _SUFFIX if _SUFFIX else "") + ".so")
-SOURCES = ["capi.cu", "compose.cu", "compose_coop.cu", "compose_ws.cu", "dag_order.cu", "batch.cu", "connect.cu", "sssp.cu", "nshortest.cu", "device_common.cu", "queue_plan.cpp"]
+SOURCES = ["capi.cu", "compose.cu", "compose_coop.cu", "compose_ws.cu", "dag_order.cu", "batch.cu", "iso.cu", "connect.cu", "sssp.cu", "nshortest.cu", "device_common.cu", "queue_plan.cpp"]
 HEADERS = ["algos.h", "compose_common.cuh", "compose_match.cuh", "bulk_async.cuh", "coop_utils.cuh", "device_common.cuh", "fst_types.h", "host_fst.h", os.path.join("..", "..", "include", "rustfst_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--cudart", "static",

@@ -119,6 +119,10 @@ struct ProvArcs {
 DevFst connect_waves_device(const DevFst& in, const uint32_t* d_wave_lo, uint32_t n_waves, uint64_t* launches,
                             cudaStream_t s, const TrimExtras* extras = nullptr, const ProvArcs* pa = nullptr);
 
+// isomorphic() on the device (iso.cu; isomorphic.rs:49-160 with delta = KDELTA): 1 = isomorphic, 0 = not, -1 = undecided
+// (the reference's answer would depend on its visiting order: take the host restatement, host_fst.h isomorphic()).
+int isomorphic_device(const DevFst& a, const DevFst& b, float delta, cudaStream_t s);
+
 // Stable per-state arc sort by input or output label, in place on the device (algorithms/tr_sort.rs:51-62).
 void tr_sort_device(DevFst& f, bool ilabel, cudaStream_t s);
 

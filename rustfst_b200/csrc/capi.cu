@@ -293,8 +293,25 @@ RUSTFST_FFI_RESULT fst_reverse(const CFst* ptr, const CFst** res_ptr) {
 }
 RUSTFST_FFI_RESULT fst_isomorphic(const CFst* fst, const CFst* other_fst, size_t* is_isomorphic) {
   return wrap([&] {
-    *is_isomorphic = isomorphic(vec_alg(fst, "fst")->fst.checked(), vec_alg(other_fst, "other_fst")->fst.checked()) ? 1 : 0;
+    const CsrFst& ha = vec_alg(fst, "fst")->fst.checked();
+    const CsrFst& hb = vec_alg(other_fst, "other_fst")->fst.checked();
+    // Large machines (a composed lattice being verified) are paired on the device; the sequential restatement handles
+    // small ones, machines with Some(+inf) final weights, boxes without a GPU, and the cases the device leaves undecided
+    // (the reference's non-determinism error depends on its visiting order).  B200_ISO_DEVICE=1 forces the device path.
+    int ndev = 0;
+    const bool big = ha.arcs.size() + hb.arcs.size() >= (1u << 16) || std::getenv("B200_ISO_DEVICE") != nullptr;
+    if (big && ha.inf_finals.empty() && hb.inf_finals.empty() && cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) {
+      Stream st;
+      DevFst da = upload(ha, st.s), db = upload(hb, st.s);
+      const int r = isomorphic_device(da, db, kDelta, st.s);
+      if (r >= 0) { *is_isomorphic = (size_t)r; return; }
+    }
+    cudaGetLastError();
+    *is_isomorphic = isomorphic(ha, hb) ? 1 : 0;
   });
+}
+RUSTFST_FFI_RESULT b200_device_isomorphic(const B200DeviceFst* a, const B200DeviceFst* b, int32_t* result) {
+  return wrap([&] { *result = isomorphic_device(nn(a, "fst_1")->d, nn(b, "fst_2")->d, kDelta, a->stream.s); });
 }
 RUSTFST_FFI_RESULT fst_top_sort(CFst* ptr) {
   return wrap([&] {  // top_sort.rs:75-95: the DFS is the reference's sequential one, the renumbering one pass over the CSR

@@ -955,6 +955,7 @@ bool compose_device_coop(const DevFst& fa, const DevFst& fb, const ComposeOption
 // when the result cannot be represented by the kernel at all (the caller then uses the multi-kernel back end).
 bool compose_device_persistent(const DevFst& a, const DevFst& b, const ComposeOptions& opt, ComposeStats* stats,
                                cudaStream_t s, DevFst* out, const BatchStarts* batch) {
+  DeviceExclusive excl(device_exclusive());  // the persistent kernels want every SM (device_common.cu)
   const char* impl = std::getenv("B200_COMPOSE_IMPL");
   if (impl && std::string(impl) == "coop") return compose_device_coop(a, b, opt, stats, s, out, batch);
   WsCaps caps;

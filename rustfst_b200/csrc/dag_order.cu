@@ -305,6 +305,7 @@ int coop_grid(const void* kern, int threads) {
 bool dag_top_order_device(const DevFst& f, DevBuf<uint32_t>& order, float* ms, uint64_t* launches, cudaStream_t s) {
   const uint32_t n = f.num_states, a = f.num_arcs;
   if (n == 0 || !f.has_start) return false;
+  DeviceExclusive excl(device_exclusive());  // the persistent kernels want every SM (device_common.cu)
   cudaEvent_t e0, e1;
   B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
   B200_CUDA(cudaEventRecord(e0, s));

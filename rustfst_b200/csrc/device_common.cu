@@ -45,6 +45,16 @@ void configure_device_pool(int dev) {
   }
 }
 
+// The persistent cooperative kernels (compose, trim, relaxation, DFS order) each want every SM: two of them from
+// different calls can become co-resident, or one of them only PARTLY resident, and then spin at their grid barriers
+// while they wait for each other's CTAs to leave (measured: 15 ms per compose with two callers on a good run, 150 ms on
+// a bad one).  So the kernel section of a call is exclusive per process; uploads and downloads stay outside it and
+// overlap with another caller's kernels.
+std::recursive_mutex& device_exclusive() {
+  static std::recursive_mutex m;
+  return m;
+}
+
 void require_device() {
   std::call_once(g_once, init_device);
   if (!g_init_error.empty()) throw CudaError(g_init_error);
@@ -87,8 +97,8 @@ namespace {
 constexpr size_t kPinThreshold = 256 * 1024;          // smaller blocks: plain malloc
 size_t pool_keep_bytes() {                             // cached free blocks above this are returned to the driver
   static const size_t v = [] {
-    const char* e = std::getenv("B200_PINNED_POOL_MB");  // default 8 GiB; the C3 end-to-end path cycles ~1.4 GB
-    return e ? (size_t)std::strtoull(e, nullptr, 10) << 20 : (size_t)8 << 30;
+    const char* e = std::getenv("B200_PINNED_POOL_MB");  // default 16 GiB; the C3 end-to-end path cycles ~1.4 GB
+    return e ? (size_t)std::strtoull(e, nullptr, 10) << 20 : (size_t)16 << 30;
   }();
   return v;
 }
@@ -140,9 +150,25 @@ void host_pool_free(void* p, size_t bytes) noexcept {
   auto& reg = g_pool_free[0];
   for (size_t i = 0; i < reg.size(); i++)
     if (reg[i] == p) { reg[i] = reg.back(); reg.pop_back(); std::free(p); return; }
-  if (g_pool_cached + cls > pool_keep_bytes()) { cudaFreeHost(p); return; }
   g_pool_free[cls].push_back(p);
   g_pool_cached += cls;
+  // Over the cap: give the LARGEST cached blocks back to the driver first.  (Returning whatever block happens to be freed
+  // made a full cache thrash: every 20 MB result block of a batched call then cost a cudaFreeHost + cudaHostAlloc pair.)
+  while (g_pool_cached > pool_keep_bytes()) {
+    auto it = g_pool_free.end();
+    bool evicted = false;
+    while (it != g_pool_free.begin()) {
+      --it;
+      if (it->first != 0 && !it->second.empty()) {
+        cudaFreeHost(it->second.back());
+        it->second.pop_back();
+        g_pool_cached -= it->first;
+        evicted = true;
+        break;
+      }
+    }
+    if (!evicted) break;
+  }
 }
 
 void exclusive_sum_u32(const uint32_t* in, uint32_t* out, size_t n, DevBuf<uint8_t>& temp, cudaStream_t s) {

@@ -35,6 +35,10 @@ void require_device();
 int sm_count();
 void configure_device_pool(int dev);
 
+// Held around the kernel section of a call (see device_common.cu): the persistent kernels are exclusive users of the GPU.
+std::recursive_mutex& device_exclusive();
+using DeviceExclusive = std::lock_guard<std::recursive_mutex>;
+
 // One stream per C-ABI call: concurrent calls from different host threads do not serialise on the legacy stream.
 struct Stream {
   cudaStream_t s = nullptr;

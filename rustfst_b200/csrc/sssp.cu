@@ -829,6 +829,7 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
   st.plan_host_ms = plan.host_ms;
   const uint32_t n = f.num_states;
   if (!f.has_start || n == 0) return build_path_fst(false, {}, 0.0f);  // shortest_path.rs:186-189
+  DeviceExclusive excl(device_exclusive());  // the persistent kernels want every SM (device_common.cu)
 
   cudaEvent_t ev0, ev1;
   B200_CUDA(cudaEventCreate(&ev0)); B200_CUDA(cudaEventCreate(&ev1));
@@ -960,6 +961,7 @@ void shortest_distance_device(const DevFst& f, const QueuePlan& plan, float delt
   const uint32_t n = f.num_states;
   out.reserve_discard(n ? n : 1);
   if (!f.has_start || n == 0) return;
+  DeviceExclusive excl(device_exclusive());  // the persistent kernels want every SM (device_common.cu)
   EventPairs relax_events;
   DevBuf<uint32_t> d_order(s);
   const uint32_t* order_p = nullptr;

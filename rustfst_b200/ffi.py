@@ -162,6 +162,7 @@ _sig("b200_device_shortest_path", _P, _P, _PP, C.POINTER(SsspStats), C.c_bool)
 _sig("b200_device_shortest_path_with_config", _P, _P, _P, _PP, C.POINTER(SsspStats), C.c_bool)
 _sig("b200_compose_batch", C.POINTER(C.c_void_p), C.c_size_t, _P, _P, C.POINTER(C.c_void_p), C.POINTER(ComposeStats))
 _sig("b200_shortest_path_queue_plan", _P, C.POINTER(C.c_int32), _P, _P, C.POINTER(C.c_uint32))
+_sig("b200_device_isomorphic", _P, _P, C.POINTER(C.c_int32))
 _sig("b200_compose_batch_packed", _P, C.c_size_t, _P, _P, _P, _PP, C.POINTER(ComposeStats))
 _sig("b200_packed_batch_info", _P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
 _sig("b200_packed_batch_get", _P, C.c_size_t, _PP)

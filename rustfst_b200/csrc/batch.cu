@@ -7,10 +7,17 @@
 // is a STABLE partition of the states by component: one radix sort of (component, state), a prefix sum of the
 // out-degrees in the new order and one gather that rewrites next states to component-local ids.  The results leave
 // the device as one packed block (PackedBatch): no per-result allocation, copy or handle.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "algos.h"
 
 namespace b200 {
 namespace {
+double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // component of every result state: the acceptor whose union-state range contains its fst1 component
 __global__ void k_split_keys(const uint32_t* __restrict__ tag, uint32_t n_states, const uint32_t* __restrict__ base_state,
@@ -78,6 +85,8 @@ __global__ void k_split_starts(const uint32_t* __restrict__ start_map, const uin
 void split_batch_device(const DevFst& r, const uint32_t* d_tag, const uint32_t* d_start_map,
                         const std::vector<uint32_t>& base_state, PackedBatch& out, uint64_t* launches, cudaStream_t s) {
   const uint32_t n_acc = (uint32_t)base_state.size() - 1, ns = r.num_states, na = r.num_arcs;
+  const bool trace = std::getenv("B200_BATCH_TRACE") != nullptr;
+  const double t0 = wall_ms();
   out.n = n_acc;
   out.state_off.assign((size_t)n_acc + 1, 0);
   out.arc_off.assign((size_t)n_acc + 1, 0);
@@ -93,6 +102,7 @@ void split_batch_device(const DevFst& r, const uint32_t* d_tag, const uint32_t* 
   DevBuf<Tr> narcs(s, na ? na : 1);
   DevBuf<float> nfin(s, ns);
   DevBuf<uint8_t> tmp(s);
+  const double t1 = wall_ms();
   B200_CUDA(cudaMemcpyAsync(d_base.p, base_state.data(), ((size_t)n_acc + 1) * 4, cudaMemcpyHostToDevice, s));
   k_split_keys<<<blocks_for(ns), kThreads, 0, s>>>(d_tag, ns, d_base.p, n_acc, k_in.p, v_in.p);
   int bits = 1;
@@ -106,13 +116,21 @@ void split_batch_device(const DevFst& r, const uint32_t* d_tag, const uint32_t* 
   k_split_starts<<<blocks_for((size_t)n_acc + 1), kThreads, 0, s>>>(d_start_map, inv.p, d_state_off.p, noff.p, n_acc,
                                                                     d_starts.p, d_arc_off.p);
   if (launches) *launches += 7;
-  B200_CUDA(cudaMemcpyAsync(out.state_off.data(), d_state_off.p, ((size_t)n_acc + 1) * 4, cudaMemcpyDeviceToHost, s));
-  B200_CUDA(cudaMemcpyAsync(out.arc_off.data(), d_arc_off.p, ((size_t)n_acc + 1) * 4, cudaMemcpyDeviceToHost, s));
-  B200_CUDA(cudaMemcpyAsync(out.starts.data(), d_starts.p, (size_t)n_acc * 4, cudaMemcpyDeviceToHost, s));
+  double t2 = t1;
+  if (trace) { B200_CUDA(cudaStreamSynchronize(s)); t2 = wall_ms(); }
+  // the three big arrays land in page-locked memory (PoolVec) and are queued first; the three small ones are ordinary
+  // vectors — an asynchronous copy into pageable memory queued behind running kernels took milliseconds here, so they
+  // are fetched after the stream has drained
   B200_CUDA(cudaMemcpyAsync(out.offsets.data(), noff.p, ((size_t)ns + 1) * 4, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaMemcpyAsync(out.finals.data(), nfin.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
   if (na) B200_CUDA(cudaMemcpyAsync(out.arcs.data(), narcs.p, (size_t)na * sizeof(Tr), cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
+  B200_CUDA(cudaMemcpy(out.state_off.data(), d_state_off.p, ((size_t)n_acc + 1) * 4, cudaMemcpyDeviceToHost));
+  B200_CUDA(cudaMemcpy(out.arc_off.data(), d_arc_off.p, ((size_t)n_acc + 1) * 4, cudaMemcpyDeviceToHost));
+  B200_CUDA(cudaMemcpy(out.starts.data(), d_starts.p, (size_t)n_acc * 4, cudaMemcpyDeviceToHost));
+  if (trace)
+    std::fprintf(stderr, "[split] host arrays + device buffers %.2f ms, kernels %.2f ms, download %.2f ms (%u states, %u arcs)\n",
+                 t1 - t0, t2 - t1, wall_ms() - t2, ns, na);
 }
 
 // ---- PackedBatch <-> one contiguous byte block (what travels over NCCL to rank 0)

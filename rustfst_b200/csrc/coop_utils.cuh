@@ -25,6 +25,15 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// Last-resort watchdog of the spin loops below: a grid-wide wait that lasts longer than 20 s can only be a bug (a CTA
+// that never arrives); the kernel then traps — the call fails with a CUDA error — instead of hanging the device.
+// (k_compose_ws has its own, recoverable watchdog; see compose_ws.cu.)
+__device__ __forceinline__ void spin_watchdog(unsigned long long& t_start) {
+  const unsigned long long now = globaltimer_ns();
+  if (!t_start) t_start = now;
+  else if (now - t_start > 20ull * 1000 * 1000 * 1000) __trap();
+}
+
 // Grid-wide barrier on a monotonically increasing arrival counter (no reset, so no second phase): the k-th barrier
 // completes when the counter reaches k * gridDim.x.  Requires all CTAs to be co-resident (cooperative launch).
 // Lighter than cg::grid_group::sync(): one release atomic and acquire-load polling by one thread per CTA, no L1
@@ -37,9 +46,12 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __threadfence();
     atomicAdd(counter, 1u);
     unsigned int v;
-    do {
+    unsigned long long t_start = 0;
+    for (unsigned int it = 1;; it++) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-    } while ((int)(v - target) < 0);
+      if ((int)(v - target) >= 0) break;
+      if ((it & 0xFFFFu) == 0) spin_watchdog(t_start);
+    }
   }
   __syncthreads();
 }
@@ -133,10 +145,12 @@ __device__ __forceinline__ void cta_prefix_wait_to_smem(const unsigned long long
                                                         uint32_t* s_out, uint32_t* s_warp, uint32_t poll_ns = 0) {
   for (uint32_t i = threadIdx.x; i < n; i += kCoopThreads) {
     unsigned long long v;
-    while (true) {
+    unsigned long long t_start = 0;
+    for (unsigned int it = 1;; it++) {
       asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(part + i) : "memory");
       if ((uint32_t)(v >> 32) == tag) break;
       if (poll_ns) __nanosleep(poll_ns);
+      if ((it & 0xFFFFu) == 0) spin_watchdog(t_start);
     }
     s_out[i] = (uint32_t)v;
   }

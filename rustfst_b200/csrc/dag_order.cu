@@ -18,17 +18,19 @@
 //   * Hence parent(v) = the in-arc (u, pos) that minimises path(u) . pos, and two candidates are compared without
 //     materialising the strings: lift the deeper source to the depth of the other (binary lifting), and either one
 //     source is an ancestor of the other — compare the arc taken below it with the candidate's own position — or the
-//     sources part at their lowest common ancestor — compare the positions of its two children.
+//     sources part at their lowest common ancestor — compare the positions of its two children.  (Tried and
+//     dropped: carrying the first five positions of every path as a packed key so that two loads decide most
+//     comparisons — 7.4 vs 7.1 ms on C4: the comparisons are not what the kernel waits for.)
 //   * States are processed in Kahn levels (a state after all its predecessors), one grid barrier per level: every
 //     processed state PUSHES its candidacy to its successors with a compare-and-swap loop on a packed
-//     (source, position) word, then decrements their in-degree; no reverse CSR is needed.  The lane that takes the last
-//     in-arc of a state away records the state's depth and ancestor table, so everything a comparison reads was
-//     written before the previous grid barrier.
+//     (source, position) word, then decrements their in-degree; no reverse CSR is needed.  A level starts by recording
+//     depth and ancestor table of its own states (their parents are final), then a second barrier, then the candidacies:
+//     everything a comparison reads was written before a grid barrier.
 //   * Reverse finish order of a tree = visit a node, then its children from RIGHT to LEFT:
 //       order(child_i) = order(parent) + 1 + sum of the subtree sizes of the children to the right of child_i.
 //     Subtree sizes are accumulated in one reverse sweep over the levels, the orders in one forward sweep.
 //
-// Cost: O((n + a) log depth) work in 3 x (#Kahn levels) grid barriers.  Very deep machines (more levels than
+// Cost: O((n + a) log depth) work in 4 x (#Kahn levels) grid barriers.  Very deep machines (more levels than
 // kMaxLevels, e.g. a long chain) are left to the host DFS of queue_plan.cpp, which is fast exactly there.
 #include <cooperative_groups.h>
 
@@ -148,20 +150,31 @@ k_dag_tree(DagParams P) {
     if (c == 0 && tid == 0) { P.lev_off[level] = lo; P.ctl[(level + 2) % 3] = 0u; }
     uint32_t* const next_cnt = &P.ctl[(level + 1) % 3];
     const uint32_t count = hi - lo;
-    // uniform trip count per warp: the lanes of a warp synchronise inside the loop
+    // ---- phase 1: every in-arc of the states of this level was processed in an earlier level, so their tree parents
+    // are final: record depth and the binary-lifting ancestor table (one thread per state; a chain of log2(depth)
+    // dependent loads that would otherwise serialise inside the diverged lane that takes a state's last in-arc away)
+    for (uint32_t i = c * kDagThreads + tid; i < count; i += G * kDagThreads) {
+      const uint32_t v = __ldcg(&P.lev_nodes[lo + i]);
+      const uint32_t parent = (uint32_t)(__ldcg(&P.best[v]) >> 32);
+      const uint32_t dv = __ldcg(&P.depth[parent]) + 1u;
+      P.depth[v] = dv;
+      uint32_t* upv = P.up + v;
+      upv[0] = parent;
+      uint32_t anc = parent;
+      for (uint32_t j = 1; (1u << j) <= dv; j++) { anc = up_at(P, j - 1, anc); upv[(size_t)j * (P.n + 1)] = anc; }
+    }
+    grid_barrier(P.ctl + 5, bar_epoch);  // a comparison below may meet any state of this level as the other candidate
+    // ---- phase 2: candidacies.  Uniform trip count per warp: the lanes of a warp vote inside the loop.
     for (uint32_t g0 = grp - (lane / kSub); g0 < count; g0 += n_grp) {
       const uint32_t g = g0 + lane / kSub;
       const bool live = g < count;
-      // depth / ancestors of v were written when v became ready (an earlier level, i.e. before a grid barrier), so
-      // nothing that is read below is written during this level
       uint32_t v = 0, d = 0, a_lo = 0, a_hi = 0;
       if (live) {
         v = __ldcg(&P.lev_nodes[lo + g]);
         d = __ldcg(&P.depth[v]);
         a_lo = __ldg(&P.off[v]); a_hi = __ldg(&P.off[v + 1]);
       }
-      const uint32_t rounds_mine = live ? (a_hi - a_lo + kSub - 1) / kSub : 0u;
-      uint32_t rounds = rounds_mine;
+      uint32_t rounds = live ? (a_hi - a_lo + kSub - 1) / kSub : 0u;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xFFFFFFFFu, rounds, o));
       for (uint32_t r = 0; r < rounds; r++) {
@@ -178,20 +191,10 @@ k_dag_tree(DagParams P) {
             if (old == cur) break;
             cur = old;
           }
-          __threadfence();  // the candidacy is in place before the in-degree says so
-          ready = atomicSub(&P.indeg[t], 1u) == 1u;
-          if (ready) {
-            // last in-arc: every candidacy for t has been made, its tree parent is final.  Record depth and ancestors
-            // now; t is processed in a later level, after a grid barrier.
-            __threadfence();
-            const uint32_t parent = (uint32_t)(atomicAdd(&P.best[t], 0ull) >> 32);
-            const uint32_t dt = __ldcg(&P.depth[parent]) + 1u;
-            P.depth[t] = dt;
-            uint32_t* upt = P.up + t;
-            upt[0] = parent;
-            uint32_t anc = parent;
-            for (uint32_t j = 1; (1u << j) <= dt; j++) { anc = up_at(P, j - 1, anc); upt[(size_t)j * (P.n + 1)] = anc; }
-          }
+          // No fence between the candidacy and the count-down: the loop above only ends once a compare-and-swap has
+          // RETURNED (or none was needed), i.e. after it was performed at L2, the point of coherence of both atomics, and
+          // best[t] is next read after a grid barrier.
+          ready = atomicSub(&P.indeg[t], 1u) == 1u;  // last in-arc: t joins the next level
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, ready);
         if (m) {

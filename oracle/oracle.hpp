@@ -17,8 +17,12 @@
 // The nshortest > 1 route (shortest_distance, reverse, n_shortest_path) has no in-tree known answer; it is pinned
 // by the criterion of the reference's own test (tests_openfst/algorithms/shortest_path.rs:62-92: number of paths,
 // weights position by position, paths exist in the input) against a brute-force enumeration of all paths of small
-// machines — tests/test_oracle_nshortest.py.  unique = true is not restated: the reference's own output is
-// process-dependent there (HashMap iteration order in determinize_fsa_op.rs:154-165).
+// machines — tests/test_oracle_nshortest.py.  unique = true (determinize_with_distance of the reversed machine first)
+// is restated with ONE stated difference: the reference rebuilds every weighted subset from HashMap::values() of a
+// RandomState map (determinize_fsa_op.rs:154-165), so the element order of a subset — hence subset identity, state
+// numbering and even the number of states of its own determinized machine — changes from process to process; here
+// subsets are kept sorted by state.  The n paths and their weights do not depend on that order; they are pinned by the
+// same brute-force criterion over DISTINCT label sequences.
 //
 // All paths below are relative to /root/reference/.
 #pragma once
@@ -27,6 +31,7 @@
 #include <cmath>
 #include <deque>
 #include <limits>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -1268,6 +1273,102 @@ inline Fst n_shortest_path(const Fst& ifst, const std::vector<float>& distance, 
   return ofst;
 }
 
+// determinize_with_distance — algorithms/determinize/determinize_static.rs:24-39 over DeterminizeFsaOp
+// (determinize_fsa_op.rs:44-54 start, :56-101 arcs of a subset state, :103-120 final weight, :147-178 norm_tr), the state
+// table (state_table.rs:20-35 out_dist of a new subset, :76-96 ids in order of first lookup), DefaultCommonDivisor
+// (divisors.rs:16-22: plus), quantisation (semiring.rs:132-145), division (tropical_weight.rs:127-132: plain
+// subtraction) and the breadth-first materialisation of a lazy FST (lazy/lazy_fst.rs:226-259).
+// Subsets are kept sorted by state (see the header of this file for why the reference's own order is not reproducible).
+struct DetElement { StateId state; float weight; };
+struct DetTuple { std::vector<DetElement> subset; StateId filter_state; };
+struct DetResult { Fst fst; std::vector<float> out_dist; };
+inline float w_quantize(float v, float delta) {  // semiring.rs:135-142
+  if (std::isinf(v)) return v;
+  return std::floor((v / delta) + 0.5f) * delta;
+}
+inline DetResult determinize_with_distance(const Fst& ifst, const std::vector<float>& in_dist, float delta) {
+  if (!(ifst.props & P::ACCEPTOR))  // determinize_fsa_op.rs:137-139
+    throw std::runtime_error("DeterminizeFsaImpl : expected acceptor as argument");
+  DetResult res;
+  std::vector<DetTuple> tuples;
+  std::map<std::vector<uint64_t>, StateId> ids;
+  auto find_state = [&](const DetTuple& t) -> StateId {  // state_table.rs:76-96
+    std::vector<uint64_t> key;
+    key.reserve(t.subset.size() + 1);
+    key.push_back(t.filter_state);
+    for (const DetElement& e : t.subset) {
+      float w = e.weight == 0.0f ? 0.0f : e.weight;  // -0.0 and 0.0 hash alike (OrderedFloat)
+      uint32_t bits;
+      std::memcpy(&bits, &w, 4);
+      key.push_back(((uint64_t)e.state << 32) | bits);
+    }
+    auto it = ids.find(key);
+    if (it != ids.end()) return it->second;
+    StateId id = (StateId)tuples.size();
+    ids.emplace(std::move(key), id);
+    tuples.push_back(t);
+    float outd = W_ZERO;  // state_table.rs:20-35
+    for (const DetElement& e : t.subset)
+      outd = w_plus(outd, w_times(e.weight, e.state < in_dist.size() ? in_dist[e.state] : W_ZERO));
+    res.out_dist.push_back(outd);
+    return id;
+  };
+  if (!ifst.has_start) return res;  // lazy_fst.rs:227-232
+  StateId start = find_state(DetTuple{{DetElement{ifst.start, W_ONE}}, ifst.start});  // determinize_fsa_op.rs:44-54
+  Fst& out = res.fst;
+  out.add_states((size_t)start + 1);
+  out.set_start(start);
+  std::deque<StateId> queue;
+  std::vector<bool> visited((size_t)start + 1, false);
+  visited[start] = true;
+  queue.push_back(start);
+  struct DetTr { Label label; float weight; DetTuple dest; };
+  while (!queue.empty()) {
+    StateId s = queue.front();
+    queue.pop_front();
+    const DetTuple src = tuples[s];  // a copy: find_state below grows `tuples`
+    std::map<Label, DetTr> label_map;  // BTreeMap: arcs leave in label order (:57-82)
+    for (const DetElement& se : src.subset)
+      for (const Tr& tr : ifst.states[se.state].trs) {
+        auto it = label_map.find(tr.ilabel);
+        if (it == label_map.end()) it = label_map.emplace(tr.ilabel, DetTr{tr.ilabel, W_ZERO, DetTuple{{}, 0}}).first;
+        it->second.dest.subset.push_back(DetElement{tr.nextstate, w_times(se.weight, tr.weight)});
+      }
+    std::vector<Tr> trs;
+    for (auto& kv : label_map) {  // norm_tr (:147-178)
+      DetTr& d = kv.second;
+      std::stable_sort(d.dest.subset.begin(), d.dest.subset.end(),
+                       [](const DetElement& x, const DetElement& y) { return x.state < y.state; });
+      for (const DetElement& e : d.dest.subset) d.weight = w_plus(d.weight, e.weight);
+      std::vector<DetElement> merged;  // one element per state, weights combined with plus; ascending state
+      for (const DetElement& e : d.dest.subset) {
+        if (!merged.empty() && merged.back().state == e.state) merged.back().weight = w_plus(merged.back().weight, e.weight);
+        else merged.push_back(e);
+      }
+      for (DetElement& e : merged) e.weight = w_quantize(e.weight - d.weight, delta);
+      d.dest.subset = std::move(merged);
+    }
+    for (auto& kv : label_map) {  // :92-99
+      const DetTr& d = kv.second;
+      trs.push_back(Tr{d.label, d.label, d.weight, find_state(d.dest)});
+    }
+    for (const Tr& tr : trs) {  // lazy_fst.rs:242-254
+      if (tr.nextstate >= visited.size()) visited.resize((size_t)tr.nextstate + 1, false);
+      if (!visited[tr.nextstate]) { queue.push_back(tr.nextstate); visited[tr.nextstate] = true; }
+      if (tr.nextstate >= out.num_states()) out.add_states((size_t)tr.nextstate - out.num_states() + 1);
+    }
+    out.set_trs_unchecked(s, std::move(trs));
+    float fw = W_ZERO;  // determinize_fsa_op.rs:103-120
+    for (const DetElement& e : src.subset) {
+      const State& st = ifst.states[e.state];
+      fw = w_plus(fw, w_times(e.weight, st.has_final ? st.final_weight : W_ZERO));
+    }
+    if (!w_is_zero(fw)) out.set_final(s, fw);
+  }
+  out.props = 0;  // lazy_fst.rs:260 with DeterminizeFsaOp::properties() = empty (:122-125); nobody reads it
+  return res;
+}
+
 // shortest_path.rs:107-171 (dispatch), :173-239 single_shortest_path, :241-282 backtrace
 inline Fst shortest_path(const Fst& ifst, const ShortestPathConfig& cfg, SsspStats* stats = nullptr,
                          std::vector<float>* distance_out = nullptr) {
@@ -1285,13 +1386,10 @@ inline Fst shortest_path(const Fst& ifst, const ShortestPathConfig& cfg, SsspSta
     distance_2.push_back(d);
     distance_2.insert(distance_2.end(), distance.begin(), distance.end());
     if (distance_out) *distance_out = distance;
-    if (cfg.unique)
-      // determinize_with_distance (determinize_fsa_op.rs:154-165) rebuilds each weighted subset from
-      // `HashMap::values()` of a RandomState map: element order, hence subset identity, state numbering and even
-      // the number of states, change from process to process in the reference itself.  There is no reproducible
-      // answer to restate.
-      throw std::runtime_error("oracle: unique n-shortest paths are not restated (reference output is "
-                               "process-dependent: HashMap iteration order in determinize_fsa_op.rs:154-165)");
+    if (cfg.unique) {  // :156-165 (reverse weights of the tropical semiring are the weights themselves)
+      DetResult det = determinize_with_distance(rfst, distance_2, cfg.delta);
+      return n_shortest_path(det.fst, det.out_dist, cfg.nshortest, cfg.delta);
+    }
     return n_shortest_path(rfst, distance_2, cfg.nshortest, cfg.delta);
   }
 

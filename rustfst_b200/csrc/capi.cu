@@ -760,7 +760,27 @@ static void compose_batch_core(const CFst* const* acceptors, size_t n, const CFs
       }
       base_state[n] = (uint32_t)so; base_arc[n] = (uint32_t)ao;
     }
-    parallel_ranges(n, [&](size_t lo_i, size_t hi_i) {
+    // The union is built in page-locked memory chunk by chunk and every chunk goes to the device as soon as it is
+    // complete: host threads fill chunk k + 1 while the copy engine moves chunk k (the upload is PCIe-bound).
+    u.offsets[sum_states] = base_arc[n];
+    u.has_start = true; u.start = starts[0];
+    u.props = and_props & props::kTrinary;
+    DevFst du(st.s);
+    du.offsets.reserve_discard(sum_states + 1);
+    du.arcs.reserve_discard(sum_arcs ? sum_arcs : 1);
+    du.finals.reserve_discard(sum_states ? sum_states : 1);
+    du.num_states = (uint32_t)sum_states; du.num_arcs = (uint32_t)sum_arcs;
+    du.has_start = true; du.start = u.start; du.props = u.props;
+    DevBuf<uint32_t> d_starts(st.s, n), d_s1(st.s), d_map(st.s);
+    B200_CUDA(cudaMemcpyAsync(d_starts.p, starts.data(), n * 4, cudaMemcpyHostToDevice, st.s));
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = n < 64 ? 1 : std::min<size_t>(hw ? hw : 1, 8);
+    const size_t n_chunks = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, n), sum_arcs / (128 * 1024)));
+    std::vector<size_t> bound(n_chunks + 1);
+    for (size_t k = 0; k <= n_chunks; k++) bound[k] = n * k / n_chunks;
+    std::vector<std::atomic<uint32_t>> chunk_done(n_chunks);
+    for (auto& d : chunk_done) d.store(0);
+    auto build = [&](size_t lo_i, size_t hi_i) {
       for (size_t i = lo_i; i < hi_i; i++) {
         const CsrFst& h = *hs[i];
         const size_t so = base_state[i], ao = base_arc[i], ns = h.num_states(), na = h.arcs.size();
@@ -768,17 +788,40 @@ static void compose_batch_core(const CFst* const* acceptors, size_t n, const CFs
         std::memcpy(u.finals.data() + so, h.finals.data(), ns * 4);
         for (size_t k = 0; k < na; k++) { Tr t = h.arcs[k]; t.nextstate += (uint32_t)so; u.arcs[ao + k] = t; }
       }
-    }, 64);
-    u.offsets[sum_states] = base_arc[n];
-    u.has_start = true; u.start = starts[0];
-    u.props = and_props & props::kTrinary;
-    const double t_union = now_ms() - tu0;
-    t0 = now_ms();
-    DevFst du = upload(u, st.s);
-    DevBuf<uint32_t> d_starts(st.s, n), d_s1(st.s), d_map(st.s);
-    B200_CUDA(cudaMemcpyAsync(d_starts.p, starts.data(), n * 4, cudaMemcpyHostToDevice, st.s));
+    };
+    auto worker = [&](size_t t) {
+      for (size_t k = 0; k < n_chunks; k++) {
+        const size_t len = bound[k + 1] - bound[k], share = (len + nt - 1) / nt;
+        const size_t lo_i = std::min(bound[k + 1], bound[k] + t * share), hi_i = std::min(bound[k + 1], lo_i + share);
+        build(lo_i, hi_i);
+        chunk_done[k].fetch_add(1, std::memory_order_release);
+      }
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; t++) th.emplace_back(worker, t);
+    double t_union = 0;
+    try {
+      for (size_t k = 0; k < n_chunks; k++) {
+        {  // the calling thread takes share 0 of every chunk
+          const size_t len = bound[k + 1] - bound[k], share = (len + nt - 1) / nt;
+          build(bound[k], std::min(bound[k + 1], bound[k] + share));
+          chunk_done[k].fetch_add(1, std::memory_order_release);
+        }
+        while (chunk_done[k].load(std::memory_order_acquire) < nt) std::this_thread::yield();
+        const size_t s0 = base_state[bound[k]], s1 = base_state[bound[k + 1]], a0 = base_arc[bound[k]], a1 = base_arc[bound[k + 1]];
+        const size_t n_off = s1 - s0 + (k + 1 == n_chunks ? 1 : 0);  // the last chunk carries the closing offset
+        if (n_off) B200_CUDA(cudaMemcpyAsync(du.offsets.p + s0, u.offsets.data() + s0, n_off * 4, cudaMemcpyHostToDevice, st.s));
+        if (s1 > s0) B200_CUDA(cudaMemcpyAsync(du.finals.p + s0, u.finals.data() + s0, (s1 - s0) * 4, cudaMemcpyHostToDevice, st.s));
+        if (a1 > a0) B200_CUDA(cudaMemcpyAsync(du.arcs.p + a0, u.arcs.data() + a0, (a1 - a0) * sizeof(Tr), cudaMemcpyHostToDevice, st.s));
+      }
+      t_union = now_ms() - tu0;
+    } catch (...) {
+      for (auto& t : th) t.join();
+      throw;
+    }
+    for (auto& t : th) t.join();
     B200_CUDA(cudaStreamSynchronize(st.s));
-    acc.ms_h2d += (float)(now_ms() - t0);
+    acc.ms_h2d += (float)(now_ms() - tu0);
     BatchStarts bs;
     bs.d_starts1 = d_starts.p; bs.n = (uint32_t)n; bs.out_s1 = &d_s1; bs.out_start_map = &d_map;
     ComposeStats cs;
@@ -798,7 +841,7 @@ static void compose_batch_core(const CFst* const* acceptors, size_t n, const CFs
       acc.ms_d2h += (float)(now_ms() - t0);
       fill(&acc, cs, acc.ms_h2d, acc.ms_d2h);
       if (std::getenv("B200_BATCH_TRACE"))
-        std::fprintf(stderr, "[batch] n=%zu union build %.2f ms, h2d %.2f, expand %.2f, connect %.2f, split + d2h %.2f ms\n",
+        std::fprintf(stderr, "[batch] n=%zu union build (overlapped with the upload) %.2f ms, union + h2d %.2f, expand %.2f, connect %.2f, split + d2h %.2f ms\n",
                      n, t_union, acc.ms_h2d, cs.ms_expand, cs.ms_connect, acc.ms_d2h);
       done = true;
     }

@@ -38,6 +38,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "algos.h"
 #include "coop_utils.cuh"
@@ -49,59 +50,102 @@ using namespace coop;
 constexpr uint32_t kDagThreads = 512;
 constexpr uint32_t kSub = 8;             // lanes that share one state (its arcs are strided over them)
 constexpr uint32_t kMaxLevels = 1u << 16;
+constexpr uint32_t kReadyBuf = 96;         // per-warp buffer of newly ready states (shared memory)
 enum DagStatus : uint32_t { kDagCyclic = 1, kDagTooDeep = 2 };
+
+constexpr uint32_t kLow = 6;  // ancestors 2^0 .. 2^5 of a state live in its record; higher ones in the table up_hi
+
+// Everything a comparison needs to know about a processed state, in ONE 32-byte sector (one 256-bit load):
+// depth, position of the tree arc in the parent's list, and the 2^j-th ancestors for j < kLow (R where the path is shorter).
+struct alignas(32) NodeRec { uint32_t depth, pos, up[kLow]; };
 
 struct DagParams {
   const uint32_t* off; const Tr* arcs; uint32_t n; uint32_t start;
   uint32_t* indeg;            // in-arcs of every state that are still to be processed
   unsigned long long* best;   // n + 1: (tree parent << 32 | position of the tree arc in the parent's list); node n = R
-  uint32_t* depth;            // n + 1, depth[R] = 0
-  uint32_t* up;               // up[j * (n + 1) + v] = 2^j-th ancestor of v, written for 2^j <= depth[v]
+  NodeRec* rec;               // n + 1 records, rec[R] = {0, 0, R ...}; written when the state's level starts
+  uint32_t* up_hi;            // up_hi[(j - kLow) * (n + 1) + v] = 2^j-th ancestor of v, written for kLow <= j, 2^j <= depth[v]
   uint32_t* lev_nodes;        // states in Kahn level order; level k = lev_nodes[lev_off[k] .. lev_off[k + 1])
   uint32_t* lev_off;
   uint32_t* sizes;            // subtree sizes
   uint32_t* order;            // result
   uint32_t* ctl;              // [0..2] rotating level counters, [3] #levels, [4] status, [5] barrier of k_dag_tree, [6] #states processed,
                               // [7] barrier of k_dag_orders
+  unsigned long long* trace;  // optional (B200_COOP_TRACE): ns of CTA 0 in [0] records, [1] barrier, [2] candidacies, [3] barrier, [4] sizes
 };
 
 __device__ __forceinline__ unsigned long long pack_cand(uint32_t node, uint32_t pos) {
   return ((unsigned long long)node << 32) | pos;
 }
-__device__ __forceinline__ uint32_t up_at(const DagParams& P, uint32_t j, uint32_t v) {
-  return __ldcg(&P.up[(size_t)j * (P.n + 1) + v]);
+// L2-coherent 256-bit accesses (LDG/STG.E.ENL2.256): records are written by other SMs one grid barrier earlier
+__device__ __forceinline__ NodeRec ld_rec(const DagParams& P, uint32_t v) {
+  NodeRec r;
+  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.depth), "=r"(r.pos), "=r"(r.up[0]), "=r"(r.up[1]), "=r"(r.up[2]), "=r"(r.up[3]), "=r"(r.up[4]), "=r"(r.up[5])
+               : "l"(P.rec + v));
+  return r;
 }
-__device__ __forceinline__ uint32_t pos_in_parent(const DagParams& P, uint32_t v) {
-  return (uint32_t)__ldcg(&P.best[v]);
+__device__ __forceinline__ void st_rec(const DagParams& P, uint32_t v, const NodeRec& r) {
+  asm volatile("st.global.cg.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+               :: "r"(r.depth), "r"(r.pos), "r"(r.up[0]), "r"(r.up[1]), "r"(r.up[2]), "r"(r.up[3]), "r"(r.up[4]), "r"(r.up[5]), "l"(P.rec + v)
+               : "memory");
 }
-__device__ __forceinline__ uint32_t lift(const DagParams& P, uint32_t v, uint32_t k) {
-  while (k) { const uint32_t j = 31u - __clz(k); v = up_at(P, j, v); k -= 1u << j; }
-  return v;
+__device__ __forceinline__ uint32_t ld_next_state(const Tr* arc) {  // pinned in program order: issued a round ahead of its use
+  uint32_t t;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(t) : "l"(&arc->nextstate));
+  return t;
 }
-// path(a) . pa  <  path(b) . pb   (lexicographic; a and b are processed states or R, a at depth da)
-__device__ __forceinline__ bool cand_less(const DagParams& P, uint32_t a, uint32_t pa, uint32_t da, uint32_t b, uint32_t pb) {
+__device__ __forceinline__ uint32_t up_low(const NodeRec& r, uint32_t j) {  // j < kLow, not a compile-time constant
+  uint32_t u = r.up[0];
+#pragma unroll
+  for (uint32_t k = 1; k < kLow; k++) u = j == k ? r.up[k] : u;
+  return u;
+}
+__device__ __forceinline__ uint32_t up_hi_at(const DagParams& P, uint32_t j, uint32_t v) {
+  return __ldcg(&P.up_hi[(size_t)(j - kLow) * (P.n + 1) + v]);
+}
+// climbs k levels from x, whose record is in rx; leaves the record of the state it arrives at in rx
+__device__ __forceinline__ void lift(const DagParams& P, uint32_t& x, NodeRec& rx, uint32_t k) {
+  while (k) {
+    const uint32_t j = 31u - __clz(k);
+    x = j < kLow ? up_low(rx, j) : up_hi_at(P, j, x);
+    rx = ld_rec(P, x);
+    k -= 1u << j;
+  }
+}
+// path(a) . pa  <  path(b) . pb   (lexicographic; a and b are processed states or R; rx = record of a, consumed).
+// Typical cost on a lattice (candidates of similar depth that part a few levels up): the record of b plus one pair of
+// records per set bit of the distance to the parting point.
+__device__ __forceinline__ bool cand_less(const DagParams& P, uint32_t a, NodeRec& rx, uint32_t pa, uint32_t b, uint32_t pb) {
   if (a == b) return pa < pb;
-  const uint32_t db = __ldcg(&P.depth[b]);
-  uint32_t x = a, y = b, d = da;
-  if (da > db) {  // is b an ancestor of a?  then a's path leaves b through the arc towards a
-    x = lift(P, a, da - db - 1);
-    const uint32_t px = up_at(P, 0, x);
-    if (px == b) return pos_in_parent(P, x) < pb;
-    x = px; d = db;
-  } else if (db > da) {
-    y = lift(P, b, db - da - 1);
-    const uint32_t py = up_at(P, 0, y);
-    if (py == a) return pa < pos_in_parent(P, y);
-    y = py;
+  NodeRec ry = ld_rec(P, b);
+  uint32_t x = a, y = b, d = rx.depth;
+  if (rx.depth > ry.depth) {  // is b an ancestor of a?  then a's path leaves b through the arc towards a
+    lift(P, x, rx, rx.depth - ry.depth - 1);
+    if (rx.up[0] == b) return rx.pos < pb;
+    x = rx.up[0]; rx = ld_rec(P, x); d = ry.depth;
+  } else if (ry.depth > rx.depth) {
+    lift(P, y, ry, ry.depth - rx.depth - 1);
+    if (ry.up[0] == a) return pa < ry.pos;
+    y = ry.up[0]; ry = ld_rec(P, y);
   }
   if (x == y) return false;  // cannot happen on a DAG (one candidate's path would run through the target)
   // x != y at the same depth d >= 1: climb to the children of their lowest common ancestor
-  for (int j = 31 - __clz(d); j >= 0; j--) {
-    if ((1u << j) > d) continue;
-    const uint32_t ux = up_at(P, j, x), uy = up_at(P, j, y);
-    if (ux != uy) { x = ux; y = uy; d -= 1u << j; }
+  if (d >> kLow) {
+    bool moved = false;
+    for (int j = 31 - __clz(d); j >= (int)kLow; j--) {
+      if ((1u << j) > d) continue;
+      const uint32_t ux = up_hi_at(P, j, x), uy = up_hi_at(P, j, y);
+      if (ux != uy) { x = ux; y = uy; d -= 1u << j; moved = true; }
+    }
+    if (moved) { rx = ld_rec(P, x); ry = ld_rec(P, y); }
   }
-  return pos_in_parent(P, x) < pos_in_parent(P, y);
+#pragma unroll
+  for (int j = (int)kLow - 1; j >= 0; j--) {  // ancestors beyond the root read R on both sides: no depth test needed
+    const uint32_t ux = rx.up[j], uy = ry.up[j];
+    if (ux != uy) { x = ux; y = uy; rx = ld_rec(P, x); ry = ld_rec(P, y); }
+  }
+  return rx.pos < ry.pos;
 }
 
 // in-degrees, initial candidates (R, position of the virtual arc: start first, then the states by id), sizes
@@ -112,7 +156,9 @@ __global__ void k_dag_init(DagParams P) {
     P.sizes[v] = 1u;
   } else if (v == P.n) {
     P.best[v] = pack_cand(P.n, 0u);
-    P.depth[v] = 0u;
+    NodeRec r; r.depth = 0u; r.pos = 0u;
+    for (uint32_t j = 0; j < kLow; j++) r.up[j] = P.n;
+    st_rec(P, v, r);
     for (int k = 0; k < 8; k++) P.ctl[k] = 0u;
   }
 }
@@ -129,22 +175,21 @@ __global__ void k_dag_seed(DagParams P) {
   uint32_t base = 0;
   if (lane == leader) base = atomicAdd(&P.ctl[0], __popc(m));
   base = __shfl_sync(0xFFFFFFFFu, base, leader);
-  if (ready) {
-    P.lev_nodes[base + __popc(m & ((1u << lane) - 1u))] = v;
-    P.depth[v] = 1u;   // no in-arc: a child of R
-    P.up[v] = P.n;
-  }
+  if (ready) P.lev_nodes[base + __popc(m & ((1u << lane) - 1u))] = v;  // no in-arc: a child of R
 }
 
 // Kahn levels + tree parents + subtree sizes.  Level counters rotate over three words so that nobody reads a counter
 // while it is reset or appended to: during level L appends go to ctl[(L + 1) % 3], ctl[(L + 2) % 3] is cleared, and
 // ctl[L % 3] (the size of level L) was read by everybody before any append of level L + 1 can happen.
-__global__ void __launch_bounds__(kDagThreads)
+__global__ void __launch_bounds__(kDagThreads, 2)
 k_dag_tree(DagParams P) {
   const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31u;
-  const uint32_t sub = lane & (kSub - 1), grp = (c * kDagThreads + tid) / kSub, n_grp = G * kDagThreads / kSub;
+  __shared__ uint32_t s_ready[kDagThreads / 32u][kReadyBuf];
   unsigned int bar_epoch = 0;
   uint32_t lo = 0, hi = __ldcg(&P.ctl[0]), level = 0, status = 0;
+  const bool tracing = P.trace != nullptr && tid == 0;
+  unsigned long long t_prev = tracing ? globaltimer_ns() : 0ull, t_acc[5] = {0, 0, 0, 0, 0};
+  auto lap = [&](int k) { if (tracing) { const unsigned long long t = globaltimer_ns(); t_acc[k] += t - t_prev; t_prev = t; } };
   while (lo < hi) {
     if (level + 2 >= kMaxLevels) { status = kDagTooDeep; break; }  // uniform
     if (c == 0 && tid == 0) { P.lev_off[level] = lo; P.ctl[(level + 2) % 3] = 0u; }
@@ -155,58 +200,116 @@ k_dag_tree(DagParams P) {
     // dependent loads that would otherwise serialise inside the diverged lane that takes a state's last in-arc away)
     for (uint32_t i = c * kDagThreads + tid; i < count; i += G * kDagThreads) {
       const uint32_t v = __ldcg(&P.lev_nodes[lo + i]);
-      const uint32_t parent = (uint32_t)(__ldcg(&P.best[v]) >> 32);
-      const uint32_t dv = __ldcg(&P.depth[parent]) + 1u;
-      P.depth[v] = dv;
-      uint32_t* upv = P.up + v;
-      upv[0] = parent;
-      uint32_t anc = parent;
-      for (uint32_t j = 1; (1u << j) <= dv; j++) { anc = up_at(P, j - 1, anc); upv[(size_t)j * (P.n + 1)] = anc; }
-    }
-    grid_barrier(P.ctl + 5, bar_epoch);  // a comparison below may meet any state of this level as the other candidate
-    // ---- phase 2: candidacies.  Uniform trip count per warp: the lanes of a warp vote inside the loop.
-    for (uint32_t g0 = grp - (lane / kSub); g0 < count; g0 += n_grp) {
-      const uint32_t g = g0 + lane / kSub;
-      const bool live = g < count;
-      uint32_t v = 0, d = 0, a_lo = 0, a_hi = 0;
-      if (live) {
-        v = __ldcg(&P.lev_nodes[lo + g]);
-        d = __ldcg(&P.depth[v]);
-        a_lo = __ldg(&P.off[v]); a_hi = __ldg(&P.off[v + 1]);
-      }
-      uint32_t rounds = live ? (a_hi - a_lo + kSub - 1) / kSub : 0u;
+      const unsigned long long bv = __ldcg(&P.best[v]);
+      const uint32_t parent = (uint32_t)(bv >> 32);
+      const NodeRec rp = ld_rec(P, parent);
+      NodeRec r;
+      r.depth = rp.depth + 1u; r.pos = (uint32_t)bv; r.up[0] = parent; r.up[1] = rp.up[0];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xFFFFFFFFu, rounds, o));
-      for (uint32_t r = 0; r < rounds; r++) {
-        const uint32_t e = a_lo + r * kSub + sub;
-        bool ready = false;
-        uint32_t t = 0;
-        if (live && e < a_hi) {
-          t = __ldg(&P.arcs[e].nextstate);
-          const uint32_t pos = e - a_lo;
-          const unsigned long long mine = pack_cand(v, pos);
-          unsigned long long cur = __ldcg(&P.best[t]);
-          while (cand_less(P, v, pos, d, (uint32_t)(cur >> 32), (uint32_t)cur)) {
-            const unsigned long long old = atomicCAS(&P.best[t], cur, mine);
+      for (uint32_t j = 2; j < kLow; j++) r.up[j] = __ldcg(&P.rec[r.up[j - 1]].up[j - 1]);  // rec[R].up[*] = R
+      st_rec(P, v, r);
+      uint32_t anc = r.up[kLow - 1];
+      for (uint32_t j = kLow; (1u << j) <= r.depth; j++) {
+        anc = j == kLow ? __ldcg(&P.rec[anc].up[kLow - 1]) : up_hi_at(P, j - 1, anc);
+        P.up_hi[(size_t)(j - kLow) * (P.n + 1) + v] = anc;
+      }
+    }
+    __syncthreads(); lap(0);
+    grid_barrier(P.ctl + 5, bar_epoch);  // a comparison below may meet any state of this level as the other candidate
+    lap(1);
+    // ---- phase 2: candidacies, one lane per ARC.  A warp takes a tile of consecutive states of the level (sized so that
+    // every warp of the grid gets one), scans their degrees, and its lanes walk the tile's arcs 32 at a time; the owner
+    // state of an arc is found by a binary search over the scanned degrees held in the lanes.
+    const uint32_t n_warps = G * (kDagThreads / 32u), gw = c * (kDagThreads / 32u) + (tid >> 5);
+    uint32_t* const my_ready = s_ready[tid >> 5];
+    uint32_t n_buf = 0;  // warp-uniform: states that became ready and wait in shared memory for one common append
+    auto flush = [&]() {
+      __syncwarp();
+      uint32_t nb = 0;
+      if (lane == 0) nb = atomicAdd(next_cnt, n_buf);
+      nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
+      for (uint32_t i = lane; i < n_buf; i += 32u) P.lev_nodes[hi + nb + i] = my_ready[i];
+      __syncwarp();
+      n_buf = 0;
+    };
+    const uint32_t tile = min(32u, max(1u, (count + n_warps - 1u) / n_warps));
+    for (uint32_t base = gw * tile; base < count; base += n_warps * tile) {
+      const bool own = lane < tile && base + lane < count;
+      uint32_t v_own = 0, lo_own = 0, deg = 0;
+      if (own) {
+        v_own = __ldcg(&P.lev_nodes[lo + base + lane]);
+        lo_own = __ldg(&P.off[v_own]); deg = __ldg(&P.off[v_own + 1]) - lo_own;
+      }
+      uint32_t incl = deg;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += x; }
+      const uint32_t excl = incl - deg, total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      // Software pipeline over the rounds of 32 arcs: each stage's loads are issued one iteration before their results
+      // are needed, so that a round's critical path is the comparison and the compare-and-swap only.  Iteration i runs
+      //   [B] best[t] and the source's record for round i-1 (t arrived during the previous iteration),
+      //   [A] the arc of round i,
+      //   [C] comparison, compare-and-swap and the in-degree count-down for round i-2,
+      //   [D] the answer of the count-down of round i-3.
+      // A stale best[t] costs at most a failed compare-and-swap, which returns the current value.
+      const uint32_t rounds = (total + 31u) >> 5;
+      uint32_t tA = 0, vA = 0, posA = 0, tB = 0, vB = 0, posB = 0, tD = 0, oldD = 0;
+      bool actA = false, actB = false, actD = false;
+      unsigned long long curB = 0;
+      NodeRec rvB{};
+      for (uint32_t i = 0; i < rounds + 3u; i++) {
+        const uint32_t tC = tB, vC = vB, posC = posB;
+        const bool actC = actB;
+        unsigned long long cur = curB;
+        NodeRec rvC = rvB;
+        // [B]
+        tB = tA; vB = vA; posB = posA; actB = actA;
+        if (actB) { curB = __ldcg(&P.best[tB]); rvB = ld_rec(P, vB); }
+        // [A]
+        const uint32_t k = i * 32u + lane;
+        actA = i < rounds && k < total;
+        {
+          uint32_t o = 0;  // first lane whose inclusive degree sum exceeds k
+#pragma unroll
+          for (uint32_t step = 16; step > 0; step >>= 1) {
+            const uint32_t probe = __shfl_sync(0xFFFFFFFFu, incl, (o + step - 1u) & 31u);
+            if (probe <= k) o += step;
+          }
+          o = actA ? o : 0u;
+          vA = __shfl_sync(0xFFFFFFFFu, v_own, o);
+          posA = k - __shfl_sync(0xFFFFFFFFu, excl, o);
+          const uint32_t e = __shfl_sync(0xFFFFFFFFu, lo_own, o) + posA;
+          if (actA) tA = ld_next_state(P.arcs + e);
+        }
+        // [C]
+        uint32_t old_c = 0;
+        if (actC) {
+          const unsigned long long mine = pack_cand(vC, posC);
+          while (cand_less(P, vC, rvC, posC, (uint32_t)(cur >> 32), (uint32_t)cur)) {
+            const unsigned long long old = atomicCAS(&P.best[tC], cur, mine);
             if (old == cur) break;
             cur = old;
+            rvC = ld_rec(P, vC);  // the comparison consumed its copy
           }
           // No fence between the candidacy and the count-down: the loop above only ends once a compare-and-swap has
           // RETURNED (or none was needed), i.e. after it was performed at L2, the point of coherence of both atomics, and
           // best[t] is next read after a grid barrier.
-          ready = atomicSub(&P.indeg[t], 1u) == 1u;  // last in-arc: t joins the next level
+          old_c = atomicSub(&P.indeg[tC], 1u);
         }
+        // [D] whoever takes the last in-arc away appends the state to the next level
+        const bool ready = actD && oldD == 1u;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, ready);
-        if (m) {
-          const uint32_t leader = __ffs(m) - 1;
-          uint32_t base = 0;
-          if (lane == leader) base = atomicAdd(next_cnt, __popc(m));
-          base = __shfl_sync(0xFFFFFFFFu, base, leader);
-          if (ready) P.lev_nodes[hi + base + __popc(m & ((1u << lane) - 1u))] = t;
+        if (m) {  // one append to the next level per kReadyBuf states, not per round: the counter is ONE address
+          if (n_buf + __popc(m) > kReadyBuf) flush();
+          if (ready) my_ready[n_buf + __popc(m & ((1u << lane) - 1u))] = tD;
+          n_buf += __popc(m);
         }
+        tD = tC; oldD = old_c; actD = actC;
       }
     }
+    if (n_buf) flush();
+    __syncthreads(); lap(2);
     grid_barrier(P.ctl + 5, bar_epoch);
+    lap(3);
     lo = hi;
     hi += __ldcg(next_cnt);
     level++;
@@ -220,6 +323,7 @@ k_dag_tree(DagParams P) {
     P.ctl[4] = status;
   }
   if (status || lo < P.n) return;  // uniform
+  t_prev = tracing ? globaltimer_ns() : 0ull;
   // ---- subtree sizes: reverse sweep over the levels (the children of a state sit in later levels)
   grid_barrier(P.ctl + 5, bar_epoch);  // lev_off is complete
   const uint32_t gtid = c * kDagThreads + tid, gsize = G * kDagThreads;
@@ -232,6 +336,8 @@ k_dag_tree(DagParams P) {
     }
     grid_barrier(P.ctl + 5, bar_epoch);
   }
+  lap(4);
+  if (tracing) for (int k = 0; k < 5; k++) P.trace[(size_t)c * 8 + k] = t_acc[k];
 }
 
 // Roots (children of R): start comes first, then the other roots by id, so in reverse finish order start follows all the
@@ -298,6 +404,7 @@ int coop_grid(const void* kern, int threads) {
   int per_sm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
   if (per_sm < 1) throw FstError("cooperative kernel does not fit on the device");
+  if (const char* e = std::getenv("B200_DAG_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));
   return sm_count() * per_sm;
 }
 
@@ -315,21 +422,28 @@ bool dag_top_order_device(const DevFst& f, DevBuf<uint32_t>& order, float* ms, u
   uint32_t log_n = 1;
   while ((1ull << log_n) <= (unsigned long long)n + 1) log_n++;
   order.reserve_discard(n);
-  DevBuf<uint32_t> indeg(s, n), depth(s, (size_t)n + 1), lev_nodes(s, n), lev_off(s, kMaxLevels + 2), sizes(s, n), ctl(s, 8);
-  DevBuf<uint32_t> up(s, (size_t)log_n * ((size_t)n + 1)), g(s, (size_t)n + 1), pref(s, (size_t)n + 1);
+  DevBuf<uint32_t> indeg(s, n), lev_nodes(s, n), lev_off(s, kMaxLevels + 2), sizes(s, n), ctl(s, 8);
+  DevBuf<uint32_t> up_hi(s, (size_t)(log_n > kLow ? log_n - kLow : 1) * ((size_t)n + 1)), g(s, (size_t)n + 1), pref(s, (size_t)n + 1);
   DevBuf<unsigned long long> best(s, (size_t)n + 1);
+  DevBuf<NodeRec> rec(s, (size_t)n + 1);
   DevBuf<uint8_t> scan_tmp(s);
   DagParams P{};
   P.off = f.offsets.p; P.arcs = f.arcs.p; P.n = n; P.start = f.start;
-  P.indeg = indeg.p; P.best = best.p; P.depth = depth.p; P.up = up.p; P.lev_nodes = lev_nodes.p; P.lev_off = lev_off.p;
+  P.indeg = indeg.p; P.best = best.p; P.rec = rec.p; P.up_hi = up_hi.p; P.lev_nodes = lev_nodes.p; P.lev_off = lev_off.p;
   P.sizes = sizes.p; P.order = order.p; P.ctl = ctl.p;
+  const bool tracing = std::getenv("B200_COOP_TRACE") != nullptr;
+  DevBuf<unsigned long long> trace(s, 8 * 4096);
+  if (tracing) { B200_CUDA(cudaMemsetAsync(trace.p, 0, 8 * 8 * 4096, s)); P.trace = trace.p; }
   B200_CUDA(cudaMemsetAsync(indeg.p, 0, (size_t)n * 4, s));
   k_dag_init<<<blocks_for((size_t)n + 1), kThreads, 0, s>>>(P);
   if (a) k_dag_indeg<<<blocks_for(a), kThreads, 0, s>>>(f.arcs.p, a, indeg.p);
   k_dag_seed<<<blocks_for(n), kThreads, 0, s>>>(P);
+  cudaEvent_t e_a = nullptr, e_b = nullptr;
+  if (tracing) { B200_CUDA(cudaEventCreate(&e_a)); B200_CUDA(cudaEventCreate(&e_b)); B200_CUDA(cudaEventRecord(e_a, s)); }
   void* args[] = {(void*)&P};
   const int grid_a = coop_grid((void*)k_dag_tree, kDagThreads);
   B200_CUDA(cudaLaunchCooperativeKernel((void*)k_dag_tree, dim3(grid_a), dim3(kDagThreads), args, 0, s));
+  if (tracing) B200_CUDA(cudaEventRecord(e_b, s));
   uint32_t h[8];
   B200_CUDA(cudaMemcpyAsync(h, ctl.p, 32, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
@@ -344,11 +458,29 @@ bool dag_top_order_device(const DevFst& f, DevBuf<uint32_t>& order, float* ms, u
     const int grid_b = coop_grid((void*)k_dag_orders, kDagThreads);
     B200_CUDA(cudaLaunchCooperativeKernel((void*)k_dag_orders, dim3(grid_b), dim3(kDagThreads), args_b, 0, s));
     if (launches) *launches += 4;
-    if (std::getenv("B200_COOP_TRACE")) std::fprintf(stderr, "[dag-order] %u states, %u arcs, %u levels\n", n, a, n_levels);
+    if (tracing) {
+      std::vector<unsigned long long> all((size_t)8 * grid_a);
+      B200_CUDA(cudaMemcpyAsync(all.data(), trace.p, all.size() * 8, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      const unsigned long long* t = all.data();
+      std::vector<double> cand;
+      for (int k = 0; k < grid_a; k++) cand.push_back(all[(size_t)k * 8 + 2] * 1e-6);
+      std::sort(cand.begin(), cand.end());
+      std::fprintf(stderr, "[dag-order] candidacies per CTA ms: min %.3f median %.3f p90 %.3f max %.3f\n", cand.front(), cand[cand.size() / 2],
+                   cand[cand.size() * 9 / 10], cand.back());
+      std::fprintf(stderr, "[dag-order] %u states, %u arcs, %u levels; CTA 0 ms: records %.3f barrier %.3f candidacies %.3f barrier %.3f sizes %.3f\n",
+                   n, a, n_levels, t[0] * 1e-6, t[1] * 1e-6, t[2] * 1e-6, t[3] * 1e-6, t[4] * 1e-6);
+    }
   }
   B200_CUDA(cudaEventRecord(e1, s));
   B200_CUDA(cudaStreamSynchronize(s));
   if (ms) B200_CUDA(cudaEventElapsedTime(ms, e0, e1));
+  if (tracing) {
+    float t_pre = 0, t_tree = 0, t_post = 0;
+    cudaEventElapsedTime(&t_pre, e0, e_a); cudaEventElapsedTime(&t_tree, e_a, e_b); cudaEventElapsedTime(&t_post, e_b, e1);
+    std::fprintf(stderr, "[dag-order] ms: in-degrees + seed %.3f, tree kernel %.3f, host read-back + orders %.3f\n", t_pre, t_tree, t_post);
+    cudaEventDestroy(e_a); cudaEventDestroy(e_b);
+  }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return ok;
 }

@@ -140,3 +140,69 @@ def test_nbest_runs_on_fixture_machines(name):
             off, arcs, fin = r1.to_csr()
             total = float(np.float32(arcs["weight"].astype(np.float64).sum() + fin[np.isfinite(fin)].sum()))
             assert abs(total - w[0]) < 1e-3
+
+
+# ---- unique = true: determinize_with_distance of the reversed machine, then the same n-best search ----------------
+
+def check_unique_nbest(o, n, shortest_path=None):
+    """The reference's criterion (tests_openfst/algorithms/shortest_path.rs:62-92) against brute force over DISTINCT
+    label strings: determinization treats epsilon as an ordinary symbol (determinize_fsa_op.rs:62-82), so two paths are
+    the same string iff their raw label sequences are equal, and a string weighs what its lightest path weighs."""
+    r = (shortest_path or O.shortest_path)(o, nshortest=n, unique=True)
+    best = {}
+    for il, ol, w in all_paths(o):
+        assert il == ol
+        best[il] = min(best.get(il, np.float32(np.inf)), w)
+    truth = sorted(best.items(), key=lambda kv: kv[1])
+    got = result_paths(r)
+    assert len(got) == min(n, len(truth))
+    for g, t in zip(got, truth):  # residual weights are quantised to multiples of delta = 1e-6: compare approximately
+        assert abs(float(g[2]) - float(t[1])) < 1e-3, f"weight at the same position differs: {g[2]} vs {t[1]}"
+    seen = set()
+    for il, ol, w in got:
+        assert il == ol
+        key = strip_eps(il)
+        cands = [wt for s, wt in best.items() if strip_eps(s) == key]
+        assert any(abs(float(w) - float(c)) < 1e-3 for c in cands), "returned path is not a path of the input"
+        # the result spells strings with its own 0:0 bridge arcs, so distinctness is checked on (string, weight)
+        assert (il, float(w)) not in seen
+        seen.add((il, float(w)))
+    return r
+
+
+@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("n", [2, 3, 6])
+def test_unique_nbest_matches_bruteforce_on_random_acyclic_acceptors(seed, n):
+    rng = np.random.default_rng(4000 + seed)
+    # few labels and many arcs: plenty of paths that spell the same string
+    d = random_fst(rng, n_states=int(rng.integers(4, 11)), max_arcs=4, n_labels=2, eps_prob=0.1, acceptor=True, cyclic=False)
+    o = O.OFst.from_csr(d["offsets"].astype(np.uint64), d["arcs"], d["finals"], d["start"], d["props"])
+    check_unique_nbest(o, n)
+
+
+def test_unique_nbest_kat_duplicate_strings():
+    """Three paths, two of which spell `1 2`: unique n-best returns `1 2` once (with its lighter weight) and `1 3`."""
+    o = O.OFst()
+    for _ in range(4):
+        o.add_state()
+    o.set_start(0)
+    o.set_final(3, 0.0)
+    o.add_tr(0, 1, 1, 1.0, 1)
+    o.add_tr(0, 1, 1, 2.0, 2)
+    o.add_tr(1, 2, 2, 1.0, 3)   # 1 2 / 2.0
+    o.add_tr(2, 2, 2, 0.5, 3)   # 1 2 / 2.5  (same string, heavier)
+    o.add_tr(2, 3, 3, 1.0, 3)   # 1 3 / 3.0
+    plain = [(strip_eps(p[0]), float(p[2])) for p in result_paths(O.shortest_path(o, nshortest=3))]
+    assert plain == [((1, 2), 2.0), ((1, 2), 2.5), ((1, 3), 3.0)]
+    uniq = [(strip_eps(p[0]), round(float(p[2]), 4)) for p in result_paths(check_unique_nbest(o, 3))]
+    assert uniq == [((1, 2), 2.0), ((1, 3), 3.0)]
+
+
+def test_unique_nbest_refuses_transducers():
+    """determinize_fsa_op.rs:137-139: the reversed machine must be an acceptor."""
+    o = O.OFst()
+    o.add_state(); o.add_state()
+    o.set_start(0); o.set_final(1, 0.0)
+    o.add_tr(0, 1, 2, 1.0, 1)
+    with pytest.raises(Exception, match="expected acceptor"):
+        O.shortest_path(o, nshortest=2, unique=True)

@@ -92,9 +92,10 @@ RUSTFST_FFI_RESULT fst_matcher_config_destroy(CMatcherConfig* ptr);         /* c
 
 /* rustfst-ffi/src/algorithms/shortest_path.rs:44-57 (ShortestPathConfig::default(): nshortest = 1) */
 RUSTFST_FFI_RESULT fst_shortest_path(const CFst* ptr, const CFst** res_fst);
-/* rustfst-ffi/src/algorithms/shortest_path.rs:62-83.  nshortest > 1 with unique = true returns KO: the reference
- * determinizes through a RandomState HashMap iteration (determinize_fsa_op.rs:154-165), so its own output differs from
- * process to process and there is no answer to be identical to. */
+/* rustfst-ffi/src/algorithms/shortest_path.rs:62-83.  nshortest > 1 with unique = true (shortest_path.rs:156-165)
+ * needs an acceptor, like the reference ("DeterminizeFsaImpl : expected acceptor as argument"); the subsets of the
+ * determinized reversed machine are built on demand and kept sorted by state (the reference's own subset order comes
+ * out of a RandomState HashMap, determinize_fsa_op.rs:154-165, and is not reproducible; paths and weights are). */
 RUSTFST_FFI_RESULT fst_shortest_path_with_config(const CFst* ptr, const CShortestPathConfig* config,
                                                  const CFst** res_fst);
 /* rustfst-ffi/src/algorithms/shortest_path.rs:22-39 */

@@ -184,16 +184,18 @@ DevFst reverse_device(const DevFst& fst, cudaStream_t s, uint64_t* launches = nu
 // The same as a host FST with the reference's property word (fst_reverse).
 CsrFst reverse_fst_device(const DevFst& fst, cudaStream_t s);
 
-// n > 1 shortest paths (shortest_path.rs:135-170 with unique = false, n_shortest_path :409-518): distances and the
+// n > 1 shortest paths (shortest_path.rs:135-170, n_shortest_path :409-518; unique = true walks the reversed machine
+// determinized on demand, :156-165): distances and the
 // reversed machine are built on the device, the n-best heap search runs on the host over rows fetched on demand,
 // the result tree is trimmed on the device.  (Machines with `Some(+inf)` final weights are refused by upload().)
 struct NShortestStats {
   SsspStats distance;
   uint64_t heap_pops = 0, rows_fetched = 0, rows_cached = 0, arcs_fetched = 0, states_before_trim = 0;
+  uint64_t det_states_expanded = 0;  // unique = true: subset states whose arcs were built
   float ms_distance = 0, ms_reverse = 0, ms_search_host = 0, ms_total = 0;
 };
 CsrFst n_shortest_paths_device(const DevFst& fst, const QueuePlan& plan,
                                size_t nshortest, float delta, NShortestStats* stats, cudaStream_t s,
-                               bool force_serial = false);
+                               bool force_serial = false, bool unique = false);
 
 }  // namespace b200

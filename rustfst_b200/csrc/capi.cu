@@ -169,21 +169,14 @@ CFst* compose_host(const CFst* a, const CFst* b, const CComposeConfig* cfg, B200
 }
 
 // shortest_path_with_config (shortest_path.rs:107-171) on a device-resident machine: nshortest == 1 -> single
-// shortest path; > 1 -> distances + reversed machine + n-best search; unique is refused (see the message).
-void check_sp_config(const CShortestPathConfig* cfg) {
-  if (cfg && cfg->nshortest > 1 && cfg->unique)
-    // shortest_path.rs:156-165 determinizes the reversed machine; determinize_fsa_op.rs:154-165 rebuilds every
-    // weighted subset from HashMap::values() of a RandomState map, so the reference's own answer (subset identity,
-    // state numbering, even the number of states) changes from process to process: nothing to be identical to.
-    throw FstError("shortest_path with nshortest > 1 and unique = true is not supported by this build of "
-                   "librustfst_b200 (the reference result is process-dependent; use unique = false)");
-}
+// shortest path; > 1 -> distances + reversed machine (determinized on demand when unique) + n-best search.
+void check_sp_config(const CShortestPathConfig*) {}  // every combination is served (unique: nshortest.cu)
 CsrFst shortest_path_dispatch(const DevFst& d, const QueuePlan& plan, const CShortestPathConfig* cfg,
                               B200SsspStats* stats, float ms_h2d, cudaStream_t s, bool force_serial) {
   const size_t nshortest = cfg ? cfg->nshortest : 1;  // shortest_path.rs:30-38 defaults
   if (nshortest != 1) {                                // shortest_path.rs:135-170
     NShortestStats ns;
-    CsrFst r = n_shortest_paths_device(d, plan, nshortest, cfg->delta, &ns, s, force_serial);
+    CsrFst r = n_shortest_paths_device(d, plan, nshortest, cfg->delta, &ns, s, force_serial, cfg->unique);
     ns.distance.ms_device = ns.ms_total;
     fill(stats, ns.distance, (int)plan.kind, ms_h2d);
     return r;

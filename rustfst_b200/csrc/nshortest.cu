@@ -16,12 +16,15 @@
 // thousand arcs.  It runs on the host (as SURVEY.md §8f ranks it) over rows of the reversed machine fetched on
 // demand from HBM — the reversed machine never leaves the device.  The search tree is a host structure (one arc per
 // state, all chains ending in the final state), so its `connect` is a walk along the n result chains.
+// With unique = true (shortest_path.rs:156-165) the search walks the determinized reversed machine, whose subset states
+// are built when the search pops them (see n_shortest_paths_device).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <unordered_map>
 #include <vector>
 
@@ -138,6 +141,30 @@ k_fetch_row(const uint32_t* __restrict__ roff, const Tr* __restrict__ rarcs, con
   }
 }
 
+// Rows of MANY states of the reversed machine at once (unique = true: one subset state of the determinized machine can
+// hold thousands of states): degrees, then — after an exclusive scan — the arcs and the forward distances of their
+// targets, packed row after row in the order of `states`.
+__global__ void __launch_bounds__(kThreads)
+k_rows_deg(const uint32_t* __restrict__ roff, const uint32_t* __restrict__ states, uint32_t m, uint32_t* __restrict__ deg) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) { const uint32_t q = states[i]; deg[i] = roff[q + 1] - roff[q]; }
+  else if (i == m) deg[i] = 0u;
+}
+__global__ void __launch_bounds__(kThreads)
+k_rows_gather(const uint32_t* __restrict__ roff, const Tr* __restrict__ rarcs, const float* __restrict__ dist, uint32_t n,
+              const uint32_t* __restrict__ states, uint32_t m, const uint32_t* __restrict__ off,
+              int4* __restrict__ out, float* __restrict__ dists) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (w >= m) return;
+  const uint32_t q = states[w], b = roff[q], deg = roff[q + 1] - b, o = off[w];
+  for (uint32_t k = lane; k < deg; k += 32u) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(&rarcs[b + k]));
+    out[o + k] = v;
+    const uint32_t src = (uint32_t)v.w - 1u;
+    dists[o + k] = (dist && src < n) ? dist[src] : w_zero();
+  }
+}
+
 // Mapped page-locked staging area: [header + cap arcs as int4][cap distances].
 struct Staging {
   void* base = nullptr;
@@ -211,11 +238,10 @@ DevFst reverse_device(const DevFst& f, cudaStream_t s, uint64_t* launches) {
   return r;
 }
 
-CsrFst reverse_fst_device(const DevFst& f, cudaStream_t s) {
-  DevFst r = reverse_device(f, s, nullptr);
-  // Property word: replay reverse.rs' mutation sequence on VectorFst::new() — add_state, add_states(n), set_final of
-  // the old start, every set_trs_unchecked (an order-independent function of the arcs' events, one reduction on
-  // the device), set_start — then OR in reverse_properties(input, true)  (reverse.rs:40-83).
+// Property word of reverse(f): replay reverse.rs' mutation sequence on VectorFst::new() — add_state, add_states(n),
+// set_final of the old start, every set_trs_unchecked (an order-independent function of the arcs' events, one
+// reduction on the device), set_start — then OR in reverse_properties(input, true)  (reverse.rs:40-83).
+static uint64_t reversed_props(const DevFst& f, const DevFst& r, cudaStream_t s) {
   DevBuf<uint32_t> ev(s, 1);
   B200_CUDA(cudaMemsetAsync(ev.p, 0, 4, s));
   k_arc_events<<<blocks_for(r.num_states), kThreads, 0, s>>>(r.offsets.p, r.arcs.p, r.num_states, ev.p);
@@ -227,13 +253,18 @@ CsrFst reverse_fst_device(const DevFst& f, cudaStream_t s) {
   if (f.has_start) p = props::on_set_final(p, nullptr, &one);
   p = props::apply_arc_events(p, events, r.num_arcs > 0);
   p = props::on_set_start(p);
-  r.props = (props::of_reverse(f.props, true) | p) & props::kTrinary;
+  return (props::of_reverse(f.props, true) | p) & props::kTrinary;
+}
+
+CsrFst reverse_fst_device(const DevFst& f, cudaStream_t s) {
+  DevFst r = reverse_device(f, s, nullptr);
+  r.props = reversed_props(f, r, s);
   return download(r, s);
 }
 
 CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
                                size_t nshortest, float delta, NShortestStats* stats, cudaStream_t s,
-                               bool force_serial) {
+                               bool force_serial, bool unique) {
   NShortestStats local;
   NShortestStats& st = stats ? *stats : local;
   st = NShortestStats();
@@ -251,6 +282,8 @@ CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
   t0 = now_ms();
   DevFst r = reverse_device(f, s, &st.distance.kernel_launches);
   const size_t r_row0_len = read_u32(r.offsets.p + 1, s);
+  if (unique && !(reversed_props(f, r, s) & props::kAcceptor))  // determinize_fsa_op.rs:137-139
+    throw FstError("DeterminizeFsaImpl : expected acceptor as argument");
   st.ms_reverse = (float)(now_ms() - t0);
   t0 = now_ms();
 
@@ -316,6 +349,129 @@ CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
   const std::vector<float> row0_dist = row_dist;
   for (size_t k = 0; k < row0.size(); k++) d0 = w_plus(d0, w_times(row0[k].weight, row0_dist[k]));  // :144-150
 
+
+  const uint32_t rfinal = f.has_start ? f.start + 1 : kNoState;
+  // ---- unique = true (shortest_path.rs:156-165): the search below walks the DETERMINIZED reversed machine.  The
+  // reference materialises determinize_with_distance(rfst, distance_2) completely first (lazy_fst.rs:226-259); the
+  // search only ever looks at the subset states it pops, so here a subset state gets its arcs the first time it is
+  // popped (determinize_fsa_op.rs:56-101 + norm_tr :147-178) from rows of the reversed machine fetched as above, and
+  // its distance (state_table.rs:20-35) when it is first seen.  Subsets are kept sorted by state — the reference's own
+  // element order comes out of a RandomState HashMap (:158-171) and is not reproducible; paths and weights do not
+  // depend on it.  Identity of a subset: its filter state (the start state for the start subset, 0 otherwise), its
+  // states and the bit patterns of its quantised residual weights (Hash of the reference's tuple).
+  struct DetElem { uint32_t state; float w; float d2; };  // d2 = distance_2[state], delivered with the arc that led here
+  struct DetRow { std::vector<Tr> arcs; std::vector<float> dists; float fin = w_zero(); bool built = false; };
+  std::vector<std::vector<DetElem>> det_subset;
+  std::vector<float> det_dist;
+  std::vector<DetRow> det_rows;
+  std::map<std::vector<uint64_t>, uint32_t> det_ids;
+  auto det_find = [&](const std::vector<DetElem>& sub, uint32_t filter_state) -> uint32_t {
+    std::vector<uint64_t> key;
+    key.reserve(sub.size() + 1);
+    key.push_back(filter_state);
+    for (const DetElem& e : sub) {
+      const float w = e.w == 0.0f ? 0.0f : e.w;  // -0.0 and 0.0 hash alike
+      uint32_t bits;
+      std::memcpy(&bits, &w, 4);
+      key.push_back(((uint64_t)e.state << 32) | bits);
+    }
+    auto it = det_ids.find(key);
+    if (it != det_ids.end()) return it->second;
+    const uint32_t id = (uint32_t)det_subset.size();
+    det_ids.emplace(std::move(key), id);
+    det_subset.push_back(sub);
+    float outd = w_zero();
+    for (const DetElem& e : sub) outd = w_plus(outd, w_times(e.w, e.d2));
+    det_dist.push_back(outd);
+    det_rows.emplace_back();
+    return id;
+  };
+  auto quantize = [&](float v) -> float {  // semiring.rs:135-142
+    if (std::isinf(v)) return v;
+    return std::floor((v / delta) + 0.5f) * delta;
+  };
+  std::vector<Tr> many_arcs;
+  std::vector<float> many_dist;
+  std::vector<uint32_t> many_off;
+  auto fetch_rows = [&](const std::vector<uint32_t>& states) {  // rows of `states`, packed: row i = [many_off[i], many_off[i + 1])
+    const uint32_t m = (uint32_t)states.size();
+    DevBuf<uint32_t> d_states(s, m), d_deg(s, (size_t)m + 1), d_off(s, (size_t)m + 1);
+    DevBuf<uint8_t> tmp(s);
+    B200_CUDA(cudaMemcpyAsync(d_states.p, states.data(), (size_t)m * 4, cudaMemcpyHostToDevice, s));
+    k_rows_deg<<<blocks_for((size_t)m + 1), kThreads, 0, s>>>(r.offsets.p, d_states.p, m, d_deg.p);
+    exclusive_sum_u32(d_deg.p, d_off.p, (size_t)m + 1, tmp, s);
+    many_off.resize((size_t)m + 1);
+    B200_CUDA(cudaMemcpyAsync(many_off.data(), d_off.p, ((size_t)m + 1) * 4, cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    const uint32_t total = many_off[m];
+    many_arcs.resize(total); many_dist.resize(total);
+    if (total) {
+      DevBuf<int4> d_out(s, total);
+      DevBuf<float> d_dists(s, total);
+      k_rows_gather<<<blocks_for((size_t)m * 32), kThreads, 0, s>>>(r.offsets.p, r.arcs.p, d_dist_p, n, d_states.p, m, d_off.p,
+                                                                    d_out.p, d_dists.p);
+      B200_CUDA(cudaMemcpyAsync(many_arcs.data(), d_out.p, (size_t)total * 16, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaMemcpyAsync(many_dist.data(), d_dists.p, (size_t)total * 4, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+    }
+    st.distance.kernel_launches += 3;
+    st.rows_fetched += m; st.arcs_fetched += total;
+  };
+  auto det_row = [&](uint32_t q) -> const DetRow& {
+    if (det_rows[q].built) return det_rows[q];
+    const std::vector<DetElem> src = det_subset[q];  // a copy: det_find below grows the tables
+    std::map<uint32_t, std::vector<DetElem>> label_map;  // BTreeMap: arcs leave in label order
+    float fin = w_zero();
+    constexpr size_t kOneByOne = 4;  // small subsets go through the per-row fetch and its one-hop cache
+    std::vector<uint32_t> want;
+    if (src.size() > kOneByOne) {
+      for (const DetElem& e : src) if (e.state != 0) want.push_back(e.state);
+      fetch_rows(want);
+    }
+    size_t wi = 0;
+    for (const DetElem& e : src) {
+      const Tr* prow = row0.data();
+      const float* pdist = row0_dist.data();
+      size_t len = row0.size();
+      if (e.state != 0) {
+        if (src.size() > kOneByOne) {
+          prow = many_arcs.data() + many_off[wi]; pdist = many_dist.data() + many_off[wi];
+          len = many_off[wi + 1] - many_off[wi];
+          wi++;
+        } else {
+          fetch_row(e.state);
+          prow = row.data(); pdist = row_dist.data(); len = row.size();
+        }
+      }
+      for (size_t k = 0; k < len; k++) {
+        const Tr& tr = prow[k];
+        label_map[tr.ilabel].push_back(DetElem{tr.nextstate, w_times(e.w, tr.weight), pdist[k]});
+      }
+      // final weight (:103-120): the reversed machine has one final state, the old start, with weight one()
+      fin = w_plus(fin, w_times(e.w, e.state == rfinal ? 0.0f : w_zero()));
+    }
+    DetRow built;
+    built.fin = fin;
+    for (auto& kv : label_map) {
+      std::vector<DetElem>& d = kv.second;
+      std::stable_sort(d.begin(), d.end(), [](const DetElem& x, const DetElem& y) { return x.state < y.state; });
+      float w = w_zero();
+      for (const DetElem& e : d) w = w_plus(w, e.w);  // DefaultCommonDivisor: plus (divisors.rs:16-22)
+      std::vector<DetElem> merged;
+      for (const DetElem& e : d) {
+        if (!merged.empty() && merged.back().state == e.state) merged.back().w = w_plus(merged.back().w, e.w);
+        else merged.push_back(e);
+      }
+      for (DetElem& e : merged) e.w = quantize(e.w - w);  // divide (tropical_weight.rs:127-132), then quantize
+      const uint32_t dest = det_find(merged, 0);
+      built.arcs.push_back(Tr{kv.first, kv.first, w, dest});
+      built.dists.push_back(det_dist[dest]);
+    }
+    built.built = true;
+    det_rows[q] = std::move(built);
+    st.det_states_expanded++;
+    return det_rows[q];
+  };
   // ---- host: n_shortest_path (shortest_path.rs:409-518) over the reversed machine
   if (w_is_zero(d0)) { st.ms_total = (float)(now_ms() - t_begin); return empty; }  // :427-434 (istart = 0 always exists)
   // The result tree is written straight in CSR form: state 0 = start (arcs appended as complete paths are popped),
@@ -382,12 +538,15 @@ CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
   };
   pairs.reserve(r_row0_len + 1024); keys.reserve(r_row0_len + 1024); single_arc.reserve(r_row0_len + 1024);
   heap.reserve(r_row0_len + 1024);
+  if (unique) {
+    const uint32_t det_start = det_find(std::vector<DetElem>{DetElem{0u, 0.0f, d0}}, 0u);  // {(start, one)}, filter state = start = 0
+    (void)det_start;                                                                     // = 0 = istart of the search below
+  }
   push(final_state);
   const float limit = w_times(d0, w_zero());  // weight_threshold = zero(): :448-449
   // r of :451 — the reference grows a dense vector up to the largest popped state id (tens of MB on a multi-million-
   // state lattice for a few hundred pops); a hash map holds the same counters
   std::unordered_map<uint32_t, size_t> seen;
-  const uint32_t rfinal = f.has_start ? f.start + 1 : kNoState;
   while (!heap.empty()) {
     const StateId state = pop();
     st.heap_pops++;
@@ -406,15 +565,21 @@ CsrFst n_shortest_paths_device(const DevFst& f, const QueuePlan& plan,
     if (!p.some) continue;
     const std::vector<Tr>* prow = &row0;
     const std::vector<float>* pdist = &row0_dist;
-    if (p.state != 0) { fetch_row(p.state); prow = &row; pdist = &row_dist; }
+    float fin = p.state == rfinal ? 0.0f : w_zero();  // the only final state of the reversed machine: reverse.rs:54-56
+    if (unique) {
+      const DetRow& dr = det_row(p.state);
+      prow = &dr.arcs; pdist = &dr.dists; fin = dr.fin;
+    } else if (p.state != 0) {
+      fetch_row(p.state); prow = &row; pdist = &row_dist;
+    }
     for (size_t k = 0; k < prow->size(); k++) {
       const Tr& rarc = (*prow)[k];
       const StateId next = new_state(Tr{rarc.ilabel, rarc.olabel, rarc.weight, state},
                                      Pair{true, rarc.nextstate, w_times(p.w, rarc.weight)}, (*pdist)[k]);
       push(next);
     }
-    if (p.state == rfinal) {  // the only final state of the reversed machine, weight one(): reverse.rs:54-56
-      const StateId next = new_state(Tr{0, 0, 0.0f, state}, Pair{false, 0, w_times(p.w, 0.0f)}, 0.0f);
+    if (!w_is_zero(fin)) {  // :494-505
+      const StateId next = new_state(Tr{0, 0, fin, state}, Pair{false, 0, w_times(p.w, fin)}, 0.0f);
       push(next);
     }
   }

@@ -12,11 +12,11 @@ pytestmark = pytest.mark.gpu
 NS = [2, 3, 5]
 
 
-def _both(p, o, n, delta=None, force_serial=False):
+def _both(p, o, n, delta=None, force_serial=False, unique=False):
     import rustfst_b200 as R
-    cfg = R.ShortestPathConfig(nshortest=n, unique=False, delta=delta)
+    cfg = R.ShortestPathConfig(nshortest=n, unique=unique, delta=delta)
     got, st = R.shortestpath_with_stats(p, cfg, force_serial=force_serial)
-    exp = O.shortest_path(o, nshortest=n, delta=1e-6 if delta is None else delta)
+    exp = O.shortest_path(o, nshortest=n, unique=unique, delta=1e-6 if delta is None else delta)
     return got, exp, st
 
 
@@ -76,9 +76,9 @@ def test_nshortest_python_style_kat():
     o.add_tr(1, 3, 3, 1.0, 3)
     o.add_tr(2, 4, 4, 0.25, 3)
     assert_same(r, O.shortest_path(o, nshortest=2), "two-path KAT")
-    # unique = true is refused with an explanation, never answered wrongly
-    with pytest.raises(ValueError, match="unique"):
-        f.shortest_path(R.ShortestPathConfig(nshortest=2, unique=True))
+    # unique = true on an acceptor: the same two strings (they are distinct)
+    assert_same(f.shortest_path(R.ShortestPathConfig(nshortest=2, unique=True)),
+                O.shortest_path(o, nshortest=2, unique=True), "two-path KAT, unique")
     # degenerate inputs: shortest_path.rs:427-434
     e = R.VectorFst()
     assert e.shortest_path(R.ShortestPathConfig(nshortest=3)).num_states() == 0
@@ -146,3 +146,78 @@ def test_reverse_device_matches_oracle_reverse_through_nbest_of_large_fanin():
     for nsh in (2, 50):
         got, exp, st = _both(p, o, nsh)
         assert_same(got, exp, f"hub n={nsh}")
+
+
+# ---- unique = true (shortest_path.rs:156-165): the reversed machine is determinized first -------------------------
+
+def _paths(v):
+    """(label string without epsilons, weight) of every path of an n-best result, in the order of the start's arcs."""
+    off, arcs, fin, start = v.to_csr()
+    out = []
+    if start is None:
+        return out
+    for k in range(int(off[start]), int(off[start + 1])):
+        a = arcs[k]
+        labels, w, s = [int(a["ilabel"])], float(a["weight"]), int(a["nextstate"])
+        while off[s + 1] > off[s]:
+            b = arcs[int(off[s])]
+            assert b["ilabel"] == b["olabel"]
+            labels.append(int(b["ilabel"])); w += float(b["weight"]); s = int(b["nextstate"])
+        out.append((tuple(x for x in labels if x), w + float(fin[s])))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_unique_nshortest_matches_oracle_on_random_acyclic_acceptors(seed):
+    """Bit-exact against the oracle (which determinizes the whole reversed machine first, as the reference does, and is
+    pinned by brute force over distinct strings in tests/test_oracle_nshortest.py); the device route determinizes only
+    the subset states the search pops."""
+    rng = np.random.default_rng(9000 + seed)
+    d = random_fst(rng, int(rng.integers(3, 14)), 4, 2 + seed % 3, eps_prob=0.1, acceptor=True, cyclic=False,
+                   weight_grid=(seed % 4 < 3))
+    p, o = both_from_dict(d)
+    for n in (2, 3, 7):
+        got, exp, st = _both(p, o, n, unique=True)
+        assert_same(got, exp, f"unique n-best seed={seed} n={n}")
+    got, exp, _ = _both(p, o, 4, unique=True, delta=0.25)  # a coarse delta quantises the residual weights visibly
+    assert_same(got, exp, f"unique n-best seed={seed} delta=0.25")
+
+
+def test_unique_nshortest_refuses_transducers_like_the_reference():
+    """determinize_fsa_op.rs:137-139: `DeterminizeFsaImpl : expected acceptor as argument`."""
+    import rustfst_b200 as R
+    f = R.VectorFst()
+    f.add_state(); f.add_state()
+    f.set_start(0); f.set_final(1, 0.0)
+    f.add_tr(0, R.Tr(1, 2, 1.0, 1))
+    with pytest.raises(ValueError, match="expected acceptor"):
+        f.shortest_path(R.ShortestPathConfig(nshortest=2, unique=True))
+    # nshortest = 1 ignores `unique` (shortest_path.rs:124-133)
+    assert f.shortest_path(R.ShortestPathConfig(nshortest=1, unique=True)).num_states() == 2
+
+
+def test_unique_nshortest_on_a_lattice_agrees_with_deduplicated_plain_nbest():
+    """A 100K-state acceptor lattice with a 4-symbol alphabet: many paths spell the same string.  The reference would
+    determinize the whole reversed lattice first (exponential here); the device route builds subset states on demand.
+    Check: the unique n best strings = the plain n-best list (bit-exact against the oracle above) with repeated strings
+    dropped, weights equal up to the quantisation of residuals (delta = 1e-6)."""
+    import rustfst_b200 as R
+    from rustfst_b200 import synth
+    g = synth.layered_acceptor(100_000, 1_000_000, 4, 6, 12)
+    p, _ = both_from_dict(g)
+    plain = _paths(p.shortest_path(R.ShortestPathConfig(nshortest=400, unique=False)))
+    dedup, seen = [], set()
+    for labels, w in plain:
+        if labels not in seen:
+            seen.add(labels); dedup.append((labels, w))
+    n = min(10, len(dedup) - 1)
+    assert n >= 3, "the sample should hold several distinct strings"
+    got, st = R.shortestpath_with_stats(p, R.ShortestPathConfig(nshortest=n, unique=True))
+    uniq = _paths(got)
+    assert len(uniq) == n
+    assert len({labels for labels, _ in uniq}) == n, "strings must be distinct"
+    for (gl, gw), (el, ew) in zip(uniq, dedup):
+        assert abs(gw - ew) < 1e-3, (gw, ew)
+    # strings of equal weight may come out in either order: compare as weight-sorted multisets up to the last weight
+    cut = uniq[-1][1] - 1e-3
+    assert sorted(l for l, w in uniq if w < cut) == sorted(l for l, w in dedup[:n] if w < cut)

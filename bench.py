@@ -298,7 +298,8 @@ def run_extras(args, R, synth, torch, peak_gbs, barrier):
         machine (HBM-resident) instead of 32 slots per level; both start states fan out (a 20 000-arc hub), labels
         are drawn from 93 symbols so that the product neither dies nor explodes (~1 successor per product state).
       * sssp_window — SURVEY.md 8d's acyclic acceptor with arcs to targets up to 1000 ids ahead: arcs skip levels, the
-        longest path has tens of thousands of hops, and a label-correcting relaxation re-relaxes states many times."""
+        longest path has tens of thousands of hops, and a label-correcting relaxation re-relaxes states many times
+        (the visit budget trips and the in-order sweep of sssp.cu takes over)."""
     from tests import oracle_lib as O
     out = {}
     steps = max(1, min(args.steps, 5))
@@ -360,8 +361,11 @@ def run_extras(args, R, synth, torch, peak_gbs, barrier):
         "value": n_edges * wsteps / (ms * 1e-3), "unit": "edges/s (distinct edges of the machine / call time)",
         "ms_per_step": ms / wsteps, "relaxation_waves": waves, "arcs_relaxed_per_call": relaxed // wsteps,
         "re_relaxation_factor": relaxed / wsteps / max(1, n_edges), "device_path": sst["path"],
-        "note": "label-correcting waves revisit a state whenever a shorter route arrives; a topological pass touches every "
-                "arc once, which is what the CPU does"}
+        "in_order_sweep": int(sst.get("sweep", 0)),
+        "note": "label-correcting waves revisit a state whenever a shorter route arrives (456 visits per state here, 387 ms); "
+                "they are cut off after 4 visits per state and a top-sorted machine goes to the in-order sweep (one CTA, "
+                "distances of the next 8192 ids in a shared-memory ring); relaxation_waves / arcs_relaxed include the "
+                "abandoned waves"}
     if not args.no_cpu_baseline:
         og = O.OFst.from_csr(g["offsets"].astype(np.uint64), g["arcs"], g["finals"], g["start"], g["props"])
         _, cst = O.shortest_path(og, want_stats=True)
@@ -381,8 +385,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="C5: number of linear acceptors")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only; full size = 1.0)")
     ap.add_argument("--callers", type=int, default=2, help="host threads of the supplementary concurrent e2e figure (1 = skip); "
-                    "the persistent kernels own the whole GPU, so beyond two callers calls only queue (measured: 2 callers "
-                    "15.0 ms per compose, 3 callers 27.5 ms)")
+                    "the persistent kernels own the whole GPU (one at a time), so callers overlap their transfers with each "
+                    "other's kernels and beyond two or three callers calls only queue")
     ap.add_argument("--no-sssp", action="store_true")
     ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the two extra workloads (spread compose, window-DAG SSSP)")
@@ -511,9 +515,12 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     e2e_arcs, d2h = 0, 0
+    e2e_parts = {"ms_h2d": 0.0, "ms_expand": 0.0, "ms_connect": 0.0, "ms_d2h": 0.0}
     for _ in range(steps):
         res, st = R.compose_with_stats(h1, h2)  # fst_compose path: H2D of both operands, kernels, D2H of the result
         e2e_arcs += st["arcs_emitted"]
+        for k in e2e_parts:
+            e2e_parts[k] += st[k]
         d2h = 4 * (res.num_states() + 1) + 16 * res.num_trs_total() + 4 * res.num_states()
         del res
     e1.record()
@@ -521,7 +528,12 @@ def main():
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e = {"value": sum_over_ranks(float(e2e_arcs)) / (e2e_ms * 1e-3), "unit": "arcs/s",
            "h2d_bytes_per_step": csr_bytes(a1) + csr_bytes(a2), "d2h_bytes_per_step": int(d2h),
-           "api": "fst_compose (b200_compose_with_stats) on host VectorFst handles"}
+           "api": "fst_compose (b200_compose_with_stats) on host VectorFst handles",
+           "ms_per_step": e2e_ms / steps,
+           "inside_the_call_ms_per_step": {"h2d": e2e_parts["ms_h2d"] / steps, "kernels": (e2e_parts["ms_expand"] + e2e_parts["ms_connect"]) / steps,
+                                           "d2h": e2e_parts["ms_d2h"] / steps},
+           "note": "the three parts depend on each other inside one call (operands -> kernels -> result), so a single caller is "
+                   "bound by link time + kernel time; concurrent callers overlap one call's transfers with another's kernels"}
     # Same calls issued by several host threads at once (the C-ABI is re-entrant, every call owns a stream): the PCIe
     # link is full duplex, so one caller's upload overlaps another's kernels and download.  Supplementary figure; the
     # headline `value` above is the single-caller number.
@@ -529,19 +541,25 @@ def main():
         import threading
         done = [0] * args.callers
 
-        def worker(k):
-            for _ in range(steps):
+        def worker(k, n_calls):
+            for _ in range(n_calls):
                 r, s = R.compose_with_stats(h1, h2)
                 done[k] += s["arcs_emitted"]
                 del r
+
+        def run_callers(n_calls):
+            th = [threading.Thread(target=worker, args=(k, n_calls)) for k in range(args.callers)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            check_ffi_error(lib.b200_device_synchronize(), "sync")
+
+        run_callers(2)  # warm-up WITH the same concurrency: every caller needs its own set of page-locked result buffers
+        done = [0] * args.callers
         barrier()
         t0 = time.perf_counter()
-        th = [threading.Thread(target=worker, args=(k,)) for k in range(args.callers)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        check_ffi_error(lib.b200_device_synchronize(), "sync")
+        run_callers(steps)
         dt = time.perf_counter() - t0
         e2e["concurrent_callers"] = {"callers": args.callers, "value": float(sum(done)) / dt, "unit": "arcs/s",
                                      "ms_per_compose": dt * 1e3 / (steps * args.callers), "timer": "host wall clock"}

@@ -239,6 +239,8 @@ typedef struct B200SsspStats {
   double ms_queue_plan_host; /* host time spent building the queue plan (0 when the order was computed on the device) */
   float ms_order_device;     /* device time of the TopOrderQueue order of an acyclic machine (dag_order.cu), else 0 */
   int32_t order_on_device;   /* 1: that order was computed on the device, 0: host DFS or no DFS order needed */
+  int32_t sweep;             /* 1: the relaxation waves went over their visit budget (a deep top-sorted DAG with skip
+                                arcs) and the distances come from the in-order sweep kernel */
 } B200SsspStats;
 /* Same as fst_compose_with_config (config may be NULL = default) but also reports stats. */
 RUSTFST_FFI_RESULT b200_compose_with_stats(const CFst* fst_1, const CFst* fst_2, const CComposeConfig* config,

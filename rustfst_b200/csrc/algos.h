@@ -164,6 +164,7 @@ struct SsspStats {
   double plan_host_ms = 0;
   float order_device_ms = 0;   // device time of the TopOrderQueue order (dag_order.cu)
   bool order_on_device = false;
+  bool sweep = false;          // the waves went over their visit budget: distances came from the in-order sweep
 };
 
 // Returns the single-shortest-path FST exactly as rustfst's single_shortest_path + backtrace would

@@ -5,6 +5,9 @@
 #include <chrono>
 #include <cmath>
 #include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <mutex>
 #include <cstdio>
 #include <cstdlib>
@@ -123,6 +126,7 @@ void fill(B200SsspStats* out, const SsspStats& st, int kind, float h2d) {
   out->queue_kind = kind; out->ms_device = st.ms_device; out->ms_relax_kernel = st.ms_relax_kernel;
   out->ms_h2d = h2d; out->ms_queue_plan_host = st.plan_host_ms;
   out->ms_order_device = st.order_device_ms; out->order_on_device = st.order_on_device ? 1 : 0;
+  out->sweep = st.sweep ? 1 : 0;
 }
 
 // Queue plan (AutoQueue::new, auto_queue.rs:23-99) of a machine that is resident on the device.  The discipline follows
@@ -777,10 +781,29 @@ static void compose_batch_core(const CFst* const* acceptors, size_t n, const CFs
       for (size_t i = lo_i; i < hi_i; i++) {
         const CsrFst& h = *hs[i];
         const size_t so = base_state[i], ao = base_arc[i], ns = h.num_states(), na = h.arcs.size();
+#if defined(__SSE2__)
+        // Streaming stores: the copy engine reads these buffers next, and lines that sit dirty in a CPU cache are
+        // served to it several times slower than lines that went straight to memory.
+        uint32_t* const uo = u.offsets.data() + so;
+        int* const uf = reinterpret_cast<int*>(u.finals.data() + so);
+        const int* const hf = reinterpret_cast<const int*>(h.finals.data());
+        for (size_t s = 0; s < ns; s++) {
+          _mm_stream_si32(reinterpret_cast<int*>(uo + s), (int)(uint32_t)(ao + h.offsets[s]));
+          _mm_stream_si32(uf + s, hf[s]);
+        }
+        __m128i* const ua = reinterpret_cast<__m128i*>(u.arcs.data() + ao);  // 16-byte records in a 16-byte aligned pool block
+        const __m128i add = _mm_set_epi32((int)(uint32_t)so, 0, 0, 0);           // nextstate is the last word of a record
+        for (size_t k = 0; k < na; k++)
+          _mm_stream_si128(ua + k, _mm_add_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i*>(&h.arcs[k])), add));
+#else
         for (size_t s = 0; s < ns; s++) u.offsets[so + s] = (uint32_t)(ao + h.offsets[s]);
         std::memcpy(u.finals.data() + so, h.finals.data(), ns * 4);
         for (size_t k = 0; k < na; k++) { Tr t = h.arcs[k]; t.nextstate += (uint32_t)so; u.arcs[ao + k] = t; }
+#endif
       }
+#if defined(__SSE2__)
+      _mm_sfence();  // streaming stores are weakly ordered: make them globally visible before the chunk is announced
+#endif
     };
     auto worker = [&](size_t t) {
       for (size_t k = 0; k < n_chunks; k++) {

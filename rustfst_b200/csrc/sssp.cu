@@ -30,6 +30,7 @@
 //
 // The backtrace runs on the device as well; only the shortest path itself (a few hundred bytes) returns to the host.
 #include <cooperative_groups.h>
+#include <cuda_pipeline.h>
 
 #include <cstdlib>
 #include <vector>
@@ -91,8 +92,11 @@ template <int kG, int kT, bool kPreTest, int kS>
 __global__ void __launch_bounds__(kT)
 k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t* __restrict__ dist,
              uint32_t* __restrict__ stamp, uint32_t* __restrict__ fr_a, uint32_t* __restrict__ fr_b,
-             uint32_t* __restrict__ cnt /*3*/, uint32_t* __restrict__ out, unsigned long long* __restrict__ out64) {
+             uint32_t* __restrict__ cnt /*3*/, uint32_t* __restrict__ out, unsigned long long* __restrict__ out64,
+             unsigned long long budget) {
   unsigned int bar_epoch = 0;  // out[2] = arrival counter of the grid barrier (zero-initialised)
+  unsigned long long visits = 0;  // frontier entries so far (every thread reads the same counters: uniform)
+  bool over_budget = false;
   constexpr uint32_t kQCap = kQueueCap * (kT / 256);
   __shared__ uint32_t s_q[kQCap];
   __shared__ uint32_t s_qn, s_gbase;
@@ -106,6 +110,8 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
   while (true) {
     const uint32_t nf = __ldcg(&cnt[wave % 3]);
     if (nf == 0 || wave > n) break;
+    visits += nf;
+    if (visits > budget) { over_budget = true; break; }  // states are revisited over and over (a deep DAG with skip arcs)
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt[(wave + 2) % 3] = 0;
     if (threadIdx.x == 0) s_qn = 0;
     __syncthreads();
@@ -189,7 +195,115 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
     settled += __shfl_down_sync(0xFFFFFFFFu, settled, o);
   }
   if ((threadIdx.x & 31) == 0) { if (relaxed) atomicAdd(&out64[0], relaxed); if (settled) atomicAdd(&out64[1], settled); }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = wave; out[1] = (wave > n) ? 1u : 0u; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = wave; out[1] = over_budget ? 2u : (wave > n) ? 1u : 0u; }
+}
+
+// ---- IN-ORDER SWEEP for deep top-sorted DAGs ---------------------------------------------------------------------------
+// Label-correcting waves revisit a state every time a shorter route reaches it; on a DAG whose arcs skip levels (targets
+// up to 1000 ids ahead, longest path tens of thousands of hops) that is hundreds of visits per state and thousands of
+// grid-wide waves.  What such a machine needs is the reference's own plan — states in id order, every arc once — with
+// the hop latency of shared memory instead of L2.  (Tried first and dropped: a Kahn-style dataflow kernel over the whole
+// grid, one visit per state, ready list + tickets: 415 ms on the 5 M-state window DAG — its critical path is the LONGEST
+// path, ~55 000 hops of ~7 us through L2 atomics — against 387 ms for the waves.)
+// ONE CTA walks the states of a TOP_SORTED machine in blocks of kSwB ids.  The distances of the ids
+// [base, base + kSwRing) live in a shared-memory ring; one thread per state of the block pushes its candidates with
+// shared-memory atomicMin and the block iterates until none of ITS states improved (arcs inside a block are few hops
+// deep), then retires: final distances go to global memory, the ring advances, and the slice that enters the ring is
+// read back from global memory, where candidates for ids beyond the ring were pushed with global atomicMin.
+// ctl[0] = 1 if an arc points backwards (the property word lied), out64 as in k_relax_coop.
+constexpr uint32_t kSwB = 512, kSwRing = 8192, kSwThreads = kSwB;
+constexpr uint32_t kSwArcCap = 5632;  // arcs of one block staged in shared memory (2 buffers x 88 KB); larger blocks read global memory
+constexpr size_t kSwSmem = (size_t)kSwRing * 4 + 2 * ((size_t)kSwArcCap * 16 + (kSwB + 1) * 4);
+__global__ void __launch_bounds__(kSwThreads)
+k_relax_sweep(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t* __restrict__ dist,
+              uint32_t* __restrict__ ctl, unsigned long long* __restrict__ out64) {
+  extern __shared__ __align__(16) unsigned char sw_smem[];
+  int4* const s_arcs0 = reinterpret_cast<int4*>(sw_smem);
+  int4* const s_arcs1 = s_arcs0 + kSwArcCap;
+  uint32_t* const s_off0 = reinterpret_cast<uint32_t*>(s_arcs1 + kSwArcCap);
+  uint32_t* const s_off1 = s_off0 + (kSwB + 1);
+  uint32_t* const ring = s_off1 + (kSwB + 1);
+  const uint32_t tid = threadIdx.x;
+  constexpr uint32_t kMask = kSwRing - 1u;
+  for (uint32_t i = tid; i < kSwRing; i += kSwThreads) ring[i] = i < n ? __ldcg(&dist[i]) : kEncInf;
+  unsigned long long relaxed = 0, settled = 0;
+  bool backwards = false;
+  // arc range [lo, hi) of the block that starts at state `base` (every thread reads the same two words)
+  auto bounds = [&](uint32_t base, uint32_t& lo, uint32_t& hi) {
+    lo = hi = 0;
+    if (base < n) { lo = __ldg(&off[base]); hi = __ldg(&off[min(base + kSwB, n)]); }
+  };
+  // asynchronous copy of a block's offsets and (when they fit) arcs into buffer `which`
+  auto prefetch = [&](uint32_t base, uint32_t lo, uint32_t hi, uint32_t which) {
+    if (base < n) {
+      uint32_t* so = which ? s_off1 : s_off0;
+      int4* sa = which ? s_arcs1 : s_arcs0;
+      if (base + tid <= n && tid <= kSwB) __pipeline_memcpy_async(so + tid, off + base + tid, 4);
+      if (tid == 0 && base + kSwB <= n) __pipeline_memcpy_async(so + kSwB, off + base + kSwB, 4);
+      if (hi - lo <= kSwArcCap)
+        for (uint32_t k = lo + tid; k < hi; k += kSwThreads) __pipeline_memcpy_async(sa + (k - lo), arcs + k, 16);
+    }
+    __pipeline_commit();
+  };
+  uint32_t lo0, hi0, lo1, hi1;  // bounds of the current and of the next block
+  bounds(0, lo0, hi0);
+  bounds(kSwB, lo1, hi1);
+  prefetch(0, lo0, hi0, 0);
+  for (uint32_t base = 0, it = 0; base < n; base += kSwB, it++) {
+    const uint32_t cur = it & 1u;
+    prefetch(base + kSwB, lo1, hi1, cur ^ 1u);      // the next block travels while this one is worked on
+    uint32_t lo2, hi2;
+    bounds(base + 2 * kSwB, lo2, hi2);               // consumed one block later
+    __pipeline_wait_prior(1);                        // this block's copies have landed
+    __syncthreads();
+    const uint32_t* so = cur ? s_off1 : s_off0;
+    const int4* sa = cur ? s_arcs1 : s_arcs0;
+    const bool staged = hi0 - lo0 <= kSwArcCap;
+    const uint32_t s = base + tid;
+    const bool live = s < n;
+    uint32_t b = 0, e = 0;
+    if (live) { b = so[tid]; e = so[tid + 1]; }
+    uint32_t last = kEncInf;  // the distance my arcs were last relaxed with
+    while (true) {
+      bool changed = false;
+      const uint32_t d = live ? ring[s & kMask] : kEncInf;
+      if (d != last) {
+        last = d;
+        const float ds = dec_f32(d);
+        relaxed += e - b;
+        for (uint32_t k = b; k < e; k++) {
+          const int4 v = staged ? sa[k - lo0] : __ldg(reinterpret_cast<const int4*>(&arcs[k]));
+          const uint32_t t = (uint32_t)v.w;
+          const float c = w_times(ds, __int_as_float(v.z));
+          if (c == w_zero()) continue;
+          const uint32_t ec = enc_f32(c);
+          if (t <= s) { backwards = true; continue; }
+          if (t - base < kSwRing) {  // in the ring (t > s >= base)
+            const uint32_t old = atomicMin(&ring[t & kMask], ec);
+            if (ec < old && t < base + kSwB) changed = true;  // a state of this block improved: one more round
+          } else {
+            atomicMin(&dist[t], ec);
+          }
+        }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+    if (live) { dist[s] = ring[s & kMask]; if (last != kEncInf) settled++; }
+    __syncthreads();  // everybody is done with the slice that is overwritten next
+    {  // ids [base + kSwRing, base + kSwRing + kSwB) enter the ring in the slots the retired block leaves
+      const uint32_t id = base + kSwRing + tid;
+      ring[id & kMask] = id < n ? __ldcg(&dist[id]) : kEncInf;
+    }
+    lo0 = lo1; hi0 = hi1; lo1 = lo2; hi1 = hi2;
+    // the next iteration's barrier (after its wait) orders these ring writes before anybody reads them
+  }
+  __pipeline_wait_prior(0);
+  if (backwards) atomicExch(&ctl[0], 1u);
+  for (int o = 16; o > 0; o >>= 1) {
+    relaxed += __shfl_down_sync(0xFFFFFFFFu, relaxed, o);
+    settled += __shfl_down_sync(0xFFFFFFFFu, settled, o);
+  }
+  if ((tid & 31u) == 0) { if (relaxed) atomicAdd(&out64[0], relaxed); if (settled) atomicAdd(&out64[1], settled); }
 }
 
 // Parent selection + certificate over all arcs of reached states.  flags[0] = certificate violations.
@@ -676,9 +790,42 @@ CsrFst build_path_fst(bool found, const std::vector<Tr>& path, float final_w) {
 
 using EventPairs = std::vector<std::pair<cudaEvent_t, cudaEvent_t>>;
 
+// Exact minima on a TOP_SORTED machine by the in-order sweep (k_relax_sweep); dist as in run_relax_coop.
+void run_relax_sweep(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, EventPairs& relax_events, cudaStream_t s) {
+  const uint32_t n = f.num_states;
+  DevBuf<uint32_t> ctl(s, 4);
+  DevBuf<unsigned long long> out64(s, 2);
+  dist.reserve_discard(n);
+  k_fill_u32<<<blocks_for(n), kThreads, 0, s>>>(dist.p, kEncInf, n);
+  const uint32_t zero_enc = enc_f32(0.0f);
+  B200_CUDA(cudaMemcpyAsync(dist.p + f.start, &zero_enc, 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemsetAsync(ctl.p, 0, 16, s));
+  B200_CUDA(cudaMemsetAsync(out64.p, 0, 16, s));
+  cudaEvent_t ea, eb;
+  B200_CUDA(cudaEventCreate(&ea)); B200_CUDA(cudaEventCreate(&eb));
+  B200_CUDA(cudaEventRecord(ea, s));
+  static const bool attr_set = [] {
+    B200_CUDA(cudaFuncSetAttribute((const void*)k_relax_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmem));
+    return true;
+  }();
+  (void)attr_set;
+  k_relax_sweep<<<1, kSwThreads, kSwSmem, s>>>(f.offsets.p, f.arcs.p, n, dist.p, ctl.p, out64.p);
+  B200_CUDA(cudaEventRecord(eb, s));
+  relax_events.emplace_back(ea, eb);
+  st.relax_launches++; st.kernel_launches += 2;
+  uint32_t hctl[4]; unsigned long long h64[2];
+  B200_CUDA(cudaMemcpyAsync(hctl, ctl.p, 16, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaMemcpyAsync(h64, out64.p, 16, cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  if (hctl[0]) throw FstError("shortest_path: the machine's property word says it is topologically sorted, but an arc points backwards");
+  st.arcs_relaxed += h64[0]; st.states_settled += h64[1];
+  st.sweep = true;
+}
+
 // Exact minima from f.start by frontier relaxation waves: one cooperative launch of k_relax_coop.
 // dist receives the order-preserving integer images (kEncInf = unreached).
-void run_relax_coop(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, EventPairs& relax_events, cudaStream_t s) {
+void run_relax_coop(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, EventPairs& relax_events, cudaStream_t s,
+                    bool top_sorted) {
   const uint32_t n = f.num_states;
   DevBuf<uint32_t> stamp(s, n), fr_a(s, n), fr_b(s, n), cnt(s, 3), outw(s, 3);
   DevBuf<unsigned long long> out64(s, 2);
@@ -721,7 +868,11 @@ void run_relax_coop(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, Even
   uint32_t nn = n;
   uint32_t* a_dist = dist.p; uint32_t* a_stamp = stamp.p; uint32_t* a_fa = fr_a.p; uint32_t* a_fb = fr_b.p;
   uint32_t* a_cnt = cnt.p; uint32_t* a_out = outw.p; unsigned long long* a_out64 = out64.p;
-  void* args[] = {&a_off, &a_arcs, &nn, &a_dist, &a_stamp, &a_fa, &a_fb, &a_cnt, &a_out, &a_out64};
+  // Visit budget: a state of a layered lattice is visited a handful of times; hundreds of visits per state mean a deep
+  // DAG with skip arcs.  A TOP_SORTED machine (StateOrderQueue) is then handed to the in-order sweep.
+  unsigned long long budget = top_sorted ? 4ull * n + 65536ull : ~0ull;
+  if (const char* e = std::getenv("B200_RELAX_VISIT_BUDGET")) { if (top_sorted) budget = std::strtoull(e, nullptr, 10); }
+  void* args[] = {&a_off, &a_arcs, &nn, &a_dist, &a_stamp, &a_fa, &a_fb, &a_cnt, &a_out, &a_out64, &budget};
   cudaEvent_t ea, eb;
   B200_CUDA(cudaEventCreate(&ea)); B200_CUDA(cudaEventCreate(&eb));
   B200_CUDA(cudaEventRecord(ea, s));
@@ -733,8 +884,9 @@ void run_relax_coop(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, Even
   B200_CUDA(cudaMemcpyAsync(hw, outw.p, 8, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaMemcpyAsync(h64, out64.p, 16, cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
-  if (hw[1]) throw FstError("shortest_path: relaxation did not converge (negative cycle?)");
   st.waves = hw[0]; st.arcs_relaxed = h64[0]; st.states_settled = h64[1];
+  if (hw[1] == 2) { run_relax_sweep(f, dist, st, relax_events, s); return; }  // over the visit budget
+  if (hw[1]) throw FstError("shortest_path: relaxation did not converge (negative cycle?)");
 }
 
 // Order-faithful parallel fold (see k_of_fold).  Returns false when the graph turned out to be cyclic.
@@ -862,7 +1014,7 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
     B200_CUDA(cudaMemsetAsync(fkey.p, 0xFF, 8, s));
     B200_CUDA(cudaMemsetAsync(flags.p, 0, 4, s));
     st.kernel_launches += 1;
-    run_relax_coop(f, dist, st, relax_events, s);  // one cooperative launch runs every relaxation wave
+    run_relax_coop(f, dist, st, relax_events, s, plan.kind == kStateOrderQueue);  // one cooperative launch runs every wave
     k_parents<false><<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, dist.p, order_p, pkey.p, flags.p,
                                                         kDelta);
     k_final_min<<<blocks_for(n), kThreads, 0, s>>>(f.finals.p, n, dist.p, order_p, fkey.p);
@@ -983,7 +1135,7 @@ void shortest_distance_device(const DevFst& f, const QueuePlan& plan, float delt
     // Exact minima + the certificate "no candidate in (m, m + delta]" therefore reproduce it (see k_parents).
     DevBuf<uint32_t> dist(s), flags(s, 1);
     B200_CUDA(cudaMemsetAsync(flags.p, 0, 4, s));
-    run_relax_coop(f, dist, st, relax_events, s);
+    run_relax_coop(f, dist, st, relax_events, s, plan.kind == kStateOrderQueue);
     k_parents<true><<<blocks_for(n), kThreads, 0, s>>>(f.offsets.p, f.arcs.p, n, dist.p, order_p, nullptr, flags.p,
                                                        delta);
     st.kernel_launches++;

@@ -46,7 +46,8 @@ class SsspStats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("relax_launches", C.c_uint64),
                 ("path", C.c_int32), ("queue_kind", C.c_int32),
                 ("ms_device", C.c_float), ("ms_relax_kernel", C.c_float), ("ms_h2d", C.c_float),
-                ("ms_queue_plan_host", C.c_double), ("ms_order_device", C.c_float), ("order_on_device", C.c_int32)]
+                ("ms_queue_plan_host", C.c_double), ("ms_order_device", C.c_float), ("order_on_device", C.c_int32),
+                ("sweep", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -96,6 +96,7 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
              unsigned long long budget) {
   unsigned int bar_epoch = 0;  // out[2] = arrival counter of the grid barrier (zero-initialised)
   unsigned long long visits = 0;  // frontier entries so far (every thread reads the same counters: uniform)
+  unsigned long long fresh = 0;   // states this thread reached for the first time (summed into out64[2] wave by wave)
   bool over_budget = false;
   constexpr uint32_t kQCap = kQueueCap * (kT / 256);
   __shared__ uint32_t s_q[kQCap];
@@ -111,7 +112,10 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
     const uint32_t nf = __ldcg(&cnt[wave % 3]);
     if (nf == 0 || wave > n) break;
     visits += nf;
-    if (visits > budget) { over_budget = true; break; }  // states are revisited over and over (a deep DAG with skip arcs)
+    // States are revisited over and over (a deep DAG with skip arcs): more than `budget` visits in all, or — early, so
+    // that little is thrown away — eight times as many visits as states reached so far.
+    if (visits > budget) { over_budget = true; break; }
+    if (budget != ~0ull && wave >= 16 && visits > 8ull * __ldcg(&out64[2]) + 65536ull) { over_budget = true; break; }
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt[(wave + 2) % 3] = 0;
     if (threadIdx.x == 0) s_qn = 0;
     __syncthreads();
@@ -155,6 +159,7 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
               ec[q] = enc_f32(c);
               // kPreTest: a plain load filters most candidates before the atomic
               if (!kPreTest || ec[q] < __ldcg(&dist[(uint32_t)v[q].w])) old[q] = atomicMin(&dist[(uint32_t)v[q].w], ec[q]);
+              if (old[q] == kEncInf && ec[q] < old[q]) fresh++;
             }
           }
         }
@@ -185,6 +190,12 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
     if (threadIdx.x == 0 && qn) s_gbase = atomicAdd(next_count, qn);
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < qn; i += kT) nxt[s_gbase + i] = s_q[i];
+    {  // newly reached states of this wave, one atomic per warp (read by everybody after the barrier)
+      unsigned long long f = fresh;
+      fresh = 0;
+      for (int o = 16; o > 0; o >>= 1) f += __shfl_down_sync(0xFFFFFFFFu, f, o);
+      if ((threadIdx.x & 31) == 0 && f) atomicAdd(&out64[2], f);
+    }
     wave++;
     uint32_t* tmp = cur; cur = nxt; nxt = tmp;
     coop::grid_barrier(&out[2], bar_epoch);  // lighter than cg::grid_group::sync() (measured 3.4 us less per barrier)
@@ -206,26 +217,35 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
 // grid, one visit per state, ready list + tickets: 415 ms on the 5 M-state window DAG — its critical path is the LONGEST
 // path, ~55 000 hops of ~7 us through L2 atomics — against 387 ms for the waves.)
 // ONE CTA walks the states of a TOP_SORTED machine in blocks of kSwB ids.  The distances of the ids
-// [base, base + kSwRing) live in a shared-memory ring; one thread per state of the block pushes its candidates with
-// shared-memory atomicMin and the block iterates until none of ITS states improved (arcs inside a block are few hops
-// deep), then retires: final distances go to global memory, the ring advances, and the slice that enters the ring is
-// read back from global memory, where candidates for ids beyond the ring were pushed with global atomicMin.
+// [base, base + kSwRing) live in a shared-memory ring; a block's offsets and arcs arrive through cp.async while the
+// previous block is worked on.  Inside a block, sub-blocks of kSub consecutive states are taken in id order with one
+// thread per ARC: when a sub-block starts, every arc into it from earlier states has been relaxed with a final distance,
+// so only arcs inside the sub-block can ask for another round (shared-memory atomicMin + one CTA barrier per round).
+// Then the block retires: final distances go to global memory, the ring advances, and the slice that enters the ring
+// is the minimum of what global memory held for it when the block started (candidates for ids beyond the ring are
+// pushed with global atomicMin) and of the candidates this block collected for it in shared memory.
+// (One thread per STATE iterating the whole block to a fixpoint took ~46 rounds per block: 122 ms instead of 89.)
 // ctl[0] = 1 if an arc points backwards (the property word lied), out64 as in k_relax_coop.
-constexpr uint32_t kSwB = 512, kSwRing = 8192, kSwThreads = kSwB;
-constexpr uint32_t kSwArcCap = 5632;  // arcs of one block staged in shared memory (2 buffers x 88 KB); larger blocks read global memory
-constexpr size_t kSwSmem = (size_t)kSwRing * 4 + 2 * ((size_t)kSwArcCap * 16 + (kSwB + 1) * 4);
-__global__ void __launch_bounds__(kSwThreads)
+constexpr uint32_t kSwRing = 8192;
+// arcs of one block staged in shared memory: 11 per state (2 buffers x 88 KB at 512 states); larger blocks read global memory
+template <uint32_t kSwB> constexpr uint32_t sw_arc_cap() { return 11u * kSwB; }
+template <uint32_t kSwB> constexpr size_t sw_smem() { return (size_t)kSwRing * 4 + (size_t)kSwB * 4 + 2 * ((size_t)sw_arc_cap<kSwB>() * 16 + (kSwB + 1) * 4); }
+template <uint32_t kSwB, uint32_t kSub>
+__global__ void __launch_bounds__(kSwB)
 k_relax_sweep(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t* __restrict__ dist,
               uint32_t* __restrict__ ctl, unsigned long long* __restrict__ out64) {
+  constexpr uint32_t kSwThreads = kSwB, kSwArcCap = sw_arc_cap<kSwB>();
   extern __shared__ __align__(16) unsigned char sw_smem[];
   int4* const s_arcs0 = reinterpret_cast<int4*>(sw_smem);
   int4* const s_arcs1 = s_arcs0 + kSwArcCap;
   uint32_t* const s_off0 = reinterpret_cast<uint32_t*>(s_arcs1 + kSwArcCap);
   uint32_t* const s_off1 = s_off0 + (kSwB + 1);
   uint32_t* const ring = s_off1 + (kSwB + 1);
+  uint32_t* const pending = ring + kSwRing;  // candidates for the slice that enters the ring when this block retires
   const uint32_t tid = threadIdx.x;
   constexpr uint32_t kMask = kSwRing - 1u;
   for (uint32_t i = tid; i < kSwRing; i += kSwThreads) ring[i] = i < n ? __ldcg(&dist[i]) : kEncInf;
+  pending[tid] = kEncInf;
   unsigned long long relaxed = 0, settled = 0;
   bool backwards = false;
   // arc range [lo, hi) of the block that starts at state `base` (every thread reads the same two words)
@@ -254,46 +274,73 @@ k_relax_sweep(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uin
     prefetch(base + kSwB, lo1, hi1, cur ^ 1u);      // the next block travels while this one is worked on
     uint32_t lo2, hi2;
     bounds(base + 2 * kSwB, lo2, hi2);               // consumed one block later
+    // The slice [base + kSwRing, base + kSwRing + kSwB) enters the ring when this block retires.  Its distances are
+    // requested now (a DRAM round trip that would otherwise sit between two blocks); candidates this block produces for
+    // it are collected in `pending` and merged at the end.  Earlier blocks pushed theirs to global memory before the
+    // barrier that ended them.
+    const uint32_t enter_id = base + kSwRing + tid;
+    const uint32_t enter_pre = enter_id < n ? __ldcg(&dist[enter_id]) : kEncInf;
     __pipeline_wait_prior(1);                        // this block's copies have landed
     __syncthreads();
     const uint32_t* so = cur ? s_off1 : s_off0;
     const int4* sa = cur ? s_arcs1 : s_arcs0;
     const bool staged = hi0 - lo0 <= kSwArcCap;
-    const uint32_t s = base + tid;
-    const bool live = s < n;
-    uint32_t b = 0, e = 0;
-    if (live) { b = so[tid]; e = so[tid + 1]; }
-    uint32_t last = kEncInf;  // the distance my arcs were last relaxed with
-    while (true) {
-      bool changed = false;
-      const uint32_t d = live ? ring[s & kMask] : kEncInf;
-      if (d != last) {
-        last = d;
-        const float ds = dec_f32(d);
-        relaxed += e - b;
-        for (uint32_t k = b; k < e; k++) {
-          const int4 v = staged ? sa[k - lo0] : __ldg(reinterpret_cast<const int4*>(&arcs[k]));
-          const uint32_t t = (uint32_t)v.w;
-          const float c = w_times(ds, __int_as_float(v.z));
+    const uint32_t live_states = min(kSwB, n - base);
+    // Tag every staged arc with its source (the label fields are not needed here), one thread per state; the relaxation
+    // below runs one thread per ARC.
+    if (staged && tid < live_states) {
+      int4* const sa_w = cur ? s_arcs1 : s_arcs0;
+      for (uint32_t k = so[tid]; k < so[tid + 1]; k++) sa_w[k - lo0].x = (int)tid;
+    }
+    __syncthreads();
+    // Sub-blocks of kSub consecutive states, in id order: when a sub-block starts, every arc into it from earlier states
+    // has been relaxed with a final distance, so only arcs INSIDE the sub-block can ask for another round.
+    for (uint32_t j0 = 0; j0 < live_states; j0 += kSub) {
+      const uint32_t j1 = min(j0 + kSub, live_states);
+      const uint32_t a_lo = so[j0], a_hi = so[j1];
+      while (true) {
+        bool changed = false;
+        for (uint32_t k = a_lo + tid; k < a_hi; k += kSwThreads) {
+          int4 v;
+          uint32_t src;
+          if (staged) {
+            v = sa[k - lo0];
+            src = (uint32_t)v.x;
+          } else {  // a block with more arcs than the staging buffer holds: global reads, source by binary search
+            v = __ldg(reinterpret_cast<const int4*>(&arcs[k]));
+            uint32_t l = j0, h = j1;
+            while (h - l > 1) { const uint32_t m = (l + h) >> 1; if (so[m] <= k) l = m; else h = m; }
+            src = l;
+          }
+          const uint32_t s = base + src;
+          const uint32_t d = ring[s & kMask];
+          if (d == kEncInf) continue;
+          relaxed++;
+          const float c = w_times(dec_f32(d), __int_as_float(v.z));
           if (c == w_zero()) continue;
-          const uint32_t ec = enc_f32(c);
+          const uint32_t ec = enc_f32(c), t = (uint32_t)v.w;
           if (t <= s) { backwards = true; continue; }
           if (t - base < kSwRing) {  // in the ring (t > s >= base)
             const uint32_t old = atomicMin(&ring[t & kMask], ec);
-            if (ec < old && t < base + kSwB) changed = true;  // a state of this block improved: one more round
+            if (ec < old && t < base + j1) changed = true;  // a state of this sub-block improved: one more round
+          } else if (t - base < kSwRing + kSwB) {
+            atomicMin(&pending[t - base - kSwRing], ec);
           } else {
             atomicMin(&dist[t], ec);
           }
         }
+        if (!__syncthreads_or(changed)) break;
       }
-      if (!__syncthreads_or(changed)) break;
     }
-    if (live) { dist[s] = ring[s & kMask]; if (last != kEncInf) settled++; }
+    if (tid < live_states) {
+      const uint32_t d = ring[(base + tid) & kMask];
+      dist[base + tid] = d;
+      if (d != kEncInf) settled++;
+    }
     __syncthreads();  // everybody is done with the slice that is overwritten next
-    {  // ids [base + kSwRing, base + kSwRing + kSwB) enter the ring in the slots the retired block leaves
-      const uint32_t id = base + kSwRing + tid;
-      ring[id & kMask] = id < n ? __ldcg(&dist[id]) : kEncInf;
-    }
+    // ids [base + kSwRing, base + kSwRing + kSwB) enter the ring in the slots the retired block leaves
+    ring[enter_id & kMask] = min(enter_pre, pending[tid]);
+    pending[tid] = kEncInf;
     lo0 = lo1; hi0 = hi1; lo1 = lo2; hi1 = hi2;
     // the next iteration's barrier (after its wait) orders these ring writes before anybody reads them
   }
@@ -804,12 +851,20 @@ void run_relax_sweep(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, Eve
   cudaEvent_t ea, eb;
   B200_CUDA(cudaEventCreate(&ea)); B200_CUDA(cudaEventCreate(&eb));
   B200_CUDA(cudaEventRecord(ea, s));
-  static const bool attr_set = [] {
-    B200_CUDA(cudaFuncSetAttribute((const void*)k_relax_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmem));
-    return true;
-  }();
-  (void)attr_set;
-  k_relax_sweep<<<1, kSwThreads, kSwSmem, s>>>(f.offsets.p, f.arcs.p, n, dist.p, ctl.p, out64.p);
+  int block = 512, sub = 128;  // states per block (= threads of the CTA) and per sub-block
+  if (const char* e = std::getenv("B200_SWEEP_BLOCK")) block = std::atoi(e);
+  if (const char* e = std::getenv("B200_SWEEP_SUB")) sub = std::atoi(e);
+#define B200_SWEEP_CASE(B, S)                                                                                              \
+  if (block == B && sub == S) {                                                                                            \
+    B200_CUDA(cudaFuncSetAttribute((const void*)k_relax_sweep<B, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                   (int)sw_smem<B>()));                                                                    \
+    k_relax_sweep<B, S><<<1, B, sw_smem<B>(), s>>>(f.offsets.p, f.arcs.p, n, dist.p, ctl.p, out64.p);                      \
+    launched = true;                                                                                                       \
+  }
+  bool launched = false;
+  B200_SWEEP_CASE(512, 16) B200_SWEEP_CASE(512, 32) B200_SWEEP_CASE(512, 64) B200_SWEEP_CASE(512, 128) B200_SWEEP_CASE(256, 32)
+  if (!launched) { block = 512; sub = 128; B200_SWEEP_CASE(512, 128) }
+#undef B200_SWEEP_CASE
   B200_CUDA(cudaEventRecord(eb, s));
   relax_events.emplace_back(ea, eb);
   st.relax_launches++; st.kernel_launches += 2;
@@ -828,7 +883,7 @@ void run_relax_coop(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, Even
                     bool top_sorted) {
   const uint32_t n = f.num_states;
   DevBuf<uint32_t> stamp(s, n), fr_a(s, n), fr_b(s, n), cnt(s, 3), outw(s, 3);
-  DevBuf<unsigned long long> out64(s, 2);
+  DevBuf<unsigned long long> out64(s, 3);
   dist.reserve_discard(n);
   k_fill_u32<<<blocks_for(n), kThreads, 0, s>>>(dist.p, kEncInf, n);
   B200_CUDA(cudaMemsetAsync(stamp.p, 0xFF, (size_t)n * 4, s));
@@ -838,7 +893,7 @@ void run_relax_coop(const DevFst& f, DevBuf<uint32_t>& dist, SsspStats& st, Even
   B200_CUDA(cudaMemcpyAsync(fr_a.p, &src, 4, cudaMemcpyHostToDevice, s));
   B200_CUDA(cudaMemcpyAsync(cnt.p, init_cnt, 12, cudaMemcpyHostToDevice, s));
   B200_CUDA(cudaMemsetAsync(outw.p, 0, 12, s));
-  B200_CUDA(cudaMemsetAsync(out64.p, 0, 16, s));
+  B200_CUDA(cudaMemsetAsync(out64.p, 0, 24, s));
   B200_CUDA(cudaStreamSynchronize(s));  // the sources of the small copies are host temporaries
   st.kernel_launches += 1;
   // lanes per frontier state: few lanes = more states in flight (the relaxation is latency-bound)

@@ -219,7 +219,8 @@ def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_ove
     accs = R.AcceptorBatch([synth.to_vector_fst(d) for d in acc_dicts])  # the C-ABI's array of handles, built once
     dev = torch.device("cuda", local_rank)
 
-    call_ms = []
+    call_ms, ser_ms, xfer_ms = [], [], []
+    stage = [None]  # page-locked staging buffer for the block that goes to rank 0, reused from step to step
 
     def step():
         tc = time.perf_counter()
@@ -227,7 +228,15 @@ def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_ove
         call_ms.append(1e3 * (time.perf_counter() - tc))
         blocks = None
         if dist is not None:
-            blocks = gather_buffers(torch.from_numpy(pb.to_numpy()), dist, device=dev)
+            t1 = time.perf_counter()
+            nbytes = pb.info()["bytes"]
+            if stage[0] is None or stage[0].numel() < nbytes:
+                stage[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+            pb.to_numpy(out=stage[0].numpy())
+            t2 = time.perf_counter()
+            blocks = gather_buffers(stage[0][:nbytes], dist, device=dev)
+            torch.cuda.synchronize()  # the staging buffer is reused by the next step: its copy and the send are done
+            ser_ms.append(1e3 * (t2 - t1)); xfer_ms.append(1e3 * (time.perf_counter() - t2))
         return pb, st, blocks
 
     pb = None
@@ -287,7 +296,10 @@ def run_c5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_ove
             "inside_the_call_ms_per_step": {"union_upload": inside["ms_h2d"] / args.steps, "expand": inside["ms_expand"] / args.steps,
                                             "connect": inside["ms_connect"] / args.steps,
                                             "split_and_download": inside["ms_d2h"] / args.steps},
-            "gather": check, "cpu_baseline": cpu, "gpu_launches": int(launches),
+            "gather": check,
+            "gather_ms_per_step_rank0": None if not ser_ms else {"serialize_into_pinned": float(np.mean(ser_ms[-args.steps:])),
+                                                                 "h2d_sizes_send_recv_sync": float(np.mean(xfer_ms[-args.steps:]))},
+            "cpu_baseline": cpu, "gpu_launches": int(launches),
             "timer": "max(CUDA events, host wall clock) around K host-driven steps, max over ranks"}
 
 

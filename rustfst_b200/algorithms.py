@@ -207,10 +207,17 @@ class PackedBatch:
         check_ffi_error(lib.b200_packed_batch_get(self.ptr, i, C.byref(out)), "Error fetching a batch result")
         return VectorFst(out)
 
-    def to_numpy(self):
-        """The block as a uint8 array (one copy)."""
+    def to_numpy(self, out=None):
+        """The block as a uint8 array (one copy).  `out`: a caller-owned uint8 array to serialise into (e.g. a view of a
+        page-locked buffer that is reused from call to call); the returned array is the used prefix of it."""
         import numpy as np
-        buf = np.empty(self.info()["bytes"], dtype=np.uint8)
+        nbytes = self.info()["bytes"]
+        if out is None:
+            buf = np.empty(nbytes, dtype=np.uint8)
+        else:
+            if out.dtype != np.uint8 or out.ndim != 1 or out.nbytes < nbytes or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"PackedBatch.to_numpy: `out` must be a contiguous uint8 array of at least {nbytes} bytes")
+            buf = out[:nbytes]
         check_ffi_error(lib.b200_packed_batch_serialize(self.ptr, buf.ctypes.data, buf.nbytes), "Error serialising")
         return buf
 

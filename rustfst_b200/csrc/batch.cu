@@ -137,7 +137,14 @@ void split_batch_device(const DevFst& r, const uint32_t* d_tag, const uint32_t* 
 namespace {
 constexpr uint64_t kPackMagic = 0x4B434150'30303242ull;  // "B200PACK"
 template <class T>
-void put(uint8_t*& w, const T* p, size_t n) { if (n) std::memcpy(w, p, n * sizeof(T)); w += n * sizeof(T); }
+void put(uint8_t*& w, const T* p, size_t n) {
+  const size_t bytes = n * sizeof(T);
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(p);
+  uint8_t* dst = w;
+  // large arrays (the arcs of a batch are tens of MB) are copied by several host threads
+  parallel_ranges(bytes, [&](size_t lo, size_t hi) { std::memcpy(dst + lo, src + lo, hi - lo); }, (size_t)4 << 20);
+  w += bytes;
+}
 template <class T>
 void get(const uint8_t*& r, const uint8_t* end, T* p, size_t n) {
   if ((size_t)(end - r) < n * sizeof(T)) throw FstError("packed batch: truncated block");

@@ -43,7 +43,7 @@ using namespace composeimpl;
 using namespace coop;
 
 constexpr uint32_t kClaimed = 0xFFFFFFFEu;  // slot.id from the rank phase of the discovery wave until the id is published
-constexpr uint32_t kKeyBits = 20;           // emission key = global warp << 20 | warp-local arc index
+constexpr uint32_t kKeyBits = kCoopThreads > 864 ? 19 : 20;  // emission key = global warp << kKeyBits | warp-local arc index
 constexpr uint32_t kWarps = kCoopThreads / 32;
 constexpr uint32_t kMaxProbes = 1u << 14;
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;

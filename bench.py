@@ -561,6 +561,8 @@ def main():
                 r, s = R.compose_with_stats(h1, h2)
                 del r
             gate.wait()
+            time.sleep(0.009 * k)  # callers that start in lockstep upload together, queue for the kernels together and
+            #                        download together: nothing overlaps.  Half a call of offset de-phases them.
             for _ in range(n_calls):
                 r, s = R.compose_with_stats(h1, h2)
                 done[k] += s["arcs_emitted"]

@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "algos.h"
+#include "bulk_async.cuh"
 #include "coop_utils.cuh"
 
 namespace cg = cooperative_groups;
@@ -89,18 +90,19 @@ __global__ void k_fill_u64(unsigned long long* p, unsigned long long v, uint32_t
 // out[0] = waves, out[1] = non-convergence flag, out64[0] = arcs relaxed, out64[1] = states settled.
 constexpr uint32_t kQueueCap = 2048;
 template <int kG, int kT, bool kPreTest, int kS>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 2048 / kT)  // the kernel scales with resident threads: stay at 2048 per SM
 k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t* __restrict__ dist,
              uint32_t* __restrict__ stamp, uint32_t* __restrict__ fr_a, uint32_t* __restrict__ fr_b,
              uint32_t* __restrict__ cnt /*3*/, uint32_t* __restrict__ out, unsigned long long* __restrict__ out64,
              unsigned long long budget) {
   unsigned int bar_epoch = 0;  // out[2] = arrival counter of the grid barrier (zero-initialised)
-  unsigned long long visits = 0;  // frontier entries so far (every thread reads the same counters: uniform)
-  unsigned long long fresh = 0;   // states this thread reached for the first time (summed into out64[2] wave by wave)
+  uint32_t visits = 0;  // frontier entries so far, saturating (every thread reads the same counters: uniform)
+  uint32_t fresh = 0;   // states this thread reached for the first time (summed into out64[2] wave by wave)
   bool over_budget = false;
+  const uint32_t budget32 = budget > 0xFFFFFFFEull ? 0xFFFFFFFFu : (uint32_t)budget;  // 0xFFFFFFFF = no budget
   constexpr uint32_t kQCap = kQueueCap * (kT / 256);
   __shared__ uint32_t s_q[kQCap];
-  __shared__ uint32_t s_qn, s_gbase;
+  __shared__ uint32_t s_qn, s_gbase, s_fresh;
   const uint32_t lane = threadIdx.x % kG;
   const uint32_t groups = gridDim.x * (kT / kG);
   const uint32_t gid = blockIdx.x * (kT / kG) + threadIdx.x / kG;
@@ -111,13 +113,15 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
   while (true) {
     const uint32_t nf = __ldcg(&cnt[wave % 3]);
     if (nf == 0 || wave > n) break;
-    visits += nf;
+    visits = visits + nf < visits ? 0xFFFFFFFEu : min(visits + nf, 0xFFFFFFFEu);
     // States are revisited over and over (a deep DAG with skip arcs): more than `budget` visits in all, or — early, so
     // that little is thrown away — eight times as many visits as states reached so far.
-    if (visits > budget) { over_budget = true; break; }
-    if (budget != ~0ull && wave >= 16 && visits > 8ull * __ldcg(&out64[2]) + 65536ull) { over_budget = true; break; }
+    if (budget32 != 0xFFFFFFFFu) {
+      if (visits > budget32) { over_budget = true; break; }
+      if (wave >= 16 && (unsigned long long)visits > 8ull * __ldcg(&out64[2]) + 65536ull) { over_budget = true; break; }
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt[(wave + 2) % 3] = 0;
-    if (threadIdx.x == 0) s_qn = 0;
+    if (threadIdx.x == 0) { s_qn = 0; if (wave == 0) s_fresh = 0; }
     __syncthreads();
     uint32_t* next_count = &cnt[(wave + 1) % 3];
     // kS frontier states per group and round: their loads, and then their atomics, are issued together (the kernel is
@@ -185,17 +189,20 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
         }
       }
     }
-    __syncthreads();
-    const uint32_t qn = min(s_qn, kQCap);
-    if (threadIdx.x == 0 && qn) s_gbase = atomicAdd(next_count, qn);
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < qn; i += kT) nxt[s_gbase + i] = s_q[i];
-    {  // newly reached states of this wave, one atomic per warp (read by everybody after the barrier)
-      unsigned long long f = fresh;
+    {  // newly reached states of this wave: warp sums into shared memory, ONE global atomic per CTA below
+      uint32_t f = fresh;
       fresh = 0;
       for (int o = 16; o > 0; o >>= 1) f += __shfl_down_sync(0xFFFFFFFFu, f, o);
-      if ((threadIdx.x & 31) == 0 && f) atomicAdd(&out64[2], f);
+      if ((threadIdx.x & 31) == 0 && f) atomicAdd(&s_fresh, f);
     }
+    __syncthreads();
+    const uint32_t qn = min(s_qn, kQCap);
+    if (threadIdx.x == 0) {
+      if (qn) s_gbase = atomicAdd(next_count, qn);
+      if (s_fresh) { atomicAdd(&out64[2], (unsigned long long)s_fresh); s_fresh = 0; }  // read by everybody after the barrier
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < qn; i += kT) nxt[s_gbase + i] = s_q[i];
     wave++;
     uint32_t* tmp = cur; cur = nxt; nxt = tmp;
     coop::grid_barrier(&out[2], bar_epoch);  // lighter than cg::grid_group::sync() (measured 3.4 us less per barrier)
@@ -229,7 +236,7 @@ k_relax_coop(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint
 constexpr uint32_t kSwRing = 8192;
 // arcs of one block staged in shared memory: 11 per state (2 buffers x 88 KB at 512 states); larger blocks read global memory
 template <uint32_t kSwB> constexpr uint32_t sw_arc_cap() { return 11u * kSwB; }
-template <uint32_t kSwB> constexpr size_t sw_smem() { return (size_t)kSwRing * 4 + (size_t)kSwB * 4 + 2 * ((size_t)sw_arc_cap<kSwB>() * 16 + (kSwB + 1) * 4); }
+template <uint32_t kSwB> constexpr size_t sw_smem() { return (size_t)kSwRing * 4 + (size_t)kSwB * 4 + 2 * ((size_t)sw_arc_cap<kSwB>() * 16 + (kSwB + 1) * 4) + 24; }
 template <uint32_t kSwB, uint32_t kSub>
 __global__ void __launch_bounds__(kSwB)
 k_relax_sweep(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uint32_t n, uint32_t* __restrict__ dist,
@@ -242,10 +249,14 @@ k_relax_sweep(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uin
   uint32_t* const s_off1 = s_off0 + (kSwB + 1);
   uint32_t* const ring = s_off1 + (kSwB + 1);
   uint32_t* const pending = ring + kSwRing;  // candidates for the slice that enters the ring when this block retires
+  // two transaction barriers (8-byte aligned: every array before them is a multiple of 8 bytes... kSwB + 1 words twice = even)
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(pending + kSwB);
   const uint32_t tid = threadIdx.x;
   constexpr uint32_t kMask = kSwRing - 1u;
   for (uint32_t i = tid; i < kSwRing; i += kSwThreads) ring[i] = i < n ? __ldcg(&dist[i]) : kEncInf;
   pending[tid] = kEncInf;
+  if (tid == 0) { bulk::mbar_init(&bars[0], 1); bulk::mbar_init(&bars[1], 1); bulk::fence_mbar_init(); }
+  __syncthreads();
   unsigned long long relaxed = 0, settled = 0;
   bool backwards = false;
   // arc range [lo, hi) of the block that starts at state `base` (every thread reads the same two words)
@@ -253,19 +264,26 @@ k_relax_sweep(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uin
     lo = hi = 0;
     if (base < n) { lo = __ldg(&off[base]); hi = __ldg(&off[min(base + kSwB, n)]); }
   };
-  // asynchronous copy of a block's offsets and (when they fit) arcs into buffer `which`
+  // Asynchronous copy of a block's offsets (cp.async, one word per thread) and — when they fit — of its arcs into
+  // buffer `which`: ONE bulk copy through the TMA unit (the arcs of consecutive states are one contiguous range of
+  // 16-byte records), completion counted on the buffer's transaction barrier.  The buffer was last touched by ordinary
+  // shared-memory accesses (the source tags), hence the proxy fence before the copy engine writes it again.
   auto prefetch = [&](uint32_t base, uint32_t lo, uint32_t hi, uint32_t which) {
     if (base < n) {
       uint32_t* so = which ? s_off1 : s_off0;
       int4* sa = which ? s_arcs1 : s_arcs0;
       if (base + tid <= n && tid <= kSwB) __pipeline_memcpy_async(so + tid, off + base + tid, 4);
       if (tid == 0 && base + kSwB <= n) __pipeline_memcpy_async(so + kSwB, off + base + kSwB, 4);
-      if (hi - lo <= kSwArcCap)
-        for (uint32_t k = lo + tid; k < hi; k += kSwThreads) __pipeline_memcpy_async(sa + (k - lo), arcs + k, 16);
+      if (tid == 0 && hi > lo && hi - lo <= kSwArcCap) {
+        bulk::fence_async_smem();
+        bulk::mbar_expect_tx(&bars[which], (hi - lo) * 16u);
+        bulk::g2s(sa, arcs + lo, (hi - lo) * 16u, &bars[which]);
+      }
     }
     __pipeline_commit();
   };
   uint32_t lo0, hi0, lo1, hi1;  // bounds of the current and of the next block
+  uint32_t bar_phase = 0;       // bit b = parity of the next completion of bars[b] (a buffer without a bulk copy skips its turn)
   bounds(0, lo0, hi0);
   bounds(kSwB, lo1, hi1);
   prefetch(0, lo0, hi0, 0);
@@ -280,7 +298,8 @@ k_relax_sweep(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uin
     // barrier that ended them.
     const uint32_t enter_id = base + kSwRing + tid;
     const uint32_t enter_pre = enter_id < n ? __ldcg(&dist[enter_id]) : kEncInf;
-    __pipeline_wait_prior(1);                        // this block's copies have landed
+    __pipeline_wait_prior(1);                        // this block's offsets have landed
+    if (hi0 > lo0 && hi0 - lo0 <= kSwArcCap) { bulk::mbar_wait(&bars[cur], (bar_phase >> cur) & 1u); bar_phase ^= 1u << cur; }  // ... and its arcs
     __syncthreads();
     const uint32_t* so = cur ? s_off1 : s_off0;
     const int4* sa = cur ? s_arcs1 : s_arcs0;
@@ -337,6 +356,7 @@ k_relax_sweep(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, uin
       dist[base + tid] = d;
       if (d != kEncInf) settled++;
     }
+    bulk::fence_async_smem();  // my ordinary accesses to this block's arc buffer precede the next bulk copy into it
     __syncthreads();  // everybody is done with the slice that is overwritten next
     // ids [base + kSwRing, base + kSwRing + kSwB) enter the ring in the slots the retired block leaves
     ring[enter_id & kMask] = min(enter_pre, pending[tid]);
@@ -438,13 +458,25 @@ __global__ void k_backtrace_keys(const uint32_t* __restrict__ off, const Tr* __r
     uint32_t pord = (uint32_t)(key >> 32), pos = (uint32_t)(key & 0xFFFFFFFFull);
     uint32_t src = inv_order ? inv_order[pord] : pord;
     if (L >= cap || L >= n) { meta[3] = 1; break; }
-    Tr tr = arcs[off[src] + pos];
-    tr.nextstate = L;  // previous output state
+    // only (source, position) here: the walk is one dependent load per hop; k_backtrace_fill fetches the arcs in parallel
+    Tr tr; tr.ilabel = src; tr.olabel = pos; tr.weight = 0.0f; tr.nextstate = L;
     out_arcs[L] = tr;
     L++;
     state = src;
   }
   meta[1] = L;
+}
+// out_arcs[k] = arc `position` of state `source` (as left by k_backtrace_keys), pointing at output state k
+__global__ void __launch_bounds__(kThreads)
+k_backtrace_fill(const uint32_t* __restrict__ off, const Tr* __restrict__ arcs, Tr* __restrict__ out_arcs,
+                 const uint32_t* __restrict__ meta) {
+  const uint32_t L = meta[1];
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
+    const Tr ref = out_arcs[k];
+    Tr tr = arcs[off[ref.ilabel] + ref.olabel];
+    tr.nextstate = k;  // previous output state
+    out_arcs[k] = tr;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1084,7 +1116,8 @@ CsrFst shortest_path_device(const DevFst& f, const QueuePlan& plan, SsspStats* s
         inv_p = inv.p; st.kernel_launches++;
       }
       k_backtrace_keys<<<1, 32, 0, s>>>(f.offsets.p, f.arcs.p, n, pkey.p, fkey.p, inv_p, out_arcs.p, cap, meta.p);
-      st.kernel_launches++;
+      k_backtrace_fill<<<64, kThreads, 0, s>>>(f.offsets.p, f.arcs.p, out_arcs.p, meta.p);
+      st.kernel_launches += 2;
       B200_CUDA(cudaMemcpyAsync(hmeta, meta.p, 16, cudaMemcpyDeviceToHost, s));
       B200_CUDA(cudaStreamSynchronize(s));
       st.path = 0;

@@ -51,13 +51,19 @@ constexpr uint32_t kDagThreads = 512;
 constexpr uint32_t kSub = 8;             // lanes that share one state (its arcs are strided over them)
 constexpr uint32_t kMaxLevels = 1u << 16;
 constexpr uint32_t kReadyBuf = 96;         // per-warp buffer of newly ready states (shared memory)
-enum DagStatus : uint32_t { kDagCyclic = 1, kDagTooDeep = 2 };
+enum DagStatus : uint32_t { kDagCyclic = 1, kDagTooDeep = 2, kDagNeedRows = 4 };
 
-constexpr uint32_t kLow = 6;  // ancestors 2^0 .. 2^5 of a state live in its record; higher ones in the table up_hi
+constexpr uint32_t kLow = 4;  // ancestors 2^0 .. 2^3 of a state live in its record; higher ones in the table up_hi
+constexpr uint32_t kWinDigits = 8, kWinOver = 15;  // the record's window: the last 8 arc positions of the path, 4 bits each
 
 // Everything a comparison needs to know about a processed state, in ONE 32-byte sector (one 256-bit load):
-// depth, position of the tree arc in the parent's list, and the 2^j-th ancestors for j < kLow (R where the path is shorter).
-struct alignas(32) NodeRec { uint32_t depth, pos, up[kLow]; };
+// depth, position of the tree arc in the parent's list, position of the path's FIRST arc (the one that leaves R), the
+// last kWinDigits positions of the path packed 4 bits each (oldest in the top nibble; kWinOver = "15 or more"), and the
+// 2^j-th ancestors for j < kLow (R where the path is shorter).
+struct alignas(32) NodeRec { uint32_t depth, pos, rootpos, win, up[kLow]; };
+__device__ __forceinline__ bool win_overflows(uint32_t w) {  // some nibble equals 15
+  return ((w & (w >> 1) & (w >> 2) & (w >> 3)) & 0x11111111u) != 0u;
+}
 
 struct DagParams {
   const uint32_t* off; const Tr* arcs; uint32_t n; uint32_t start;
@@ -71,6 +77,7 @@ struct DagParams {
   uint32_t* order;            // result
   uint32_t* ctl;              // [0..2] rotating level counters, [3] #levels, [4] status, [5] barrier of k_dag_tree, [6] #states processed,
                               // [7] barrier of k_dag_orders
+  uint32_t hi_rows;           // rows of up_hi that exist: ancestors up to 2^(kLow + hi_rows - 1)
   unsigned long long* trace;  // optional (B200_COOP_TRACE): ns of CTA 0 in [0] records, [1] barrier, [2] candidacies, [3] barrier, [4] sizes
 };
 
@@ -81,13 +88,13 @@ __device__ __forceinline__ unsigned long long pack_cand(uint32_t node, uint32_t 
 __device__ __forceinline__ NodeRec ld_rec(const DagParams& P, uint32_t v) {
   NodeRec r;
   asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r.depth), "=r"(r.pos), "=r"(r.up[0]), "=r"(r.up[1]), "=r"(r.up[2]), "=r"(r.up[3]), "=r"(r.up[4]), "=r"(r.up[5])
+               : "=r"(r.depth), "=r"(r.pos), "=r"(r.rootpos), "=r"(r.win), "=r"(r.up[0]), "=r"(r.up[1]), "=r"(r.up[2]), "=r"(r.up[3])
                : "l"(P.rec + v));
   return r;
 }
 __device__ __forceinline__ void st_rec(const DagParams& P, uint32_t v, const NodeRec& r) {
   asm volatile("st.global.cg.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
-               :: "r"(r.depth), "r"(r.pos), "r"(r.up[0]), "r"(r.up[1]), "r"(r.up[2]), "r"(r.up[3]), "r"(r.up[4]), "r"(r.up[5]), "l"(P.rec + v)
+               :: "r"(r.depth), "r"(r.pos), "r"(r.rootpos), "r"(r.win), "r"(r.up[0]), "r"(r.up[1]), "r"(r.up[2]), "r"(r.up[3]), "l"(P.rec + v)
                : "memory");
 }
 __device__ __forceinline__ uint32_t ld_next_state(const Tr* arc) {  // pinned in program order: issued a round ahead of its use
@@ -118,7 +125,13 @@ __device__ __forceinline__ void lift(const DagParams& P, uint32_t& x, NodeRec& r
 // records per set bit of the distance to the parting point.
 __device__ __forceinline__ bool cand_less(const DagParams& P, uint32_t a, NodeRec& rx, uint32_t pa, uint32_t b, uint32_t pb) {
   if (a == b) return pa < pb;
+  if (b == P.n) return rx.rootpos < pb;  // b's candidate is an arc of R itself: the first arcs decide (they cannot be equal)
   NodeRec ry = ld_rec(P, b);
+  // Same depth and the same ancestor eight levels up (or both paths shorter than that): the paths are that ancestor's
+  // path followed by the two windows, so the windows decide — no further loads.  A window with a position >= 15 in it
+  // takes the general route.
+  if (rx.depth == ry.depth && rx.up[3] == ry.up[3] && rx.win != ry.win && !win_overflows(rx.win) && !win_overflows(ry.win))
+    return rx.win < ry.win;
   uint32_t x = a, y = b, d = rx.depth;
   if (rx.depth > ry.depth) {  // is b an ancestor of a?  then a's path leaves b through the arc towards a
     lift(P, x, rx, rx.depth - ry.depth - 1);
@@ -156,7 +169,7 @@ __global__ void k_dag_init(DagParams P) {
     P.sizes[v] = 1u;
   } else if (v == P.n) {
     P.best[v] = pack_cand(P.n, 0u);
-    NodeRec r; r.depth = 0u; r.pos = 0u;
+    NodeRec r; r.depth = 0u; r.pos = 0u; r.rootpos = 0u; r.win = 0u;
     for (uint32_t j = 0; j < kLow; j++) r.up[j] = P.n;
     st_rec(P, v, r);
     for (int k = 0; k < 8; k++) P.ctl[k] = 0u;
@@ -192,6 +205,8 @@ k_dag_tree(DagParams P) {
   auto lap = [&](int k) { if (tracing) { const unsigned long long t = globaltimer_ns(); t_acc[k] += t - t_prev; t_prev = t; } };
   while (lo < hi) {
     if (level + 2 >= kMaxLevels) { status = kDagTooDeep; break; }  // uniform
+    // a state of Kahn level L sits at depth <= L + 1: the ancestor table must reach that far (the host retries with all rows)
+    if (P.hi_rows < 32u - kLow && level + 1 >= (1u << (kLow + P.hi_rows))) { status = kDagNeedRows; break; }
     if (c == 0 && tid == 0) { P.lev_off[level] = lo; P.ctl[(level + 2) % 3] = 0u; }
     uint32_t* const next_cnt = &P.ctl[(level + 1) % 3];
     const uint32_t count = hi - lo;
@@ -205,6 +220,8 @@ k_dag_tree(DagParams P) {
       const NodeRec rp = ld_rec(P, parent);
       NodeRec r;
       r.depth = rp.depth + 1u; r.pos = (uint32_t)bv; r.up[0] = parent; r.up[1] = rp.up[0];
+      r.rootpos = parent == P.n ? r.pos : rp.rootpos;
+      r.win = (rp.win << 4) | min(r.pos, kWinOver);  // the window of R is empty
 #pragma unroll
       for (uint32_t j = 2; j < kLow; j++) r.up[j] = __ldcg(&P.rec[r.up[j - 1]].up[j - 1]);  // rec[R].up[*] = R
       st_rec(P, v, r);
@@ -410,11 +427,11 @@ int coop_grid(const void* kern, int threads) {
 
 }  // namespace
 
-// order[s] of the reference's TopOrderQueue for an acyclic machine (see the header of this file).  Returns false when
-// the machine is cyclic or has more Kahn levels than the device path handles; the caller then takes the host DFS.
-bool dag_top_order_device(const DevFst& f, DevBuf<uint32_t>& order, float* ms, uint64_t* launches, cudaStream_t s) {
+// One attempt with the short (all_rows = false) or the full ancestor table: 1 = done, 0 = cyclic / too many levels, -1 = the
+// machine is deeper than the short table reaches.
+static int dag_top_order_try(const DevFst& f, DevBuf<uint32_t>& order, float* ms, uint64_t* launches, cudaStream_t s, bool all_rows) {
   const uint32_t n = f.num_states, a = f.num_arcs;
-  if (n == 0 || !f.has_start) return false;
+  if (n == 0 || !f.has_start) return 0;
   DeviceExclusive excl(device_exclusive());  // the persistent kernels want every SM (device_common.cu)
   cudaEvent_t e0, e1;
   B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
@@ -423,13 +440,17 @@ bool dag_top_order_device(const DevFst& f, DevBuf<uint32_t>& order, float* ms, u
   while ((1ull << log_n) <= (unsigned long long)n + 1) log_n++;
   order.reserve_discard(n);
   DevBuf<uint32_t> indeg(s, n), lev_nodes(s, n), lev_off(s, kMaxLevels + 2), sizes(s, n), ctl(s, 8);
-  DevBuf<uint32_t> up_hi(s, (size_t)(log_n > kLow ? log_n - kLow : 1) * ((size_t)n + 1)), g(s, (size_t)n + 1), pref(s, (size_t)n + 1);
+  // Ancestors 2^kLow and up live in a side table of (n + 1)-word rows.  A lattice is a few dozen to a few hundred levels
+  // deep: six rows (depth < 1024) are allocated first, all log2(n) rows only when the machine turns out to be deeper.
+  const uint32_t full_rows = log_n > kLow ? log_n - kLow : 1;
+  const uint32_t hi_rows = all_rows ? full_rows : std::min<uint32_t>(full_rows, 6u);
+  DevBuf<uint32_t> up_hi(s, (size_t)hi_rows * ((size_t)n + 1)), g(s, (size_t)n + 1), pref(s, (size_t)n + 1);
   DevBuf<unsigned long long> best(s, (size_t)n + 1);
   DevBuf<NodeRec> rec(s, (size_t)n + 1);
   DevBuf<uint8_t> scan_tmp(s);
   DagParams P{};
   P.off = f.offsets.p; P.arcs = f.arcs.p; P.n = n; P.start = f.start;
-  P.indeg = indeg.p; P.best = best.p; P.rec = rec.p; P.up_hi = up_hi.p; P.lev_nodes = lev_nodes.p; P.lev_off = lev_off.p;
+  P.indeg = indeg.p; P.best = best.p; P.rec = rec.p; P.up_hi = up_hi.p; P.hi_rows = hi_rows; P.lev_nodes = lev_nodes.p; P.lev_off = lev_off.p;
   P.sizes = sizes.p; P.order = order.p; P.ctl = ctl.p;
   const bool tracing = std::getenv("B200_COOP_TRACE") != nullptr;
   DevBuf<unsigned long long> trace(s, 8 * 4096);
@@ -482,7 +503,17 @@ bool dag_top_order_device(const DevFst& f, DevBuf<uint32_t>& order, float* ms, u
     cudaEventDestroy(e_a); cudaEventDestroy(e_b);
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return ok;
+  return ok ? 1 : (h[4] == kDagNeedRows ? -1 : 0);
+}
+
+// order[s] of the reference's TopOrderQueue for an acyclic machine (see the header of this file).  Returns false when
+// the machine is cyclic or has more Kahn levels than the device path handles; the caller then takes the host DFS.
+bool dag_top_order_device(const DevFst& f, DevBuf<uint32_t>& order, float* ms, uint64_t* launches, cudaStream_t s) {
+  float ms1 = 0, ms2 = 0;
+  int r = dag_top_order_try(f, order, &ms1, launches, s, false);
+  if (r < 0) r = dag_top_order_try(f, order, &ms2, launches, s, true);  // deeper than the short ancestor table reaches
+  if (ms) *ms = ms1 + ms2;
+  return r > 0;
 }
 
 }  // namespace b200

@@ -55,6 +55,28 @@ std::recursive_mutex& device_exclusive() {
   return m;
 }
 
+namespace {
+struct ThreadStreams {
+  std::vector<cudaStream_t> idle;
+  ~ThreadStreams() { for (cudaStream_t s : idle) cudaStreamDestroy(s); }
+};
+thread_local ThreadStreams t_streams;
+}  // namespace
+cudaStream_t acquire_thread_stream() {
+  if (!t_streams.idle.empty()) {
+    cudaStream_t s = t_streams.idle.back();
+    t_streams.idle.pop_back();
+    return s;
+  }
+  cudaStream_t s = nullptr;
+  B200_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  return s;
+}
+void release_thread_stream(cudaStream_t s) {
+  cudaStreamSynchronize(s);  // nothing of this call may still be running when the next call reuses the stream
+  t_streams.idle.push_back(s);
+}
+
 void require_device() {
   std::call_once(g_once, init_device);
   if (!g_init_error.empty()) throw CudaError(g_init_error);

@@ -40,13 +40,19 @@ std::recursive_mutex& device_exclusive();
 using DeviceExclusive = std::lock_guard<std::recursive_mutex>;
 
 // One stream per C-ABI call: concurrent calls from different host threads do not serialise on the legacy stream.
+// One CUDA stream per call, taken from a per-host-thread cache: the stream-ordered allocator hands a freed block back
+// to the SAME stream at once, whereas blocks freed on a stream that was destroyed after the call are only reused when
+// the allocator happens to notice that the free has completed — otherwise the pool grows by hundreds of MB (50-100 ms
+// of cuMemCreate / map in the middle of a 5 ms call; seen as outliers of the shortest-path order in a fresh process).
+cudaStream_t acquire_thread_stream();
+void release_thread_stream(cudaStream_t s);
 struct Stream {
   cudaStream_t s = nullptr;
   Stream() {
     require_device();
-    B200_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    s = acquire_thread_stream();
   }
-  ~Stream() { if (s) cudaStreamDestroy(s); }
+  ~Stream() { if (s) release_thread_stream(s); }
   Stream(const Stream&) = delete;
   Stream& operator=(const Stream&) = delete;
   void sync() const { B200_CUDA(cudaStreamSynchronize(s)); }

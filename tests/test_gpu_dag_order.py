@@ -102,6 +102,16 @@ def test_wide_skip_level_dag_and_unreachable_states():
     _check(d, "many roots")
 
 
+def test_deep_dags_take_the_full_ancestor_table():
+    """More than 1024 Kahn levels: the first attempt (six rows of the 2^j-ancestor table) gives up and the call is
+    repeated with all log2(n) rows; ancestors 16 and more levels up are then read from the side table."""
+    rng = np.random.default_rng(12)
+    d = _dag(rng, 6_000, 3, window=3)       # arcs reach at most three positions ahead: thousands of levels
+    _check(d, "narrow deep dag")
+    d = _dag(rng, 3_000, 2, window=40)      # a few hundred levels, comparisons across many depths
+    _check(d, "medium deep dag")
+
+
 def test_layered_lattice_and_shortest_path_through_the_device_order():
     import rustfst_b200 as R
     from rustfst_b200 import props as PR

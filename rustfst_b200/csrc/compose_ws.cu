@@ -93,7 +93,6 @@ constexpr uint32_t kEA = B200_WS_EA, kRA = B200_WS_RA;
 static_assert(kEA == 1, "the emit phase locates records with a 32-bit start mask: one arc per lane and round");
 constexpr uint32_t kMT = 32;        // items per match tile (one per lane)
 constexpr uint32_t kET = 32 * kEA;  // arcs per emit round
-constexpr uint32_t kSegN = (kMT > kET ? kMT : kET) + 1;
 
 struct __align__(128) WarpSmem {
   StRec win[2][kMT + 2];      // match: state records of the current / next tile (kMT + 1 used)

@@ -1,7 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests/test_gpu_dag_order.py -x -q -m gpu 2>&1 | tail -2
-echo "== sssp on a composed-lattice property word, 8 reps"
-timeout 600 python tools/profile_run.py --no-compose --sssp-top --reps 8 2>&1 | grep -E "ms_order" | cut -c150-330
-echo "== host-API compose + sssp (e2e probe)"
-timeout 600 python tools/e2e_probe.py 2>&1 | tail -9 | cut -c1-200
+for p in 1 0; do
+echo "== pipelined=$p"
+B200_DAG_PIPELINED=$p timeout 900 python -m pytest tests/test_gpu_dag_order.py -x -q -m gpu 2>&1 | tail -1
+B200_DAG_PIPELINED=$p B200_COOP_TRACE=1 timeout 600 python tools/profile_run.py --no-compose --sssp-top --reps 3 2>&1 | grep -E "dag-order" | tail -3 | cut -c1-300
+B200_DAG_PIPELINED=$p timeout 600 python tools/profile_run.py --no-compose --sssp-top --reps 5 2>&1 | grep -E "ms_order" | tail -3 | cut -c150-330
+done

@@ -57,6 +57,29 @@ def test_block_round_trip_and_results():
         assert rs == (st if st >= 0 else None) and r.properties == p
     with pytest.raises(ValueError):
         pb.result(3)
+    # serialising into a caller-owned (e.g. page-locked, reused) buffer: the used prefix comes back
+    big = np.full(len(blob) + 100, 0xAB, dtype=np.uint8)
+    view = pb.to_numpy(out=big)
+    assert view.nbytes == len(blob) and view.tobytes() == blob and np.shares_memory(view, big)
+    assert (big[len(blob):] == 0xAB).all()
+    with pytest.raises(ValueError, match="at least"):
+        pb.to_numpy(out=np.zeros(len(blob) - 1, dtype=np.uint8))
+    with pytest.raises(ValueError):
+        pb.to_numpy(out=np.zeros(len(blob), dtype=np.uint16))
+
+
+def test_large_block_round_trips_through_the_threaded_copy():
+    """Arrays of more than 4 MB are serialised by several host threads (batch.cu put())."""
+    n_states, n_arcs = 300_000, 600_000
+    arcs = np.zeros(n_arcs, dtype=TR_DTYPE)
+    rng = np.random.default_rng(5)
+    arcs["ilabel"] = rng.integers(1, 1000, n_arcs); arcs["olabel"] = arcs["ilabel"]
+    arcs["weight"] = rng.integers(0, 64, n_arcs) / 8.0
+    arcs["nextstate"] = rng.integers(0, n_states, n_arcs)
+    offs = np.arange(0, n_arcs + 1, 2, dtype=np.uint32)
+    blob = _block([(list(offs), arcs, list(np.zeros(n_states, dtype=np.float32)), 0, 0)])
+    pb = R.PackedBatch.from_buffer(blob)
+    assert pb.info()["num_trs"] == n_arcs and pb.to_bytes() == blob
 
 
 @pytest.mark.parametrize("damage", ["truncate", "magic", "nextstate", "start", "offsets", "totals"])

@@ -487,7 +487,7 @@ def main():
     value = arcs_all / (ms_region * 1e-3)
     steps = args.steps
     bytes_compose = 16.0 * tot["arcs_iterated"] + 48.0 * tot["arcs_emitted"] + 32.0 * tot["states_expanded"]
-    # Dominant kernel = the persistent BFS kernel k_compose_coop (one launch per compose): algorithmic bytes of the
+    # Dominant kernel = the persistent BFS kernel k_compose_ws (one launch per compose): algorithmic bytes of the
     # whole expansion (16*A_it + 48*A_out + 32*S) over its CUDA-event duration.  The arc-scan phase of
     # that kernel (phase B: gather matched arc, table probe, write output arc = 48 B/arc) is timed inside the kernel
     # with %globaltimer and reported separately.
@@ -501,7 +501,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {
-        "bound": "hbm", "kernel": "k_compose_coop (persistent cooperative kernel: the whole BFS expansion)",
+        "bound": "hbm", "kernel": "k_compose_ws (persistent warp-stream kernel: the whole BFS expansion in one launch)",
         "achieved": kern_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": kern_gbs / peak_gbs, "peak_source": peak_src,
         "traffic": traffic,
         "algorithmic_bytes_per_launch": bytes_compose / max(1, tot["emit_launches"]),

@@ -65,6 +65,8 @@ struct WsParams {
   float* out_finals;
   uint2* st_first;          // per canonical state: (run index, warp-local index) of its first arc
   Tr* prov_arcs; uint32_t arcs_cap; unsigned long long* arc_cursor;
+  uint32_t* prov_next;  // the next-state word of every provisional arc once more, dense: the rank phase and the final
+                        // next-state pass read 4 bytes per arc instead of a 32-byte sector per two arcs
   uint32_t* run_src; uint32_t* run_cnt; uint32_t runs_cap;
   Slot* slots; uint32_t mask; uint32_t table_cap;
   StRec* st_rec; StCold* st_cold; uint32_t* st_cursor;   // record region of the current frontier
@@ -531,6 +533,7 @@ k_compose_ws(WsParams P) {
     const unsigned long long tm2 = globaltimer_ns();
     const uint32_t ekey = gw << kKeyBits;
     Tr* __restrict__ run_arcs = P.prov_arcs + prov;
+    uint32_t* __restrict__ run_next = P.prov_next + prov;
     if (emit_ok) {
       // Tried and dropped: keeping the warp's records (and the next-state words for the rank phase) in shared memory so
       // that the emit phase needs no fence / copy / wait.  With 160 records + 256 words per warp (201 KB per CTA) the
@@ -638,6 +641,7 @@ k_compose_ws(WsParams P) {
                                     bulk::U128{key[q], ((unsigned long long)e << 32) | kUnassigned});
             }
             store_tr(&run_arcs[el[q]], out[q]);
+            run_next[el[q]] = out[q].nextstate;
           }
         }
         cursor = cursor_next;
@@ -664,7 +668,7 @@ k_compose_ws(WsParams P) {
 #pragma unroll
         for (uint32_t q = 0; q < kRA; q++) {
           const uint32_t el = e0 + 32u * q + lane;
-          ns[q] = el < e_end ? __ldcg(&run_arcs[el].nextstate) : 0u;
+          ns[q] = el < e_end ? __ldcg(&run_next[el]) : 0u;
         }
 #pragma unroll
         for (uint32_t q = 0; q < kRA; q++)
@@ -805,15 +809,17 @@ __global__ void k_ws_offsets(const uint2* __restrict__ st_first, const uint32_t*
 constexpr uint32_t kMoveWarps = 8;
 template <bool kWholeArcs>
 __global__ void __launch_bounds__(kMoveWarps * 32)
-k_ws_move(const Tr* __restrict__ prov, const uint32_t* __restrict__ run_src, const uint32_t* __restrict__ run_cnt,
-          const uint32_t* __restrict__ run_dst, uint32_t n_runs, const Slot* __restrict__ slots,
-          Tr* __restrict__ out_arcs, uint32_t* __restrict__ out_next) {
+k_ws_move(const Tr* __restrict__ prov, const uint32_t* __restrict__ prov_next, const uint32_t* __restrict__ run_src,
+          const uint32_t* __restrict__ run_cnt, const uint32_t* __restrict__ run_dst, uint32_t n_runs,
+          const Slot* __restrict__ slots, Tr* __restrict__ out_arcs, uint32_t* __restrict__ out_next) {
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   const uint32_t warps = gridDim.x * kMoveWarps;
   for (uint32_t r = blockIdx.x * kMoveWarps + wid; r < n_runs; r += warps) {
     const uint32_t cnt = __ldg(&run_cnt[r]);
     if (!cnt) continue;
-    const Tr* __restrict__ src = prov + __ldg(&run_src[r]);
+    const uint32_t first = __ldg(&run_src[r]);
+    const Tr* __restrict__ src = prov + first;
+    const uint32_t* __restrict__ src_next = prov_next + first;
     const uint32_t dst = __ldg(&run_dst[r]);
     for (uint32_t e0 = 0; e0 < cnt; e0 += 128) {
       int4 v[4];
@@ -822,7 +828,7 @@ k_ws_move(const Tr* __restrict__ prov, const uint32_t* __restrict__ run_src, con
       for (int q = 0; q < 4; q++) {
         const uint32_t e = e0 + 32u * q + lane;
         if (kWholeArcs) { v[q] = e < cnt ? __ldg(reinterpret_cast<const int4*>(&src[e])) : make_int4(0, 0, 0, 0); ns[q] = (uint32_t)v[q].w; }
-        else ns[q] = e < cnt ? __ldg(&src[e].nextstate) : 0u;
+        else ns[q] = e < cnt ? __ldg(&src_next[e]) : 0u;
       }
 #pragma unroll
       for (int q = 0; q < 4; q++)
@@ -975,6 +981,7 @@ int compose_device_ws(const DevFst& fa, const DevFst& fb, const ComposeOptions& 
   DevFst out(s);
   out.finals.reserve_discard(cp.states);
   DevBuf<Tr> prov_arcs(s, cp.arcs);
+  DevBuf<uint32_t> prov_next(s, cp.arcs);
   DevBuf<unsigned long long> tuples(s, cp.states), dstats(s, 16), cursors(s, 2);
   DevBuf<uint2> st_first(s, cp.states);
   DevBuf<Slot> slots(s, table_cap);
@@ -990,7 +997,7 @@ int compose_device_ws(const DevFst& fa, const DevFst& fb, const ComposeOptions& 
   B200_CUDA(cudaMemsetAsync(parts.p, 0, 2 * 2048 * sizeof(unsigned long long), s));  // tag 0 = nothing published yet
   P.tuples = tuples.p; P.states_cap = (uint32_t)cp.states;
   P.out_finals = out.finals.p; P.st_first = st_first.p;
-  P.prov_arcs = prov_arcs.p; P.arcs_cap = (uint32_t)cp.arcs; P.arc_cursor = cursors.p;
+  P.prov_arcs = prov_arcs.p; P.prov_next = prov_next.p; P.arcs_cap = (uint32_t)cp.arcs; P.arc_cursor = cursors.p;
   P.run_src = run_src.p; P.run_cnt = run_cnt.p; P.runs_cap = (uint32_t)cp.runs;
   P.slots = slots.p; P.mask = (uint32_t)table_cap - 1; P.table_cap = (uint32_t)std::min<size_t>(table_cap, 0xFFFFFFFFull);
   P.st_rec = st_rec.p; P.st_cold = st_cold.p; P.st_cursor = reinterpret_cast<uint32_t*>(cursors.p + 1);
@@ -1041,10 +1048,10 @@ int compose_device_ws(const DevFst& fa, const DevFst& fb, const ComposeOptions& 
   DevBuf<uint32_t> next(s);
   if (opt.connect) {  // the trim only needs the resolved next states; it gathers the arcs from their runs itself
     next.reserve_discard(n_arcs ? n_arcs : 1);
-    if (n_runs) k_ws_move<false><<<move_grid, kMoveWarps * 32, 0, s>>>(prov_arcs.p, run_src.p, run_cnt.p, run_dst.p, n_runs, slots.p, nullptr, next.p);
+    if (n_runs) k_ws_move<false><<<move_grid, kMoveWarps * 32, 0, s>>>(prov_arcs.p, prov_next.p, run_src.p, run_cnt.p, run_dst.p, n_runs, slots.p, nullptr, next.p);
   } else {
     out.arcs.reserve_discard(n_arcs ? n_arcs : 1);
-    if (n_runs) k_ws_move<true><<<move_grid, kMoveWarps * 32, 0, s>>>(prov_arcs.p, run_src.p, run_cnt.p, run_dst.p, n_runs, slots.p, out.arcs.p, nullptr);
+    if (n_runs) k_ws_move<true><<<move_grid, kMoveWarps * 32, 0, s>>>(prov_arcs.p, prov_next.p, run_src.p, run_cnt.p, run_dst.p, n_runs, slots.p, out.arcs.p, nullptr);
   }
   st.kernel_launches += 3;
   out.num_states = n_states; out.num_arcs = n_arcs;

@@ -23,6 +23,8 @@ ap.add_argument("--spread", action="store_true", help="transducer targets depend
 ap.add_argument("--sssp-top", action="store_true", help="C4 with the property word compose leaves (device DFS order)")
 ap.add_argument("--sssp-window", type=int, default=0, help="SSSP on a window DAG (skip-level arcs) with this window")
 args = ap.parse_args()
+if args.spread and args.vocab == 32 and not args.fanout:  # the bench's compose_spread shape: with 32 labels the product explodes
+    args.vocab, args.fanout = 93, True
 
 n, a = int(1_000_000 * args.scale), int(10_000_000 * args.scale)
 a1 = synth.layered_acceptor(n, a, args.vocab, 3, args.levels, start_fanout=args.fanout)

@@ -971,6 +971,18 @@ bool compose_device_persistent(const DevFst& a, const DevFst& b, const ComposeOp
     if (rc & kOvRuns) grow(caps.runs, 0xFFFFFFF0ull);
     if (rc & kOvWaves) grow(caps.waves, 0x7FFFFFF0ull);
     if (!grown) return false;
+    // A product that keeps outgrowing its buffers would end in an allocation failure somewhere inside the next attempt;
+    // say what happened instead.  Working set of an attempt: 20 B per provisional arc, 20 B per match item, ~72 B per
+    // state (records, tuples, first-arc index, finals) + a 16-B table slot for at least two slots per state.
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
+      const double need = 20.0 * (double)caps.arcs + 20.0 * (double)caps.items + (72.0 + 64.0) * (double)caps.states;
+      if (need > 0.9 * (double)total_b)
+        throw FstError("compose: the composition outgrew " + std::to_string((unsigned long long)(need / 1e9)) +
+                       " GB of working memory (" + std::to_string((unsigned long long)caps.states) + " states, " +
+                       std::to_string((unsigned long long)caps.arcs) + " transitions reserved) on a device with " +
+                       std::to_string((unsigned long long)(total_b / 1e9)) + " GB; the product is too large for one GPU");
+    }
   }
   return false;
 }

@@ -38,3 +38,25 @@ def test_product_does_not_depend_on_the_oracle():
             if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.replace("oracle/ ", ""), f"{f} mentions the oracle"
+
+
+def test_stats_structs_have_the_layout_of_the_public_header(tmp_path):
+    """The ctypes mirrors of B200ComposeStats / B200SsspStats (rustfst_b200/ffi.py) against what a C compiler sees in
+    include/rustfst_b200.h: size and the offset of every field (tests/cpp/abi_layout.c prints them)."""
+    import subprocess
+    from rustfst_b200 import ffi
+    exe = tmp_path / "abi_layout"
+    subprocess.run(["gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "abi_layout.c"),
+                    "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        name, value = line.split()
+        struct, field = name.split(".")
+        mirror = {"B200ComposeStats": ffi.ComposeStats, "B200SsspStats": ffi.SsspStats}[struct]
+        if field == "sizeof":
+            assert ctypes.sizeof(mirror) == int(value), (name, ctypes.sizeof(mirror), value)
+        else:
+            assert getattr(mirror, field).offset == int(value), (name, getattr(mirror, field).offset, value)
+        seen += 1
+    assert seen >= 24
